@@ -1,0 +1,105 @@
+// Shared device helpers: streaming 128-bit accesses and the pointwise op
+// "program" that both the eager ops and the fused chain kernels execute.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mpk {
+
+constexpr int kMaxPw = 8;  // pointwise ops one fused segment can carry
+
+enum PwKind : int {
+    PW_NONE = 0,
+    PW_BRIGHTNESS = 1,  // a = delta                     src/millipyde_image.cpp:384-398
+    PW_GAMMA = 2,       // a = gamma, b = gain           :438-454
+    PW_COLORIZE = 3,    // a, b, c = r, g, b multipliers :494-524 (float analogue)
+};
+
+struct PwOp {
+    int kind;
+    float a, b, c;
+};
+
+struct PwProgram {
+    int n;
+    PwOp ops[kMaxPw];
+};
+
+// Streaming (evict-first) 128-bit global accesses: every byte of an image is
+// touched once per op, so nothing should linger in L1/L2 ahead of the halo rows
+// the stencil kernels do want cached.
+__device__ __forceinline__ float4 ld_stream(const float4 *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float4 *p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(uint4 *p, uint4 v) { __stcs(p, v); }
+__device__ __forceinline__ double2 ld_stream(const double2 *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(double2 *p, double2 v) { __stcs(p, v); }
+
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+
+// One pointwise op on one fp32 sample of channel `ch` of a C-channel image.
+// Alpha (ch == 3) is never touched, as in the reference's RGBA kernels.
+template <int C>
+__device__ __forceinline__ float pw_apply_one(const PwOp &op, float v, int ch)
+{
+    if (C == 4 && ch == 3) return v;
+    switch (op.kind) {
+        case PW_BRIGHTNESS: return clamp01(v + op.a);
+        case PW_GAMMA: return clamp01(op.b * powf(v, op.a));
+        case PW_COLORIZE:
+            if (C >= 3) return fminf(1.f, v * (ch == 0 ? op.a : (ch == 1 ? op.b : op.c)));
+            return v;
+        default: return v;
+    }
+}
+
+template <int C>
+__device__ __forceinline__ float pw_apply(const PwProgram &prog, float v, int ch)
+{
+    for (int i = 0; i < prog.n; ++i) v = pw_apply_one<C>(prog.ops[i], v, ch);
+    return v;
+}
+
+// Luma of skimage.color.rgb2gray / src/millipyde_image.cpp:64, fp32 flavour.
+__device__ __forceinline__ float luma_f32(float r, float g, float b)
+{
+    return fminf(1.f, fmaf(0.0721f, b, fmaf(0.7154f, g, 0.2125f * r)));
+}
+
+
+// ---- parameter blocks shared between host launch code and the kernels -------
+
+// fp64 pointwise op (reference greyscale layout)
+struct PwOp64 {
+    int kind;
+    double a, b;
+};
+
+// One byte -> byte op of the packed-RGBA8 path.
+struct U8Op {
+    int kind;
+    int d8;          // brightness: (char)(delta * 255), computed on the host (:613)
+    double a, b, c;  // gamma: a = gamma, b = gain; colorize: r, g, b multipliers
+};
+
+struct U8Program {
+    int n;
+    U8Op ops[kMaxPw];
+};
+
+// Bilinear rotate: cos/sin of the angle and the centre, all fp64.
+struct RotateParams {
+    double c, s;    // cos, sin of the angle
+    double cx, cy;  // centre
+};
+
+constexpr int kGaussMaxRadius = 127;
+
+// Symmetric 1-D kernel: w[d] = weight at distance d.
+template <typename T>
+struct GaussParams {
+    int radius;
+    T w[kGaussMaxRadius + 1];  // w[d] = weight at distance d (kernel is symmetric)
+};
+
+}  // namespace mpk

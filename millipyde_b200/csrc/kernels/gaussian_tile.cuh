@@ -1,0 +1,136 @@
+// Separable Gaussian, generic tile kernel (any dtype, any channel count, any
+// width): ONE launch does both passes -- the halo'd input tile is staged in
+// shared memory (zero outside the image = mode "constant", cval 0), the row pass
+// writes a shared intermediate, the column pass writes global.  No intermediate
+// image, no host sync between passes, weights travel as kernel parameters.
+//
+// Replaces g_gaussian_{row,col}_{one,four}_channel + the host choreography of
+// _gaussian_greyscale/_gaussian_rgba (src/millipyde_image.cpp:146-381, :725-856):
+// two launches with a hipStreamSynchronize between them, a scratch image, and
+// weights pushed through a mutable __constant__ symbol shared by all workers.
+//
+// This is the correctness-first path and the fallback for ragged widths; the
+// fp32 roofline path is kernels/gaussian_stream.cuh.
+#pragma once
+#include "common.cuh"
+
+namespace mpk {
+
+
+
+template <typename T>
+__device__ __forceinline__ T fma_t(T a, T b, T c);
+template <>
+__device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <>
+__device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
+
+// CLAMP0: fmax(0, .) after the column pass (the reference's fp64 kernel, :240).
+template <typename T, int C, bool CLAMP0>
+__global__ void __launch_bounds__(256)
+gauss_tile_kernel(const T *__restrict__ in, T *__restrict__ out, int width, int height, int tile_h,
+                  int tile_wp, const __grid_constant__ GaussParams<T> gp)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R = gp.radius;
+    const int in_w = (tile_wp + 2 * R) * C;  // elements per staged row
+    const int in_h = tile_h + 2 * R;
+    const int out_w = tile_wp * C;
+    T *s_in = reinterpret_cast<T *>(smem_raw);
+    T *s_h = s_in + (size_t)in_h * in_w;
+
+    const int x0 = blockIdx.x * tile_wp, y0 = blockIdx.y * tile_h;
+    const int row_elems = width * C;
+    const int gx_base = (x0 - R) * C;
+
+    for (int i = threadIdx.x; i < in_h * in_w; i += blockDim.x) {
+        int r = i / in_w, j = i - r * in_w;
+        int gy = y0 - R + r, gx = gx_base + j;
+        T v = (T)0;
+        if (gy >= 0 && gy < height && gx >= 0 && gx < row_elems) v = in[(size_t)gy * row_elems + gx];
+        s_in[i] = v;
+    }
+    __syncthreads();
+
+    // row pass, taps in the reference's order k = -R .. R
+    for (int i = threadIdx.x; i < in_h * out_w; i += blockDim.x) {
+        int r = i / out_w, j = i - r * out_w;
+        const T *p = s_in + r * in_w + j + R * C;
+        T acc = (T)0;
+        for (int k = -R; k <= R; ++k) acc = fma_t<T>(p[k * C], gp.w[k < 0 ? -k : k], acc);
+        s_h[i] = acc;
+    }
+    __syncthreads();
+
+    for (int i = threadIdx.x; i < tile_h * out_w; i += blockDim.x) {
+        int r = i / out_w, j = i - r * out_w;
+        int gy = y0 + r, gx = x0 * C + j;
+        if (gy >= height || gx >= row_elems) continue;
+        const T *p = s_h + (r + R) * out_w + j;
+        T acc = (T)0;
+        for (int k = -R; k <= R; ++k) acc = fma_t<T>(p[k * out_w], gp.w[k < 0 ? -k : k], acc);
+        if (CLAMP0) acc = acc > (T)0 ? acc : (T)0;
+        out[(size_t)gy * row_elems + gx] = acc;
+    }
+}
+
+// Packed RGBA8, the reference's integer rule (src/millipyde_image.cpp:247-381):
+// per byte lane sum_k (int)(byte * w_k) -- each product truncated before the
+// integer add -- then & 0xff; the column pass forces bits 24..31 to 0xff.
+// Weights are the reference's doubles (float expf, normalised in double).
+__global__ void __launch_bounds__(256)
+gauss_rgba8_tile_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int width,
+                        int height, int tile_h, int tile_w, const __grid_constant__ GaussParams<double> gp)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R = gp.radius;
+    const int in_w = tile_w + 2 * R, in_h = tile_h + 2 * R;
+    uint32_t *s_in = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *s_h = s_in + (size_t)in_h * in_w;
+    const int x0 = blockIdx.x * tile_w, y0 = blockIdx.y * tile_h;
+
+    for (int i = threadIdx.x; i < in_h * in_w; i += blockDim.x) {
+        int r = i / in_w, j = i - r * in_w;
+        int gy = y0 - R + r, gx = x0 - R + j;
+        uint32_t v = 0;
+        if (gy >= 0 && gy < height && gx >= 0 && gx < width) v = in[(size_t)gy * width + gx];
+        s_in[i] = v;
+    }
+    __syncthreads();
+
+    for (int i = threadIdx.x; i < in_h * tile_w; i += blockDim.x) {
+        int r = i / tile_w, j = i - r * tile_w;
+        const uint32_t *p = s_in + r * in_w + j + R;
+        int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        for (int k = -R; k <= R; ++k) {
+            uint32_t v = p[k];
+            double w = gp.w[k < 0 ? -k : k];
+            s0 += (int)((v & 0xff) * w);
+            s1 += (int)(((v >> 8) & 0xff) * w);
+            s2 += (int)(((v >> 16) & 0xff) * w);
+            s3 += (int)(((v >> 24) & 0xff) * w);
+        }
+        s_h[i] = ((uint32_t)(s3 & 0xff) << 24) | ((uint32_t)(s2 & 0xff) << 16) |
+                 ((uint32_t)(s1 & 0xff) << 8) | (uint32_t)(s0 & 0xff);
+    }
+    __syncthreads();
+
+    for (int i = threadIdx.x; i < tile_h * tile_w; i += blockDim.x) {
+        int r = i / tile_w, j = i - r * tile_w;
+        int gy = y0 + r, gx = x0 + j;
+        if (gy >= height || gx >= width) continue;
+        const uint32_t *p = s_h + (r + R) * tile_w + j;
+        int s0 = 0, s1 = 0, s2 = 0;
+        for (int k = -R; k <= R; ++k) {
+            uint32_t v = p[k * tile_w];
+            double w = gp.w[k < 0 ? -k : k];
+            s0 += (int)((v & 0xff) * w);
+            s1 += (int)(((v >> 8) & 0xff) * w);
+            s2 += (int)(((v >> 16) & 0xff) * w);
+        }
+        out[(size_t)gy * width + gx] = 0xff000000u | ((uint32_t)(s2 & 0xff) << 16) |
+                                       ((uint32_t)(s1 & 0xff) << 8) | (uint32_t)(s0 & 0xff);
+    }
+}
+
+}  // namespace mpk

@@ -1,0 +1,163 @@
+// Index / resampling kernels: transpose, fliplr, rotate.
+//
+// Replaces g_transpose<T>, g_flip_horizontal<T>, g_rotate<T>
+// (src/millipyde_image.cpp:73-139).  The pixel is the unit of motion; a pixel
+// is K 32-bit words (K = 1: RGBA8 or fp32 grey, 2: fp64 grey, 3: fp32 RGB,
+// 4: fp32 RGBA), so one kernel template serves every layout bit-exactly.
+#pragma once
+#include "common.cuh"
+
+namespace mpk {
+
+// ------------------------------------------------------------------ transpose
+// 32 x 32 pixel tile through shared memory.  A tile row is 32*K words plus K
+// words of padding, i.e. a pitch of 33*K == K (mod 32): the transposed
+// read-back of word j = y*K + c of output row x hits bank (j + const) mod 32,
+// conflict-free for every K.  (The reference tile is unpadded: 32-way
+// conflicts, src/millipyde_image.cpp:76,94.)  Global accesses are contiguous
+// 32*K-word row segments on both sides.
+template <int K>
+__global__ void __launch_bounds__(256)
+transpose_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int width, int height)
+{
+    constexpr int P = 33 * K;
+    __shared__ uint32_t tile[32 * P];
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    const int tw = min(32, width - x0), th = min(32, height - y0);
+
+    // load: row r of the tile = words [x0*K, (x0+tw)*K) of input row y0+r
+    for (int i = threadIdx.x; i < 32 * 32 * K; i += 256) {
+        int r = i / (32 * K), j = i - r * (32 * K);
+        if (r < th && j < tw * K)
+            tile[r * P + j] = in[((size_t)(y0 + r) * width + x0) * K + j];
+    }
+    __syncthreads();
+    // store: output row x0+r holds pixels y0..y0+th-1 -> words j = y*K + c
+    for (int i = threadIdx.x; i < 32 * 32 * K; i += 256) {
+        int r = i / (32 * K), j = i - r * (32 * K);
+        int y = j / K, c = j - y * K;
+        if (r < tw && y < th)
+            out[((size_t)(x0 + r) * height + y0) * K + j] = tile[y * P + r * K + c];
+    }
+}
+
+// --------------------------------------------------------------------- fliplr
+// Vector path (width % 4 == 0): a thread moves 4 pixels = K 16-byte vectors,
+// reading the mirrored 4-pixel block and reversing the pixel order in
+// registers; both sides are aligned 128-bit accesses.
+template <int K>
+__global__ void __launch_bounds__(256)
+fliplr_vec_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int width, size_t nblocks4)
+{
+    const int bpr = width / 4;  // 4-pixel blocks per row
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nblocks4; b += stride) {
+        size_t row = b / bpr;
+        int bx = (int)(b - row * bpr);
+        const uint4 *src = in + (row * bpr + (bpr - 1 - bx)) * K;
+        uint4 v[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = ld_stream(src + k);
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(v);
+        uint4 o[K];
+        uint32_t *ow = reinterpret_cast<uint32_t *>(o);
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int c = 0; c < K; ++c) ow[p * K + c] = w[(3 - p) * K + c];
+        uint4 *dst = out + (row * bpr + bx) * K;
+#pragma unroll
+        for (int k = 0; k < K; ++k) st_stream(dst + k, o[k]);
+    }
+}
+
+// Scalar path for ragged widths: one 32-bit word per thread, coalesced stores.
+template <int K>
+__global__ void __launch_bounds__(256)
+fliplr_scalar_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int width, size_t nwords)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t row_words = (size_t)width * K;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride) {
+        size_t row = i / row_words;
+        int j = (int)(i - row * row_words);
+        int x = j / K, c = j - x * K;
+        out[i] = in[row * row_words + (size_t)(width - 1 - x) * K + c];
+    }
+}
+
+// ------------------------------------------------------------ rotate, nearest
+// The reference's rule (src/millipyde_image.cpp:114-139): inverse map about
+// (W/2, H/2), int truncation toward zero, zero fill.  The expressions are kept
+// in the reference's shape (and sin/cos evaluated on the device in fp64) so the
+// compiler's FMA contraction and the resulting truncation match the reference's
+// kernel bit for bit.
+template <int K>
+__global__ void __launch_bounds__(256)
+rotate_nearest_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int width, int height,
+                      double angle)
+{
+    int x = threadIdx.x + blockIdx.x * blockDim.x;
+    int y = threadIdx.y + blockIdx.y * blockDim.y;
+
+    int x_rot = ((double)x - ((double)width / 2)) * cos(angle) -
+                ((double)y - ((double)height / 2)) * sin(angle) + ((double)width / 2);
+    int y_rot = ((double)x - ((double)width / 2)) * sin(angle) +
+                ((double)y - ((double)height / 2)) * cos(angle) + ((double)height / 2);
+
+    if (x < width && y < height) {
+        size_t o = ((size_t)y * width + x) * K;
+        if (x_rot >= 0 && x_rot < width && y_rot >= 0 && y_rot < height) {
+            size_t s = ((size_t)y_rot * width + x_rot) * K;
+#pragma unroll
+            for (int c = 0; c < K; ++c) out[o + c] = __ldg(in + s + c);
+        } else {
+#pragma unroll
+            for (int c = 0; c < K; ++c) out[o + c] = 0u;
+        }
+    }
+}
+
+// ----------------------------------------------------------- rotate, bilinear
+// skimage.transform.rotate defaults (order=1, mode='constant', cval=0, centre
+// (W/2-0.5, H/2-0.5)).  Source coordinates in fp64 (fp32 would carry ~2.4e-4 px
+// at x ~ 3840, 24x the tolerance), blend in the image's precision.  Each corner
+// is the pixel if inside, else 0.  A warp covers a 32 x 1 run of output pixels
+// and a block a 32 x 8 patch, so the four-corner gathers of neighbouring lanes
+// fall in the same few 128-byte lines and are served by L1 after the first
+// touch (the read-only path, __ldg).
+
+template <typename T, int C>
+__global__ void __launch_bounds__(256)
+rotate_bilinear_kernel(const T *__restrict__ in, T *__restrict__ out, int width, int height,
+                       RotateParams rp)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= width || y >= height) return;
+    const double fx = (double)x - rp.cx, fy = (double)y - rp.cy;
+    const double xs = rp.c * fx - rp.s * fy + rp.cx;
+    const double ys = rp.s * fx + rp.c * fy + rp.cy;
+    const double xf = floor(xs), yf = floor(ys);
+    const int x0 = (int)xf, y0 = (int)yf;
+    const int x1 = (int)ceil(xs), y1 = (int)ceil(ys);
+    const T dx = (T)(xs - xf), dy = (T)(ys - yf);
+    const bool in_x0 = x0 >= 0 && x0 < width, in_x1 = x1 >= 0 && x1 < width;
+    const bool in_y0 = y0 >= 0 && y0 < height, in_y1 = y1 >= 0 && y1 < height;
+    const T *r0 = in + (size_t)(in_y0 ? y0 : 0) * width * C;
+    const T *r1 = in + (size_t)(in_y1 ? y1 : 0) * width * C;
+    const size_t c0 = (size_t)(in_x0 ? x0 : 0) * C, c1 = (size_t)(in_x1 ? x1 : 0) * C;
+    T *o = out + ((size_t)y * width + x) * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        T p00 = (in_y0 && in_x0) ? __ldg(r0 + c0 + c) : (T)0;
+        T p01 = (in_y0 && in_x1) ? __ldg(r0 + c1 + c) : (T)0;
+        T p10 = (in_y1 && in_x0) ? __ldg(r1 + c0 + c) : (T)0;
+        T p11 = (in_y1 && in_x1) ? __ldg(r1 + c1 + c) : (T)0;
+        T top = ((T)1 - dx) * p00 + dx * p01;
+        T bot = ((T)1 - dx) * p10 + dx * p11;
+        o[c] = ((T)1 - dy) * top + dy * bot;
+    }
+}
+
+}  // namespace mpk

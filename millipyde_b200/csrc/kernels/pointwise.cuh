@@ -1,0 +1,219 @@
+// Pointwise kernels: brightness / adjust_gamma / colorize / rgb2grey on the three
+// layout families.  All are one-touch HBM streams: 128-bit loads and stores,
+// grid-stride over a grid sized in multiples of the SM count, no shared memory
+// (except the 768-byte LUT of the RGBA8 path).
+//
+// Replaces g_color_to_greyscale, g_brightness_*, g_adjust_gamma_*,
+// g_colorize_four_channel (src/millipyde_image.cpp:50-66, :384-524), which use
+// one scalar element per thread on a (W/32, H/32) x (32, 32) grid.
+#pragma once
+#include "common.cuh"
+
+namespace mpk {
+
+// ---------------------------------------------------------------- fp32, HWC
+// A thread owns 12 consecutive floats = lcm(3, 4): three 16-byte vectors whose
+// channel pattern is the same for every group, so `j % C` is a compile-time
+// constant and the op program runs without index arithmetic.
+template <int C>
+__global__ void __launch_bounds__(256)
+pw_f32_kernel(const float *__restrict__ in, float *__restrict__ out, size_t n,
+              const __grid_constant__ PwProgram prog)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t ngroups = n / 12;
+    for (size_t g = tid; g < ngroups; g += stride) {
+        const float4 *src = reinterpret_cast<const float4 *>(in + g * 12);
+        float4 v[3] = {ld_stream(src), ld_stream(src + 1), ld_stream(src + 2)};
+        float *r = reinterpret_cast<float *>(v);
+#pragma unroll
+        for (int j = 0; j < 12; ++j) r[j] = pw_apply<C>(prog, r[j], j % C);
+        float4 *dst = reinterpret_cast<float4 *>(out + g * 12);
+        st_stream(dst, v[0]);
+        st_stream(dst + 1, v[1]);
+        st_stream(dst + 2, v[2]);
+    }
+    for (size_t e = ngroups * 12 + tid; e < n; e += stride)
+        out[e] = pw_apply<C>(prog, in[e], (int)(e % C));
+}
+
+// rgb2grey on fp32 H x W x {3,4} -> H x W, with optional pointwise programs
+// before (per colour channel) and after (on the grey value) for fused chains.
+template <int C>
+__global__ void __launch_bounds__(256)
+grey_f32_kernel(const float *__restrict__ in, float *__restrict__ out, size_t npix,
+                const __grid_constant__ PwProgram pre, const __grid_constant__ PwProgram post)
+{
+    static_assert(C == 3 || C == 4, "colour input");
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t ngroups = npix / 4;  // 4 pixels in, one float4 out
+    for (size_t g = tid; g < ngroups; g += stride) {
+        const float4 *src = reinterpret_cast<const float4 *>(in + g * 4 * C);
+        float4 v[C];
+#pragma unroll
+        for (int k = 0; k < C; ++k) v[k] = ld_stream(src + k);
+        float *r = reinterpret_cast<float *>(v);
+        float o[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            float cr = pw_apply<C>(pre, r[p * C + 0], 0);
+            float cg = pw_apply<C>(pre, r[p * C + 1], 1);
+            float cb = pw_apply<C>(pre, r[p * C + 2], 2);
+            o[p] = pw_apply<1>(post, luma_f32(cr, cg, cb), 0);
+        }
+        st_stream(reinterpret_cast<float4 *>(out + g * 4), make_float4(o[0], o[1], o[2], o[3]));
+    }
+    for (size_t p = ngroups * 4 + tid; p < npix; p += stride) {
+        float cr = pw_apply<C>(pre, in[p * C + 0], 0);
+        float cg = pw_apply<C>(pre, in[p * C + 1], 1);
+        float cb = pw_apply<C>(pre, in[p * C + 2], 2);
+        out[p] = pw_apply<1>(post, luma_f32(cr, cg, cb), 0);
+    }
+}
+
+// ------------------------------------------------ uint8 colour -> fp64 grey
+// The reference's only channel-generic kernel (src/millipyde_image.cpp:50-66):
+// bytes 0..2 of each pixel, alpha ignored, result double.
+__device__ __forceinline__ double luma_u8(unsigned r, unsigned g, unsigned b)
+{
+    return fmin(1.0, (0.2125 * r + 0.7154 * g + 0.0721 * b) / 255);
+}
+
+__global__ void __launch_bounds__(256)
+grey_rgba8_kernel(const uint32_t *__restrict__ in, double *__restrict__ out, size_t npix)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t ngroups = npix / 4;
+    for (size_t g = tid; g < ngroups; g += stride) {
+        uint4 px = ld_stream(reinterpret_cast<const uint4 *>(in) + g);
+        const uint32_t w[4] = {px.x, px.y, px.z, px.w};
+        double o[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) o[p] = luma_u8(w[p] & 0xff, (w[p] >> 8) & 0xff, (w[p] >> 16) & 0xff);
+        double2 *dst = reinterpret_cast<double2 *>(out + g * 4);
+        st_stream(dst, make_double2(o[0], o[1]));
+        st_stream(dst + 1, make_double2(o[2], o[3]));
+    }
+    for (size_t p = ngroups * 4 + tid; p < npix; p += stride) {
+        uint32_t w = in[p];
+        out[p] = luma_u8(w & 0xff, (w >> 8) & 0xff, (w >> 16) & 0xff);
+    }
+}
+
+// Generic channel count (RGB8 and anything the reference's kernel would accept).
+__global__ void __launch_bounds__(256)
+grey_u8_generic_kernel(const uint8_t *__restrict__ in, double *__restrict__ out, size_t npix, int channels)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {
+        const uint8_t *q = in + p * channels;
+        out[p] = luma_u8(q[0], q[1], q[2]);
+    }
+}
+
+// fp64 H x W x 3 -> H x W (skimage.color.rgb2gray on a float64 image).
+__global__ void __launch_bounds__(256)
+grey_f64_kernel(const double *__restrict__ in, double *__restrict__ out, size_t npix, int channels)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {
+        const double *q = in + p * channels;
+        out[p] = fmin(1.0, 0.2125 * q[0] + 0.7154 * q[1] + 0.0721 * q[2]);
+    }
+}
+
+// ---------------------------------------------------------------- fp64, H x W
+
+// `float_pow`: reference semantics -- powf on float-converted operands
+// (src/millipyde_image.cpp:447); otherwise pow in double (the test oracle).
+__device__ __forceinline__ double pw64(const PwOp64 &op, double v, bool float_pow)
+{
+    if (op.kind == PW_BRIGHTNESS) {
+        v = v + op.a;
+    } else if (op.kind == PW_GAMMA) {
+        v = float_pow ? op.b * powf(v, op.a) : op.b * pow(v, op.a);
+    } else {
+        return v;
+    }
+    v = (v < 0 ? 0 : v);
+    v = (v > 1 ? 1 : v);
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+pw_f64_kernel(const double *__restrict__ in, double *__restrict__ out, size_t n, PwOp64 op, bool float_pow)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nvec = n / 2;
+    for (size_t i = tid; i < nvec; i += stride) {
+        double2 v = ld_stream(reinterpret_cast<const double2 *>(in) + i);
+        v.x = pw64(op, v.x, float_pow);
+        v.y = pw64(op, v.y, float_pow);
+        st_stream(reinterpret_cast<double2 *>(out) + i, v);
+    }
+    if (tid == 0 && (n & 1)) out[n - 1] = pw64(op, in[n - 1], float_pow);
+}
+
+// ------------------------------------------------------------ packed RGBA8
+// brightness, adjust_gamma and colorize are all byte -> byte maps per colour
+// channel (alpha untouched), so a chain of them is three 256-entry tables.  The
+// tables are built on the device with exactly the reference's expressions
+// (device powf, float product, truncating casts), then every pixel is three
+// shared-memory lookups: bit-identical to evaluating the ops one by one.
+
+
+__device__ __forceinline__ unsigned u8_apply(const U8Op &op, unsigned v, int ch)
+{
+    switch (op.kind) {
+        case PW_BRIGHTNESS: {
+            int t = (int)v + op.d8;
+            return (unsigned)(op.d8 > 0 ? min(255, t) : max(0, t)) & 0xffu;
+        }
+        case PW_GAMMA: {
+            double t = op.b * (255 * powf((double)v / 255, op.a));
+            t = (t < 0 ? 0 : t);
+            return t > 255 ? 255u : (unsigned)(unsigned char)t;
+        }
+        case PW_COLORIZE: {
+            double t = (double)v * (ch == 0 ? op.a : (ch == 1 ? op.b : op.c));
+            return t > 255 ? 255u : (unsigned)(unsigned char)t;
+        }
+        default: return v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pw_rgba8_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t npix,
+                const __grid_constant__ U8Program prog)
+{
+    __shared__ uint8_t lut[3][256];
+    for (int e = threadIdx.x; e < 768; e += blockDim.x) {
+        int ch = e >> 8;
+        unsigned v = e & 255;
+        for (int i = 0; i < prog.n; ++i) v = u8_apply(prog.ops[i], v, ch);
+        lut[ch][e & 255] = (uint8_t)v;
+    }
+    __syncthreads();
+    auto map = [&](uint32_t w) -> uint32_t {
+        return (w & 0xff000000u) | ((uint32_t)lut[2][(w >> 16) & 0xff] << 16) |
+               ((uint32_t)lut[1][(w >> 8) & 0xff] << 8) | lut[0][w & 0xff];
+    };
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t ngroups = npix / 4;
+    for (size_t g = tid; g < ngroups; g += stride) {
+        uint4 px = ld_stream(reinterpret_cast<const uint4 *>(in) + g);
+        px.x = map(px.x);
+        px.y = map(px.y);
+        px.z = map(px.z);
+        px.w = map(px.w);
+        st_stream(reinterpret_cast<uint4 *>(out) + g, px);
+    }
+    for (size_t p = ngroups * 4 + tid; p < npix; p += stride) out[p] = map(in[p]);
+}
+
+}  // namespace mpk

@@ -1,0 +1,54 @@
+// Internal glue shared by the translation units of libmp_b200.so.  Not part of
+// the C ABI (see include/*.h for that).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+
+#include "mp_abi.h"
+#include "mp_devices.h"
+
+namespace mp {
+
+// Record a failed CUDA call for mp_last_error() and stderr; never exits (the
+// reference's HIP_CHECK prints and exit(1)s, src/include/millipyde_hip_util.h:7-16).
+void record_cuda_error(cudaError_t err, const char *expr, const char *file, int line);
+
+// Lazily runs mpdev_initialize() once; returns its status.
+MPStatus ensure_initialized();
+
+cudaStream_t device_stream(int device_id, int index);
+
+// Per-device stream-ordered pool (cudaMallocAsync on the device's default pool
+// with the release threshold lifted, so steady state never calls the OS).
+void *pool_alloc(int device_id, cudaStream_t stream, size_t nbytes);
+void pool_free(int device_id, cudaStream_t stream, void *ptr);
+
+// The stream an op should use for `obj`: obj->stream, or the device's stream 0
+// when a foreign caller left it NULL.
+cudaStream_t stream_of(const MPObjData *obj);
+
+extern std::atomic<unsigned long long> g_launch_count;
+inline void count_launch(unsigned n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count(int device_id);
+
+}  // namespace mp
+
+#define MP_CUDA_TRY(expr)                                           \
+    do {                                                            \
+        cudaError_t mp_e_ = (expr);                                 \
+        if (mp_e_ != cudaSuccess) {                                 \
+            mp::record_cuda_error(mp_e_, #expr, __FILE__, __LINE__); \
+            return MP_ERROR_CUDA_RUNTIME;                           \
+        }                                                           \
+    } while (0)
+
+// For void functions of the reference ABI (mpobj_*, mpdev_*): record and go on.
+#define MP_CUDA_WARN(expr)                                          \
+    do {                                                            \
+        cudaError_t mp_e_ = (expr);                                 \
+        if (mp_e_ != cudaSuccess)                                   \
+            mp::record_cuda_error(mp_e_, #expr, __FILE__, __LINE__); \
+    } while (0)

@@ -1,0 +1,47 @@
+// Host-side helpers shared by the eager ops (mp_image_ops.cu) and the fused
+// chain executor (mp_pipeline.cu).  Internal; not part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kernels/common.cuh"
+#include "mp_abi.h"
+
+namespace mp {
+
+enum Family {
+    FAM_RGBA8,      // uint8 H x W x 4, the reference's packed-uint32 path
+    FAM_U8_OTHER,   // uint8 with another channel count (rgb2grey only, like the reference)
+    FAM_F64,        // float64 H x W, the reference's greyscale path
+    FAM_F64_OTHER,  // float64 colour (rgb2grey only)
+    FAM_F32,        // float32 H x W [x 1|3|4], the B200 path
+};
+
+struct Img {
+    int H, W, C;
+    int type;      // numpy typenum
+    int esize;     // bytes per channel sample
+    Family fam;
+    size_t npix;
+};
+
+bool describe(const MPObjData *o, Img *d);
+int words_per_pixel(const Img &d);
+int grid_for(int device, size_t work_items, int threads);
+
+int oracle_weights(double sigma, double *w, int max_radius);
+int effective_radius(const double *w, int r, double eps);
+void reference_weights(double sigma, double *w_half);
+
+mpk::RotateParams rotate_params(int W, int H, double angle_deg);
+mpk::U8Op u8_brightness_op(double delta);
+
+// Both passes of the blur from `in` to `out` (distinct buffers) on stream s.
+MPStatus launch_gaussian(int device, cudaStream_t s, const Img &d, const void *in, void *out, double sigma,
+                         bool ref_rule);
+
+// fp32 roofline path (kernels/gaussian_stream.cuh)
+bool gauss_stream_supported(int W, int C, int radius);
+MPStatus launch_gauss_stream(int device, cudaStream_t s, const Img &d, const float *in, float *out,
+                             const mpk::GaussParams<float> &gp);
+
+}  // namespace mp

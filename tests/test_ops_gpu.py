@@ -1,0 +1,227 @@
+"""Parity of every operator, called through the C ABI (libmp_b200.so), against
+the CPU oracle on the same seeded inputs.
+
+Bars: bit-exact for index ops, transfers, clone and every uint8 path;
+max-abs <= 1e-5 on [0,1] fp32 for float ops (BASELINE.json north star);
+<= 1e-12 for the fp64 layouts.  Shapes include BASELINE config 1 (512 x 512
+RGBA8, grey + transpose), ragged widths and the reference's own PNG fixture."""
+import numpy as np
+import pytest
+
+from oracle import ref_exact as rx
+from oracle import skimage_oracle as so
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL32 = 1e-5
+TOL64 = 1e-12
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from millipyde_b200 import capi as m
+    m.initialize()
+    m.lib().mpimg_set_semantics(m.SEMANTICS_ORACLE)
+    return m
+
+
+def dev(capi, a):
+    return capi.DeviceImage(a)
+
+
+SHAPES = [(64, 48), (97, 131), (256, 512)]
+CHANNELS = [1, 3, 4]
+
+
+# ------------------------------------------------------------------ transfers
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32, np.float64, np.int64, np.int32])
+def test_round_trip_bit_exact(capi, dtype):
+    rng = np.random.default_rng(7)
+    a = (rng.random((33, 21, 3)) * 200).astype(dtype)
+    assert np.array_equal(dev(capi, a).numpy(), a)
+
+
+def test_clone_is_deep(capi):
+    a = synth.rgba8(64, 80, 1000)
+    d = dev(capi, a)
+    c = d.clone()
+    c.apply("rgb2grey")
+    assert np.array_equal(d.numpy(), a)
+    assert np.abs(c.numpy() - so.rgb2grey(a)).max() < TOL64
+
+
+# ------------------------------------------------------------------ fp32 path
+@pytest.mark.parametrize("c", CHANNELS)
+@pytest.mark.parametrize("shape", SHAPES)
+def test_f32_index_ops_bit_exact(capi, shape, c):
+    a = synth.noise_f32(*shape, c, 2000 + c)
+    assert np.array_equal(dev(capi, a).apply("transpose").numpy(), so.transpose(a))
+    assert np.array_equal(dev(capi, a).apply("fliplr").numpy(), so.fliplr(a))
+    assert np.array_equal(dev(capi, a).apply("transpose").apply("transpose").numpy(), a)
+
+
+@pytest.mark.parametrize("c", CHANNELS)
+@pytest.mark.parametrize("shape", SHAPES)
+def test_f32_pointwise(capi, shape, c):
+    a = synth.noise_f32(*shape, c, 3000 + c)
+    got = dev(capi, a).apply("brightness", 0.25).numpy()
+    want = so.brightness(a, 0.25)
+    if c == 4:
+        want[..., 3] = a[..., 3]
+    assert np.abs(got - want).max() <= TOL32
+    got = dev(capi, a).apply("brightness", -0.4).numpy()
+    want = so.brightness(a, -0.4)
+    if c == 4:
+        want[..., 3] = a[..., 3]
+    assert np.abs(got - want).max() <= TOL32
+    for gamma, gain in [(2.0, 1.0), (1.5, 1.0), (0.5, 0.8)]:
+        got = dev(capi, a).apply("adjust_gamma", gamma, gain).numpy()
+        want = np.clip(so.adjust_gamma(a, gamma, gain), 0, 1)
+        if c == 4:
+            want[..., 3] = a[..., 3]
+        assert np.abs(got - want).max() <= TOL32, (gamma, gain)
+    got = dev(capi, a).apply("colorize", 0.5, 1.5, 1.1).numpy()
+    assert np.abs(got - so.colorize(a, 0.5, 1.5, 1.1)).max() <= TOL32
+
+
+@pytest.mark.parametrize("c", [3, 4])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_f32_grey(capi, shape, c):
+    a = synth.noise_f32(*shape, c, 4000 + c)
+    d = dev(capi, a).apply("rgb2grey")
+    assert d.shape == shape and d.dtype == np.float32
+    want = a[..., :3].astype(np.float64) @ np.array(so.LUMA)
+    assert np.abs(d.numpy() - np.minimum(want, 1.0)).max() <= TOL32
+
+
+@pytest.mark.parametrize("c", CHANNELS)
+@pytest.mark.parametrize("sigma", [2.0, 0.7, 3.3])
+def test_f32_gaussian(capi, c, sigma):
+    for shape, img in [((97, 131), None), ((256, 512), None), ((128, 96), "smooth")]:
+        a = synth.smooth_f32(*shape, c) if img else synth.noise_f32(*shape, c, 5000 + c)
+        got = dev(capi, a).apply("gaussian", sigma).numpy()
+        want = so.gaussian(a, sigma)
+        assert got.dtype == np.float32 and got.shape == a.shape
+        assert np.abs(got - want).max() <= TOL32, (shape, sigma)
+
+
+def test_f32_gaussian_edge_cases(capi):
+    a = synth.noise_f32(5, 7, 3, 1)                 # smaller than the kernel support
+    assert np.abs(dev(capi, a).apply("gaussian", 2.0).numpy() - so.gaussian(a, 2.0)).max() <= TOL32
+    a = synth.noise_f32(1, 300, 1, 2)               # single row
+    assert np.abs(dev(capi, a).apply("gaussian", 2.0).numpy() - so.gaussian(a, 2.0)).max() <= TOL32
+    a = synth.noise_f32(40, 40, 3, 3)
+    assert np.array_equal(dev(capi, a).apply("gaussian", 0.0).numpy(), a)   # scipy: sigma 0 copies
+
+
+@pytest.mark.parametrize("c", CHANNELS)
+@pytest.mark.parametrize("angle", [30.0, 45.0, -17.5, 90.0, 180.0, 0.0, 360.0])
+def test_f32_rotate_bilinear(capi, c, angle):
+    for shape in [(97, 131), (128, 96)]:
+        a = synth.noise_f32(*shape, c, 6000 + c)
+        got = dev(capi, a).apply("rotate", angle).numpy()
+        assert np.abs(got - so.rotate(a, angle)).max() <= TOL32, (shape, angle)
+
+
+def test_f32_chain_config3(capi):
+    """BASELINE config 3's chain, op by op (the fused path is tested separately)."""
+    a = synth.noise_f32(135, 240, 3, 3000)
+    chain = [("rotate", 30.0), ("fliplr",), ("adjust_gamma", 1.5, 1.0), ("gaussian", 2.0)]
+    got = dev(capi, a).apply_chain(chain).numpy()
+    assert np.abs(got - so.apply_chain(a, chain)).max() <= TOL32
+
+
+# --------------------------------------------------------- RGBA8 (reference)
+def rgba_inputs(charlie_small):
+    return [synth.rgba8(512, 512, 1000), synth.rgba8(97, 131, 1001), charlie_small]
+
+
+def test_config1_grey_transpose(capi, charlie_small):
+    """BASELINE config 1: rgb2grey + transpose on 512 x 512 RGBA8 vs the test
+    suite's oracle (tests/millipyde_tests.py:128-137)."""
+    for a in rgba_inputs(charlie_small):
+        d = dev(capi, a).apply("rgb2grey")
+        assert d.dtype == np.float64 and d.shape == a.shape[:2]
+        g = d.numpy()
+        assert np.abs(g - so.rgb2grey(a)).max() < TOL64
+        assert np.abs(g - rx.grey_u8(a)).max() < TOL64
+        t = d.apply("transpose").numpy()
+        assert np.array_equal(t, g.T)
+
+
+def test_rgba8_index_ops_bit_exact(capi, charlie_small):
+    for a in rgba_inputs(charlie_small):
+        assert np.array_equal(dev(capi, a).apply("transpose").numpy(), rx.transpose(a))
+        assert np.array_equal(dev(capi, a).apply("fliplr").numpy(), rx.fliplr(a))
+
+
+def test_rgba8_pointwise_bit_exact(capi, charlie_small):
+    for a in rgba_inputs(charlie_small):
+        for gamma, gain in [(2.0, 1.0), (1.5, 1.0), (0.5, 1.0), (2.2, 0.9)]:
+            got = dev(capi, a).apply("adjust_gamma", gamma, gain).numpy()
+            assert np.array_equal(got, rx.adjust_gamma(a, gamma, gain)), (gamma, gain)
+        # reference test oracle (skimage 0.18.2), tests/millipyde_tests.py:570-578
+        assert np.array_equal(dev(capi, a).apply("adjust_gamma", 2.0, 1.0).numpy(),
+                              so.adjust_gamma_rgba(a, 2.0, 1.0))
+        for delta in [0.1, -0.1, 0.5, -0.5, 0.0]:
+            assert np.array_equal(dev(capi, a).apply("brightness", delta).numpy(), rx.brightness(a, delta))
+        assert np.array_equal(dev(capi, a).apply("colorize", 0.5, 1.5, 1.1).numpy(),
+                              rx.colorize(a, 0.5, 1.5, 1.1))
+
+
+def test_rgba8_gaussian_bit_exact(capi, charlie_small):
+    for a in rgba_inputs(charlie_small):
+        for sigma in [2.0, 1.0]:
+            assert np.array_equal(dev(capi, a).apply("gaussian", sigma).numpy(), rx.gaussian(a, sigma))
+
+
+def test_rgba8_rotate_nearest(capi, charlie_small):
+    for a in rgba_inputs(charlie_small):
+        for angle in [45.0, 30.0, 10.0]:
+            got = dev(capi, a).apply("rotate", angle).numpy()
+            want = rx.rotate(a, angle)
+            # device vs glibc sin/cos can differ in the last ulp: a source coordinate
+            # within an ulp of an integer may truncate differently (oracle/ref_exact.c)
+            frac = np.mean(np.any(got != want, axis=-1))
+            assert frac < 1e-4, (angle, frac)
+
+
+# ------------------------------------------------------------- fp64 greyscale
+def test_f64_ops_oracle_semantics(capi, charlie_small):
+    g = so.rgb2grey(charlie_small)
+    # reference tests: gaussian :547-555, gamma :558-568 (decimal=4 there)
+    assert np.abs(dev(capi, g).apply("gaussian", 2.0).numpy() - so.gaussian(g, 2.0)).max() < 1e-9
+    assert np.abs(dev(capi, g).apply("adjust_gamma", 2.0, 1.0).numpy() - so.adjust_gamma(g, 2.0, 1.0)).max() < TOL64
+    assert np.abs(dev(capi, g).apply("brightness", 0.3).numpy() - so.brightness(g, 0.3)).max() < TOL64
+    assert np.abs(dev(capi, g).apply("rotate", 30.0).numpy() - so.rotate(g, 30.0)).max() < 1e-9
+    assert np.array_equal(dev(capi, g).apply("fliplr").numpy(), so.fliplr(g))
+    assert np.array_equal(dev(capi, g).apply("transpose").numpy(), so.transpose(g))
+    assert np.array_equal(dev(capi, g).apply("colorize", 2.0, 2.0, 2.0).numpy(), g)   # no-op on grey
+
+
+def test_f64_ops_reference_semantics(capi, charlie_small):
+    g = so.rgb2grey(charlie_small)
+    L = capi.lib()
+    L.mpimg_set_semantics(capi.SEMANTICS_REFERENCE)
+    try:
+        assert np.abs(dev(capi, g).apply("gaussian", 2.0).numpy() - rx.gaussian(g, 2.0)).max() < TOL64
+        assert np.abs(dev(capi, g).apply("adjust_gamma", 2.0, 1.0).numpy() - rx.adjust_gamma(g, 2.0, 1.0)).max() < 1e-6
+        got = dev(capi, g).apply("rotate", 45.0).numpy()
+        want = rx.rotate(g, 45.0)
+        assert np.mean(got != want) < 1e-4
+        # the reference's own test_long_pipeline chain on its own layouts (:349-395)
+        chain = [("gaussian", 2.0), ("rgb2grey",), ("transpose",), ("transpose",), ("rotate", 45.0)]
+        got = dev(capi, charlie_small).apply_chain(chain).numpy()
+        want = rx.apply_chain(charlie_small, chain)
+        assert np.mean(np.abs(got - want) > TOL64) < 1e-4
+    finally:
+        L.mpimg_set_semantics(capi.SEMANTICS_ORACLE)
+
+
+def test_unsupported_layout_is_an_error(capi):
+    a = np.zeros((8, 8, 2), np.float32)
+    with pytest.raises(capi.MillipydeError):
+        dev(capi, a).apply("fliplr")
+    with pytest.raises(capi.MillipydeError):
+        dev(capi, np.zeros((8, 8), np.int64)).apply("gaussian", 2.0)
