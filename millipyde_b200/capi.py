@@ -191,7 +191,9 @@ def initialize() -> int:
 
 _TYPENUM = {np.dtype(np.uint8): NPY_UBYTE, np.dtype(np.float32): NPY_FLOAT,
             np.dtype(np.float64): NPY_DOUBLE}
-_DTYPE = {v: k for k, v in _TYPENUM.items()}
+_DTYPE = {np.dtype(t).num: np.dtype(t) for t in
+          (np.bool_, np.int8, np.uint8, np.int16, np.uint16, np.int32, np.uint32,
+           np.int64, np.uint64, np.float16, np.float32, np.float64)}
 
 _OPS = {
     # name -> (symbol, args struct or None)
@@ -243,7 +245,7 @@ class DeviceImage:
 
     @property
     def dtype(self):
-        return _DTYPE.get(self.obj.type) or np.dtype(np.sctypeDict[self.obj.type])
+        return _DTYPE[self.obj.type]
 
     @property
     def device(self) -> int:

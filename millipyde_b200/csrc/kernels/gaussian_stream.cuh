@@ -1,2 +1,301 @@
-// placeholder: filled in by the streaming kernel
+// Separable Gaussian, fp32 HWC, streaming kernel -- the roofline path.
+//
+// One HBM read and one HBM write per sample, both passes in one launch, no
+// intermediate image.  Work item = (image, column strip of TW floats, row chunk);
+// a persistent grid of CTAs walks the items.  Inside an item the CTA marches down
+// the rows in steps of Q rows:
+//
+//   1. TMA:   one elected thread issues 1-D bulk copies (cp.async.bulk, SASS
+//             UBLKCP) of the next rows' [x0-HALO, x0+TW+HALO) segments into a
+//             2-stage shared-memory ring; completion is an mbarrier transaction
+//             count, so no thread spends registers or issue slots on the loads.
+//   2. rows:  warp q filters row q of the step horizontally.  A lane owns PH = 20
+//             consecutive floats; it reads its 20 + 2*HALO window as aligned
+//             LDS.128 (lane pitch 80 B = 5 x 16 B, odd => conflict-free) and
+//             scatters every loaded sample into the <= 2R+1 accumulators it
+//             feeds (taps are C floats apart: channels stay interleaved).  All
+//             indices are compile-time, the weights are constant-bank operands.
+//   3. cols:  thread t owns float columns 2t, 2t+1 for the whole item and keeps
+//             the 2R+1 partially accumulated output rows of each in registers.
+//             Each new filtered row costs ONE LDS.64 per thread: it is scattered
+//             into the live accumulators, the oldest one is complete and leaves
+//             as a coalesced 8-byte store.  The accumulator that retires is the
+//             one the next row opens, so the register file acts as the ring; the
+//             rotation is resolved at compile time by a switch over row % (2R+1).
+//
+// Per output sample: 2 x (2R+1) FMAs, ~7.4 shared-memory words, 8 HBM bytes.
+// With R = 11 that is 46 FMA per 8 bytes = 5.75 flop/B x 2: above the fp32-pipe
+// ridge of this part (~72 TFLOP/s / 6.4 TB/s = 11 flop/B), so the kernel is
+// bound by the FMA pipe, not by HBM; DESIGN.md carries the arithmetic.
+//
+// Zero padding (scipy mode="constant", cval=0): rows outside the image are never
+// loaded (their filtered row is written as zeros), columns outside are zeroed in
+// the ring once per item.
+//
+// Requirements: (W*C) % 4 == 0 (16-byte row pitch for the bulk copies) and the
+// effective radius within the instantiated buckets; everything else takes
+// kernels/gaussian_tile.cuh.
 #pragma once
+#include "common.cuh"
+
+namespace mpk {
+
+constexpr int kGsQ = 10;            // rows per step = warps per CTA
+constexpr int kGsThreads = 32 * kGsQ;
+constexpr int kGsPH = 2 * kGsQ;     // floats per lane in the row pass
+constexpr int kGsTW = 32 * kGsPH;   // strip width in floats (640)
+
+template <int C, int R>
+struct GsGeom {
+    static constexpr int HALO = (R * C + 3) / 4 * 4;          // halo rounded up to 16 bytes
+    static constexpr int ROW = kGsTW + 2 * HALO;              // floats per staged row
+    static constexpr int NA = 2 * R + 1;                      // live output rows per column
+    static constexpr size_t IN_BYTES = 2ull * kGsQ * ROW * 4;  // 2-stage input ring
+    static constexpr size_t H_BYTES = 2ull * kGsQ * kGsTW * 4; // 2-stage filtered-row ring
+    static constexpr size_t SMEM = IN_BYTES + H_BYTES + 64;
+};
+
+struct GaussStreamParams {
+    const float *in;             // single image / contiguous batch base (or null)
+    float *out;
+    const float *const *in_tab;  // per-image pointers (device memory) when the batch is scattered
+    float *const *out_tab;
+    size_t image_stride;         // floats between images of a contiguous batch
+    int n_images;
+    int height;
+    int row_elems;               // W * C
+    int n_strips;                // ceil(row_elems / TW)
+    int chunk_rows;              // rows per work item
+    int n_chunks;
+    int radius;                  // actual radius (<= R); w[d] = 0 beyond it
+    float w[16];
+};
+
+// ---- mbarrier / bulk-copy PTX ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared 1-D bulk copy through the TMA unit; bytes % 16 == 0, both sides 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- row pass: scatter one aligned window into PH accumulators ---------------
+template <int C, int R>
+__device__ __forceinline__ void gs_row_pass(const float *__restrict__ win, float (&acc)[kGsPH],
+                                            const GaussStreamParams &p)
+{
+    constexpr int HALO = GsGeom<C, R>::HALO;
+    constexpr int NV = (kGsPH + 2 * HALO) / 4;
+#pragma unroll
+    for (int i = 0; i < kGsPH; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const float4 x4 = *reinterpret_cast<const float4 *>(win + 4 * v);
+        const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int k = -R; k <= R; ++k) {
+                // sample at window offset 4v+u is tap k of output i
+                const int i = 4 * v + u - HALO - k * C;
+                if (i >= 0 && i < kGsPH) acc[i] = fmaf(p.w[k < 0 ? -k : k], x[u], acc[i]);
+            }
+        }
+    }
+}
+
+// ---- column pass: one filtered row into the register ring --------------------
+// PHASE = (row index) mod NA.  Slot of output row (r + d) is (PHASE + d) mod NA.
+template <int R, int PHASE>
+__device__ __forceinline__ float2 gs_col_row(float (&a0)[2 * R + 1], float (&a1)[2 * R + 1], float2 v,
+                                             const GaussStreamParams &p)
+{
+    constexpr int NA = 2 * R + 1;
+#pragma unroll
+    for (int d = -R; d < R; ++d) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int s = (PHASE + d + NA) % NA;
+        const float w = p.w[d < 0 ? -d : d];
+        a0[s] = fmaf(w, v.x, a0[s]);
+        a1[s] = fmaf(w, v.y, a1[s]);
+    }
+    {   // the output row that opens at this input row starts its sum here
+        const int s = (PHASE + R) % NA;
+        a0[s] = p.w[R] * v.x;
+        a1[s] = p.w[R] * v.y;
+    }
+    const int done = (PHASE - R + NA) % NA;  // output row r - R is complete
+    return make_float2(a0[done], a1[done]);
+}
+
+template <int R, int PHASE = 0>
+struct GsColDispatch {
+    static __device__ __forceinline__ float2 run(int phase, float (&a0)[2 * R + 1], float (&a1)[2 * R + 1],
+                                                 float2 v, const GaussStreamParams &p)
+    {
+        if constexpr (PHASE >= 2 * R + 1) {
+            return make_float2(0.f, 0.f);
+        } else {
+            if (phase == PHASE) return gs_col_row<R, PHASE>(a0, a1, v, p);
+            return GsColDispatch<R, PHASE + 1>::run(phase, a0, a1, v, p);
+        }
+    }
+};
+
+template <int C, int R>
+__global__ void __launch_bounds__(kGsThreads, 2)
+gauss_stream_kernel(const __grid_constant__ GaussStreamParams p)
+{
+    using G = GsGeom<C, R>;
+    constexpr int NA = G::NA;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *s_in = reinterpret_cast<float *>(smem_raw);                    // [2][Q][ROW]
+    float *s_h = reinterpret_cast<float *>(smem_raw + G::IN_BYTES);        // [2][Q][TW]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + G::IN_BYTES + G::H_BYTES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    uint32_t parity_bits = 0;  // bit s = parity the next wait on stage s expects
+    const int items_per_image = p.n_strips * p.n_chunks;
+    const long n_items = (long)p.n_images * items_per_image;
+
+    for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int img = (int)(item / items_per_image);
+        const int rem = (int)(item - (long)img * items_per_image);
+        // strips vary fastest so CTAs that run together share halo columns in L2
+        const int chunk = rem / p.n_strips, strip = rem - chunk * p.n_strips;
+        const float *__restrict__ src = p.in_tab ? p.in_tab[img] : p.in + (size_t)img * p.image_stride;
+        float *__restrict__ dst = p.out_tab ? p.out_tab[img] : p.out + (size_t)img * p.image_stride;
+
+        const int x0 = strip * kGsTW;                 // first output column (floats)
+        const int y0 = chunk * p.chunk_rows;
+        const int y1 = min(p.height, y0 + p.chunk_rows);
+        const int r_begin = y0 - R;                   // first filtered row needed
+        const int n_rows = (y1 - y0) + 2 * R;
+        const int n_steps = (n_rows + kGsQ - 1) / kGsQ;
+
+        // columns of the staged row that exist in the image: [lo, hi) in ring coordinates
+        const int gx_start = x0 - G::HALO;
+        const int lo = gx_start < 0 ? -gx_start : 0;
+        const int hi = min(G::ROW, p.row_elems - gx_start);
+        const uint32_t row_bytes = (uint32_t)(hi - lo) * 4u;
+
+        // all reads of the previous item are done; zero the never-copied border columns
+        __syncthreads();
+        if (lo > 0 || hi < G::ROW) {
+            for (int i = tid; i < 2 * kGsQ * G::ROW; i += kGsThreads) {
+                const int col = i % G::ROW;
+                if (col < lo || col >= hi) s_in[i] = 0.f;
+            }
+            fence_proxy_async();
+            __syncthreads();
+        }
+
+        auto issue = [&](int step) {  // thread 0 only
+            const int stage = step & 1;
+            uint32_t bytes = 0;
+            for (int q = 0; q < kGsQ; ++q) {
+                const int r = r_begin + step * kGsQ + q;
+                if (r >= 0 && r < p.height && r < r_begin + n_rows) bytes += row_bytes;
+            }
+            mbar_expect_tx(&bars[stage], bytes);
+            for (int q = 0; q < kGsQ; ++q) {
+                const int r = r_begin + step * kGsQ + q;
+                if (r >= 0 && r < p.height && r < r_begin + n_rows)
+                    bulk_g2s(s_in + ((size_t)stage * kGsQ + q) * G::ROW + lo,
+                             src + (size_t)r * p.row_elems + gx_start + lo, row_bytes, &bars[stage]);
+            }
+        };
+        if (tid == 0) {
+            issue(0);
+            if (n_steps > 1) issue(1);
+        }
+
+        float a0[NA], a1[NA];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) a0[i] = a1[i] = 0.f;
+        int phase = 0;  // (row - r_begin) mod NA
+
+        for (int step = 0; step < n_steps; ++step) {
+            const int stage = step & 1;
+            mbar_wait(&bars[stage], (parity_bits >> stage) & 1u);
+            parity_bits ^= 1u << stage;
+
+            // ---- row pass: warp = row of the step, lane = 20-float segment
+            {
+                const int r = r_begin + step * kGsQ + warp;
+                float *hrow = s_h + ((size_t)stage * kGsQ + warp) * kGsTW + lane * kGsPH;
+                float acc[kGsPH];
+                if (r >= 0 && r < p.height && r < r_begin + n_rows) {
+                    const float *win = s_in + ((size_t)stage * kGsQ + warp) * G::ROW + lane * kGsPH;
+                    gs_row_pass<C, R>(win, acc, p);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < kGsPH; ++i) acc[i] = 0.f;
+                }
+#pragma unroll
+                for (int v = 0; v < kGsPH / 4; ++v)
+                    *reinterpret_cast<float4 *>(hrow + 4 * v) =
+                        make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+            }
+            __syncthreads();  // filtered rows visible; this stage's input rows are free
+            if (tid == 0 && step + 2 < n_steps) issue(step + 2);
+
+            // ---- column pass: thread = float columns 2*tid, 2*tid+1
+            const int gx = x0 + 2 * tid;
+            const bool col_ok = gx < p.row_elems;
+#pragma unroll 1
+            for (int q = 0; q < kGsQ; ++q) {
+                const int r = r_begin + step * kGsQ + q;
+                const float2 v = *reinterpret_cast<const float2 *>(s_h + ((size_t)stage * kGsQ + q) * kGsTW + 2 * tid);
+                const float2 o = GsColDispatch<R>::run(phase, a0, a1, v, p);
+                phase = (phase + 1 == NA) ? 0 : phase + 1;
+                const int orow = r - R;
+                if (col_ok && orow >= y0 && orow < y1)
+                    __stcs(reinterpret_cast<float2 *>(dst + (size_t)orow * p.row_elems + gx), o);
+            }
+        }
+    }
+}
+
+}  // namespace mpk

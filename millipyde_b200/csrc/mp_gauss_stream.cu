@@ -1,11 +1,99 @@
-// fp32 streaming Gaussian launcher (stub until the kernel lands)
+// Launcher of the fp32 streaming Gaussian (kernels/gaussian_stream.cuh).
+//
+// Radius buckets: the kernel is fully unrolled over the taps, so it is
+// instantiated for a few radii and a request uses the smallest bucket that
+// holds its effective radius (weights beyond the radius are zero).  sigma = 2
+// (effective radius 11) lands exactly on a bucket.
+#include "kernels/gaussian_stream.cuh"
 #include "mp_internal.h"
 #include "mp_ops_internal.h"
 
+using namespace mpk;
+
 namespace mp {
-bool gauss_stream_supported(int, int, int) { return false; }
-MPStatus launch_gauss_stream(int, cudaStream_t, const Img &, const float *, float *, const mpk::GaussParams<float> &)
+
+static const int kBuckets[] = {3, 5, 7, 9, 11, 13};
+
+static int bucket_for(int radius)
 {
-    return MP_ERROR_INVALID_ARGUMENT;
+    for (int b : kBuckets)
+        if (radius <= b) return b;
+    return 0;
 }
+
+bool gauss_stream_supported(int W, int C, int radius)
+{
+    return ((size_t)W * C) % 4 == 0 && (size_t)W * C >= 64 && bucket_for(radius) != 0;
+}
+
+template <int C, int R>
+static MPStatus launch_cr(int device, cudaStream_t s, GaussStreamParams &p)
+{
+    auto kern = gauss_stream_kernel<C, R>;
+    static bool configured[64] = {};  // per device
+    if (device >= 0 && device < 64 && !configured[device]) {
+        MP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)GsGeom<C, R>::SMEM));
+        configured[device] = true;
+    }
+    // Row chunks only when the batch alone cannot fill the machine: every extra
+    // chunk re-filters 2R rows.
+    const int slots = 2 * (sm_count(device) ? sm_count(device) : 148);
+    long items = (long)p.n_images * p.n_strips;
+    int chunks = 1;
+    while (items * chunks < 2L * slots && p.height / (chunks * 2) >= 8 * R) chunks *= 2;
+    p.n_chunks = chunks;
+    p.chunk_rows = (p.height + chunks - 1) / chunks;
+    items *= chunks;
+    const int grid = (int)(items < slots ? items : slots);
+    kern<<<grid, kGsThreads, GsGeom<C, R>::SMEM, s>>>(p);
+    count_launch();
+    return MILLIPYDE_SUCCESS;
+}
+
+template <int C>
+static MPStatus launch_c(int device, cudaStream_t s, GaussStreamParams &p, int bucket)
+{
+    switch (bucket) {
+        case 3: return launch_cr<C, 3>(device, s, p);
+        case 5: return launch_cr<C, 5>(device, s, p);
+        case 7: return launch_cr<C, 7>(device, s, p);
+        case 9: return launch_cr<C, 9>(device, s, p);
+        case 11: return launch_cr<C, 11>(device, s, p);
+        case 13: return launch_cr<C, 13>(device, s, p);
+        default: return MP_ERROR_INVALID_ARGUMENT;
+    }
+}
+
+MPStatus launch_gauss_stream_batch(int device, cudaStream_t s, int H, int W, int C, int n_images,
+                                   const float *in, float *out, size_t image_stride,
+                                   const float *const *in_tab, float *const *out_tab,
+                                   const GaussParams<float> &gp)
+{
+    const int bucket = bucket_for(gp.radius);
+    if (!bucket) return MP_ERROR_INVALID_ARGUMENT;
+    GaussStreamParams p = {};
+    p.in = in;
+    p.out = out;
+    p.in_tab = in_tab;
+    p.out_tab = out_tab;
+    p.image_stride = image_stride;
+    p.n_images = n_images;
+    p.height = H;
+    p.row_elems = W * C;
+    p.n_strips = (p.row_elems + kGsTW - 1) / kGsTW;
+    p.radius = gp.radius;
+    for (int d = 0; d < 16; ++d) p.w[d] = d <= gp.radius ? gp.w[d] : 0.f;
+    if (C == 1) return launch_c<1>(device, s, p, bucket);
+    if (C == 3) return launch_c<3>(device, s, p, bucket);
+    if (C == 4) return launch_c<4>(device, s, p, bucket);
+    return MP_ERROR_UNSUPPORTED_LAYOUT;
+}
+
+MPStatus launch_gauss_stream(int device, cudaStream_t s, const Img &d, const float *in, float *out,
+                             const GaussParams<float> &gp)
+{
+    return launch_gauss_stream_batch(device, s, d.H, d.W, d.C, 1, in, out, 0, nullptr, nullptr, gp);
+}
+
 }  // namespace mp

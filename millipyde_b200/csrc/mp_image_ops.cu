@@ -10,7 +10,6 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "kernels/gaussian_stream.cuh"
 #include "kernels/gaussian_tile.cuh"
 #include "kernels/geometry.cuh"
 #include "kernels/pointwise.cuh"

@@ -43,5 +43,11 @@ MPStatus launch_gaussian(int device, cudaStream_t s, const Img &d, const void *i
 bool gauss_stream_supported(int W, int C, int radius);
 MPStatus launch_gauss_stream(int device, cudaStream_t s, const Img &d, const float *in, float *out,
                              const mpk::GaussParams<float> &gp);
+// n_images of one shape in one launch: either a contiguous batch (in/out +
+// image_stride floats) or per-image device pointer tables.
+MPStatus launch_gauss_stream_batch(int device, cudaStream_t s, int H, int W, int C, int n_images,
+                                   const float *in, float *out, size_t image_stride,
+                                   const float *const *in_tab, float *const *out_tab,
+                                   const mpk::GaussParams<float> &gp);
 
 }  // namespace mp
