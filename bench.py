@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline benchmark (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic images: the
+workload is BASELINE.json configs[1] -- Gaussian blur sigma=2 on a batch of
+3840x2160 RGB fp32 images (256 per GPU; fewer only if device memory is short,
+and then `config` says so).  `value` = images/s with the batch resident in HBM
+when the timed region starts, timed with CUDA events on the launching stream,
+max over ranks.  `e2e` = the same metric through the public call with HOST
+buffers: pinned host memory -> device -> blur -> pinned host memory, every copy
+inside the timed region.
+
+Multi-GPU: images are independent, so the batch is sharded over ranks with no
+data-path collective ("scaling": "weak", 256 images per GPU).  Under torchrun
+each rank owns GPU LOCAL_RANK; torch.distributed is used only for the barrier
+and the max-over-ranks of the device times.
+
+--impl reference times the reference's CPU path for the same workload: the
+scikit-image calls of its test suite, restated on scipy (oracle/, kind "port")
+on all host cores, on a bounded sample of the batch.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, C = 2160, 3840, 3
+SIGMA = 2.0
+BATCH_PER_GPU = 256
+ALGO_BYTES_PER_IMAGE = 2 * H * W * C * 4          # read once + written once
+WORKLOAD = "gaussian sigma=2, 3840x2160 RGB fp32, batch 256/GPU (BASELINE configs[1])"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step")
+    ap.add_argument("--e2e-images", type=int, default=32, help="images per e2e step")
+    ap.add_argument("--cpu-images", type=int, default=0, help="images in the CPU sample (0 = one per core)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- CPU leg
+def _cpu_one(seed):
+    import numpy as np
+    from oracle import skimage_oracle as so
+    rng = np.random.default_rng(seed)
+    img = rng.random((H, W, C), dtype=np.float32)
+    t0 = time.perf_counter()
+    out = so.gaussian(img, SIGMA)
+    dt = time.perf_counter() - t0
+    return dt, float(out[H // 2, W // 2, 0])
+
+
+def cpu_baseline(n_images: int):
+    """The oracle's Gaussian (scipy.ndimage.gaussian_filter -- the call
+    skimage.filters.gaussian makes) on `n_images` images, one process per core."""
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    n = n_images or cores
+    procs = min(cores, n)
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_one, [2000 + k for k in range(n)])
+    wall = time.perf_counter() - t0
+    return {"value": n / wall, "unit": "images/s", "cores": procs, "kind": "port",
+            "sample": f"{n} of the step's images, scipy.ndimage.gaussian_filter(sigma=2, truncate=8, "
+                      f"mode=constant) per image, {procs} processes, wall {wall:.1f}s"}
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []          # (arrival time, fields)
+        self.window = None      # (t0, t1) of the timed region
+        self.proc = None
+        self.gpu = gpu_index
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], 0, set(), 0.0
+        rows = self.rows
+        if self.window:
+            inside = [x for x in rows if self.window[0] <= x[0] <= self.window[1] + 0.15]
+            # a timed region shorter than the sampling period: fall back to every sample taken
+            # since the warm-up started (the GPU was under the same load throughout)
+            rows = inside if len(inside) >= 3 else rows
+        for _, r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                power = max(power, float(r[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # median of the upper half: the samples taken while the kernels were running
+        busy = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx or None,
+                "power_w_max": power, "samples": len(sm), "reasons": sorted(reasons),
+                "note": "nvidia-smi -lms 100 from warm-up to the end of the timed region; median of the busy half"}
+
+
+# --------------------------------------------------------------------------- dist
+class Dist:
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.pg = None
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group(backend="gloo", rank=self.rank, world_size=self.world)
+            self.pg = dist
+
+    def barrier(self):
+        if self.pg:
+            self.pg.barrier()
+
+    def max(self, x: float) -> float:
+        if not self.pg:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        self.pg.all_reduce(t, op=self.pg.ReduceOp.MAX)
+        return float(t[0])
+
+    def sum(self, x: float) -> float:
+        if not self.pg:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        self.pg.all_reduce(t, op=self.pg.ReduceOp.SUM)
+        return float(t[0])
+
+    def close(self):
+        if self.pg:
+            self.pg.destroy_process_group()
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args, dist):
+    if dist.rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    n = args.cpu_images or cores
+    vals = []
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_baseline(min(n, cores))
+    t_all0 = time.perf_counter()
+    for _ in range(args.steps):
+        vals.append(cpu_baseline(n))
+    wall = time.perf_counter() - t_all0
+    v = sum(x["value"] for x in vals) / len(vals)
+    base = vals[-1]
+    base["value"] = v
+    line = {
+        "impl": "reference", "metric": "augmented images/sec (4K RGB fp32 pipeline)", "value": v,
+        "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_images_per_step": n,
+                   "note": "reference CPU path = the scikit-image calls of its test suite restated on scipy "
+                           "(scikit-image is not installable here); runs on host cores only"},
+        "cpu_baseline": base,
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- B200 arm
+def run_b200(args, dist):
+    import numpy as np
+    if dist.world > 1:
+        # one rank per GPU: this process only ever sees its own device
+        os.environ["CUDA_VISIBLE_DEVICES"] = os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[dist.local] \
+            if os.environ.get("CUDA_VISIBLE_DEVICES") else str(dist.local)
+    from millipyde_b200 import capi
+    from millipyde_b200 import engine
+
+    ndev = capi.initialize()
+    L = capi.lib()
+    in_process_gpus = args.gpus if dist.world == 1 else 1
+    if in_process_gpus > ndev:
+        raise SystemExit(f"--gpus {args.gpus} but only {ndev} device(s) visible")
+    devices = list(range(in_process_gpus))
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        hbm_peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+
+    # ---- batch: a few distinct host images, replicated on the device -------------
+    free_b, total_b = ctypes.c_size_t(), ctypes.c_size_t()
+    L.mpdev_mem_info(0, ctypes.byref(free_b), ctypes.byref(total_b))
+    img_bytes = H * W * C * 4
+    batch = args.batch
+    # inputs + outputs of one step live together (the op is out-of-place into pool memory)
+    while batch > 8 and 2.2 * batch * img_bytes > free_b.value:
+        batch //= 2
+    rng = np.random.default_rng(2000)
+    seeds = [rng.random((H, W, C), dtype=np.float32) for _ in range(2)]
+    shards = []
+    for d in devices:
+        L.mpdev_set_target_device(d)
+        base = [capi.DeviceImage(s) for s in seeds]
+        imgs = [base[k % len(base)].clone(device=d) for k in range(batch)]
+        for b in base:
+            b.close()
+        shards.append(imgs)
+    L.mpdev_set_target_device(capi.DEVICE_LOC_NO_AFFINITY)
+    L.mpdev_synchronize_all()
+
+    pipe = engine.Chain([("gaussian", SIGMA)])
+
+    def step():
+        # the public batch call: one Pipeline-style run per device shard
+        engine.run_batches(pipe, shards, devices)
+
+    sampler = ClockSampler(dist.local if dist.world > 1 else 0)
+    sampler.start()
+    t_warm = time.time()
+    while True:     # >= W warm-up steps and long enough for the clock sampler to come up
+        for _ in range(max(args.warmup, 3)):
+            step()
+        L.mpdev_synchronize_all()
+        if time.time() - t_warm > 1.0:
+            break
+    dist.barrier()
+    L.mpdev_synchronize_all()
+    t_region0 = time.time()
+    launches0 = L.mpdev_launch_count()
+    evs = [(L.mpdev_event_create(d), L.mpdev_event_create(d)) for d in devices]
+    t0 = time.perf_counter()
+    for (e0, _), d in zip(evs, devices):
+        L.mpdev_event_record(e0, engine.timing_stream(d))
+    for _ in range(args.steps):
+        step()
+    for (_, e1), d in zip(evs, devices):
+        L.mpdev_event_record(e1, engine.timing_stream(d))
+    dev_ms = max(L.mpdev_event_elapsed_ms(e0, e1) for e0, e1 in evs)
+    L.mpdev_synchronize_all()
+    wall_ms = (time.perf_counter() - t0) * 1000.0
+    launches = L.mpdev_launch_count() - launches0
+    dist.barrier()
+    sampler.window = (t_region0, time.time())
+    clocks = sampler.stop()
+    for e0, e1 in evs:
+        L.mpdev_event_destroy(e0)
+        L.mpdev_event_destroy(e1)
+
+    dev_ms = dist.max(dev_ms)
+    images_per_step = dist.sum(float(batch * len(devices)))
+    ms_per_step = dev_ms / args.steps
+    value = images_per_step / (ms_per_step / 1000.0)
+
+    # roofline of the dominant kernel (the Gaussian): launches run back to back on the timing
+    # stream, so average launch duration = device time / launches on this rank
+    kern_launches = max(1, launches // max(1, len(devices)))
+    avg_launch_ms = (dev_ms if dist.world == 1 else dev_ms) / kern_launches
+    images_per_launch = batch * args.steps / kern_launches
+    achieved = images_per_launch * ALGO_BYTES_PER_IMAGE / (avg_launch_ms / 1000.0) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": _ncu_traffic(images_per_launch),
+                "kernel": "gauss_stream_kernel<3,11>", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": images_per_launch * ALGO_BYTES_PER_IMAGE,
+                "avg_launch_ms": avg_launch_ms}
+
+    # ---- e2e: host buffers in, host buffers out ----------------------------------
+    e2e = engine.e2e_gaussian(devices, args.e2e_images, (H, W, C), SIGMA, steps=max(2, min(args.steps, 3)))
+    e2e_value = dist.sum(e2e["images_per_s"])
+
+    line = {
+        "metric": "augmented images/sec (4K RGB fp32 pipeline)", "value": value, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "images_per_gpu_per_step": batch, "image_shape": [H, W, C],
+                   "sigma": SIGMA, "effective_radius": 11, "l2": "inputs (25.5 GB/GPU) far exceed the 126 MB L2",
+                   "parallelism": f"{args.gpus} GPU(s), images sharded, no collective",
+                   "launcher": "torchrun ranks" if dist.world > 1 else "one process"},
+        "roofline": roofline,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": e2e["h2d_bytes"],
+                "d2h_bytes_per_step": e2e["d2h_bytes"], "images_per_step": e2e["images"],
+                "note": "pinned host -> device -> blur -> pinned host, copies in the timed region"},
+        "gpu_launches": int(launches), "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
+    }
+    if dist.rank == 0 and not args.no_cpu and args.gpus == 1:
+        line["cpu_baseline"] = cpu_baseline(args.cpu_images)
+    elif dist.rank == 0:
+        line["cpu_baseline"] = None
+    if dist.rank == 0:
+        print(json.dumps(line), flush=True)
+    for imgs in shards:
+        for i in imgs:
+            i.close()
+
+
+def _ncu_traffic(images_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
+    ncu capture (profiles/), scaled to this run's images per launch; None if no
+    capture has been committed yet."""
+    p = os.path.join(ROOT, "profiles", "gauss_stream_dram.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return d["dram_bytes_per_image"] * images_per_launch
+
+
+def main():
+    args = parse()
+    dist = Dist()
+    try:
+        if args.impl == "reference":
+            run_reference(args, dist)
+        else:
+            run_b200(args, dist)
+    finally:
+        dist.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,83 @@
+/*
+ * mp_pipeline.h -- the Operation-chain executor (C ABI): fusion pass, batched
+ * launches, device sharding and cross-device hand-off.
+ *
+ * This is the body of the reference's Pipeline, lifted out of the CPython type:
+ *   mppipe_create      <- the MPRunnable[] pre-resolution of PyGPUPipeline_init
+ *                         (src/gpupipeline.c:152-161)
+ *   mppipe_connect     <- PyGPUPipeline_connect_to (src/gpupipeline.c:186-218)
+ *   mppipe_run         <- PyGPUPipeline_run + gpupipeline_run_sequence
+ *                         (src/gpupipeline.c:234-312, :352-403)
+ *   mppipe_run_host    <- the Generator's clone -> ops -> D2H loop
+ *                         (src/gpugenerator.c:203-281), as a pinned, multi-stream
+ *                         host->device->host stream
+ *
+ * What changes behind it (BASELINE.json north star, item 2): the stage loop no
+ * longer calls one kernel + one stream sync per stage per image.  Per-image coin
+ * flips are drawn first; images with the same layout and the same surviving op
+ * list form a group; each group's op list is compiled into segments
+ * (index/resample + pointwise -> at most one stencil -> pointwise), and every
+ * segment is ONE launch over the whole group (pointer tables), so a chain costs
+ * one HBM round trip per segment per image.  Stages whose MPFunc is not one of
+ * libmp_b200's eight operators are called one image at a time, as the reference
+ * does.
+ */
+#ifndef MP_B200_PIPELINE_H
+#define MP_B200_PIPELINE_H
+#include "mp_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mp_pipeline MPPipeline;
+
+/* device_id: a device ordinal, or DEVICE_LOC_NO_AFFINITY ("use the target device if one is set,
+ * else spread the inputs over every device", src/gpupipeline.c:245-264).  The stage array and the
+ * *Args blocks of libmp_b200's own operators are copied. */
+MPPipeline *mppipe_create(const MPRunnable *stages, int num_stages, int device_id);
+void mppipe_destroy(MPPipeline *p);
+
+int mppipe_get_device(const MPPipeline *p);
+void mppipe_set_device(MPPipeline *p, int device_id);
+
+/* `from`'s results are handed to `to` (NVLink peer copy when the devices differ). */
+void mppipe_connect(MPPipeline *from, MPPipeline *to);
+
+/* Run every stage (and every connected pipeline) on every object; returns when all devices
+ * involved are idle.  Objects are mutated in place like the eager ops do. */
+MPStatus mppipe_run(MPPipeline *p, MPObjData **objs, int n);
+
+/* Asynchronous halves of mppipe_run, for callers that drive several pipelines at once. */
+MPStatus mppipe_submit(MPPipeline *p, MPObjData **objs, int n);
+MPStatus mppipe_wait(MPPipeline *p);
+
+/* Layout of one result of mppipe_run_host. */
+typedef struct {
+    int ndims;
+    long shape[3];
+    int type;      /* numpy typenum */
+    size_t nbytes;
+    int status;    /* MPStatus of this image */
+} MPHostResult;
+
+/* Stream n host images of one layout through the chain: upload (full PCIe rate when host_in is
+ * page-locked) -> ops -> download, `depth` images in flight per device on separate streams so
+ * copies overlap kernels.  host_out[i] must hold out_capacity bytes. */
+MPStatus mppipe_run_host(MPPipeline *p, const void *const *host_in, void *const *host_out,
+                         size_t out_capacity, MPHostResult *results, int n, int ndims,
+                         const long *shape, int typenum);
+
+/* Fusion on (default) / off: off reproduces the reference's one-kernel-per-stage execution with the
+ * same kernels, for A/B parity tests. */
+void mppipe_set_fusion(int enabled);
+int mppipe_get_fusion(void);
+
+/* Kernel launches and fused segments issued by the most recent run of `p` (all devices). */
+unsigned long long mppipe_last_launches(const MPPipeline *p);
+int mppipe_last_segments(const MPPipeline *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MP_B200_PIPELINE_H */

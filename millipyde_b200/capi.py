@@ -74,6 +74,13 @@ class MPRunnable(C.Structure):
 
 _OBJ = C.POINTER(MPObjData)
 
+
+class MPHostResult(C.Structure):
+    """include/mp_pipeline.h"""
+    _fields_ = [("ndims", C.c_int), ("shape", C.c_long * 3), ("type", C.c_int),
+                ("nbytes", C.c_size_t), ("status", C.c_int)]
+
+
 # name -> (restype, argtypes); every symbol include/*.h declares
 SYMBOLS = {
     # mp_abi.h
@@ -147,6 +154,21 @@ SYMBOLS = {
     "mpdev_sm_count": (C.c_int, [C.c_int]),
     "mpdev_flush_l2": (None, [C.c_int, C.c_void_p]),
     "mpdev_launch_count": (C.c_ulonglong, []),
+    # mp_pipeline.h
+    "mppipe_create": (C.c_void_p, [C.POINTER(MPRunnable), C.c_int, C.c_int]),
+    "mppipe_destroy": (None, [C.c_void_p]),
+    "mppipe_get_device": (C.c_int, [C.c_void_p]),
+    "mppipe_set_device": (None, [C.c_void_p, C.c_int]),
+    "mppipe_connect": (None, [C.c_void_p, C.c_void_p]),
+    "mppipe_run": (C.c_int, [C.c_void_p, C.POINTER(_OBJ), C.c_int]),
+    "mppipe_submit": (C.c_int, [C.c_void_p, C.POINTER(_OBJ), C.c_int]),
+    "mppipe_wait": (C.c_int, [C.c_void_p]),
+    "mppipe_run_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t,
+                                  C.POINTER(MPHostResult), C.c_int, C.c_int, C.POINTER(C.c_long), C.c_int]),
+    "mppipe_set_fusion": (None, [C.c_int]),
+    "mppipe_get_fusion": (C.c_int, []),
+    "mppipe_last_launches": (C.c_ulonglong, [C.c_void_p]),
+    "mppipe_last_segments": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

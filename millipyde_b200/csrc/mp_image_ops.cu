@@ -202,9 +202,8 @@ int mpimg_gaussian_effective_radius(double sigma, int *full)
 }
 
 /* ------------------------------------------------------------------ rgb2grey */
-MPStatus mpimg_color_to_greyscale(MPObjData *obj, void *args)
+static MPStatus grey_impl(MPObjData *obj, const PwProgram &pre, const PwProgram &post)
 {
-    MP_UNUSED(args);
     mp::Img d;
     cudaStream_t s;
     MPStatus st = begin(obj, &d, &s);
@@ -218,12 +217,11 @@ MPStatus mpimg_color_to_greyscale(MPObjData *obj, void *args)
     if ((st = fresh(obj, s, out_bytes, &out)) != MILLIPYDE_SUCCESS) return st;
 
     if (f32) {
-        PwProgram none = {};
         int grid = mp::grid_for(obj->mem_loc, d.npix / 4 + 1, 256);
         if (d.C == 3)
-            grey_f32_kernel<3><<<grid, 256, 0, s>>>((const float *)obj->device_data, (float *)out, d.npix, none, none);
+            grey_f32_kernel<3><<<grid, 256, 0, s>>>((const float *)obj->device_data, (float *)out, d.npix, pre, post);
         else
-            grey_f32_kernel<4><<<grid, 256, 0, s>>>((const float *)obj->device_data, (float *)out, d.npix, none, none);
+            grey_f32_kernel<4><<<grid, 256, 0, s>>>((const float *)obj->device_data, (float *)out, d.npix, pre, post);
     } else if (d.fam == mp::FAM_RGBA8) {
         int grid = mp::grid_for(obj->mem_loc, d.npix / 4 + 1, 256);
         grey_rgba8_kernel<<<grid, 256, 0, s>>>((const uint32_t *)obj->device_data, (double *)out, d.npix);
@@ -243,6 +241,13 @@ MPStatus mpimg_color_to_greyscale(MPObjData *obj, void *args)
     obj->dims[2] = (int)(d.W * out_es);
     obj->dims[3] = (int)out_es;
     return MILLIPYDE_SUCCESS;
+}
+
+MPStatus mpimg_color_to_greyscale(MPObjData *obj, void *args)
+{
+    MP_UNUSED(args);
+    PwProgram none = {};
+    return grey_impl(obj, none, none);
 }
 
 /* ----------------------------------------------------------------- transpose */
@@ -338,6 +343,7 @@ MPStatus mpimg_rotate(MPObjData *obj, void *args)
 /* ------------------------------------------------ brightness / gamma / colorize */
 static MPStatus pointwise_f32(MPObjData *obj, const mp::Img &d, cudaStream_t s, const PwProgram &prog)
 {
+    if (prog.n == 0) return MILLIPYDE_SUCCESS;
     void *out;
     MPStatus st = fresh(obj, s, obj->nbytes, &out);
     if (st != MILLIPYDE_SUCCESS) return st;
@@ -365,6 +371,7 @@ static MPStatus pointwise_f64(MPObjData *obj, const mp::Img &d, cudaStream_t s, 
 
 static MPStatus pointwise_rgba8(MPObjData *obj, const mp::Img &d, cudaStream_t s, const U8Program &prog)
 {
+    if (prog.n == 0) return MILLIPYDE_SUCCESS;
     void *out;
     MPStatus st = fresh(obj, s, obj->nbytes, &out);
     if (st != MILLIPYDE_SUCCESS) return st;
@@ -547,6 +554,35 @@ MPStatus launch_gaussian(int device, cudaStream_t s, const Img &d, const void *i
     if (d.C == 1) return launch_tile<float, 1, false>(s, d, in, out, gp);
     if (d.C == 3) return launch_tile<float, 3, false>(s, d, in, out, gp);
     return launch_tile<float, 4, false>(s, d, in, out, gp);
+}
+
+}  // namespace mp
+
+namespace mp {
+
+MPStatus op_pointwise_f32(MPObjData *obj, const PwProgram &prog)
+{
+    Img d;
+    cudaStream_t s;
+    MPStatus st = begin(obj, &d, &s);
+    if (st != MILLIPYDE_SUCCESS) return st;
+    if (d.fam != FAM_F32) return MP_ERROR_UNSUPPORTED_LAYOUT;
+    return pointwise_f32(obj, d, s, prog);
+}
+
+MPStatus op_pointwise_rgba8(MPObjData *obj, const U8Program &prog)
+{
+    Img d;
+    cudaStream_t s;
+    MPStatus st = begin(obj, &d, &s);
+    if (st != MILLIPYDE_SUCCESS) return st;
+    if (d.fam != FAM_RGBA8) return MP_ERROR_UNSUPPORTED_LAYOUT;
+    return pointwise_rgba8(obj, d, s, prog);
+}
+
+MPStatus op_grey_f32(MPObjData *obj, const PwProgram &pre, const PwProgram &post)
+{
+    return grey_impl(obj, pre, post);
 }
 
 }  // namespace mp

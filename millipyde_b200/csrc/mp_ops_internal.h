@@ -39,6 +39,12 @@ mpk::U8Op u8_brightness_op(double delta);
 MPStatus launch_gaussian(int device, cudaStream_t s, const Img &d, const void *in, void *out, double sigma,
                          bool ref_rule);
 
+// Program-level entry points the fusion pass uses (same begin/alloc/launch/retire
+// protocol as the eager mpimg_* ops).
+MPStatus op_pointwise_f32(MPObjData *obj, const mpk::PwProgram &prog);
+MPStatus op_pointwise_rgba8(MPObjData *obj, const mpk::U8Program &prog);
+MPStatus op_grey_f32(MPObjData *obj, const mpk::PwProgram &pre, const mpk::PwProgram &post);
+
 // fp32 roofline path (kernels/gaussian_stream.cuh)
 bool gauss_stream_supported(int W, int C, int radius);
 MPStatus launch_gauss_stream(int device, cudaStream_t s, const Img &d, const float *in, float *out,

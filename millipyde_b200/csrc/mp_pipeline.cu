@@ -1,0 +1,712 @@
+// Operation-chain executor: coin flips -> grouping -> fusion pass -> batched
+// launches -> sharding over devices -> peer hand-off between connected pipelines.
+//
+// Replaces PyGPUPipeline_run / gpupipeline_run_sequence / gpupipeline_send_input
+// (src/gpupipeline.c:234-403) and the serial Generator loop
+// (src/gpugenerator.c:203-281).  See include/mp_pipeline.h for the contract.
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "mp_devices.h"
+#include "mp_image.h"
+#include "mp_internal.h"
+#include "mp_objects.h"
+#include "mp_ops_internal.h"
+#include "mp_pipeline.h"
+
+using namespace mpk;
+
+namespace {
+
+enum OpKind {
+    OP_GREY, OP_TRANSPOSE, OP_GAUSSIAN, OP_FLIPLR, OP_ROTATE, OP_BRIGHTNESS, OP_GAMMA, OP_COLORIZE,
+    OP_FOREIGN,  // an MPFunc that is not one of ours: called as-is, one image at a time
+    OP_NULL,     // func == NULL: skipped, as src/gpupipeline.c:393-396
+};
+
+struct Stage {
+    OpKind kind;
+    MPFunc func;
+    void *args;          // owned copy for our operators, caller's pointer for foreign ones
+    double a[3];
+    double probability;  // <= 0: always (the reference tests `probability > 0`, :380)
+};
+
+std::atomic<int> g_fusion{1};
+
+OpKind classify(MPFunc f, size_t *arg_bytes)
+{
+    *arg_bytes = 0;
+    if (!f) return OP_NULL;
+    if (f == mpimg_color_to_greyscale) return OP_GREY;
+    if (f == mpimg_transpose) return OP_TRANSPOSE;
+    if (f == mpimg_fliplr) return OP_FLIPLR;
+    if (f == mpimg_gaussian) { *arg_bytes = sizeof(GaussianArgs); return OP_GAUSSIAN; }
+    if (f == mpimg_rotate) { *arg_bytes = sizeof(RotateArgs); return OP_ROTATE; }
+    if (f == mpimg_brightness) { *arg_bytes = sizeof(BrightnessArgs); return OP_BRIGHTNESS; }
+    if (f == mpimg_adjust_gamma) { *arg_bytes = sizeof(GammaArgs); return OP_GAMMA; }
+    if (f == mpimg_colorize) { *arg_bytes = sizeof(ColorizeArgs); return OP_COLORIZE; }
+    return OP_FOREIGN;
+}
+
+bool is_pointwise(OpKind k) { return k == OP_BRIGHTNESS || k == OP_GAMMA || k == OP_COLORIZE; }
+
+// Per-device page-locked arena for pointer tables: grows, is reused by every run
+// on that device, and is only touched by that run's worker under `mux`.
+struct Arena {
+    std::mutex mux;
+    char *base = nullptr;
+    size_t cap = 0, used = 0;
+    void *take(size_t bytes)
+    {
+        bytes = (bytes + 63) & ~(size_t)63;
+        if (used + bytes > cap) return nullptr;
+        void *p = base + used;
+        used += bytes;
+        return p;
+    }
+};
+Arena g_arenas[64];
+
+}  // namespace
+
+struct mp_pipeline {
+    std::vector<Stage> stages;
+    int device = DEVICE_LOC_NO_AFFINITY;
+    mp_pipeline *receiver = nullptr;
+    std::atomic<unsigned long long> launches{0};
+    std::atomic<int> segments{0};
+    std::atomic<int> status{MILLIPYDE_SUCCESS};
+    // devices touched by the run in flight (for mppipe_wait)
+    std::mutex mux;
+    std::vector<int> in_flight;
+    bool cycled = false;
+};
+
+namespace {
+
+void note_status(mp_pipeline *p, MPStatus st)
+{
+    if (st != MILLIPYDE_SUCCESS) {
+        int expected = MILLIPYDE_SUCCESS;
+        p->status.compare_exchange_strong(expected, (int)st);
+    }
+}
+
+// ------------------------------------------------------------------ fusion pass
+struct Segment {
+    enum Kind { SINGLE, PW_F32, GREY_F32, PW_RGBA8 } kind;
+    const Stage *single = nullptr;  // SINGLE
+    PwProgram pre = {}, post = {};  // PW_F32 uses `pre`; GREY_F32 uses both
+    U8Program u8 = {};
+};
+
+PwOp to_pw(const Stage &s)
+{
+    switch (s.kind) {
+        case OP_BRIGHTNESS: return PwOp{PW_BRIGHTNESS, (float)s.a[0], 0.f, 0.f};
+        case OP_GAMMA: return PwOp{PW_GAMMA, (float)s.a[0], (float)s.a[1], 0.f};
+        default: return PwOp{PW_COLORIZE, (float)s.a[0], (float)s.a[1], (float)s.a[2]};
+    }
+}
+
+U8Op to_u8(const Stage &s)
+{
+    switch (s.kind) {
+        case OP_BRIGHTNESS: return mp::u8_brightness_op(s.a[0]);
+        case OP_GAMMA: return U8Op{PW_GAMMA, 0, s.a[0], s.a[1], 0};
+        default: return U8Op{PW_COLORIZE, 0, s.a[0], s.a[1], s.a[2]};
+    }
+}
+
+// Compile the surviving stages of one group into segments.  `fam`/`channels`
+// track the layout as ops change it.  Legality rules (DESIGN.md "Fusion"):
+//  * consecutive pointwise ops compose exactly -> one kernel (fp32: op program;
+//    RGBA8: composed byte tables, bit-identical to running them one by one);
+//  * rgb2grey absorbs the pointwise ops before it (per colour channel) and after
+//    it (on the grey value) -> one kernel reading C channels, writing one;
+//  * everything else is a segment of its own.
+std::vector<Segment> compile(const std::vector<const Stage *> &ops, mp::Family fam, int channels)
+{
+    std::vector<Segment> out;
+    const bool fuse = g_fusion.load() != 0;
+    size_t i = 0;
+    while (i < ops.size()) {
+        const Stage *s = ops[i];
+        if (fuse && fam == mp::FAM_F32 && (is_pointwise(s->kind) || (s->kind == OP_GREY && channels >= 3))) {
+            Segment seg;
+            seg.kind = Segment::PW_F32;
+            bool grey = false;
+            size_t j = i;
+            while (j < ops.size()) {
+                const Stage *t = ops[j];
+                if (is_pointwise(t->kind)) {
+                    PwProgram &prog = grey ? seg.post : seg.pre;
+                    if (prog.n == kMaxPw) break;
+                    if (!(grey && t->kind == OP_COLORIZE))  // colorize is a no-op on grey (:647-651)
+                        prog.ops[prog.n++] = to_pw(*t);
+                    ++j;
+                } else if (t->kind == OP_GREY && !grey && channels >= 3) {
+                    grey = true;
+                    seg.kind = Segment::GREY_F32;
+                    ++j;
+                } else {
+                    break;
+                }
+            }
+            if (j - i >= 2) {
+                if (grey) channels = 1;
+                out.push_back(seg);
+                i = j;
+                continue;
+            }
+        }
+        if (fuse && fam == mp::FAM_RGBA8 && is_pointwise(s->kind)) {
+            Segment seg;
+            seg.kind = Segment::PW_RGBA8;
+            size_t j = i;
+            while (j < ops.size() && is_pointwise(ops[j]->kind) && seg.u8.n < kMaxPw) seg.u8.ops[seg.u8.n++] = to_u8(*ops[j++]);
+            if (j - i >= 2) {
+                out.push_back(seg);
+                i = j;
+                continue;
+            }
+        }
+        Segment seg;
+        seg.kind = Segment::SINGLE;
+        seg.single = s;
+        out.push_back(seg);
+        if (s->kind == OP_GREY) {
+            if (fam == mp::FAM_RGBA8 || fam == mp::FAM_U8_OTHER || fam == mp::FAM_F64_OTHER) fam = mp::FAM_F64;
+            channels = 1;
+        }
+        ++i;
+    }
+    return out;
+}
+
+MPStatus run_segment_on(MPObjData *obj, const Segment &seg)
+{
+    switch (seg.kind) {
+        case Segment::PW_F32: return mp::op_pointwise_f32(obj, seg.pre);
+        case Segment::GREY_F32: return mp::op_grey_f32(obj, seg.pre, seg.post);
+        case Segment::PW_RGBA8: return mp::op_pointwise_rgba8(obj, seg.u8);
+        default: return seg.single->func(obj, seg.single->args);
+    }
+}
+
+// One launch for the Gaussian of a whole same-shape fp32 group (pointer tables).
+MPStatus run_gaussian_batch(mp_pipeline *p, const std::vector<MPObjData *> &objs, const mp::Img &d, double sigma,
+                            int device, cudaStream_t s, bool *handled)
+{
+    *handled = false;
+    if (!(sigma > 1e-15) || objs.size() < 2) return MILLIPYDE_SUCCESS;
+    double w[kGaussMaxRadius + 1];
+    int r = mp::oracle_weights(sigma, w, kGaussMaxRadius);
+    int eff = mp::effective_radius(w, r, ldexp(1.0, -24));
+    if (!mp::gauss_stream_supported(d.W, d.C, eff)) return MILLIPYDE_SUCCESS;
+    GaussParams<float> gp = {};
+    gp.radius = eff;
+    for (int k = 0; k <= eff; ++k) gp.w[k] = (float)w[k];
+
+    const size_t n = objs.size();
+    Arena &arena = g_arenas[device];
+    const float **h_in = (const float **)arena.take(n * sizeof(void *));
+    float **h_out = (float **)arena.take(n * sizeof(void *));
+    if (!h_in || !h_out) return MILLIPYDE_SUCCESS;  // arena exhausted: fall back to per-image launches
+    void *d_tab = mp::pool_alloc(device, s, 2 * n * sizeof(void *));
+    if (!d_tab) return MP_ERROR_DEVICE_ALLOC;
+    std::vector<void *> fresh(n);
+    for (size_t i = 0; i < n; ++i) {
+        fresh[i] = mp::pool_alloc(device, s, objs[i]->nbytes);
+        if (!fresh[i]) {
+            for (size_t k = 0; k < i; ++k) mp::pool_free(device, s, fresh[k]);
+            mp::pool_free(device, s, d_tab);
+            return MP_ERROR_DEVICE_ALLOC;
+        }
+        h_in[i] = (const float *)objs[i]->device_data;
+        h_out[i] = (float *)fresh[i];
+    }
+    // h_in and h_out are adjacent in the arena only if nothing was taken in between; copy both
+    MP_CUDA_TRY(cudaMemcpyAsync(d_tab, h_in, n * sizeof(void *), cudaMemcpyHostToDevice, s));
+    MP_CUDA_TRY(cudaMemcpyAsync((char *)d_tab + n * sizeof(void *), h_out, n * sizeof(void *),
+                                cudaMemcpyHostToDevice, s));
+    MPStatus st = mp::launch_gauss_stream_batch(device, s, d.H, d.W, d.C, (int)n, nullptr, nullptr, 0,
+                                                (const float *const *)d_tab,
+                                                (float *const *)((char *)d_tab + n * sizeof(void *)), gp);
+    cudaError_t e = cudaGetLastError();
+    if (st == MILLIPYDE_SUCCESS && e != cudaSuccess) {
+        mp::record_cuda_error(e, "gauss_stream batch launch", __FILE__, __LINE__);
+        st = MP_ERROR_CUDA_RUNTIME;
+    }
+    for (size_t i = 0; i < n; ++i) {
+        if (st == MILLIPYDE_SUCCESS) {
+            mp::pool_free(device, s, objs[i]->device_data);
+            objs[i]->device_data = fresh[i];
+        } else {
+            mp::pool_free(device, s, fresh[i]);
+        }
+    }
+    mp::pool_free(device, s, d_tab);
+    *handled = st == MILLIPYDE_SUCCESS;
+    return st;
+}
+
+// All images of `objs` share layout and surviving op list.
+void run_group(mp_pipeline *p, const std::vector<MPObjData *> &objs, const std::vector<const Stage *> &ops,
+               int device, cudaStream_t s)
+{
+    if (objs.empty() || ops.empty()) return;
+    mp::Img d;
+    const bool known = mp::describe(objs[0], &d);
+    std::vector<Segment> segs = compile(ops, known ? d.fam : mp::FAM_U8_OTHER, known ? d.C : 0);
+    p->segments.fetch_add((int)segs.size());
+    const unsigned long long before = mpdev_launch_count();
+    for (const Segment &seg : segs) {
+        if (seg.kind == Segment::SINGLE && seg.single->kind == OP_GAUSSIAN && g_fusion.load()) {
+            mp::Img cur;
+            if (mp::describe(objs[0], &cur) && cur.fam == mp::FAM_F32) {
+                bool handled = false;
+                MPStatus st = run_gaussian_batch(p, objs, cur, seg.single->a[0], device, s, &handled);
+                note_status(p, st);
+                if (handled) continue;
+            }
+        }
+        for (MPObjData *o : objs) note_status(p, run_segment_on(o, seg));
+    }
+    (void)before;
+}
+
+struct ShardTask {
+    mp_pipeline *pipe;
+    std::vector<MPObjData *> objs;
+    int device;
+};
+
+void submit_shard(mp_pipeline *p, std::vector<MPObjData *> objs, int device);
+
+void shard_worker(void *arg)
+{
+    ShardTask *t = (ShardTask *)arg;
+    mp_pipeline *p = t->pipe;
+    const int device = t->device;
+    const size_t n = t->objs.size();
+    cudaSetDevice(device);
+    cudaStream_t batch_stream = mp::device_stream(device, 1);
+    const unsigned long long launches0 = mpdev_launch_count();
+
+    Arena &arena = g_arenas[device];
+    std::unique_lock<std::mutex> arena_lock(arena.mux);
+    const size_t want = n * sizeof(void *) * 2 * (p->stages.size() + 1) + 4096;
+    if (arena.cap < want) {
+        if (arena.base) cudaFreeHost(arena.base);
+        arena.base = nullptr;
+        arena.cap = 0;
+        if (cudaHostAlloc((void **)&arena.base, want * 2, cudaHostAllocPortable) == cudaSuccess) arena.cap = want * 2;
+        else (void)cudaGetLastError();
+    }
+    arena.used = 0;
+
+    // 1. bring every object onto this device and onto the shard's stream
+    for (size_t i = 0; i < n; ++i) {
+        MPObjData *o = t->objs[i];
+        o->pinned = MP_TRUE;
+        if (o->mem_loc != device && o->device_data) mpobj_change_device(o, device);
+        mpobj_set_stream(o, (void *)batch_stream);
+    }
+
+    // 2. coin flips, 3. grouping by (layout, surviving stages)
+    const size_t ns = p->stages.size();
+    std::map<std::string, std::vector<size_t>> groups;
+    std::vector<std::string> keys(n);
+    for (size_t i = 0; i < n; ++i) {
+        MPObjData *o = t->objs[i];
+        std::string key;
+        key.reserve(ns + 48);
+        char hdr[64];
+        int c = o->ndims == 3 ? o->dims[2] : 1;
+        snprintf(hdr, sizeof hdr, "%d:%d:%d:%d:%d|", o->type, o->ndims, o->ndims > 0 ? o->dims[0] : 0,
+                 o->ndims > 1 ? o->dims[1] : 0, c);
+        key = hdr;
+        for (size_t k = 0; k < ns; ++k) {
+            const Stage &st = p->stages[k];
+            bool run = st.kind != OP_NULL;
+            if (run && st.probability > 0) {
+                double u = 0;
+                if (random_double_in_range(0.0, 1.0, &u) == MILLIPYDE_SUCCESS && u > st.probability) run = false;
+            }
+            key.push_back(run ? '1' : '0');
+        }
+        groups[key].push_back(i);
+    }
+
+    // 4. per group: fusion pass + launches
+    for (auto &g : groups) {
+        const std::string &key = g.first;
+        const char *mask = key.c_str() + key.find('|') + 1;
+        std::vector<const Stage *> ops;
+        for (size_t k = 0; k < ns; ++k)
+            if (mask[k] == '1') ops.push_back(&p->stages[k]);
+        std::vector<MPObjData *> objs;
+        for (size_t i : g.second) objs.push_back(t->objs[i]);
+        run_group(p, objs, ops, device, batch_stream);
+    }
+
+    // 5. hand the results on, or finish
+    if (p->receiver) {
+        // the receiver's worker orders itself after this stream through the objects' events
+        submit_shard(p->receiver, t->objs, p->receiver->device);
+    }
+    cudaError_t e = cudaStreamSynchronize(batch_stream);
+    if (e != cudaSuccess) {
+        mp::record_cuda_error(e, "cudaStreamSynchronize(shard)", __FILE__, __LINE__);
+        note_status(p, MP_ERROR_CUDA_RUNTIME);
+    }
+    if (!p->receiver) {
+        for (size_t i = 0; i < n; ++i) {
+            t->objs[i]->pinned = MP_FALSE;
+            t->objs[i]->stream = (void *)mp::device_stream(device, 0);  // idle: no event needed
+        }
+    }
+    p->launches.fetch_add(mpdev_launch_count() - launches0);
+    delete t;
+}
+
+void submit_shard(mp_pipeline *p, std::vector<MPObjData *> objs, int device)
+{
+    if (objs.empty()) return;
+    {
+        std::lock_guard<std::mutex> lk(p->mux);
+        p->in_flight.push_back(device);
+    }
+    ShardTask *t = new ShardTask{p, std::move(objs), device};
+    mpdev_submit_work(device, shard_worker, t);
+}
+
+void reset_counters(mp_pipeline *p)
+{
+    for (mp_pipeline *q = p; q; q = q->receiver) {
+        q->launches.store(0);
+        q->segments.store(0);
+        q->status.store(MILLIPYDE_SUCCESS);
+        std::lock_guard<std::mutex> lk(q->mux);
+        q->in_flight.clear();
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+MPPipeline *mppipe_create(const MPRunnable *stages, int num_stages, int device_id)
+{
+    if (num_stages < 0 || (num_stages > 0 && !stages)) return nullptr;
+    mp_pipeline *p = new (std::nothrow) mp_pipeline();
+    if (!p) return nullptr;
+    p->device = device_id;
+    for (int i = 0; i < num_stages; ++i) {
+        Stage s = {};
+        size_t bytes = 0;
+        s.kind = classify(stages[i].func, &bytes);
+        s.func = stages[i].func;
+        s.probability = stages[i].probability;
+        s.args = stages[i].args;
+        if (bytes && !stages[i].args) {
+            s.kind = OP_NULL;  // an operator that needs arguments but got none: skipped like func == NULL
+        } else if (bytes) {
+            s.args = malloc(bytes);
+            memcpy(s.args, stages[i].args, bytes);
+            const double *a = (const double *)s.args;
+            for (size_t k = 0; k < bytes / sizeof(double) && k < 3; ++k) s.a[k] = a[k];
+        }
+        p->stages.push_back(s);
+    }
+    return p;
+}
+
+void mppipe_destroy(MPPipeline *p)
+{
+    if (!p) return;
+    for (Stage &s : p->stages) {
+        size_t bytes = 0;
+        if (s.kind != OP_FOREIGN && s.kind != OP_NULL) {
+            classify(s.func, &bytes);
+            if (bytes) free(s.args);
+        }
+    }
+    delete p;
+}
+
+int mppipe_get_device(const MPPipeline *p) { return p ? p->device : DEVICE_LOC_NO_AFFINITY; }
+void mppipe_set_device(MPPipeline *p, int device_id)
+{
+    if (p) p->device = device_id;
+}
+
+// Device assignment rules of PyGPUPipeline_connect_to (src/gpupipeline.c:186-218).
+void mppipe_connect(MPPipeline *self, MPPipeline *receiver)
+{
+    if (!self || !receiver) return;
+    const int recommended = mpdev_get_recommended_device();
+    const int alternative = mpdev_get_alternative_device(recommended);
+    if (alternative == DEVICE_LOC_NO_AFFINITY) {
+        self->device = recommended;
+        receiver->device = recommended;
+    } else if (self->device == DEVICE_LOC_NO_AFFINITY && receiver->device == DEVICE_LOC_NO_AFFINITY) {
+        self->device = recommended;
+        receiver->device = alternative;
+    } else if (self->device == DEVICE_LOC_NO_AFFINITY) {
+        self->device = mpdev_get_alternative_device(receiver->device);
+    } else if (receiver->device == DEVICE_LOC_NO_AFFINITY) {
+        receiver->device = mpdev_get_alternative_device(self->device);
+    }
+    self->receiver = receiver;
+}
+
+MPStatus mppipe_submit(MPPipeline *p, MPObjData **objs, int n)
+{
+    if (!p || n < 0 || (n > 0 && !objs)) return MP_ERROR_INVALID_ARGUMENT;
+    MPStatus st = mp::ensure_initialized();
+    if (st != MILLIPYDE_SUCCESS) return st;
+    reset_counters(p);
+
+    int device = p->device;
+    bool cycle = false;
+    if (device == DEVICE_LOC_NO_AFFINITY) {
+        const int target = mpdev_get_target_device();
+        if (target != DEVICE_LOC_NO_AFFINITY) {
+            device = target;
+        } else {
+            cycle = true;
+            device = mpdev_get_recommended_device();
+        }
+    }
+    if (!mpdev_is_valid_device(device)) return GPUPIPELINE_ERROR_UNUSABLE_DEVICE;
+    p->cycled = cycle;
+    for (mp_pipeline *q = p->receiver; q; q = q->receiver)
+        if (!mpdev_is_valid_device(q->device)) q->device = device;
+
+    // Image i -> device: blocks of THREADS_PER_DEVICE images, round-robin over the valid
+    // devices starting at the recommended one (src/gpupipeline.c:267-283).
+    std::map<int, std::vector<MPObjData *>> shards;
+    int cur = device;
+    for (int i = 0; i < n; ++i) {
+        if (objs[i]) shards[cur].push_back(objs[i]);
+        if (cycle && ((i + 1) % THREADS_PER_DEVICE == 0)) cur = mpdev_get_next_device(cur);
+    }
+    for (auto &kv : shards) submit_shard(p, std::move(kv.second), kv.first);
+    return MILLIPYDE_SUCCESS;
+}
+
+MPStatus mppipe_wait(MPPipeline *p)
+{
+    if (!p) return MP_ERROR_INVALID_ARGUMENT;
+    if (p->cycled) {
+        mpdev_hard_synchronize_all();
+    } else {
+        // own device first, then down the receiver chain: by the time a device's pool is
+        // drained its workers have enqueued their hand-offs (src/gpupipeline.c:293-306)
+        for (mp_pipeline *q = p; q; q = q->receiver) {
+            std::vector<int> devs;
+            {
+                std::lock_guard<std::mutex> lk(q->mux);
+                devs = q->in_flight;
+            }
+            for (int d : devs) mpdev_hard_synchronize(d);
+        }
+    }
+    MPStatus st = MILLIPYDE_SUCCESS;
+    for (mp_pipeline *q = p; q; q = q->receiver) {
+        if (q->status.load() != MILLIPYDE_SUCCESS && st == MILLIPYDE_SUCCESS) st = (MPStatus)q->status.load();
+        if (q != p) {
+            p->launches.fetch_add(q->launches.load());
+            p->segments.fetch_add(q->segments.load());
+        }
+    }
+    return st;
+}
+
+MPStatus mppipe_run(MPPipeline *p, MPObjData **objs, int n)
+{
+    MPStatus st = mppipe_submit(p, objs, n);
+    if (st != MILLIPYDE_SUCCESS) return st;
+    return mppipe_wait(p);
+}
+
+void mppipe_set_fusion(int enabled) { g_fusion.store(enabled ? 1 : 0); }
+int mppipe_get_fusion(void) { return g_fusion.load(); }
+unsigned long long mppipe_last_launches(const MPPipeline *p) { return p ? p->launches.load() : 0; }
+int mppipe_last_segments(const MPPipeline *p) { return p ? p->segments.load() : 0; }
+
+/* ------------------------------------------------------- host streaming path */
+
+}  // extern "C"
+
+namespace {
+
+struct HostTask {
+    mp_pipeline *pipe;
+    int device;
+    const void *const *host_in;
+    void *const *host_out;
+    size_t out_capacity;
+    MPHostResult *results;
+    std::vector<int> indices;
+    int ndims;
+    long shape[3];
+    int typenum;
+    size_t in_bytes;
+};
+
+void host_worker(void *arg)
+{
+    HostTask *t = (HostTask *)arg;
+    mp_pipeline *p = t->pipe;
+    const int device = t->device;
+    cudaSetDevice(device);
+    const unsigned long long launches0 = mpdev_launch_count();
+    const int depth = THREADS_PER_DEVICE;  // one image in flight per work stream
+    const size_t ns = p->stages.size();
+
+    struct Slot {
+        MPObjData obj;
+        int dims[6];
+        cudaEvent_t done;
+        bool busy;
+    } slots[THREADS_PER_DEVICE];
+    for (int k = 0; k < depth; ++k) {
+        memset(&slots[k].obj, 0, sizeof(MPObjData));
+        slots[k].busy = false;
+        cudaEventCreateWithFlags(&slots[k].done, cudaEventDisableTiming);
+    }
+
+    for (size_t n = 0; n < t->indices.size(); ++n) {
+        const int i = t->indices[n];
+        Slot &sl = slots[n % depth];
+        cudaStream_t s = mp::device_stream(device, 1 + (int)(n % depth));
+        if (sl.busy) {
+            cudaEventSynchronize(sl.done);
+            sl.busy = false;
+        }
+        MPObjData *o = &sl.obj;
+        o->ndims = t->ndims;
+        o->dims = sl.dims;
+        size_t stride = t->in_bytes;
+        for (int k = 0; k < t->ndims; ++k) {
+            stride /= (size_t)t->shape[k];
+            sl.dims[k] = (int)t->shape[k];
+            sl.dims[t->ndims + k] = (int)stride;
+        }
+        o->type = t->typenum;
+        o->mem_loc = device;
+        o->stream = (void *)s;
+        o->pinned = MP_TRUE;
+        o->nbytes = t->in_bytes;
+        o->device_data = mp::pool_alloc(device, s, t->in_bytes);
+        MPStatus st = o->device_data ? MILLIPYDE_SUCCESS : MP_ERROR_DEVICE_ALLOC;
+        if (st == MILLIPYDE_SUCCESS) st = mpobj_upload_async(o, t->host_in[i], t->in_bytes);
+
+        std::vector<const Stage *> ops;
+        for (size_t k = 0; k < ns && st == MILLIPYDE_SUCCESS; ++k) {
+            const Stage &sg = p->stages[k];
+            if (sg.kind == OP_NULL) continue;
+            if (sg.probability > 0) {
+                double u = 0;
+                if (random_double_in_range(0.0, 1.0, &u) == MILLIPYDE_SUCCESS && u > sg.probability) continue;
+            }
+            ops.push_back(&sg);
+        }
+        if (st == MILLIPYDE_SUCCESS) {
+            mp::Img d;
+            const bool known = mp::describe(o, &d);
+            std::vector<Segment> segs = compile(ops, known ? d.fam : mp::FAM_U8_OTHER, known ? d.C : 0);
+            p->segments.fetch_add((int)segs.size());
+            for (const Segment &seg : segs) {
+                st = run_segment_on(o, seg);
+                if (st != MILLIPYDE_SUCCESS) break;
+            }
+        }
+        MPHostResult &r = t->results[i];
+        r.status = (int)st;
+        r.ndims = o->ndims;
+        for (int k = 0; k < 3; ++k) r.shape[k] = k < o->ndims ? o->dims[k] : 0;
+        r.type = o->type;
+        r.nbytes = o->nbytes;
+        if (st == MILLIPYDE_SUCCESS) {
+            if (o->nbytes > t->out_capacity) {
+                r.status = (int)MP_ERROR_INVALID_ARGUMENT;
+            } else {
+                st = mpobj_download_async(o, t->host_out[i], o->nbytes);
+                if (st != MILLIPYDE_SUCCESS) r.status = (int)st;
+            }
+        }
+        note_status(p, (MPStatus)r.status);
+        if (o->device_data) mp::pool_free(device, s, o->device_data);
+        o->device_data = NULL;
+        cudaEventRecord(sl.done, s);
+        sl.busy = true;
+    }
+    for (int k = 0; k < depth; ++k) {
+        if (slots[k].busy) cudaEventSynchronize(slots[k].done);
+        cudaEventDestroy(slots[k].done);
+    }
+    p->launches.fetch_add(mpdev_launch_count() - launches0);
+    delete t;
+}
+
+}  // namespace
+
+extern "C" MPStatus mppipe_run_host(MPPipeline *p, const void *const *host_in, void *const *host_out,
+                                    size_t out_capacity, MPHostResult *results, int n, int ndims,
+                                    const long *shape, int typenum)
+{
+    if (!p || n < 0 || ndims < 2 || ndims > 3 || !shape || (n > 0 && (!host_in || !host_out || !results)))
+        return MP_ERROR_INVALID_ARGUMENT;
+    MPStatus st = mp::ensure_initialized();
+    if (st != MILLIPYDE_SUCCESS) return st;
+    reset_counters(p);
+    size_t es;
+    switch (typenum) {
+        case MP_NPY_UBYTE: es = 1; break;
+        case MP_NPY_FLOAT: es = 4; break;
+        case MP_NPY_DOUBLE: es = 8; break;
+        default: return MP_ERROR_UNSUPPORTED_LAYOUT;
+    }
+    size_t in_bytes = es;
+    for (int k = 0; k < ndims; ++k) in_bytes *= (size_t)shape[k];
+
+    int device = p->device;
+    bool cycle = false;
+    if (device == DEVICE_LOC_NO_AFFINITY) {
+        const int target = mpdev_get_target_device();
+        if (target != DEVICE_LOC_NO_AFFINITY) device = target;
+        else {
+            cycle = true;
+            device = mpdev_get_recommended_device();
+        }
+    }
+    if (!mpdev_is_valid_device(device)) return GPUPIPELINE_ERROR_UNUSABLE_DEVICE;
+    p->cycled = cycle;
+
+    std::map<int, std::vector<int>> shards;
+    int cur = device;
+    for (int i = 0; i < n; ++i) {
+        shards[cur].push_back(i);
+        if (cycle && ((i + 1) % THREADS_PER_DEVICE == 0)) cur = mpdev_get_next_device(cur);
+    }
+    for (auto &kv : shards) {
+        HostTask *t = new HostTask{p, kv.first, host_in, host_out, out_capacity, results, kv.second, ndims,
+                                   {0, 0, 0}, typenum, in_bytes};
+        for (int k = 0; k < ndims; ++k) t->shape[k] = shape[k];
+        {
+            std::lock_guard<std::mutex> lk(p->mux);
+            p->in_flight.push_back(kv.first);
+        }
+        mpdev_submit_work(kv.first, host_worker, t);
+    }
+    return mppipe_wait(p);
+}

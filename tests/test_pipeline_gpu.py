@@ -1,0 +1,187 @@
+"""The chain executor (mppipe_*, include/mp_pipeline.h) against the oracle:
+batched launches, the fusion pass (fused == unfused == oracle), per-image coin
+flips, ragged batches, the host streaming path, connected pipelines."""
+import numpy as np
+import pytest
+
+from oracle import ref_exact as rx
+from oracle import skimage_oracle as so
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+TOL32 = 1e-5
+
+
+@pytest.fixture(scope="module")
+def mp():
+    from millipyde_b200 import capi, engine
+    capi.initialize()
+    capi.lib().mpimg_set_semantics(capi.SEMANTICS_ORACLE)
+
+    class NS:
+        pass
+    ns = NS()
+    ns.capi, ns.engine, ns.lib = capi, engine, capi.lib()
+    return ns
+
+
+CONFIG3 = [("rotate", 30.0), ("fliplr",), ("adjust_gamma", 1.5, 1.0), ("gaussian", 2.0)]
+
+
+def test_batch_equals_oracle_config3_shape(mp):
+    """BASELINE config 3's chain on a (small) batch of 1920-wide RGB rows."""
+    imgs = [synth.noise_f32(108, 1920, 3, 3000 + k) for k in range(6)]
+    dev = [mp.capi.DeviceImage(a) for a in imgs]
+    ch = mp.engine.Chain(CONFIG3, device=0)
+    ch.run(dev)
+    for a, d in zip(imgs, dev):
+        assert np.abs(d.numpy() - so.apply_chain(a, CONFIG3)).max() <= TOL32
+
+
+def test_gaussian_batch_is_one_launch(mp):
+    imgs = [synth.noise_f32(96, 640, 3, 2000 + k) for k in range(9)]
+    dev = [mp.capi.DeviceImage(a) for a in imgs]
+    ch = mp.engine.Chain([("gaussian", 2.0)], device=0)
+    ch.run(dev)
+    assert ch.last_launches == 1
+    for a, d in zip(imgs, dev):
+        assert np.abs(d.numpy() - so.gaussian(a, 2.0)).max() <= TOL32
+
+
+def test_fusion_on_off_identical_and_fewer_launches(mp):
+    chain = [("brightness", 0.1), ("adjust_gamma", 1.5, 1.0), ("colorize", 0.9, 1.1, 1.0), ("rgb2grey",),
+             ("brightness", -0.05), ("transpose",)]
+    imgs = [synth.noise_f32(64, 80, 3, 10 + k) for k in range(4)]
+    results = {}
+    for fused in (1, 0):
+        mp.lib.mppipe_set_fusion(fused)
+        dev = [mp.capi.DeviceImage(a) for a in imgs]
+        ch = mp.engine.Chain(chain, device=0)
+        ch.run(dev)
+        results[fused] = ([d.numpy() for d in dev], ch.last_launches, ch.last_segments)
+    mp.lib.mppipe_set_fusion(1)
+    assert results[1][2] == 2 and results[0][2] == 6          # segments per group
+    assert results[1][1] == 2 * 4 and results[0][1] == 6 * 4  # launches
+    for f, u, a in zip(results[1][0], results[0][0], imgs):
+        want = so.apply_chain(a, chain)
+        assert f.shape == want.shape
+        assert np.abs(f - want).max() <= TOL32 and np.abs(u - want).max() <= TOL32
+        assert np.abs(f - u).max() <= 2e-7
+
+
+def test_rgba8_pointwise_chain_fuses_bit_exactly(mp, charlie_small):
+    chain = [("adjust_gamma", 2.0, 1.0), ("brightness", 0.1), ("colorize", 0.5, 1.5, 1.1), ("adjust_gamma", 0.5, 1.0)]
+    imgs = [charlie_small, synth.rgba8(128, 160, 1000)]
+    dev = [mp.capi.DeviceImage(a) for a in imgs]
+    ch = mp.engine.Chain(chain, device=0)
+    ch.run(dev)
+    assert ch.last_launches == 2      # one table kernel per image
+    for a, d in zip(imgs, dev):
+        assert np.array_equal(d.numpy(), rx.apply_chain(a, chain))
+
+
+def test_reference_long_pipeline_self_consistency(mp, charlie_small):
+    """tests/millipyde_tests.py:349-395: eager chain == 8-image Pipeline."""
+    chain = [("gaussian", 2.0), ("rgb2grey",), ("transpose",), ("transpose",), ("rotate", 45.0)]
+    control = mp.capi.DeviceImage(charlie_small).apply_chain(chain).numpy()
+    dev = [mp.capi.DeviceImage(charlie_small) for _ in range(8)]
+    mp.engine.Chain(chain).run(dev)
+    for d in dev:
+        assert np.array_equal(d.numpy(), control)
+
+
+def test_probability_is_per_image(mp):
+    a = synth.noise_f32(32, 48, 3, 77)
+    flipped = so.fliplr(a)
+    mp.lib.mprand_seed(99)
+    dev = [mp.capi.DeviceImage(a) for _ in range(64)]
+    mp.engine.Chain([("fliplr", {"probability": 0.5})], device=0).run(dev)
+    mp.lib.mprand_seed(0)
+    n_flip = 0
+    for d in dev:
+        out = d.numpy()
+        if np.array_equal(out, flipped):
+            n_flip += 1
+        else:
+            assert np.array_equal(out, a)
+    assert 16 <= n_flip <= 48
+
+
+def test_ragged_batch(mp):
+    shapes = [(40, 64, 3), (97, 131, 3), (40, 64, 3), (33, 20, 1), (64, 64, 4)]
+    imgs = [synth.noise_f32(h, w, c, 500 + i) for i, (h, w, c) in enumerate(shapes)]
+    dev = [mp.capi.DeviceImage(a) for a in imgs]
+    chain = [("gaussian", 1.0), ("fliplr",)]
+    mp.engine.Chain(chain, device=0).run(dev)
+    for a, d in zip(imgs, dev):
+        assert np.abs(d.numpy() - so.apply_chain(a, chain)).max() <= TOL32
+
+
+def test_empty_inputs_and_empty_chain(mp):
+    mp.engine.Chain([("gaussian", 2.0)], device=0).run([])
+    a = synth.noise_f32(16, 16, 3, 1)
+    d = mp.capi.DeviceImage(a)
+    mp.engine.Chain([], device=0).run([d])
+    assert np.array_equal(d.numpy(), a)
+
+
+def test_connected_pipelines_same_device(mp, charlie_small):
+    """tests/millipyde_multigpu_tests.py:69-86 shape, on however many devices exist."""
+    d = mp.capi.DeviceImage(charlie_small)
+    p1 = mp.engine.Chain([("rgb2grey",)])
+    p2 = mp.engine.Chain([("transpose",)])
+    p3 = mp.engine.Chain([("transpose",)])
+    p1.connect_to(p2)
+    p2.connect_to(p3)
+    p1.run([d])
+    assert np.abs(d.numpy() - so.rgb2grey(charlie_small)).max() < 1e-12
+
+
+def test_host_streaming_path(mp):
+    imgs = [synth.noise_f32(120, 640, 3, 900 + k) for k in range(10)]
+    ins = []
+    for a in imgs:
+        p = mp.engine.pinned_empty(a.shape, np.float32)
+        p[...] = a
+        ins.append(p)
+    outs = [mp.engine.pinned_empty(a.shape, np.float32) for a in imgs]
+    ch = mp.engine.Chain([("gaussian", 2.0), ("adjust_gamma", 1.5, 1.0)], device=0)
+    meta = ch.run_host(ins, outs)
+    for a, o, (shape, dt) in zip(imgs, outs, meta):
+        assert shape == a.shape and dt == np.float32
+        want = so.apply_chain(a, [("gaussian", 2.0), ("adjust_gamma", 1.5, 1.0)])
+        assert np.abs(o - want).max() <= TOL32
+    # shape-changing chain from pageable memory
+    ch2 = mp.engine.Chain([("rgb2grey",), ("transpose",)], device=0)
+    outs2 = [np.empty(a.shape, np.float32) for a in imgs]
+    meta2 = ch2.run_host(imgs, outs2)
+    for a, o, (shape, dt) in zip(imgs, outs2, meta2):
+        assert shape == (a.shape[1], a.shape[0])
+        got = o.reshape(-1)[: shape[0] * shape[1]].reshape(shape)
+        assert np.abs(got - so.rgb2grey(a).T).max() <= TOL32
+    for p in ins + outs:
+        mp.engine.pinned_free(p)
+
+
+def test_full_size_properties_4k(mp):
+    """BASELINE config 2 at full size: properties that need no CPU oracle pass
+    over 25M samples -- a constant image stays constant away from the border,
+    and the blur is linear."""
+    h, w, c = 2160, 3840, 3
+    const = np.full((h, w, c), 0.5, np.float32)
+    d = mp.capi.DeviceImage(const).apply("gaussian", 2.0).numpy()
+    assert np.abs(d[16:-16, 16:-16] - 0.5).max() < 2e-6
+    # border rows lose exactly the weight that falls outside (mode constant, cval 0)
+    wts = so.gaussian_weights(2.0)
+    inside = wts[16:].sum()
+    assert abs(float(d[0, 1000, 1]) - 0.5 * inside) < 2e-6
+    assert abs(float(d[0, 0, 0]) - 0.5 * inside * inside) < 2e-6
+    a = synth.noise_f32(h, w, c, 2000)
+    b = synth.smooth_f32(h, w, c)
+    ga = mp.capi.DeviceImage(a).apply("gaussian", 2.0).numpy()
+    gb = mp.capi.DeviceImage(b).apply("gaussian", 2.0).numpy()
+    gab = mp.capi.DeviceImage((0.5 * a + 0.5 * b).astype(np.float32)).apply("gaussian", 2.0).numpy()
+    assert np.abs(gab - (0.5 * ga + 0.5 * gb)).max() < 5e-6
+    # and a strip of it against the oracle (rows 0..95: full width, all strips, top border)
+    want = so.gaussian(a[:128], 2.0)[:96]
+    assert np.abs(ga[:96] - want).max() <= TOL32
