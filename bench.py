@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--e2e-images", type=int, default=32, help="images per e2e step")
     ap.add_argument("--cpu-images", type=int, default=0, help="images in the CPU sample (0 = one per core)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (profiling runs only)")
     return ap.parse_args()
 
 
@@ -316,7 +317,10 @@ def run_b200(args, dist):
                 "avg_launch_ms": avg_launch_ms}
 
     # ---- e2e: host buffers in, host buffers out ----------------------------------
-    e2e = engine.e2e_gaussian(devices, args.e2e_images, (H, W, C), SIGMA, steps=max(2, min(args.steps, 3)))
+    if args.no_e2e:
+        e2e = {"images_per_s": 0.0, "h2d_bytes": 0, "d2h_bytes": 0, "images": 0}
+    else:
+        e2e = engine.e2e_gaussian(devices, args.e2e_images, (H, W, C), SIGMA, steps=max(2, min(args.steps, 3)))
     e2e_value = dist.sum(e2e["images_per_s"])
 
     line = {
