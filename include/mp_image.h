@@ -39,6 +39,28 @@ MPStatus mpimg_colorize(MPObjData *obj, void *args);           /* :639, Colorize
 MPStatus mpimg_adjust_gamma(MPObjData *obj, void *args);       /* :620, GammaArgs */
 
 /*
+ * random_* operators (new as C-ABI entry points).  In the reference these exist only as gpuimage
+ * methods that draw on the host and call the base method (src/gpuimage.c:206-226, :272-292,
+ * :335-355, :398-432, :475-514), so a Pipeline can never run them (its name table,
+ * src/gpuoperation.c:214-257, does not know them).  Here they are MPFuncs: each draws with
+ * random_double_in_range and calls the base operator, and the chain executor draws per image.
+ */
+typedef struct { double min, max; } RandomRangeArgs;              /* rotate, gaussian, brightness */
+typedef struct { double gamma_min, gamma_max, gain_min, gain_max; } RandomGammaArgs;
+typedef struct { double r_min, r_max, g_min, g_max, b_min, b_max; } RandomColorizeArgs;
+
+MPStatus mpimg_random_rotate(MPObjData *obj, void *args);       /* RandomRangeArgs, degrees */
+MPStatus mpimg_random_gaussian(MPObjData *obj, void *args);     /* RandomRangeArgs, sigma */
+MPStatus mpimg_random_brightness(MPObjData *obj, void *args);   /* RandomRangeArgs, delta */
+MPStatus mpimg_random_adjust_gamma(MPObjData *obj, void *args); /* RandomGammaArgs */
+MPStatus mpimg_random_colorize(MPObjData *obj, void *args);     /* RandomColorizeArgs */
+
+/* Name -> operator, as gpuoperation_func_from_name (src/gpuoperation.c:214-257) plus the grey
+ * spellings (rgb2gray, rgba2grey, rgba2gray) and the random_* names.  *arg_bytes receives the size
+ * of the operator's argument block (0 if it takes none).  NULL for an unknown name. */
+MPFunc mpimg_func_from_name(const char *name, size_t *arg_bytes);
+
+/*
  * Semantics selector (new).  The reference's float kernels disagree with its own
  * test oracle in two places (findings 2 and 3):
  *   MP_SEMANTICS_ORACLE (default)  float layouts follow the scikit-image calls in

@@ -59,6 +59,20 @@ class GammaArgs(C.Structure):
     _fields_ = [("gamma", C.c_double), ("gain", C.c_double)]
 
 
+class RandomRangeArgs(C.Structure):
+    _fields_ = [("min", C.c_double), ("max", C.c_double)]
+
+
+class RandomGammaArgs(C.Structure):
+    _fields_ = [("gamma_min", C.c_double), ("gamma_max", C.c_double),
+                ("gain_min", C.c_double), ("gain_max", C.c_double)]
+
+
+class RandomColorizeArgs(C.Structure):
+    _fields_ = [("r_min", C.c_double), ("r_max", C.c_double), ("g_min", C.c_double),
+                ("g_max", C.c_double), ("b_min", C.c_double), ("b_max", C.c_double)]
+
+
 MPFunc = C.CFUNCTYPE(C.c_int, C.POINTER(MPObjData), C.c_void_p)
 
 
@@ -97,6 +111,12 @@ SYMBOLS = {
     "mpimg_brightness": (C.c_int, [_OBJ, C.c_void_p]),
     "mpimg_colorize": (C.c_int, [_OBJ, C.c_void_p]),
     "mpimg_adjust_gamma": (C.c_int, [_OBJ, C.c_void_p]),
+    "mpimg_random_rotate": (C.c_int, [_OBJ, C.c_void_p]),
+    "mpimg_random_gaussian": (C.c_int, [_OBJ, C.c_void_p]),
+    "mpimg_random_brightness": (C.c_int, [_OBJ, C.c_void_p]),
+    "mpimg_random_adjust_gamma": (C.c_int, [_OBJ, C.c_void_p]),
+    "mpimg_random_colorize": (C.c_int, [_OBJ, C.c_void_p]),
+    "mpimg_func_from_name": (C.c_void_p, [C.c_char_p, C.POINTER(C.c_size_t)]),
     "mpimg_set_semantics": (None, [C.c_int]),
     "mpimg_get_semantics": (C.c_int, []),
     "mpimg_gaussian_effective_radius": (C.c_int, [C.c_double, C.POINTER(C.c_int)]),
@@ -227,6 +247,11 @@ _OPS = {
     "brightness": ("mpimg_brightness", BrightnessArgs),
     "adjust_gamma": ("mpimg_adjust_gamma", GammaArgs),
     "colorize": ("mpimg_colorize", ColorizeArgs),
+    "random_rotate": ("mpimg_random_rotate", RandomRangeArgs),
+    "random_gaussian": ("mpimg_random_gaussian", RandomRangeArgs),
+    "random_brightness": ("mpimg_random_brightness", RandomRangeArgs),
+    "random_adjust_gamma": ("mpimg_random_adjust_gamma", RandomGammaArgs),
+    "random_colorize": ("mpimg_random_colorize", RandomColorizeArgs),
 }
 
 

@@ -69,7 +69,32 @@ struct GaussStreamParams {
     int n_chunks;
     int radius;                  // actual radius (<= R); w[d] = 0 beyond it
     float w[16];
+    unsigned long long ww[16];   // (w[d], w[d]) packed for fma.rn.f32x2
 };
+
+// ---- packed fp32x2 arithmetic (SASS FFMA2 / FMUL2): one issue slot, two FMAs ----
+__device__ __forceinline__ uint64_t pack2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b)
+{
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 
 // ---- mbarrier / bulk-copy PTX ------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void *p)
@@ -112,69 +137,86 @@ __device__ __forceinline__ void fence_proxy_async()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// ---- row pass: scatter one aligned window into PH accumulators ---------------
+// ---- row pass: scatter one aligned window into PH/2 packed accumulators -------
+// Output pair m = outputs (2m, 2m+1).  A tap whose offset k*C is even reads the
+// pair (x[2j], x[2j+1]) exactly as LDS.128 delivered it; an odd offset needs the
+// straddling pair (x[2j-1], x[2j]), rebuilt with two moves and reused by every odd
+// tap.  All indices are compile-time; dead combinations vanish.
 template <int C, int R>
-__device__ __forceinline__ void gs_row_pass(const float *__restrict__ win, float (&acc)[kGsPH],
+__device__ __forceinline__ void gs_row_pass(const float *__restrict__ win, uint64_t (&acc)[kGsPH / 2],
                                             const GaussStreamParams &p)
 {
     constexpr int HALO = GsGeom<C, R>::HALO;
     constexpr int NV = (kGsPH + 2 * HALO) / 4;
 #pragma unroll
-    for (int i = 0; i < kGsPH; ++i) acc[i] = 0.f;
+    for (int i = 0; i < kGsPH / 2; ++i) acc[i] = 0ull;
+    uint64_t prev = 0ull;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-        const float4 x4 = *reinterpret_cast<const float4 *>(win + 4 * v);
-        const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+        const ulonglong2 ld = *reinterpret_cast<const ulonglong2 *>(win + 4 * v);
+        const uint64_t e[2] = {ld.x, ld.y};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 2; ++u) {
+            const int j = 2 * v + u;  // this pair holds window offsets 2j, 2j+1
+            float a_lo, a_hi, b_lo, b_hi;
+            unpack2(prev, a_lo, a_hi);
+            unpack2(e[u], b_lo, b_hi);
+            const uint64_t odd = pack2(a_hi, b_lo);  // window offsets 2j-1, 2j
 #pragma unroll
             for (int k = -R; k <= R; ++k) {
-                // sample at window offset 4v+u is tap k of output i
-                const int i = 4 * v + u - HALO - k * C;
-                if (i >= 0 && i < kGsPH) acc[i] = fmaf(p.w[k < 0 ? -k : k], x[u], acc[i]);
+                const int kc = k * C;
+                if ((kc & 1) == 0) {
+                    const int m2 = 2 * j - HALO - kc;
+                    if (m2 >= 0 && m2 < kGsPH) acc[m2 / 2] = ffma2(p.ww[k < 0 ? -k : k], e[u], acc[m2 / 2]);
+                } else {
+                    const int m2 = 2 * j - 1 - HALO - kc;
+                    if (m2 >= 0 && m2 < kGsPH) acc[m2 / 2] = ffma2(p.ww[k < 0 ? -k : k], odd, acc[m2 / 2]);
+                }
             }
+            prev = e[u];
         }
     }
 }
 
 // ---- column pass: one filtered row into the register ring --------------------
-// PHASE = (row index) mod NA.  Slot of output row (r + d) is (PHASE + d) mod NA.
+// a[s] holds the two columns of this thread packed.  PHASE = (row index) mod NA;
+// the slot of output row (r + d) is (PHASE + d) mod NA.
 template <int R, int PHASE>
-__device__ __forceinline__ float2 gs_col_row(float (&a0)[2 * R + 1], float (&a1)[2 * R + 1], float2 v,
-                                             const GaussStreamParams &p)
+__device__ __forceinline__ uint64_t gs_col_row(uint64_t (&a)[2 * R + 1], uint64_t v, const GaussStreamParams &p)
 {
     constexpr int NA = 2 * R + 1;
 #pragma unroll
     for (int d = -R; d < R; ++d) {
-        constexpr int dummy = 0;
-        (void)dummy;
         const int s = (PHASE + d + NA) % NA;
-        const float w = p.w[d < 0 ? -d : d];
-        a0[s] = fmaf(w, v.x, a0[s]);
-        a1[s] = fmaf(w, v.y, a1[s]);
+        a[s] = ffma2(p.ww[d < 0 ? -d : d], v, a[s]);
     }
-    {   // the output row that opens at this input row starts its sum here
-        const int s = (PHASE + R) % NA;
-        a0[s] = p.w[R] * v.x;
-        a1[s] = p.w[R] * v.y;
-    }
-    const int done = (PHASE - R + NA) % NA;  // output row r - R is complete
-    return make_float2(a0[done], a1[done]);
+    // the output row that opens at this input row starts its sum here
+    a[(PHASE + R) % NA] = fmul2(p.ww[R], v);
+    return a[(PHASE - R + NA) % NA];  // output row r - R is complete
 }
 
-template <int R, int PHASE = 0>
-struct GsColDispatch {
-    static __device__ __forceinline__ float2 run(int phase, float (&a0)[2 * R + 1], float (&a1)[2 * R + 1],
-                                                 float2 v, const GaussStreamParams &p)
-    {
-        if constexpr (PHASE >= 2 * R + 1) {
-            return make_float2(0.f, 0.f);
-        } else {
-            if (phase == PHASE) return gs_col_row<R, PHASE>(a0, a1, v, p);
-            return GsColDispatch<R, PHASE + 1>::run(phase, a0, a1, v, p);
-        }
+// Jump table over the NA rotations (one indirect branch per row instead of a
+// compare chain).
+template <int R>
+__device__ __forceinline__ uint64_t gs_col_dispatch(int phase, uint64_t (&a)[2 * R + 1], uint64_t v,
+                                                    const GaussStreamParams &p)
+{
+    constexpr int NA = 2 * R + 1;
+#define MP_GS_CASE(P)                                         \
+    case P:                                                   \
+        if constexpr (P < NA) return gs_col_row<R, (P < NA ? P : 0)>(a, v, p); \
+        break;
+    switch (phase) {
+        MP_GS_CASE(0) MP_GS_CASE(1) MP_GS_CASE(2) MP_GS_CASE(3) MP_GS_CASE(4) MP_GS_CASE(5) MP_GS_CASE(6)
+        MP_GS_CASE(7) MP_GS_CASE(8) MP_GS_CASE(9) MP_GS_CASE(10) MP_GS_CASE(11) MP_GS_CASE(12) MP_GS_CASE(13)
+        MP_GS_CASE(14) MP_GS_CASE(15) MP_GS_CASE(16) MP_GS_CASE(17) MP_GS_CASE(18) MP_GS_CASE(19)
+        MP_GS_CASE(20) MP_GS_CASE(21) MP_GS_CASE(22) MP_GS_CASE(23) MP_GS_CASE(24) MP_GS_CASE(25)
+        MP_GS_CASE(26)
+        default: break;
     }
-};
+#undef MP_GS_CASE
+    return 0ull;
+}
 
 template <int C, int R>
 __global__ void __launch_bounds__(kGsThreads, 2)
@@ -189,8 +231,8 @@ gauss_stream_kernel(const __grid_constant__ GaussStreamParams p)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        mbar_init(&bars[0], kGsQ);
+        mbar_init(&bars[1], kGsQ);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -231,29 +273,25 @@ gauss_stream_kernel(const __grid_constant__ GaussStreamParams p)
             __syncthreads();
         }
 
-        auto issue = [&](int step) {  // thread 0 only
+        // Stage fill, spread over the CTA: lane 0 of warp q posts the expected bytes of row q and
+        // issues its one bulk copy (10 arrivals per phase), so no single warp carries the issue work.
+        auto issue = [&](int step) {  // lane 0 of every warp
             const int stage = step & 1;
-            uint32_t bytes = 0;
-            for (int q = 0; q < kGsQ; ++q) {
-                const int r = r_begin + step * kGsQ + q;
-                if (r >= 0 && r < p.height && r < r_begin + n_rows) bytes += row_bytes;
-            }
-            mbar_expect_tx(&bars[stage], bytes);
-            for (int q = 0; q < kGsQ; ++q) {
-                const int r = r_begin + step * kGsQ + q;
-                if (r >= 0 && r < p.height && r < r_begin + n_rows)
-                    bulk_g2s(s_in + ((size_t)stage * kGsQ + q) * G::ROW + lo,
-                             src + (size_t)r * p.row_elems + gx_start + lo, row_bytes, &bars[stage]);
-            }
+            const int r = r_begin + step * kGsQ + warp;
+            const bool live = r >= 0 && r < p.height && r < r_begin + n_rows;
+            mbar_expect_tx(&bars[stage], live ? row_bytes : 0u);
+            if (live)
+                bulk_g2s(s_in + ((size_t)stage * kGsQ + warp) * G::ROW + lo,
+                         src + (size_t)r * p.row_elems + gx_start + lo, row_bytes, &bars[stage]);
         };
-        if (tid == 0) {
+        if (lane == 0) {
             issue(0);
             if (n_steps > 1) issue(1);
         }
 
-        float a0[NA], a1[NA];
+        uint64_t a[NA];
 #pragma unroll
-        for (int i = 0; i < NA; ++i) a0[i] = a1[i] = 0.f;
+        for (int i = 0; i < NA; ++i) a[i] = 0ull;
         int phase = 0;  // (row - r_begin) mod NA
 
         for (int step = 0; step < n_steps; ++step) {
@@ -265,21 +303,20 @@ gauss_stream_kernel(const __grid_constant__ GaussStreamParams p)
             {
                 const int r = r_begin + step * kGsQ + warp;
                 float *hrow = s_h + ((size_t)stage * kGsQ + warp) * kGsTW + lane * kGsPH;
-                float acc[kGsPH];
+                uint64_t acc[kGsPH / 2];
                 if (r >= 0 && r < p.height && r < r_begin + n_rows) {
                     const float *win = s_in + ((size_t)stage * kGsQ + warp) * G::ROW + lane * kGsPH;
                     gs_row_pass<C, R>(win, acc, p);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < kGsPH; ++i) acc[i] = 0.f;
+                    for (int i = 0; i < kGsPH / 2; ++i) acc[i] = 0ull;
                 }
 #pragma unroll
                 for (int v = 0; v < kGsPH / 4; ++v)
-                    *reinterpret_cast<float4 *>(hrow + 4 * v) =
-                        make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+                    *reinterpret_cast<ulonglong2 *>(hrow + 4 * v) = make_ulonglong2(acc[2 * v], acc[2 * v + 1]);
             }
             __syncthreads();  // filtered rows visible; this stage's input rows are free
-            if (tid == 0 && step + 2 < n_steps) issue(step + 2);
+            if (lane == 0 && step + 2 < n_steps) issue(step + 2);
 
             // ---- column pass: thread = float columns 2*tid, 2*tid+1
             const int gx = x0 + 2 * tid;
@@ -287,12 +324,16 @@ gauss_stream_kernel(const __grid_constant__ GaussStreamParams p)
 #pragma unroll 1
             for (int q = 0; q < kGsQ; ++q) {
                 const int r = r_begin + step * kGsQ + q;
-                const float2 v = *reinterpret_cast<const float2 *>(s_h + ((size_t)stage * kGsQ + q) * kGsTW + 2 * tid);
-                const float2 o = GsColDispatch<R>::run(phase, a0, a1, v, p);
+                const uint64_t v =
+                    *reinterpret_cast<const uint64_t *>(s_h + ((size_t)stage * kGsQ + q) * kGsTW + 2 * tid);
+                const uint64_t o = gs_col_dispatch<R>(phase, a, v, p);
                 phase = (phase + 1 == NA) ? 0 : phase + 1;
                 const int orow = r - R;
-                if (col_ok && orow >= y0 && orow < y1)
-                    __stcs(reinterpret_cast<float2 *>(dst + (size_t)orow * p.row_elems + gx), o);
+                if (col_ok && orow >= y0 && orow < y1) {
+                    float o_lo, o_hi;
+                    unpack2(o, o_lo, o_hi);
+                    __stcs(reinterpret_cast<float2 *>(dst + (size_t)orow * p.row_elems + gx), make_float2(o_lo, o_hi));
+                }
             }
         }
     }

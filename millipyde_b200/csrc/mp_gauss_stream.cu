@@ -4,6 +4,8 @@
 // instantiated for a few radii and a request uses the smallest bucket that
 // holds its effective radius (weights beyond the radius are zero).  sigma = 2
 // (effective radius 11) lands exactly on a bucket.
+#include <cstring>
+
 #include "kernels/gaussian_stream.cuh"
 #include "mp_internal.h"
 #include "mp_ops_internal.h"
@@ -83,7 +85,12 @@ MPStatus launch_gauss_stream_batch(int device, cudaStream_t s, int H, int W, int
     p.row_elems = W * C;
     p.n_strips = (p.row_elems + kGsTW - 1) / kGsTW;
     p.radius = gp.radius;
-    for (int d = 0; d < 16; ++d) p.w[d] = d <= gp.radius ? gp.w[d] : 0.f;
+    for (int d = 0; d < 16; ++d) {
+        p.w[d] = d <= gp.radius ? gp.w[d] : 0.f;
+        unsigned int bits;
+        memcpy(&bits, &p.w[d], 4);
+        p.ww[d] = ((unsigned long long)bits << 32) | bits;
+    }
     if (C == 1) return launch_c<1>(device, s, p, bucket);
     if (C == 3) return launch_c<3>(device, s, p, bucket);
     if (C == 4) return launch_c<4>(device, s, p, bucket);

@@ -478,6 +478,90 @@ MPStatus mpimg_gaussian(MPObjData *obj, void *args)
     return finish(obj, s, out, obj->nbytes);
 }
 
+/* ------------------------------------------------------------------ random_* */
+MPStatus mpimg_random_rotate(MPObjData *obj, void *args)
+{
+    if (!args) return MP_ERROR_INVALID_ARGUMENT;
+    const RandomRangeArgs *r = (const RandomRangeArgs *)args;
+    RotateArgs a;
+    MPStatus st = random_double_in_range(r->min, r->max, &a.angle);
+    return st != MILLIPYDE_SUCCESS ? st : mpimg_rotate(obj, &a);
+}
+
+MPStatus mpimg_random_gaussian(MPObjData *obj, void *args)
+{
+    if (!args) return MP_ERROR_INVALID_ARGUMENT;
+    const RandomRangeArgs *r = (const RandomRangeArgs *)args;
+    GaussianArgs a;
+    MPStatus st = random_double_in_range(r->min, r->max, &a.sigma);
+    return st != MILLIPYDE_SUCCESS ? st : mpimg_gaussian(obj, &a);
+}
+
+MPStatus mpimg_random_brightness(MPObjData *obj, void *args)
+{
+    if (!args) return MP_ERROR_INVALID_ARGUMENT;
+    const RandomRangeArgs *r = (const RandomRangeArgs *)args;
+    BrightnessArgs a;
+    MPStatus st = random_double_in_range(r->min, r->max, &a.delta);
+    return st != MILLIPYDE_SUCCESS ? st : mpimg_brightness(obj, &a);
+}
+
+MPStatus mpimg_random_adjust_gamma(MPObjData *obj, void *args)
+{
+    if (!args) return MP_ERROR_INVALID_ARGUMENT;
+    const RandomGammaArgs *r = (const RandomGammaArgs *)args;
+    GammaArgs a;
+    MPStatus st = random_double_in_range(r->gamma_min, r->gamma_max, &a.gamma);
+    if (st == MILLIPYDE_SUCCESS) st = random_double_in_range(r->gain_min, r->gain_max, &a.gain);
+    return st != MILLIPYDE_SUCCESS ? st : mpimg_adjust_gamma(obj, &a);
+}
+
+MPStatus mpimg_random_colorize(MPObjData *obj, void *args)
+{
+    if (!args) return MP_ERROR_INVALID_ARGUMENT;
+    const RandomColorizeArgs *r = (const RandomColorizeArgs *)args;
+    ColorizeArgs a;
+    MPStatus st = random_double_in_range(r->r_min, r->r_max, &a.r_mult);
+    if (st == MILLIPYDE_SUCCESS) st = random_double_in_range(r->g_min, r->g_max, &a.g_mult);
+    if (st == MILLIPYDE_SUCCESS) st = random_double_in_range(r->b_min, r->b_max, &a.b_mult);
+    return st != MILLIPYDE_SUCCESS ? st : mpimg_colorize(obj, &a);
+}
+
+MPFunc mpimg_func_from_name(const char *name, size_t *arg_bytes)
+{
+    static const struct {
+        const char *name;
+        MPFunc func;
+        size_t bytes;
+    } table[] = {
+        {"rgb2grey", mpimg_color_to_greyscale, 0},
+        {"rgb2gray", mpimg_color_to_greyscale, 0},
+        {"rgba2grey", mpimg_color_to_greyscale, 0},
+        {"rgba2gray", mpimg_color_to_greyscale, 0},
+        {"transpose", mpimg_transpose, 0},
+        {"fliplr", mpimg_fliplr, 0},
+        {"gaussian", mpimg_gaussian, sizeof(GaussianArgs)},
+        {"rotate", mpimg_rotate, sizeof(RotateArgs)},
+        {"brightness", mpimg_brightness, sizeof(BrightnessArgs)},
+        {"adjust_gamma", mpimg_adjust_gamma, sizeof(GammaArgs)},
+        {"colorize", mpimg_colorize, sizeof(ColorizeArgs)},
+        {"random_rotate", mpimg_random_rotate, sizeof(RandomRangeArgs)},
+        {"random_gaussian", mpimg_random_gaussian, sizeof(RandomRangeArgs)},
+        {"random_brightness", mpimg_random_brightness, sizeof(RandomRangeArgs)},
+        {"random_adjust_gamma", mpimg_random_adjust_gamma, sizeof(RandomGammaArgs)},
+        {"random_colorize", mpimg_random_colorize, sizeof(RandomColorizeArgs)},
+    };
+    if (arg_bytes) *arg_bytes = 0;
+    if (!name) return NULL;
+    for (size_t i = 0; i < sizeof(table) / sizeof(table[0]); ++i) {
+        if (strcmp(name, table[i].name) == 0) {
+            if (arg_bytes) *arg_bytes = table[i].bytes;
+            return table[i].func;
+        }
+    }
+    return NULL;
+}
+
 }  // extern "C"
 
 namespace mp {

@@ -24,6 +24,7 @@ namespace {
 
 enum OpKind {
     OP_GREY, OP_TRANSPOSE, OP_GAUSSIAN, OP_FLIPLR, OP_ROTATE, OP_BRIGHTNESS, OP_GAMMA, OP_COLORIZE,
+    OP_RANDOM,   // one of the mpimg_random_* operators: parameters are drawn per image at run time
     OP_FOREIGN,  // an MPFunc that is not one of ours: called as-is, one image at a time
     OP_NULL,     // func == NULL: skipped, as src/gpupipeline.c:393-396
 };
@@ -50,6 +51,12 @@ OpKind classify(MPFunc f, size_t *arg_bytes)
     if (f == mpimg_brightness) { *arg_bytes = sizeof(BrightnessArgs); return OP_BRIGHTNESS; }
     if (f == mpimg_adjust_gamma) { *arg_bytes = sizeof(GammaArgs); return OP_GAMMA; }
     if (f == mpimg_colorize) { *arg_bytes = sizeof(ColorizeArgs); return OP_COLORIZE; }
+    if (f == mpimg_random_rotate || f == mpimg_random_gaussian || f == mpimg_random_brightness) {
+        *arg_bytes = sizeof(RandomRangeArgs);
+        return OP_RANDOM;
+    }
+    if (f == mpimg_random_adjust_gamma) { *arg_bytes = sizeof(RandomGammaArgs); return OP_RANDOM; }
+    if (f == mpimg_random_colorize) { *arg_bytes = sizeof(RandomColorizeArgs); return OP_RANDOM; }
     return OP_FOREIGN;
 }
 
@@ -189,6 +196,61 @@ std::vector<Segment> compile(const std::vector<const Stage *> &ops, mp::Family f
     return out;
 }
 
+// Per-image realisation of the chain: coin flips (src/gpupipeline.c:380-387) and, for random_*
+// stages, the parameter draws the reference makes inside the gpuimage method.  The result is a
+// list of concrete stages (args point at the stage's own doubles) plus a key that is equal for
+// two images iff they run the same ops with the same parameters.
+void realize(const mp_pipeline *p, std::vector<Stage> *out, std::string *key)
+{
+    const size_t ns = p->stages.size();
+    out->clear();
+    out->reserve(ns);  // args pointers below rely on no reallocation
+    for (size_t k = 0; k < ns; ++k) {
+        const Stage &st = p->stages[k];
+        bool run = st.kind != OP_NULL;
+        if (run && st.probability > 0) {
+            double u = 0;
+            if (random_double_in_range(0.0, 1.0, &u) == MILLIPYDE_SUCCESS && u > st.probability) run = false;
+        }
+        if (!run) {
+            key->push_back('0');
+            continue;
+        }
+        if (st.kind != OP_RANDOM) {
+            key->push_back('1');
+            out->push_back(st);
+            continue;
+        }
+        Stage c = st;
+        c.probability = -1;
+        const double *r = (const double *)st.args;
+        auto draw = [](double lo, double hi) {
+            double v = lo;
+            random_double_in_range(lo, hi, &v);
+            return v;
+        };
+        if (st.func == mpimg_random_rotate) { c.kind = OP_ROTATE; c.func = mpimg_rotate; c.a[0] = draw(r[0], r[1]); }
+        else if (st.func == mpimg_random_gaussian) { c.kind = OP_GAUSSIAN; c.func = mpimg_gaussian; c.a[0] = draw(r[0], r[1]); }
+        else if (st.func == mpimg_random_brightness) { c.kind = OP_BRIGHTNESS; c.func = mpimg_brightness; c.a[0] = draw(r[0], r[1]); }
+        else if (st.func == mpimg_random_adjust_gamma) {
+            c.kind = OP_GAMMA; c.func = mpimg_adjust_gamma;
+            c.a[0] = draw(r[0], r[1]);
+            c.a[1] = draw(r[2], r[3]);
+        } else {
+            c.kind = OP_COLORIZE; c.func = mpimg_colorize;
+            c.a[0] = draw(r[0], r[1]);
+            c.a[1] = draw(r[2], r[3]);
+            c.a[2] = draw(r[4], r[5]);
+        }
+        char buf[96];
+        snprintf(buf, sizeof buf, "R%.17g,%.17g,%.17g;", c.a[0], c.a[1], c.a[2]);
+        key->append(buf);
+        out->push_back(c);
+    }
+    for (Stage &c : *out)
+        if (c.kind != OP_FOREIGN && c.kind != OP_GREY && c.kind != OP_TRANSPOSE && c.kind != OP_FLIPLR) c.args = (void *)c.a;
+}
+
 MPStatus run_segment_on(MPObjData *obj, const Segment &seg)
 {
     switch (seg.kind) {
@@ -319,38 +381,24 @@ void shard_worker(void *arg)
         mpobj_set_stream(o, (void *)batch_stream);
     }
 
-    // 2. coin flips, 3. grouping by (layout, surviving stages)
-    const size_t ns = p->stages.size();
+    // 2. coin flips / random draws per image, 3. grouping by (layout, realised stage list)
     std::map<std::string, std::vector<size_t>> groups;
-    std::vector<std::string> keys(n);
+    std::vector<std::vector<Stage>> realized(n);
     for (size_t i = 0; i < n; ++i) {
         MPObjData *o = t->objs[i];
-        std::string key;
-        key.reserve(ns + 48);
         char hdr[64];
         int c = o->ndims == 3 ? o->dims[2] : 1;
         snprintf(hdr, sizeof hdr, "%d:%d:%d:%d:%d|", o->type, o->ndims, o->ndims > 0 ? o->dims[0] : 0,
                  o->ndims > 1 ? o->dims[1] : 0, c);
-        key = hdr;
-        for (size_t k = 0; k < ns; ++k) {
-            const Stage &st = p->stages[k];
-            bool run = st.kind != OP_NULL;
-            if (run && st.probability > 0) {
-                double u = 0;
-                if (random_double_in_range(0.0, 1.0, &u) == MILLIPYDE_SUCCESS && u > st.probability) run = false;
-            }
-            key.push_back(run ? '1' : '0');
-        }
+        std::string key = hdr;
+        realize(p, &realized[i], &key);
         groups[key].push_back(i);
     }
 
     // 4. per group: fusion pass + launches
     for (auto &g : groups) {
-        const std::string &key = g.first;
-        const char *mask = key.c_str() + key.find('|') + 1;
         std::vector<const Stage *> ops;
-        for (size_t k = 0; k < ns; ++k)
-            if (mask[k] == '1') ops.push_back(&p->stages[k]);
+        for (const Stage &st : realized[g.second[0]]) ops.push_back(&st);
         std::vector<MPObjData *> objs;
         for (size_t i : g.second) objs.push_back(t->objs[i]);
         run_group(p, objs, ops, device, batch_stream);
@@ -570,7 +618,6 @@ void host_worker(void *arg)
     cudaSetDevice(device);
     const unsigned long long launches0 = mpdev_launch_count();
     const int depth = THREADS_PER_DEVICE;  // one image in flight per work stream
-    const size_t ns = p->stages.size();
 
     struct Slot {
         MPObjData obj;
@@ -610,16 +657,11 @@ void host_worker(void *arg)
         MPStatus st = o->device_data ? MILLIPYDE_SUCCESS : MP_ERROR_DEVICE_ALLOC;
         if (st == MILLIPYDE_SUCCESS) st = mpobj_upload_async(o, t->host_in[i], t->in_bytes);
 
+        std::vector<Stage> mine;
+        std::string unused_key;
+        realize(p, &mine, &unused_key);
         std::vector<const Stage *> ops;
-        for (size_t k = 0; k < ns && st == MILLIPYDE_SUCCESS; ++k) {
-            const Stage &sg = p->stages[k];
-            if (sg.kind == OP_NULL) continue;
-            if (sg.probability > 0) {
-                double u = 0;
-                if (random_double_in_range(0.0, 1.0, &u) == MILLIPYDE_SUCCESS && u > sg.probability) continue;
-            }
-            ops.push_back(&sg);
-        }
+        for (const Stage &sg : mine) ops.push_back(&sg);
         if (st == MILLIPYDE_SUCCESS) {
             mp::Img d;
             const bool known = mp::describe(o, &d);
