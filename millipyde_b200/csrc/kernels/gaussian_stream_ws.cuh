@@ -1,0 +1,302 @@
+// Separable Gaussian, fp32 HWC, streaming kernel, warp-specialised (v3).
+//
+// Same decomposition as gaussian_stream.cuh -- work item = (image, 640-float
+// column strip, row chunk), rows filtered horizontally into shared memory, columns
+// accumulated in registers -- but the two passes run on different warps and are
+// decoupled by mbarrier rings instead of a CTA-wide barrier per step:
+//
+//   warps 0..9   ROW warps.  Warp q owns row q of every 10-row group.  It runs its
+//                own private TMA pipeline: lane 0 issues one 1-D cp.async.bulk
+//                (UBLKCP) per row into a 3-slot ring nobody else touches, waits on the
+//                slot's mbarrier, filters the row (packed FFMA2, two accumulator sets
+//                so that even- and odd-offset taps both read the register pairs
+//                exactly as LDS.128 delivered them), stores 640 filtered floats into
+//                the group's slot of the hand-off ring and arrives on full[group].
+//   warps 10..19 COLUMN warps.  Thread t owns float columns 2t, 2t+1 and the 2R+1
+//                live output rows of each, packed in registers.  Per group: wait
+//                full[group], 10 x (LDS.64, 2R+1 FFMA2 through a jump table over the
+//                accumulator rotation, one coalesced 8-byte streaming store), arrive
+//                on empty[group].
+//
+// One CTA of 640 threads per SM (the register file splits 102 per thread, which
+// both roles fit), 3 groups in flight between the roles, 3 rows in flight per ROW
+// warp from HBM.  Per 10-row group the FMA pipe needs ~2360 cycles per SMSP and the
+// issue port ~1600, so the pipe -- not issue, not shared memory, not a barrier -- is
+// the limiter; see DESIGN.md for the arithmetic and profiles/ for the measurement.
+#pragma once
+#include "gaussian_stream.cuh"
+
+namespace mpk {
+
+constexpr int kWsRowWarps = kGsQ;             // 10
+constexpr int kWsColWarps = kGsQ;             // 10: 320 threads x 2 columns = 640 floats
+constexpr int kWsThreads = 32 * (kWsRowWarps + kWsColWarps);
+constexpr int kWsInSlots = 3;                 // rows in flight per ROW warp
+constexpr int kWsGroups = 3;                  // filtered groups in flight between the roles
+
+template <int C, int R>
+struct WsGeom {
+    static constexpr int HALO = GsGeom<C, R>::HALO;
+    static constexpr int ROW = GsGeom<C, R>::ROW;
+    static constexpr size_t IN_BYTES = (size_t)kWsRowWarps * kWsInSlots * ROW * 4;
+    static constexpr size_t H_BYTES = (size_t)kWsGroups * kGsQ * kGsTW * 4;
+    static constexpr int N_BARS = kWsRowWarps * kWsInSlots + 2 * kWsGroups;
+    static constexpr size_t SMEM = IN_BYTES + H_BYTES + 8 * N_BARS + 64;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+// ---- row pass, two accumulator sets ---------------------------------------------
+// A[m] = outputs (2m, 2m+1) fed by taps with an even offset k*C; B[m] = outputs
+// (2m-1, 2m) fed by taps with an odd offset.  Either way the operand is the aligned
+// pair (x[2j], x[2j+1]) as loaded.  out[i] = A-part + B-part.
+template <int C, int R>
+__device__ __forceinline__ void ws_row_pass(const float *__restrict__ win, float (&out)[kGsPH],
+                                            const GaussStreamParams &p)
+{
+    constexpr int HALO = GsGeom<C, R>::HALO;
+    constexpr int NV = (kGsPH + 2 * HALO) / 4;
+    constexpr int NB = kGsPH / 2 + 1;
+    uint64_t A[kGsPH / 2], B[NB];
+#pragma unroll
+    for (int i = 0; i < kGsPH / 2; ++i) A[i] = 0ull;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) B[i] = 0ull;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const ulonglong2 ld = *reinterpret_cast<const ulonglong2 *>(win + 4 * v);
+        const uint64_t e[2] = {ld.x, ld.y};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int j = 2 * v + u;  // this pair holds window offsets 2j, 2j+1
+#pragma unroll
+            for (int k = -R; k <= R; ++k) {
+                const int kc = k * C;
+                const int i0 = 2 * j - HALO - kc;  // output fed by the pair's low half
+                if ((kc & 1) == 0) {
+                    if (i0 >= 0 && i0 < kGsPH) A[i0 / 2] = ffma2(p.ww[k < 0 ? -k : k], e[u], A[i0 / 2]);
+                } else {
+                    // i0 is odd: the pair feeds outputs (i0, i0 + 1) = B[(i0 + 1) / 2]
+                    if (i0 >= -1 && i0 < kGsPH) B[(i0 + 1) / 2] = ffma2(p.ww[k < 0 ? -k : k], e[u], B[(i0 + 1) / 2]);
+                }
+            }
+        }
+    }
+    constexpr bool any_odd = (C & 1) != 0;
+#pragma unroll
+    for (int m = 0; m < kGsPH / 2; ++m) {
+        float a_lo, a_hi;
+        unpack2(A[m], a_lo, a_hi);
+        if (any_odd) {
+            float b0_lo, b0_hi, b1_lo, b1_hi;
+            unpack2(B[m], b0_lo, b0_hi);
+            unpack2(B[m + 1], b1_lo, b1_hi);
+            out[2 * m] = a_lo + b0_hi;
+            out[2 * m + 1] = a_hi + b1_lo;
+        } else {
+            out[2 * m] = a_lo;
+            out[2 * m + 1] = a_hi;
+        }
+    }
+}
+
+template <int C, int R>
+__global__ void __launch_bounds__(kWsThreads, 1)
+gauss_stream_ws_kernel(const __grid_constant__ GaussStreamParams p)
+{
+    using G = WsGeom<C, R>;
+    constexpr int NA = 2 * R + 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *s_in = reinterpret_cast<float *>(smem_raw);                // [10 warps][3 slots][ROW]
+    float *s_h = reinterpret_cast<float *>(smem_raw + G::IN_BYTES);    // [3 groups][10 rows][640]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + G::IN_BYTES + G::H_BYTES);
+    uint64_t *in_full = bars;                                        // [10][3]
+    uint64_t *h_full = bars + kWsRowWarps * kWsInSlots;               // [3]
+    uint64_t *h_empty = h_full + kWsGroups;                           // [3]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < kWsRowWarps * kWsInSlots; ++i) mbar_init(&in_full[i], 1);
+        for (int g = 0; g < kWsGroups; ++g) {
+            mbar_init(&h_full[g], kWsRowWarps);
+            mbar_init(&h_empty[g], kWsColWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();  // the only CTA-wide barrier
+
+    const int items_per_image = p.n_strips * p.n_chunks;
+    const long n_items = (long)p.n_images * items_per_image;
+
+    if (warp < kWsRowWarps) {
+        // =============================================================== ROW warp
+        float *my_in = s_in + (size_t)warp * kWsInSlots * G::ROW;
+        uint64_t *my_full = in_full + warp * kWsInSlots;
+        uint32_t loads = 0;   // rows issued so far by this warp (slot = loads % 3, parity from the count)
+        uint32_t takes = 0;   // rows consumed so far
+        uint32_t group = 0;   // groups produced so far (ring slot and parity)
+
+        for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int img = (int)(item / items_per_image);
+            const int rem = (int)(item - (long)img * items_per_image);
+            const int chunk = rem / p.n_strips, strip = rem - chunk * p.n_strips;
+            const float *__restrict__ src = p.in_tab ? p.in_tab[img] : p.in + (size_t)img * p.image_stride;
+            const int x0 = strip * kGsTW;
+            const int y0 = chunk * p.chunk_rows;
+            const int y1 = min(p.height, y0 + p.chunk_rows);
+            const int r_begin = y0 - R;
+            const int n_rows = (y1 - y0) + 2 * R;
+            const int n_steps = (n_rows + kGsQ - 1) / kGsQ;
+            const int gx_start = x0 - G::HALO;
+            const int lo = gx_start < 0 ? -gx_start : 0;
+            const int hi = min(G::ROW, p.row_elems - gx_start);
+            const uint32_t row_bytes = (uint32_t)(hi - lo) * 4u;
+
+            // every load this warp issued has been consumed: its ring is quiescent
+            if (lo > 0 || hi < G::ROW) {
+                for (int i = lane; i < kWsInSlots * G::ROW; i += 32) {
+                    const int col = i % G::ROW;
+                    if (col < lo || col >= hi) my_in[i] = 0.f;
+                }
+                fence_proxy_async();
+            }
+            __syncwarp();
+
+            auto row_live = [&](int step) {
+                const int r = r_begin + step * kGsQ + warp;
+                return r >= 0 && r < p.height && r < r_begin + n_rows;
+            };
+            auto issue = [&](int step) {  // lane 0
+                if (!row_live(step)) return;
+                const int r = r_begin + step * kGsQ + warp;
+                const uint32_t slot = loads % kWsInSlots;
+                mbar_expect_tx(&my_full[slot], row_bytes);
+                bulk_g2s(my_in + (size_t)slot * G::ROW + lo, src + (size_t)r * p.row_elems + gx_start + lo,
+                         row_bytes, &my_full[slot]);
+            };
+            // prologue: kWsInSlots - 1 rows ahead
+            for (int s = 0; s < kWsInSlots - 1 && s < n_steps; ++s) {
+                if (lane == 0) issue(s);
+                if (row_live(s)) ++loads;
+            }
+
+            for (int step = 0; step < n_steps; ++step) {
+                // keep the ring full: the slot consumed in the previous iteration is free again
+                const int ahead = step + kWsInSlots - 1;
+                if (ahead < n_steps) {
+                    if (lane == 0) issue(ahead);
+                    if (row_live(ahead)) ++loads;
+                }
+                float out[kGsPH];
+                if (row_live(step)) {
+                    const uint32_t slot = takes % kWsInSlots;
+                    mbar_wait(&my_full[slot], (takes / kWsInSlots) & 1u);
+                    ++takes;
+                    ws_row_pass<C, R>(my_in + (size_t)slot * G::ROW + lane * kGsPH, out, p);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < kGsPH; ++i) out[i] = 0.f;
+                }
+                // hand-off ring: wait until the COLUMN warps have drained this group slot
+                const uint32_t gs = group % kWsGroups;
+                mbar_wait(&h_empty[gs], ((group / kWsGroups) & 1u) ^ 1u);
+                float *hrow = s_h + ((size_t)gs * kGsQ + warp) * kGsTW + lane * kGsPH;
+#pragma unroll
+                for (int v = 0; v < kGsPH / 4; ++v)
+                    *reinterpret_cast<float4 *>(hrow + 4 * v) =
+                        make_float4(out[4 * v], out[4 * v + 1], out[4 * v + 2], out[4 * v + 3]);
+                __syncwarp();  // all lanes' stores and window reads are done
+                if (lane == 0) mbar_arrive(&h_full[gs]);
+                ++group;
+            }
+        }
+    } else {
+        // ============================================================ COLUMN warp
+        // Rows stream through one continuous rotation: row n of this warp's life uses phase
+        // n mod NA, across groups and across items (the labels are arbitrary; accumulators
+        // that are still open when an item ends belong to rows outside the next item's range
+        // and are discarded, and every output row re-opens its accumulator by assignment).  The
+        // rotation is unrolled as straight-line code, so each accumulator lives in one fixed
+        // register pair for the whole kernel; group and item boundaries are uniform branches.
+        const int vt = tid - 32 * kWsRowWarps;  // 0..319
+        uint64_t a[NA];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) a[i] = 0ull;
+
+        long item = blockIdx.x;
+        if (item < n_items) {
+            uint32_t group = 0;
+            // per-item state
+            float *__restrict__ dst = nullptr;
+            int y0 = 0, y1 = 0, orow = 0, steps_left = 0;
+            bool col_ok = false;
+            auto load_item = [&]() {
+                const int img = (int)(item / items_per_image);
+                const int rem = (int)(item - (long)img * items_per_image);
+                const int chunk = rem / p.n_strips, strip = rem - chunk * p.n_strips;
+                const int gx = strip * kGsTW + 2 * vt;
+                col_ok = gx < p.row_elems;
+                float *base = p.out_tab ? p.out_tab[img] : p.out + (size_t)img * p.image_stride;
+                dst = base + gx;
+                y0 = chunk * p.chunk_rows;
+                y1 = min(p.height, y0 + p.chunk_rows);
+                const int n_rows = (y1 - y0) + 2 * R;
+                steps_left = (n_rows + kGsQ - 1) / kGsQ;
+                orow = y0 - 2 * R;  // output row completed by the item's first filtered row
+            };
+            load_item();
+            int q = 0;
+            const float *hrow = nullptr;
+            bool running = true;
+            while (running) {
+#pragma unroll
+                for (int ph = 0; ph < NA; ++ph) {
+                    if (q == 0) {
+                        const uint32_t gs = group % kWsGroups;
+                        mbar_wait(&h_full[gs], (group / kWsGroups) & 1u);
+                        hrow = s_h + (size_t)gs * kGsQ * kGsTW + 2 * vt;
+                    }
+                    const uint64_t v = *reinterpret_cast<const uint64_t *>(hrow);
+                    hrow += kGsTW;
+                    uint64_t o;
+                    switch (ph) {  // ph is a compile-time constant after unrolling: no dispatch remains
+#define MP_WS_CASE(P) case P: o = gs_col_row<R, (P < NA ? P : 0)>(a, v, p); break;
+                        MP_WS_CASE(0) MP_WS_CASE(1) MP_WS_CASE(2) MP_WS_CASE(3) MP_WS_CASE(4) MP_WS_CASE(5)
+                        MP_WS_CASE(6) MP_WS_CASE(7) MP_WS_CASE(8) MP_WS_CASE(9) MP_WS_CASE(10) MP_WS_CASE(11)
+                        MP_WS_CASE(12) MP_WS_CASE(13) MP_WS_CASE(14) MP_WS_CASE(15) MP_WS_CASE(16)
+                        MP_WS_CASE(17) MP_WS_CASE(18) MP_WS_CASE(19) MP_WS_CASE(20) MP_WS_CASE(21)
+                        MP_WS_CASE(22) MP_WS_CASE(23) MP_WS_CASE(24) MP_WS_CASE(25) MP_WS_CASE(26)
+#undef MP_WS_CASE
+                        default: o = 0ull; break;
+                    }
+                    if (col_ok && orow >= y0 && orow < y1) {
+                        float o_lo, o_hi;
+                        unpack2(o, o_lo, o_hi);
+                        __stcs(reinterpret_cast<float2 *>(dst + (size_t)orow * p.row_elems), make_float2(o_lo, o_hi));
+                    }
+                    ++orow;
+                    if (++q == kGsQ) {
+                        q = 0;
+                        __syncwarp();  // every lane has read the group's rows
+                        if (lane == 0) mbar_arrive(&h_empty[group % kWsGroups]);
+                        ++group;
+                        if (--steps_left == 0) {
+                            item += gridDim.x;
+                            if (item < n_items) {
+                                load_item();
+                            } else {
+                                running = false;
+                                break;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace mpk
