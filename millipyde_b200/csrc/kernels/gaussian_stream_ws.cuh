@@ -14,9 +14,9 @@
 //                the group's slot of the hand-off ring and arrives on full[group].
 //   warps 10..19 COLUMN warps.  Thread t owns float columns 2t, 2t+1 and the 2R+1
 //                live output rows of each, packed in registers.  Per group: wait
-//                full[group], 10 x (LDS.64, 2R+1 FFMA2 through a jump table over the
-//                accumulator rotation, one coalesced 8-byte streaming store), arrive
-//                on empty[group].
+//                full[group], 10 x (LDS.64, 2R FFMA2 + 1 FMUL2 that accumulate AND slide
+//                the window -- A[j-1] = fma(w, v, A[j]) -- one coalesced 8-byte
+//                streaming store), arrive on empty[group].
 //
 // One CTA of 640 threads per SM (the register file splits 102 per thread, which
 // both roles fit), 3 groups in flight between the roles, 3 rows in flight per ROW
@@ -31,8 +31,8 @@ namespace mpk {
 constexpr int kWsRowWarps = kGsQ;             // 10
 constexpr int kWsColWarps = kGsQ;             // 10: 320 threads x 2 columns = 640 floats
 constexpr int kWsThreads = 32 * (kWsRowWarps + kWsColWarps);
-constexpr int kWsInSlots = 3;                 // rows in flight per ROW warp
-constexpr int kWsGroups = 3;                  // filtered groups in flight between the roles
+constexpr int kWsInSlots = 4;                 // rows in flight per ROW warp
+constexpr int kWsGroups = 4;                  // filtered groups in flight between the roles
 
 template <int C, int R>
 struct WsGeom {
@@ -215,85 +215,54 @@ gauss_stream_ws_kernel(const __grid_constant__ GaussStreamParams p)
         }
     } else {
         // ============================================================ COLUMN warp
-        // Rows stream through one continuous rotation: row n of this warp's life uses phase
-        // n mod NA, across groups and across items (the labels are arbitrary; accumulators
-        // that are still open when an item ends belong to rows outside the next item's range
-        // and are discarded, and every output row re-opens its accumulator by assignment).  The
-        // rotation is unrolled as straight-line code, so each accumulator lives in one fixed
-        // register pair for the whole kernel; group and item boundaries are uniform branches.
+        // A[j] is the partial sum of output row (r - R + j) when filtered row r arrives.  Row r
+        // adds w[|R - j|] * h[r] to it and the window slides by one: both happen in ONE
+        // instruction per accumulator, A[j-1] = fma(w, v, A[j]) -- the destination is the
+        // neighbour, so nothing rotates, no phase exists, and every row runs the same ~30
+        // instructions.  A[0] + w[R] * v is the finished output row r - R.
         const int vt = tid - 32 * kWsRowWarps;  // 0..319
-        uint64_t a[NA];
+        uint64_t A[2 * R];
 #pragma unroll
-        for (int i = 0; i < NA; ++i) a[i] = 0ull;
+        for (int i = 0; i < 2 * R; ++i) A[i] = 0ull;
+        uint32_t group = 0;
 
-        long item = blockIdx.x;
-        if (item < n_items) {
-            uint32_t group = 0;
-            // per-item state
-            float *__restrict__ dst = nullptr;
-            int y0 = 0, y1 = 0, orow = 0, steps_left = 0;
-            bool col_ok = false;
-            auto load_item = [&]() {
-                const int img = (int)(item / items_per_image);
-                const int rem = (int)(item - (long)img * items_per_image);
-                const int chunk = rem / p.n_strips, strip = rem - chunk * p.n_strips;
-                const int gx = strip * kGsTW + 2 * vt;
-                col_ok = gx < p.row_elems;
-                float *base = p.out_tab ? p.out_tab[img] : p.out + (size_t)img * p.image_stride;
-                dst = base + gx;
-                y0 = chunk * p.chunk_rows;
-                y1 = min(p.height, y0 + p.chunk_rows);
-                const int n_rows = (y1 - y0) + 2 * R;
-                steps_left = (n_rows + kGsQ - 1) / kGsQ;
-                orow = y0 - 2 * R;  // output row completed by the item's first filtered row
-            };
-            load_item();
-            int q = 0;
-            const float *hrow = nullptr;
-            bool running = true;
-            while (running) {
+        for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int img = (int)(item / items_per_image);
+            const int rem = (int)(item - (long)img * items_per_image);
+            const int chunk = rem / p.n_strips, strip = rem - chunk * p.n_strips;
+            const int gx = strip * kGsTW + 2 * vt;
+            const int y0 = chunk * p.chunk_rows;
+            const int y1 = min(p.height, y0 + p.chunk_rows);
+            const int n_rows = (y1 - y0) + 2 * R;
+            const int n_steps = (n_rows + kGsQ - 1) / kGsQ;
+            // rows [y0, y1) of columns gx, gx+1; the first filtered row completes output row y0 - 2R
+            const unsigned n_valid = gx < p.row_elems ? (unsigned)(y1 - y0) : 0u;
+            float *base = p.out_tab ? p.out_tab[img] : p.out + (size_t)img * p.image_stride;
+            float *optr = base + ((long)y0 - 2 * R) * p.row_elems + gx;  // only dereferenced when valid
+            unsigned rel = (unsigned)(-2 * R);                            // output row - y0, wraps below 0
+
+            for (int step = 0; step < n_steps; ++step) {
+                const uint32_t gs = group % kWsGroups;
+                mbar_wait(&h_full[gs], (group / kWsGroups) & 1u);
+                const float *hrow = s_h + (size_t)gs * kGsQ * kGsTW + 2 * vt;
 #pragma unroll
-                for (int ph = 0; ph < NA; ++ph) {
-                    if (q == 0) {
-                        const uint32_t gs = group % kWsGroups;
-                        mbar_wait(&h_full[gs], (group / kWsGroups) & 1u);
-                        hrow = s_h + (size_t)gs * kGsQ * kGsTW + 2 * vt;
-                    }
-                    const uint64_t v = *reinterpret_cast<const uint64_t *>(hrow);
-                    hrow += kGsTW;
-                    uint64_t o;
-                    switch (ph) {  // ph is a compile-time constant after unrolling: no dispatch remains
-#define MP_WS_CASE(P) case P: o = gs_col_row<R, (P < NA ? P : 0)>(a, v, p); break;
-                        MP_WS_CASE(0) MP_WS_CASE(1) MP_WS_CASE(2) MP_WS_CASE(3) MP_WS_CASE(4) MP_WS_CASE(5)
-                        MP_WS_CASE(6) MP_WS_CASE(7) MP_WS_CASE(8) MP_WS_CASE(9) MP_WS_CASE(10) MP_WS_CASE(11)
-                        MP_WS_CASE(12) MP_WS_CASE(13) MP_WS_CASE(14) MP_WS_CASE(15) MP_WS_CASE(16)
-                        MP_WS_CASE(17) MP_WS_CASE(18) MP_WS_CASE(19) MP_WS_CASE(20) MP_WS_CASE(21)
-                        MP_WS_CASE(22) MP_WS_CASE(23) MP_WS_CASE(24) MP_WS_CASE(25) MP_WS_CASE(26)
-#undef MP_WS_CASE
-                        default: o = 0ull; break;
-                    }
-                    if (col_ok && orow >= y0 && orow < y1) {
+                for (int q = 0; q < kGsQ; ++q) {
+                    const uint64_t v = *reinterpret_cast<const uint64_t *>(hrow + q * kGsTW);
+                    const uint64_t o = ffma2(p.ww[R], v, A[0]);
+#pragma unroll
+                    for (int j = 1; j < 2 * R; ++j) A[j - 1] = ffma2(p.ww[j < R ? R - j : j - R], v, A[j]);
+                    A[2 * R - 1] = fmul2(p.ww[R], v);
+                    if (rel < n_valid) {
                         float o_lo, o_hi;
                         unpack2(o, o_lo, o_hi);
-                        __stcs(reinterpret_cast<float2 *>(dst + (size_t)orow * p.row_elems), make_float2(o_lo, o_hi));
+                        __stcs(reinterpret_cast<float2 *>(optr), make_float2(o_lo, o_hi));
                     }
-                    ++orow;
-                    if (++q == kGsQ) {
-                        q = 0;
-                        __syncwarp();  // every lane has read the group's rows
-                        if (lane == 0) mbar_arrive(&h_empty[group % kWsGroups]);
-                        ++group;
-                        if (--steps_left == 0) {
-                            item += gridDim.x;
-                            if (item < n_items) {
-                                load_item();
-                            } else {
-                                running = false;
-                                break;
-                            }
-                        }
-                    }
+                    ++rel;
+                    optr += p.row_elems;
                 }
+                __syncwarp();  // every lane has read the group's rows
+                if (lane == 0) mbar_arrive(&h_empty[gs]);
+                ++group;
             }
         }
     }
