@@ -165,33 +165,39 @@ gauss_stream_ws_kernel(const __grid_constant__ GaussStreamParams p)
             }
             __syncwarp();
 
-            auto row_live = [&](int step) {
-                const int r = r_begin + step * kGsQ + warp;
-                return r >= 0 && r < p.height && r < r_begin + n_rows;
-            };
-            auto issue = [&](int step) {  // lane 0
-                if (!row_live(step)) return;
-                const int r = r_begin + step * kGsQ + warp;
-                const uint32_t slot = loads % kWsInSlots;
-                mbar_expect_tx(&my_full[slot], row_bytes);
-                bulk_g2s(my_in + (size_t)slot * G::ROW + lo, src + (size_t)r * p.row_elems + gx_start + lo,
-                         row_bytes, &my_full[slot]);
-            };
-            // prologue: kWsInSlots - 1 rows ahead
-            for (int s = 0; s < kWsInSlots - 1 && s < n_steps; ++s) {
-                if (lane == 0) issue(s);
-                if (row_live(s)) ++loads;
-            }
+            // This warp's rows are r_begin + warp + 10*step.  Steps [live_lo, live_hi) are the ones
+            // whose row lies inside the image and the item; everything per step is then a running
+            // pointer and two compares.
+            const int r_first = r_begin + warp;
+            const int r_end = min(p.height, r_begin + n_rows);
+            int live_lo = r_first < 0 ? (-r_first + kGsQ - 1) / kGsQ : 0;
+            int live_hi = r_end > r_first ? (r_end - r_first + kGsQ - 1) / kGsQ : 0;
+            if (live_hi > n_steps) live_hi = n_steps;
+            if (live_lo > live_hi) live_lo = live_hi;
+            const float *gptr = src + (long)(r_first + live_lo * kGsQ) * p.row_elems + gx_start + lo;
+            const long gstep = (long)kGsQ * p.row_elems;
+            int next_issue = live_lo;  // next live step to issue
 
-            for (int step = 0; step < n_steps; ++step) {
-                // keep the ring full: the slot consumed in the previous iteration is free again
-                const int ahead = step + kWsInSlots - 1;
-                if (ahead < n_steps) {
-                    if (lane == 0) issue(ahead);
-                    if (row_live(ahead)) ++loads;
+            auto issue_next = [&]() {  // all lanes keep the counters; lane 0 talks to the TMA unit
+                const uint32_t slot = loads % kWsInSlots;
+                if (lane == 0) {
+                    mbar_expect_tx(&my_full[slot], row_bytes);
+                    bulk_g2s(my_in + (size_t)slot * G::ROW + lo, gptr, row_bytes, &my_full[slot]);
                 }
+                gptr += gstep;
+                ++loads;
+                ++next_issue;
+            };
+            // prologue: up to kWsInSlots - 1 rows in flight before the first one is consumed
+            for (int s = 0; s < kWsInSlots - 1 && next_issue < live_hi; ++s) issue_next();
+
+            float *hbase = s_h + (size_t)warp * kGsTW + lane * kGsPH;
+            for (int step = 0; step < n_steps; ++step) {
+                const bool live = step >= live_lo && step < live_hi;
                 float out[kGsPH];
-                if (row_live(step)) {
+                if (live) {
+                    // the slot consumed in the previous live step is free again: keep the ring full
+                    if (next_issue < live_hi) issue_next();
                     const uint32_t slot = takes % kWsInSlots;
                     mbar_wait(&my_full[slot], (takes / kWsInSlots) & 1u);
                     ++takes;
@@ -203,7 +209,7 @@ gauss_stream_ws_kernel(const __grid_constant__ GaussStreamParams p)
                 // hand-off ring: wait until the COLUMN warps have drained this group slot
                 const uint32_t gs = group % kWsGroups;
                 mbar_wait(&h_empty[gs], ((group / kWsGroups) & 1u) ^ 1u);
-                float *hrow = s_h + ((size_t)gs * kGsQ + warp) * kGsTW + lane * kGsPH;
+                float *hrow = hbase + (size_t)gs * (kGsQ * kGsTW);
 #pragma unroll
                 for (int v = 0; v < kGsPH / 4; ++v)
                     *reinterpret_cast<float4 *>(hrow + 4 * v) =
