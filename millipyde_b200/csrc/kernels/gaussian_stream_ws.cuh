@@ -108,7 +108,6 @@ __global__ void __launch_bounds__(kWsThreads, 1)
 gauss_stream_ws_kernel(const __grid_constant__ GaussStreamParams p)
 {
     using G = WsGeom<C, R>;
-    constexpr int NA = 2 * R + 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_in = reinterpret_cast<float *>(smem_raw);                // [10 warps][3 slots][ROW]
     float *s_h = reinterpret_cast<float *>(smem_raw + G::IN_BYTES);    // [3 groups][10 rows][640]

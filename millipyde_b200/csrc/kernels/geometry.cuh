@@ -6,6 +6,7 @@
 // 4: fp32 RGBA), so one kernel template serves every layout bit-exactly.
 #pragma once
 #include "common.cuh"
+#include "gather_params.cuh"
 
 namespace mpk {
 
@@ -158,6 +159,68 @@ rotate_bilinear_kernel(const T *__restrict__ in, T *__restrict__ out, int width,
         T bot = ((T)1 - dx) * p10 + dx * p11;
         o[c] = ((T)1 - dy) * top + dy * bot;
     }
+}
+
+}  // namespace mpk
+
+namespace mpk {
+
+// ------------------------------------------------------- fused gather segment
+// One pass for a run of index ops, at most one bilinear rotate, and the pointwise
+// ops around it (fp32 HWC).  For output pixel p:
+//     q      = post(p)                       flips that come AFTER the rotate, as an index map
+//     (ys,xs)= Rot(q)  (or q itself)         fp64 source coordinates in the rotate's space
+//     corner -> pre(corner)                  flips that come BEFORE the rotate
+//     v      = sum_corners wgt * [inside ? pw_pre(src[pre(corner)]) : 0]
+//     out    = pw_post(v)
+// which is exactly what running the ops one after another computes (pointwise ops
+// commute with index maps; the rotate's zero fill is applied to the already
+// pre-processed image, so an outside corner contributes 0, not pw_pre(0)).
+// Images of a batch are addressed through pointer tables; blockIdx.z is the image.
+template <int C>
+__global__ void __launch_bounds__(256)
+gather_f32_kernel(const __grid_constant__ GatherParams g)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= g.out_w || y >= g.out_h) return;
+    const float *__restrict__ src = g.in_tab ? g.in_tab[blockIdx.z] : g.in;
+    float *__restrict__ dst = g.out_tab ? g.out_tab[blockIdx.z] : g.out;
+
+    const int qy = g.post.ay * y + g.post.by * x + g.post.cy;
+    const int qx = g.post.ax * y + g.post.bx * x + g.post.cx;
+    float acc[C];
+    auto fetch = [&](int cy, int cx, int c) -> float {
+        const int sy = g.pre.ay * cy + g.pre.by * cx + g.pre.cy;
+        const int sx = g.pre.ax * cy + g.pre.bx * cx + g.pre.cx;
+        return pw_apply<C>(g.pw_pre, __ldg(src + ((size_t)sy * g.src_w + sx) * C + c), c);
+    };
+    if (g.has_rotate) {
+        const double fx = (double)qx - g.rp.cx, fy = (double)qy - g.rp.cy;
+        const double xs = g.rp.c * fx - g.rp.s * fy + g.rp.cx;
+        const double ys = g.rp.s * fx + g.rp.c * fy + g.rp.cy;
+        const double xf = floor(xs), yf = floor(ys);
+        const int x0 = (int)xf, y0 = (int)yf, x1 = (int)ceil(xs), y1 = (int)ceil(ys);
+        const float dx = (float)(xs - xf), dy = (float)(ys - yf);
+        const bool in_x0 = x0 >= 0 && x0 < g.rot_w, in_x1 = x1 >= 0 && x1 < g.rot_w;
+        const bool in_y0 = y0 >= 0 && y0 < g.rot_h, in_y1 = y1 >= 0 && y1 < g.rot_h;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float p00 = (in_y0 && in_x0) ? fetch(y0, x0, c) : 0.f;
+            const float p01 = (in_y0 && in_x1) ? fetch(y0, x1, c) : 0.f;
+            const float p10 = (in_y1 && in_x0) ? fetch(y1, x0, c) : 0.f;
+            const float p11 = (in_y1 && in_x1) ? fetch(y1, x1, c) : 0.f;
+            const float top = (1.f - dx) * p00 + dx * p01;
+            const float bot = (1.f - dx) * p10 + dx * p11;
+            acc[c] = (1.f - dy) * top + dy * bot;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = fetch(qy, qx, c);
+    }
+    float *o = dst + ((size_t)y * g.out_w + x) * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) o[c] = pw_apply<C>(g.pw_post, acc[c], c);
 }
 
 }  // namespace mpk

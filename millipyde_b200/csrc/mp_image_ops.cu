@@ -670,3 +670,16 @@ MPStatus op_grey_f32(MPObjData *obj, const PwProgram &pre, const PwProgram &post
 }
 
 }  // namespace mp
+
+namespace mp {
+
+void launch_gather_f32(cudaStream_t s, int channels, const GatherParams &g, int n_images)
+{
+    dim3 block(32, 8), grid((g.out_w + 31) / 32, (g.out_h + 7) / 8, n_images);
+    if (channels == 1) gather_f32_kernel<1><<<grid, block, 0, s>>>(g);
+    else if (channels == 3) gather_f32_kernel<3><<<grid, block, 0, s>>>(g);
+    else gather_f32_kernel<4><<<grid, block, 0, s>>>(g);
+    count_launch();
+}
+
+}  // namespace mp

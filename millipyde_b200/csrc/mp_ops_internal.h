@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "kernels/common.cuh"
+#include "kernels/gather_params.cuh"
 #include "mp_abi.h"
 
 namespace mp {
@@ -44,6 +45,9 @@ MPStatus launch_gaussian(int device, cudaStream_t s, const Img &d, const void *i
 MPStatus op_pointwise_f32(MPObjData *obj, const mpk::PwProgram &prog);
 MPStatus op_pointwise_rgba8(MPObjData *obj, const mpk::U8Program &prog);
 MPStatus op_grey_f32(MPObjData *obj, const mpk::PwProgram &pre, const mpk::PwProgram &post);
+
+// Fused gather segment (kernels/geometry.cuh): n images through the tables in g, or one image.
+void launch_gather_f32(cudaStream_t s, int channels, const mpk::GatherParams &g, int n_images);
 
 // fp32 roofline path (kernels/gaussian_stream.cuh)
 bool gauss_stream_supported(int W, int C, int radius);

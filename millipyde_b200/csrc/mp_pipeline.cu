@@ -106,10 +106,13 @@ void note_status(mp_pipeline *p, MPStatus st)
 
 // ------------------------------------------------------------------ fusion pass
 struct Segment {
-    enum Kind { SINGLE, PW_F32, GREY_F32, PW_RGBA8 } kind;
+    enum Kind { SINGLE, PW_F32, GREY_F32, PW_RGBA8, GATHER_F32 } kind;
     const Stage *single = nullptr;  // SINGLE
-    PwProgram pre = {}, post = {};  // PW_F32 uses `pre`; GREY_F32 uses both
+    PwProgram pre = {}, post = {};  // PW_F32 uses `pre`; GREY_F32 and GATHER_F32 use both
     U8Program u8 = {};
+    // GATHER_F32: flips before / after the (optional) rotate, and its angle
+    bool flip_pre = false, flip_post = false, has_rotate = false;
+    double angle = 0;
 };
 
 PwOp to_pw(const Stage &s)
@@ -144,6 +147,36 @@ std::vector<Segment> compile(const std::vector<const Stage *> &ops, mp::Family f
     size_t i = 0;
     while (i < ops.size()) {
         const Stage *s = ops[i];
+        // fliplr / rotate (+ the pointwise ops around them) -> one gather pass
+        if (fuse && fam == mp::FAM_F32 && (s->kind == OP_FLIPLR || s->kind == OP_ROTATE || is_pointwise(s->kind))) {
+            Segment seg;
+            seg.kind = Segment::GATHER_F32;
+            size_t j = i;
+            bool geometric = false;
+            while (j < ops.size()) {
+                const Stage *t = ops[j];
+                if (t->kind == OP_FLIPLR) {
+                    (seg.has_rotate ? seg.flip_post : seg.flip_pre) ^= true;
+                    geometric = true;
+                } else if (t->kind == OP_ROTATE && !seg.has_rotate) {
+                    seg.has_rotate = true;
+                    seg.angle = t->a[0];
+                    geometric = true;
+                } else if (is_pointwise(t->kind)) {
+                    PwProgram &prog = seg.has_rotate ? seg.post : seg.pre;
+                    if (prog.n == kMaxPw) break;
+                    prog.ops[prog.n++] = to_pw(*t);
+                } else {
+                    break;
+                }
+                ++j;
+            }
+            if (geometric && j - i >= 2) {
+                out.push_back(seg);
+                i = j;
+                continue;
+            }
+        }
         if (fuse && fam == mp::FAM_F32 && (is_pointwise(s->kind) || (s->kind == OP_GREY && channels >= 3))) {
             Segment seg;
             seg.kind = Segment::PW_F32;
@@ -251,20 +284,78 @@ void realize(const mp_pipeline *p, std::vector<Stage> *out, std::string *key)
         if (c.kind != OP_FOREIGN && c.kind != OP_GREY && c.kind != OP_TRANSPOSE && c.kind != OP_FLIPLR) c.args = (void *)c.a;
 }
 
+MPStatus run_gather(const std::vector<MPObjData *> &objs, const Segment &seg, const mp::Img &d, int device,
+                    cudaStream_t s);
+
 MPStatus run_segment_on(MPObjData *obj, const Segment &seg)
 {
     switch (seg.kind) {
         case Segment::PW_F32: return mp::op_pointwise_f32(obj, seg.pre);
         case Segment::GREY_F32: return mp::op_grey_f32(obj, seg.pre, seg.post);
         case Segment::PW_RGBA8: return mp::op_pointwise_rgba8(obj, seg.u8);
+        case Segment::GATHER_F32: {
+            mp::Img d;
+            if (!mp::describe(obj, &d) || d.fam != mp::FAM_F32) return MP_ERROR_UNSUPPORTED_LAYOUT;
+            if (cudaSetDevice(obj->mem_loc) != cudaSuccess) return MP_ERROR_CUDA_RUNTIME;
+            std::vector<MPObjData *> one(1, obj);
+            return run_gather(one, seg, d, obj->mem_loc, mp::stream_of(obj));
+        }
         default: return seg.single->func(obj, seg.single->args);
     }
 }
 
-// One launch for the Gaussian of a whole same-shape fp32 group (pointer tables).
+// Batched launch plumbing: fresh output buffers for every image of a same-shape group, device
+// pointer tables (inputs then outputs) uploaded from the page-locked arena, one call of `launch`,
+// then the inputs are retired in stream order.  *handled = false (and nothing changed) if the
+// arena or the pool cannot serve the request.
+template <typename Launch>
+MPStatus run_batched(const std::vector<MPObjData *> &objs, size_t out_bytes, int device, cudaStream_t s,
+                     bool *handled, Launch launch)
+{
+    *handled = false;
+    const size_t n = objs.size();
+    Arena &arena = g_arenas[device];
+    void **h_tab = (void **)arena.take(2 * n * sizeof(void *));
+    if (!h_tab) return MILLIPYDE_SUCCESS;
+    void *d_tab = mp::pool_alloc(device, s, 2 * n * sizeof(void *));
+    if (!d_tab) return MP_ERROR_DEVICE_ALLOC;
+    std::vector<void *> fresh(n);
+    for (size_t i = 0; i < n; ++i) {
+        fresh[i] = mp::pool_alloc(device, s, out_bytes);
+        if (!fresh[i]) {
+            for (size_t k = 0; k < i; ++k) mp::pool_free(device, s, fresh[k]);
+            mp::pool_free(device, s, d_tab);
+            return MP_ERROR_DEVICE_ALLOC;
+        }
+        h_tab[i] = objs[i]->device_data;
+        h_tab[n + i] = fresh[i];
+    }
+    MP_CUDA_TRY(cudaMemcpyAsync(d_tab, h_tab, 2 * n * sizeof(void *), cudaMemcpyHostToDevice, s));
+    MPStatus st = launch((const float *const *)d_tab, (float *const *)((void **)d_tab + n), (int)n);
+    cudaError_t e = cudaGetLastError();
+    if (st == MILLIPYDE_SUCCESS && e != cudaSuccess) {
+        mp::record_cuda_error(e, "batched launch", __FILE__, __LINE__);
+        st = MP_ERROR_CUDA_RUNTIME;
+    }
+    for (size_t i = 0; i < n; ++i) {
+        if (st == MILLIPYDE_SUCCESS) {
+            mp::pool_free(device, s, objs[i]->device_data);
+            objs[i]->device_data = fresh[i];
+            objs[i]->nbytes = out_bytes;
+        } else {
+            mp::pool_free(device, s, fresh[i]);
+        }
+    }
+    mp::pool_free(device, s, d_tab);
+    *handled = st == MILLIPYDE_SUCCESS;
+    return st;
+}
+
+// One launch for the Gaussian of a whole same-shape fp32 group.
 MPStatus run_gaussian_batch(mp_pipeline *p, const std::vector<MPObjData *> &objs, const mp::Img &d, double sigma,
                             int device, cudaStream_t s, bool *handled)
 {
+    (void)p;
     *handled = false;
     if (!(sigma > 1e-15) || objs.size() < 2) return MILLIPYDE_SUCCESS;
     double w[kGaussMaxRadius + 1];
@@ -274,48 +365,61 @@ MPStatus run_gaussian_batch(mp_pipeline *p, const std::vector<MPObjData *> &objs
     GaussParams<float> gp = {};
     gp.radius = eff;
     for (int k = 0; k <= eff; ++k) gp.w[k] = (float)w[k];
+    return run_batched(objs, objs[0]->nbytes, device, s, handled,
+                       [&](const float *const *in_tab, float *const *out_tab, int n) {
+                           return mp::launch_gauss_stream_batch(device, s, d.H, d.W, d.C, n, nullptr, nullptr, 0,
+                                                                in_tab, out_tab, gp);
+                       });
+}
 
-    const size_t n = objs.size();
-    Arena &arena = g_arenas[device];
-    const float **h_in = (const float **)arena.take(n * sizeof(void *));
-    float **h_out = (float **)arena.take(n * sizeof(void *));
-    if (!h_in || !h_out) return MILLIPYDE_SUCCESS;  // arena exhausted: fall back to per-image launches
-    void *d_tab = mp::pool_alloc(device, s, 2 * n * sizeof(void *));
-    if (!d_tab) return MP_ERROR_DEVICE_ALLOC;
-    std::vector<void *> fresh(n);
-    for (size_t i = 0; i < n; ++i) {
-        fresh[i] = mp::pool_alloc(device, s, objs[i]->nbytes);
-        if (!fresh[i]) {
-            for (size_t k = 0; k < i; ++k) mp::pool_free(device, s, fresh[k]);
-            mp::pool_free(device, s, d_tab);
-            return MP_ERROR_DEVICE_ALLOC;
+// The gather segment for one image (tables null) or a same-shape group.
+GatherParams gather_params(const Segment &seg, const mp::Img &d)
+{
+    GatherParams g = {};
+    g.out_h = g.rot_h = d.H;
+    g.out_w = g.rot_w = g.src_w = d.W;
+    g.post = IndexMap{1, 0, 0, 0, seg.flip_post ? -1 : 1, seg.flip_post ? d.W - 1 : 0};
+    g.pre = IndexMap{1, 0, 0, 0, seg.flip_pre ? -1 : 1, seg.flip_pre ? d.W - 1 : 0};
+    g.has_rotate = seg.has_rotate ? 1 : 0;
+    if (seg.has_rotate) g.rp = mp::rotate_params(d.W, d.H, seg.angle);
+    g.pw_pre = seg.pre;
+    g.pw_post = seg.post;
+    return g;
+}
+
+MPStatus run_gather(const std::vector<MPObjData *> &objs, const Segment &seg, const mp::Img &d, int device,
+                    cudaStream_t s)
+{
+    GatherParams g = gather_params(seg, d);
+    auto launch = [&](const float *const *in_tab, float *const *out_tab, int n) {
+        g.in_tab = in_tab;
+        g.out_tab = out_tab;
+        mp::launch_gather_f32(s, d.C, g, n);
+        return MILLIPYDE_SUCCESS;
+    };
+    if (objs.size() >= 2) {
+        bool handled = false;
+        MPStatus st = run_batched(objs, objs[0]->nbytes, device, s, &handled, launch);
+        if (st != MILLIPYDE_SUCCESS || handled) return st;
+    }
+    for (MPObjData *o : objs) {  // one image, or the arena was exhausted
+        void *fresh = mp::pool_alloc(device, s, o->nbytes);
+        if (!fresh) return MP_ERROR_DEVICE_ALLOC;
+        g.in_tab = nullptr;
+        g.out_tab = nullptr;
+        g.in = (const float *)o->device_data;
+        g.out = (float *)fresh;
+        mp::launch_gather_f32(s, d.C, g, 1);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            mp::record_cuda_error(e, "gather launch", __FILE__, __LINE__);
+            mp::pool_free(device, s, fresh);
+            return MP_ERROR_CUDA_RUNTIME;
         }
-        h_in[i] = (const float *)objs[i]->device_data;
-        h_out[i] = (float *)fresh[i];
+        mp::pool_free(device, s, o->device_data);
+        o->device_data = fresh;
     }
-    // h_in and h_out are adjacent in the arena only if nothing was taken in between; copy both
-    MP_CUDA_TRY(cudaMemcpyAsync(d_tab, h_in, n * sizeof(void *), cudaMemcpyHostToDevice, s));
-    MP_CUDA_TRY(cudaMemcpyAsync((char *)d_tab + n * sizeof(void *), h_out, n * sizeof(void *),
-                                cudaMemcpyHostToDevice, s));
-    MPStatus st = mp::launch_gauss_stream_batch(device, s, d.H, d.W, d.C, (int)n, nullptr, nullptr, 0,
-                                                (const float *const *)d_tab,
-                                                (float *const *)((char *)d_tab + n * sizeof(void *)), gp);
-    cudaError_t e = cudaGetLastError();
-    if (st == MILLIPYDE_SUCCESS && e != cudaSuccess) {
-        mp::record_cuda_error(e, "gauss_stream batch launch", __FILE__, __LINE__);
-        st = MP_ERROR_CUDA_RUNTIME;
-    }
-    for (size_t i = 0; i < n; ++i) {
-        if (st == MILLIPYDE_SUCCESS) {
-            mp::pool_free(device, s, objs[i]->device_data);
-            objs[i]->device_data = fresh[i];
-        } else {
-            mp::pool_free(device, s, fresh[i]);
-        }
-    }
-    mp::pool_free(device, s, d_tab);
-    *handled = st == MILLIPYDE_SUCCESS;
-    return st;
+    return MILLIPYDE_SUCCESS;
 }
 
 // All images of `objs` share layout and surviving op list.
@@ -336,6 +440,14 @@ void run_group(mp_pipeline *p, const std::vector<MPObjData *> &objs, const std::
                 MPStatus st = run_gaussian_batch(p, objs, cur, seg.single->a[0], device, s, &handled);
                 note_status(p, st);
                 if (handled) continue;
+            }
+        }
+        if (seg.kind == Segment::GATHER_F32) {
+            mp::Img cur;
+            if (mp::describe(objs[0], &cur) && cur.fam == mp::FAM_F32) {
+                cudaSetDevice(device);
+                note_status(p, run_gather(objs, seg, cur, device, s));
+                continue;
             }
         }
         for (MPObjData *o : objs) note_status(p, run_segment_on(o, seg));

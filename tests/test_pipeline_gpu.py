@@ -34,8 +34,37 @@ def test_batch_equals_oracle_config3_shape(mp):
     dev = [mp.capi.DeviceImage(a) for a in imgs]
     ch = mp.engine.Chain(CONFIG3, device=0)
     ch.run(dev)
+    # rotate + fliplr + gamma fold into one gather pass, then the Gaussian: 2 launches for the batch
+    assert ch.last_segments == 2 and ch.last_launches == 2
     for a, d in zip(imgs, dev):
         assert np.abs(d.numpy() - so.apply_chain(a, CONFIG3)).max() <= TOL32
+
+
+@pytest.mark.parametrize("c", [1, 3, 4])
+def test_gather_fusion_matches_op_by_op(mp, c):
+    chains = [
+        [("fliplr",), ("brightness", 0.1)],
+        [("rotate", 30.0), ("fliplr",), ("adjust_gamma", 1.5, 1.0)],
+        [("adjust_gamma", 0.8, 0.9), ("fliplr",), ("rotate", -17.5), ("brightness", -0.05), ("fliplr",)],
+        [("fliplr",), ("fliplr",), ("colorize", 0.9, 1.1, 1.0), ("rotate", 90.0)],
+        [("brightness", 0.2), ("rotate", 45.0), ("rotate", 10.0), ("fliplr",)],     # second rotate starts a new segment
+    ]
+    for chain in chains:
+        for shape in [(97, 131), (64, 96)]:
+            imgs = [synth.noise_f32(*shape, c, 700 + k) for k in range(3)]
+            dev = [mp.capi.DeviceImage(a) for a in imgs]
+            ch = mp.engine.Chain(chain, device=0)
+            ch.run(dev)
+            single = mp.capi.DeviceImage(imgs[0])
+            mp.engine.Chain(chain, device=0).run([single])            # un-batched path
+            for a, d in zip(imgs, dev):
+                want = so.apply_chain(a, chain)
+                if c == 4:      # alpha is untouched by pointwise ops; index ops move it with the pixel
+                    want = so.apply_chain(a, [op for op in chain])
+                    alpha = so.apply_chain(a, [op for op in chain if op[0] in ("fliplr", "rotate", "transpose")])
+                    want[..., 3] = alpha[..., 3]
+                assert np.abs(d.numpy() - want).max() <= TOL32, chain
+            assert np.array_equal(single.numpy(), dev[0].numpy())
 
 
 def test_gaussian_batch_is_one_launch(mp):
