@@ -12,30 +12,52 @@
 namespace mpk {
 
 // ---------------------------------------------------------------- fp32, HWC
-// A thread owns 12 consecutive floats = lcm(3, 4): three 16-byte vectors whose
-// channel pattern is the same for every group, so `j % C` is a compile-time
-// constant and the op program runs without index arithmetic.
+// Every warp-level access is 32 consecutive 16-byte vectors (512 contiguous bytes); a warp owns
+// 96 consecutive vectors per iteration (= 384 floats, a multiple of 3 and 4, so the channel of
+// every element is known from the lane: vector v starts at channel (4v) mod C).  Measured on
+// B200 (tools/stream_peak.cu): this shape reaches 93 % of the copy bandwidth, a thread-contiguous
+// 48-byte chunk only 75 %.
 template <int C>
 __global__ void __launch_bounds__(256)
 pw_f32_kernel(const float *__restrict__ in, float *__restrict__ out, size_t n,
-              const __grid_constant__ PwProgram prog)
+              const __grid_constant__ PwProgram prog, const float *const *__restrict__ in_tab = nullptr,
+              float *const *__restrict__ out_tab = nullptr)
 {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t ngroups = n / 12;
-    for (size_t g = tid; g < ngroups; g += stride) {
-        const float4 *src = reinterpret_cast<const float4 *>(in + g * 12);
-        float4 v[3] = {ld_stream(src), ld_stream(src + 1), ld_stream(src + 2)};
-        float *r = reinterpret_cast<float *>(v);
-#pragma unroll
-        for (int j = 0; j < 12; ++j) r[j] = pw_apply<C>(prog, r[j], j % C);
-        float4 *dst = reinterpret_cast<float4 *>(out + g * 12);
-        st_stream(dst, v[0]);
-        st_stream(dst + 1, v[1]);
-        st_stream(dst + 2, v[2]);
+    if (in_tab) {  // batched launch: blockIdx.y selects the image
+        in = in_tab[blockIdx.y];
+        out = out_tab[blockIdx.y];
     }
-    for (size_t e = ngroups * 12 + tid; e < n; e += stride)
+    const size_t nvec = n / 4;
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const float4 *in4 = reinterpret_cast<const float4 *>(in);
+    float4 *out4 = reinterpret_cast<float4 *>(out);
+    for (size_t base = warp * 96; base < nvec; base += nwarps * 96) {
+        float4 v[3];
+        bool ok[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const size_t idx = base + lane + 32 * j;
+            ok[j] = idx < nvec;
+            if (ok[j]) v[j] = ld_stream(in4 + idx);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            // base is a multiple of 96, so vector idx starts at channel (4 * idx) mod 3 == (lane + 2j) mod 3
+            const int phase = (C == 3) ? (lane + 2 * j) % 3 : 0;
+            float(&r)[4] = *reinterpret_cast<float(*)[4]>(&v[j]);
+            pw_apply_tile<C, 4>(prog, r, phase);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (ok[j]) st_stream(out4 + base + lane + 32 * j, v[j]);
+    }
+    // the last n % 4 floats
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const size_t e = nvec * 4 + threadIdx.x;
         out[e] = pw_apply<C>(prog, in[e], (int)(e % C));
+    }
 }
 
 // rgb2grey on fp32 H x W x {3,4} -> H x W, with optional pointwise programs
@@ -43,9 +65,14 @@ pw_f32_kernel(const float *__restrict__ in, float *__restrict__ out, size_t n,
 template <int C>
 __global__ void __launch_bounds__(256)
 grey_f32_kernel(const float *__restrict__ in, float *__restrict__ out, size_t npix,
-                const __grid_constant__ PwProgram pre, const __grid_constant__ PwProgram post)
+                const __grid_constant__ PwProgram pre, const __grid_constant__ PwProgram post,
+                const float *const *__restrict__ in_tab = nullptr, float *const *__restrict__ out_tab = nullptr)
 {
     static_assert(C == 3 || C == 4, "colour input");
+    if (in_tab) {
+        in = in_tab[blockIdx.y];
+        out = out_tab[blockIdx.y];
+    }
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t ngroups = npix / 4;  // 4 pixels in, one float4 out

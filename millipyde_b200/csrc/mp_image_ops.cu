@@ -348,7 +348,9 @@ static MPStatus pointwise_f32(MPObjData *obj, const mp::Img &d, cudaStream_t s, 
     MPStatus st = fresh(obj, s, obj->nbytes, &out);
     if (st != MILLIPYDE_SUCCESS) return st;
     size_t n = d.npix * d.C;
-    int grid = mp::grid_for(obj->mem_loc, n / 12 + 1, 256);
+    // one warp per 96 vectors, no cap: many small CTAs stream better than a short persistent grid
+    size_t want = (n / 4 + 96 * 8 - 1) / (96 * 8);
+    int grid = (int)(want < 1 ? 1 : (want > 65535u * 16u ? 65535u * 16u : want));
     const float *in = (const float *)obj->device_data;
     if (d.C == 1) pw_f32_kernel<1><<<grid, 256, 0, s>>>(in, (float *)out, n, prog);
     else if (d.C == 3) pw_f32_kernel<3><<<grid, 256, 0, s>>>(in, (float *)out, n, prog);
@@ -679,6 +681,32 @@ void launch_gather_f32(cudaStream_t s, int channels, const GatherParams &g, int 
     if (channels == 1) gather_f32_kernel<1><<<grid, block, 0, s>>>(g);
     else if (channels == 3) gather_f32_kernel<3><<<grid, block, 0, s>>>(g);
     else gather_f32_kernel<4><<<grid, block, 0, s>>>(g);
+    count_launch();
+}
+
+}  // namespace mp
+
+namespace mp {
+
+// Batched forms used by the chain executor: n same-shape images through device pointer tables.
+void launch_pw_f32_batch(cudaStream_t s, const Img &d, const PwProgram &prog, const float *const *in_tab,
+                         float *const *out_tab, int n_images)
+{
+    const size_t n = d.npix * d.C;
+    size_t want = (n / 4 + 96 * 8 - 1) / (96 * 8);
+    dim3 grid((unsigned)(want < 1 ? 1 : want), (unsigned)n_images);
+    if (d.C == 1) pw_f32_kernel<1><<<grid, 256, 0, s>>>(nullptr, nullptr, n, prog, in_tab, out_tab);
+    else if (d.C == 3) pw_f32_kernel<3><<<grid, 256, 0, s>>>(nullptr, nullptr, n, prog, in_tab, out_tab);
+    else pw_f32_kernel<4><<<grid, 256, 0, s>>>(nullptr, nullptr, n, prog, in_tab, out_tab);
+    count_launch();
+}
+
+void launch_grey_f32_batch(cudaStream_t s, const Img &d, const PwProgram &pre, const PwProgram &post,
+                           const float *const *in_tab, float *const *out_tab, int n_images)
+{
+    dim3 grid((unsigned)grid_for(0, d.npix / 4 + 1, 256), (unsigned)n_images);
+    if (d.C == 3) grey_f32_kernel<3><<<grid, 256, 0, s>>>(nullptr, nullptr, d.npix, pre, post, in_tab, out_tab);
+    else grey_f32_kernel<4><<<grid, 256, 0, s>>>(nullptr, nullptr, d.npix, pre, post, in_tab, out_tab);
     count_launch();
 }
 

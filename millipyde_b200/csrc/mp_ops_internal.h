@@ -46,6 +46,11 @@ MPStatus op_pointwise_f32(MPObjData *obj, const mpk::PwProgram &prog);
 MPStatus op_pointwise_rgba8(MPObjData *obj, const mpk::U8Program &prog);
 MPStatus op_grey_f32(MPObjData *obj, const mpk::PwProgram &pre, const mpk::PwProgram &post);
 
+void launch_pw_f32_batch(cudaStream_t s, const Img &d, const mpk::PwProgram &prog, const float *const *in_tab,
+                         float *const *out_tab, int n_images);
+void launch_grey_f32_batch(cudaStream_t s, const Img &d, const mpk::PwProgram &pre, const mpk::PwProgram &post,
+                           const float *const *in_tab, float *const *out_tab, int n_images);
+
 // Fused gather segment (kernels/geometry.cuh): n images through the tables in g, or one image.
 void launch_gather_f32(cudaStream_t s, int channels, const mpk::GatherParams &g, int n_images);
 

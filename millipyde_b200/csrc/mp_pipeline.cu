@@ -198,7 +198,7 @@ std::vector<Segment> compile(const std::vector<const Stage *> &ops, mp::Family f
                     break;
                 }
             }
-            if (j - i >= 2) {
+            if (j - i >= 1) {  // even a single op: the segment form is the one that batches
                 if (grey) channels = 1;
                 out.push_back(seg);
                 i = j;
@@ -440,6 +440,35 @@ void run_group(mp_pipeline *p, const std::vector<MPObjData *> &objs, const std::
                 MPStatus st = run_gaussian_batch(p, objs, cur, seg.single->a[0], device, s, &handled);
                 note_status(p, st);
                 if (handled) continue;
+            }
+        }
+        if ((seg.kind == Segment::PW_F32 || seg.kind == Segment::GREY_F32) && objs.size() >= 2) {
+            // one launch for the whole group (pointer tables); the grey variant also rewrites headers
+            mp::Img cur;
+            if (mp::describe(objs[0], &cur) && cur.fam == mp::FAM_F32 &&
+                (seg.kind == Segment::PW_F32 || (cur.C >= 3 && objs[0]->ndims == 3))) {
+                cudaSetDevice(device);
+                const bool grey = seg.kind == Segment::GREY_F32;
+                const size_t out_bytes = grey ? cur.npix * 4 : objs[0]->nbytes;
+                bool handled = false;
+                MPStatus st = run_batched(objs, out_bytes, device, s, &handled,
+                                          [&](const float *const *in_tab, float *const *out_tab, int n) {
+                                              if (grey) mp::launch_grey_f32_batch(s, cur, seg.pre, seg.post, in_tab, out_tab, n);
+                                              else mp::launch_pw_f32_batch(s, cur, seg.pre, in_tab, out_tab, n);
+                                              return MILLIPYDE_SUCCESS;
+                                          });
+                note_status(p, st);
+                if (handled) {
+                    if (grey)
+                        for (MPObjData *o : objs) {  // header rewrite of mpimg_color_to_greyscale
+                            o->ndims = 2;
+                            o->type = MP_NPY_FLOAT;
+                            o->dims[2] = cur.W * 4;
+                            o->dims[3] = 4;
+                        }
+                    continue;
+                }
+                if (st != MILLIPYDE_SUCCESS) continue;
             }
         }
         if (seg.kind == Segment::GATHER_F32) {
