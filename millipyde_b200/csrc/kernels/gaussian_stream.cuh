@@ -96,47 +96,6 @@ __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b)
     return d;
 }
 
-// ---- mbarrier / bulk-copy PTX ------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void *p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_addr(bar)),
-        "r"(parity)
-        : "memory");
-}
-// global -> shared 1-D bulk copy through the TMA unit; bytes % 16 == 0, both sides 16-byte aligned
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_addr(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async()
-{
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
 // ---- row pass: scatter one aligned window into PH/2 packed accumulators -------
 // Output pair m = outputs (2m, 2m+1).  A tap whose offset k*C is even reads the
 // pair (x[2j], x[2j+1]) exactly as LDS.128 delivered it; an odd offset needs the

@@ -42,6 +42,59 @@ transpose_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, in
     }
 }
 
+// TMA-fed variant (needs (W*K) % 4 == 0 and (H*K) % 4 == 0, i.e. 16-byte row pitches on both
+// sides).  The 32 rows of a tile arrive as 32 one-dimensional bulk copies (cp.async.bulk, SASS
+// UBLKCP) issued by the 32 lanes of warp 0 -- no load instructions, no shared-memory stores, no
+// registers in flight -- landing at a pitch of 32*K + 4 words (16-byte aligned, and the 4-word
+// skew spreads a column over the banks).  Each thread then gathers four consecutive words of an
+// OUTPUT row (4 x LDS.32) and writes them as one 16-byte store, so the store side moves 128-bit
+// vectors too.  Many small CTAs (12.8 KB of shared memory each for RGB fp32) overlap each other's
+// copy latency.  Images of a batch are addressed through pointer tables (blockIdx.z).
+template <int K>
+__global__ void __launch_bounds__(256)
+transpose_tma_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int width, int height,
+                     const uint32_t *const *__restrict__ in_tab = nullptr,
+                     uint32_t *const *__restrict__ out_tab = nullptr)
+{
+    constexpr int P = 32 * K + 4;
+    __shared__ __align__(128) uint32_t tile[32 * P];
+    __shared__ __align__(8) uint64_t bar;
+    if (in_tab) {
+        in = in_tab[blockIdx.z];
+        out = out_tab[blockIdx.z];
+    }
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    const int tw = min(32, width - x0), th = min(32, height - y0);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const uint32_t row_bytes = (uint32_t)tw * K * 4u;
+        if (tid == 0) mbar_expect_tx(&bar, row_bytes * (uint32_t)th);
+        __syncwarp();
+        if (tid < th)
+            bulk_g2s(tile + tid * P, in + ((size_t)(y0 + tid) * width + x0) * K, row_bytes, &bar);
+    }
+    mbar_wait(&bar, 0);
+    // output row (x0 + r) holds pixels y0 .. y0+th-1: th*K words, written as th*K/4 vectors
+    const int vec_per_row = th * K / 4;
+    for (int i = tid; i < tw * vec_per_row; i += 256) {
+        const int r = i / vec_per_row, q = i - r * vec_per_row;
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = 4 * q + e;  // word of the output row: pixel y = j / K, channel c = j % K
+            const int y = j / K, c = j - y * K;
+            w[e] = tile[y * P + r * K + c];
+        }
+        uint4 *dst = reinterpret_cast<uint4 *>(out + ((size_t)(x0 + r) * height + y0) * K) + q;
+        st_stream(dst, make_uint4(w[0], w[1], w[2], w[3]));
+    }
+}
+
 // --------------------------------------------------------------------- fliplr
 // Vector path (width % 4 == 0): a thread moves 4 pixels = K 16-byte vectors,
 // reading the mirrored 4-pixel block and reversing the pixel order in
@@ -69,6 +122,53 @@ fliplr_vec_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int wid
         uint4 *dst = out + (row * bpr + bx) * K;
 #pragma unroll
         for (int k = 0; k < K; ++k) st_stream(dst + k, o[k]);
+    }
+}
+
+// Warp-cooperative path (width % 128 == 0): a warp mirrors 128 pixels = 32*K vectors.  Both the
+// global loads and the global stores are 32 consecutive 16-byte vectors per instruction; the
+// pixel reversal happens on the way through a 32*K-vector shared-memory stage (the per-lane
+// 16*K-byte chunks of fliplr_vec_kernel cost ~25 % of the bandwidth, tools/stream_peak.cu).
+template <int K>
+__global__ void __launch_bounds__(256)
+fliplr_warp_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int width, size_t nunits,
+                   const uint4 *const *__restrict__ in_tab = nullptr, uint4 *const *__restrict__ out_tab = nullptr)
+{
+    if (in_tab) {
+        in = in_tab[blockIdx.y];
+        out = out_tab[blockIdx.y];
+    }
+    __shared__ uint4 stage[8][32 * K];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const int upr = width / 128;  // 128-pixel units per row
+    for (size_t u = warp; u < nunits; u += nwarps) {
+        const size_t row = u / upr;
+        const int ux = (int)(u - row * upr);
+        const uint4 *src = in + (row * upr + (upr - 1 - ux)) * (32 * K);
+#pragma unroll
+        for (int j = 0; j < K; ++j) stage[wib][lane + 32 * j] = ld_stream(src + lane + 32 * j);
+        __syncwarp();
+        // lane takes the mirrored 4-pixel block (K vectors) and reverses its pixels
+        uint4 v[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = stage[wib][(31 - lane) * K + k];
+        __syncwarp();
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(v);
+        uint4 o[K];
+        uint32_t *ow = reinterpret_cast<uint32_t *>(o);
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int c = 0; c < K; ++c) ow[p * K + c] = w[(3 - p) * K + c];
+#pragma unroll
+        for (int k = 0; k < K; ++k) stage[wib][lane * K + k] = o[k];
+        __syncwarp();
+        uint4 *dst = out + (row * upr + ux) * (32 * K);
+#pragma unroll
+        for (int j = 0; j < K; ++j) st_stream(dst + lane + 32 * j, stage[wib][lane + 32 * j]);
+        __syncwarp();
     }
 }
 

@@ -62,6 +62,10 @@ pw_f32_kernel(const float *__restrict__ in, float *__restrict__ out, size_t n,
 
 // rgb2grey on fp32 H x W x {3,4} -> H x W, with optional pointwise programs
 // before (per colour channel) and after (on the grey value) for fused chains.
+// C = 3: a warp streams 96 consecutive vectors (128 pixels) with coalesced 16-byte loads into
+// its own 1.5 KB of shared memory, each lane then reads ITS four pixels back as three LDS.128
+// (lane pitch 48 B = 3 x 16 B: conflict-free) and the warp stores 32 consecutive float4.
+// C = 4: a vector is a pixel, so loads are coalesced as they are; greys leave as 4-byte stores.
 template <int C>
 __global__ void __launch_bounds__(256)
 grey_f32_kernel(const float *__restrict__ in, float *__restrict__ out, size_t npix,
@@ -73,30 +77,48 @@ grey_f32_kernel(const float *__restrict__ in, float *__restrict__ out, size_t np
         in = in_tab[blockIdx.y];
         out = out_tab[blockIdx.y];
     }
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t ngroups = npix / 4;  // 4 pixels in, one float4 out
-    for (size_t g = tid; g < ngroups; g += stride) {
-        const float4 *src = reinterpret_cast<const float4 *>(in + g * 4 * C);
-        float4 v[C];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    if (C == 3) {
+        __shared__ __align__(16) float stage[8][384];
+        const size_t ngroups = npix / 128;  // 128 pixels = 96 vectors in, 32 vectors out
+        const float4 *in4 = reinterpret_cast<const float4 *>(in);
+        for (size_t g = warp; g < ngroups; g += nwarps) {
 #pragma unroll
-        for (int k = 0; k < C; ++k) v[k] = ld_stream(src + k);
-        float *r = reinterpret_cast<float *>(v);
-        float o[4];
+            for (int j = 0; j < 3; ++j)
+                *reinterpret_cast<float4 *>(&stage[wib][4 * (lane + 32 * j)]) = ld_stream(in4 + g * 96 + lane + 32 * j);
+            __syncwarp();
+            float r[12];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            float cr = pw_apply<C>(pre, r[p * C + 0], 0);
-            float cg = pw_apply<C>(pre, r[p * C + 1], 1);
-            float cb = pw_apply<C>(pre, r[p * C + 2], 2);
-            o[p] = pw_apply<1>(post, luma_f32(cr, cg, cb), 0);
+            for (int j = 0; j < 3; ++j)
+                *reinterpret_cast<float4 *>(&r[4 * j]) = *reinterpret_cast<const float4 *>(&stage[wib][12 * lane + 4 * j]);
+            __syncwarp();
+            pw_apply_tile<3, 12>(pre, r, 0);
+            float o[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) o[p] = luma_f32(r[3 * p], r[3 * p + 1], r[3 * p + 2]);
+            pw_apply_tile<1, 4>(post, o, 0);
+            st_stream(reinterpret_cast<float4 *>(out) + g * 32 + lane, make_float4(o[0], o[1], o[2], o[3]));
         }
-        st_stream(reinterpret_cast<float4 *>(out + g * 4), make_float4(o[0], o[1], o[2], o[3]));
-    }
-    for (size_t p = ngroups * 4 + tid; p < npix; p += stride) {
-        float cr = pw_apply<C>(pre, in[p * C + 0], 0);
-        float cg = pw_apply<C>(pre, in[p * C + 1], 1);
-        float cb = pw_apply<C>(pre, in[p * C + 2], 2);
-        out[p] = pw_apply<1>(post, luma_f32(cr, cg, cb), 0);
+        // ragged tail (< 128 pixels)
+        const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (size_t p = ngroups * 128 + gtid; p < npix; p += (size_t)gridDim.x * blockDim.x) {
+            float cr = pw_apply<C>(pre, in[p * C + 0], 0);
+            float cg = pw_apply<C>(pre, in[p * C + 1], 1);
+            float cb = pw_apply<C>(pre, in[p * C + 2], 2);
+            out[p] = pw_apply<1>(post, luma_f32(cr, cg, cb), 0);
+        }
+    } else {
+        const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (size_t p = gtid; p < npix; p += (size_t)gridDim.x * blockDim.x) {
+            float4 v = ld_stream(reinterpret_cast<const float4 *>(in) + p);
+            float r[4] = {v.x, v.y, v.z, v.w};
+            pw_apply_tile<4, 4>(pre, r, 0);
+            float o[1] = {luma_f32(r[0], r[1], r[2])};
+            pw_apply_tile<1, 1>(post, o, 0);
+            out[p] = o[0];
+        }
     }
 }
 

@@ -101,6 +101,15 @@ int words_per_pixel(const Img &d)
     return (bytes % 4 == 0 && bytes / 4 <= 4) ? (int)(bytes / 4) : 0;
 }
 
+// grey_f32_kernel: a warp per 128 pixels (C = 3) or a thread per pixel (C = 4); uncapped
+int grey_grid(const Img &d)
+{
+    size_t blocks = d.C == 3 ? (d.npix / 128 + 7) / 8 : (d.npix + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 1u << 20) blocks = 1u << 20;
+    return (int)blocks;
+}
+
 int grid_for(int device, size_t work_items, int threads)
 {
     size_t blocks = (work_items + threads - 1) / threads;
@@ -165,13 +174,21 @@ template <int K>
 static void launch_transpose(const void *in, void *out, int W, int H, cudaStream_t s)
 {
     dim3 grid((W + 31) / 32, (H + 31) / 32);
-    transpose_kernel<K><<<grid, 256, 0, s>>>((const uint32_t *)in, (uint32_t *)out, W, H);
+    if (((size_t)W * K) % 4 == 0 && ((size_t)H * K) % 4 == 0)
+        transpose_tma_kernel<K><<<grid, 256, 0, s>>>((const uint32_t *)in, (uint32_t *)out, W, H);
+    else
+        transpose_kernel<K><<<grid, 256, 0, s>>>((const uint32_t *)in, (uint32_t *)out, W, H);
 }
 
 template <int K>
 static void launch_fliplr(int dev, const void *in, void *out, int W, int H, cudaStream_t s)
 {
-    if (W % 4 == 0) {
+    if (W % 128 == 0) {
+        size_t nu = (size_t)H * (W / 128);
+        size_t blocks = (nu + 7) / 8;
+        if (blocks > (1u << 20)) blocks = 1u << 20;
+        fliplr_warp_kernel<K><<<(unsigned)blocks, 256, 0, s>>>((const uint4 *)in, (uint4 *)out, W, nu);
+    } else if (W % 4 == 0) {
         size_t nb = (size_t)H * (W / 4);
         fliplr_vec_kernel<K><<<mp::grid_for(dev, nb, 256), 256, 0, s>>>((const uint4 *)in, (uint4 *)out, W, nb);
     } else {
@@ -217,7 +234,7 @@ static MPStatus grey_impl(MPObjData *obj, const PwProgram &pre, const PwProgram 
     if ((st = fresh(obj, s, out_bytes, &out)) != MILLIPYDE_SUCCESS) return st;
 
     if (f32) {
-        int grid = mp::grid_for(obj->mem_loc, d.npix / 4 + 1, 256);
+        int grid = mp::grey_grid(d);
         if (d.C == 3)
             grey_f32_kernel<3><<<grid, 256, 0, s>>>((const float *)obj->device_data, (float *)out, d.npix, pre, post);
         else
@@ -704,9 +721,59 @@ void launch_pw_f32_batch(cudaStream_t s, const Img &d, const PwProgram &prog, co
 void launch_grey_f32_batch(cudaStream_t s, const Img &d, const PwProgram &pre, const PwProgram &post,
                            const float *const *in_tab, float *const *out_tab, int n_images)
 {
-    dim3 grid((unsigned)grid_for(0, d.npix / 4 + 1, 256), (unsigned)n_images);
+    dim3 grid((unsigned)grey_grid(d), (unsigned)n_images);
     if (d.C == 3) grey_f32_kernel<3><<<grid, 256, 0, s>>>(nullptr, nullptr, d.npix, pre, post, in_tab, out_tab);
     else grey_f32_kernel<4><<<grid, 256, 0, s>>>(nullptr, nullptr, d.npix, pre, post, in_tab, out_tab);
+    count_launch();
+}
+
+}  // namespace mp
+
+namespace mp {
+
+bool fliplr_batch_supported(const Img &d) { return d.W % 128 == 0 && words_per_pixel(d) != 0; }
+
+void launch_fliplr_batch(cudaStream_t s, const Img &d, const void *const *in_tab, void *const *out_tab, int n_images)
+{
+    const int K = words_per_pixel(d);
+    const size_t nu = (size_t)d.H * (d.W / 128);
+    size_t blocks = (nu + 7) / 8;
+    if (blocks > 65535u * 8u) blocks = 65535u * 8u;
+    dim3 grid((unsigned)blocks, (unsigned)n_images);
+    const uint4 *const *it = (const uint4 *const *)in_tab;
+    uint4 *const *ot = (uint4 *const *)out_tab;
+    switch (K) {
+        case 1: fliplr_warp_kernel<1><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, nu, it, ot); break;
+        case 2: fliplr_warp_kernel<2><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, nu, it, ot); break;
+        case 3: fliplr_warp_kernel<3><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, nu, it, ot); break;
+        default: fliplr_warp_kernel<4><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, nu, it, ot); break;
+    }
+    count_launch();
+}
+
+}  // namespace mp
+
+namespace mp {
+
+bool transpose_batch_supported(const Img &d)
+{
+    const int K = words_per_pixel(d);
+    return K != 0 && ((size_t)d.W * K) % 4 == 0 && ((size_t)d.H * K) % 4 == 0;
+}
+
+void launch_transpose_batch(cudaStream_t s, const Img &d, const void *const *in_tab, void *const *out_tab,
+                            int n_images)
+{
+    const int K = words_per_pixel(d);
+    dim3 grid((d.W + 31) / 32, (d.H + 31) / 32, n_images);
+    const uint32_t *const *it = (const uint32_t *const *)in_tab;
+    uint32_t *const *ot = (uint32_t *const *)out_tab;
+    switch (K) {
+        case 1: transpose_tma_kernel<1><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, d.H, it, ot); break;
+        case 2: transpose_tma_kernel<2><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, d.H, it, ot); break;
+        case 3: transpose_tma_kernel<3><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, d.H, it, ot); break;
+        default: transpose_tma_kernel<4><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, d.H, it, ot); break;
+    }
     count_launch();
 }
 

@@ -28,6 +28,7 @@ struct Img {
 bool describe(const MPObjData *o, Img *d);
 int words_per_pixel(const Img &d);
 int grid_for(int device, size_t work_items, int threads);
+int grey_grid(const Img &d);
 
 int oracle_weights(double sigma, double *w, int max_radius);
 int effective_radius(const double *w, int r, double eps);
@@ -50,6 +51,13 @@ void launch_pw_f32_batch(cudaStream_t s, const Img &d, const mpk::PwProgram &pro
                          float *const *out_tab, int n_images);
 void launch_grey_f32_batch(cudaStream_t s, const Img &d, const mpk::PwProgram &pre, const mpk::PwProgram &post,
                            const float *const *in_tab, float *const *out_tab, int n_images);
+
+bool fliplr_batch_supported(const Img &d);
+void launch_fliplr_batch(cudaStream_t s, const Img &d, const void *const *in_tab, void *const *out_tab, int n_images);
+
+bool transpose_batch_supported(const Img &d);
+void launch_transpose_batch(cudaStream_t s, const Img &d, const void *const *in_tab, void *const *out_tab,
+                            int n_images);
 
 // Fused gather segment (kernels/geometry.cuh): n images through the tables in g, or one image.
 void launch_gather_f32(cudaStream_t s, int channels, const mpk::GatherParams &g, int n_images);

@@ -471,6 +471,45 @@ void run_group(mp_pipeline *p, const std::vector<MPObjData *> &objs, const std::
                 if (st != MILLIPYDE_SUCCESS) continue;
             }
         }
+        if (seg.kind == Segment::SINGLE && seg.single->kind == OP_FLIPLR && objs.size() >= 2 && g_fusion.load()) {
+            mp::Img cur;
+            if (mp::describe(objs[0], &cur) && mp::fliplr_batch_supported(cur)) {
+                cudaSetDevice(device);
+                bool handled = false;
+                MPStatus st = run_batched(objs, objs[0]->nbytes, device, s, &handled,
+                                          [&](const float *const *in_tab, float *const *out_tab, int n) {
+                                              mp::launch_fliplr_batch(s, cur, (const void *const *)in_tab,
+                                                                      (void *const *)out_tab, n);
+                                              return MILLIPYDE_SUCCESS;
+                                          });
+                note_status(p, st);
+                if (handled || st != MILLIPYDE_SUCCESS) continue;
+            }
+        }
+        if (seg.kind == Segment::SINGLE && seg.single->kind == OP_TRANSPOSE && objs.size() >= 2 && g_fusion.load()) {
+            mp::Img cur;
+            if (mp::describe(objs[0], &cur) && mp::transpose_batch_supported(cur)) {
+                cudaSetDevice(device);
+                bool handled = false;
+                MPStatus st = run_batched(objs, objs[0]->nbytes, device, s, &handled,
+                                          [&](const float *const *in_tab, float *const *out_tab, int n) {
+                                              mp::launch_transpose_batch(s, cur, (const void *const *)in_tab,
+                                                                         (void *const *)out_tab, n);
+                                              return MILLIPYDE_SUCCESS;
+                                          });
+                note_status(p, st);
+                if (handled) {
+                    const int pix_bytes = cur.C * cur.esize;
+                    for (MPObjData *o : objs) {  // header rewrite of mpimg_transpose
+                        o->dims[0] = cur.W;
+                        o->dims[1] = cur.H;
+                        o->dims[o->ndims] = cur.H * pix_bytes;
+                        o->dims[o->ndims + 1] = pix_bytes;
+                    }
+                }
+                if (handled || st != MILLIPYDE_SUCCESS) continue;
+            }
+        }
         if (seg.kind == Segment::GATHER_F32) {
             mp::Img cur;
             if (mp::describe(objs[0], &cur) && cur.fam == mp::FAM_F32) {

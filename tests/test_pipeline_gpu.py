@@ -90,8 +90,8 @@ def test_fusion_on_off_identical_and_fewer_launches(mp):
         results[fused] = ([d.numpy() for d in dev], ch.last_launches, ch.last_segments)
     mp.lib.mppipe_set_fusion(1)
     assert results[1][2] == 2 and results[0][2] == 6          # segments per group
-    # fused: one batched launch for [brightness, gamma, colorize, grey, brightness], then 4 transposes
-    assert results[1][1] == 1 + 4 and results[0][1] == 6 * 4
+    # fused: one batched launch for [brightness, gamma, colorize, grey, brightness], one for the transposes
+    assert results[1][1] == 2 and results[0][1] == 6 * 4
     for f, u, a in zip(results[1][0], results[0][0], imgs):
         want = so.apply_chain(a, chain)
         assert f.shape == want.shape
