@@ -233,16 +233,18 @@ __global__ void __launch_bounds__(256)
 rotate_bilinear_kernel(const T *__restrict__ in, T *__restrict__ out, int width, int height,
                        RotateParams rp)
 {
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y = blockIdx.y * 8 + threadIdx.y;
+    // a warp covers a 32 x 1 run of output pixels, the block 32 x 8 (measured: 8 x 4 warp patches
+    // are slower here -- the stores dominate and want the long runs)
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= width || y >= height) return;
     const double fx = (double)x - rp.cx, fy = (double)y - rp.cy;
     const double xs = rp.c * fx - rp.s * fy + rp.cx;
     const double ys = rp.s * fx + rp.c * fy + rp.cy;
-    const double xf = floor(xs), yf = floor(ys);
-    const int x0 = (int)xf, y0 = (int)yf;
-    const int x1 = (int)ceil(xs), y1 = (int)ceil(ys);
-    const T dx = (T)(xs - xf), dy = (T)(ys - yf);
+    // floor by cvt.rmi; ceil = floor + (frac > 0); both corner pairs share the fraction
+    const int x0 = __double2int_rd(xs), y0 = __double2int_rd(ys);
+    const T dx = (T)(xs - (double)x0), dy = (T)(ys - (double)y0);
+    const int x1 = x0 + (dx > (T)0), y1 = y0 + (dy > (T)0);
     const bool in_x0 = x0 >= 0 && x0 < width, in_x1 = x1 >= 0 && x1 < width;
     const bool in_y0 = y0 >= 0 && y0 < height, in_y1 = y1 >= 0 && y1 < height;
     const T *r0 = in + (size_t)(in_y0 ? y0 : 0) * width * C;
@@ -277,50 +279,186 @@ namespace mpk {
 // commute with index maps; the rotate's zero fill is applied to the already
 // pre-processed image, so an outside corner contributes 0, not pw_pre(0)).
 // Images of a batch are addressed through pointer tables; blockIdx.z is the image.
+// Tile form: a CTA produces a 32 x 32 output tile.  It first stages the tile's source footprint --
+// the bounding box of the rotated tile, at most 50 x 50 pixels -- in shared memory: every row of
+// the box is one contiguous global segment, so the loads are coalesced no matter the angle (a
+// 32 x 1 run of output pixels walks a rotated line across ~18 cache lines per load instruction,
+// which made the direct gather L1-wavefront-bound).  Outside-image samples are staged as zeros,
+// which IS the rotate's cval = 0 rule.  The four corner reads per output sample hit shared memory.
+//
+// The kernel is issue-bound, so instructions are what is optimised:
+//  * staging moves 16-byte vectors: each box row is copied from the 16-byte-aligned address at or
+//    below its first float, and the row's alignment shift (0..3 floats) is remembered per row;
+//    vectors that straddle the image row's ends take a masked scalar path.  (Maps with a flip
+//    before the rotate, or pointwise ops before it, use the scalar staging loop.)
+//  * source coordinates: one fp64 affine evaluation per thread, then fp64 adds down the column;
+//    floor is cvt.rmi, ceil is "floor + (frac > 0)", the blend runs in fp32.
+constexpr int kGatherTile = 32;
+constexpr int kGatherBox = 50;  // >= 32 * sqrt(2) + 4
+
+template <int C>
+struct GatherGeom {
+    // floats per staged row: box width * C plus up to 3 floats of alignment shift, rounded to a
+    // vector, plus a skew that keeps PITCH % 32 in {4, 20} so rows spread over the banks
+    static constexpr int ROW_MAX = (kGatherBox * C + 3 + 3) / 4 * 4;
+    static constexpr int PITCH = C == 1 ? 68 : (C == 3 ? 164 : 212);
+    static_assert(PITCH >= ROW_MAX && PITCH % 4 == 0, "pitch");
+    static constexpr size_t SMEM = (size_t)kGatherBox * PITCH * sizeof(float) + 64;
+};
+
 template <int C>
 __global__ void __launch_bounds__(256)
 gather_f32_kernel(const __grid_constant__ GatherParams g)
 {
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    if (x >= g.out_w || y >= g.out_h) return;
+    constexpr int PITCH = GatherGeom<C>::PITCH;
+    extern __shared__ __align__(16) float box[];  // [bh][PITCH]
+    int8_t *s_shift = reinterpret_cast<int8_t *>(box + kGatherBox * PITCH);
     const float *__restrict__ src = g.in_tab ? g.in_tab[blockIdx.z] : g.in;
     float *__restrict__ dst = g.out_tab ? g.out_tab[blockIdx.z] : g.out;
+    const int ox0 = blockIdx.x * kGatherTile, oy0 = blockIdx.y * kGatherTile;
+    const int ox1 = min(ox0 + kGatherTile, g.out_w) - 1, oy1 = min(oy0 + kGatherTile, g.out_h) - 1;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 
-    const int qy = g.post.ay * y + g.post.by * x + g.post.cy;
-    const int qx = g.post.ax * y + g.post.bx * x + g.post.cx;
-    float acc[C];
-    auto fetch = [&](int cy, int cx, int c) -> float {
-        const int sy = g.pre.ay * cy + g.pre.by * cx + g.pre.cy;
-        const int sx = g.pre.ax * cy + g.pre.bx * cx + g.pre.cx;
-        return pw_apply<C>(g.pw_pre, __ldg(src + ((size_t)sy * g.src_w + sx) * C + c), c);
-    };
-    if (g.has_rotate) {
-        const double fx = (double)qx - g.rp.cx, fy = (double)qy - g.rp.cy;
-        const double xs = g.rp.c * fx - g.rp.s * fy + g.rp.cx;
-        const double ys = g.rp.s * fx + g.rp.c * fy + g.rp.cy;
-        const double xf = floor(xs), yf = floor(ys);
-        const int x0 = (int)xf, y0 = (int)yf, x1 = (int)ceil(xs), y1 = (int)ceil(ys);
-        const float dx = (float)(xs - xf), dy = (float)(ys - yf);
-        const bool in_x0 = x0 >= 0 && x0 < g.rot_w, in_x1 = x1 >= 0 && x1 < g.rot_w;
-        const bool in_y0 = y0 >= 0 && y0 < g.rot_h, in_y1 = y1 >= 0 && y1 < g.rot_h;
+    // footprint of the tile in the rotate's space (after the post map): the map is affine, so its
+    // extremes are at the tile corners
+    double xmin = 1e30, xmax = -1e30, ymin = 1e30, ymax = -1e30;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const float p00 = (in_y0 && in_x0) ? fetch(y0, x0, c) : 0.f;
-            const float p01 = (in_y0 && in_x1) ? fetch(y0, x1, c) : 0.f;
-            const float p10 = (in_y1 && in_x0) ? fetch(y1, x0, c) : 0.f;
-            const float p11 = (in_y1 && in_x1) ? fetch(y1, x1, c) : 0.f;
-            const float top = (1.f - dx) * p00 + dx * p01;
-            const float bot = (1.f - dx) * p10 + dx * p11;
-            acc[c] = (1.f - dy) * top + dy * bot;
+    for (int k = 0; k < 4; ++k) {
+        const int px = (k & 1) ? ox1 : ox0, py = (k & 2) ? oy1 : oy0;
+        const int qy = g.post.ay * py + g.post.by * px + g.post.cy;
+        const int qx = g.post.ax * py + g.post.bx * px + g.post.cx;
+        double xs = qx, ys = qy;
+        if (g.has_rotate) {
+            const double fx = (double)qx - g.rp.cx, fy = (double)qy - g.rp.cy;
+            xs = g.rp.c * fx - g.rp.s * fy + g.rp.cx;
+            ys = g.rp.s * fx + g.rp.c * fy + g.rp.cy;
+        }
+        xmin = fmin(xmin, xs); xmax = fmax(xmax, xs);
+        ymin = fmin(ymin, ys); ymax = fmax(ymax, ys);
+    }
+    const int bx0 = __double2int_rd(xmin) - 1, by0 = __double2int_rd(ymin) - 1;
+    const int bw = min(__double2int_ru(xmax) + 2 - bx0, kGatherBox);
+    const int bh = min(__double2int_ru(ymax) + 2 - by0, kGatherBox);
+
+    const bool identity_pre = g.pre.ay == 1 && g.pre.by == 0 && g.pre.cy == 0 && g.pre.ax == 0 &&
+                              g.pre.bx == 1 && g.pre.cx == 0 && g.pw_pre.n == 0;
+    if (identity_pre) {
+        // ---- vector staging
+        const int row_floats = bw * C;
+        for (int r = w; r < bh; r += 8) {
+            const int cy = by0 + r;
+            float *brow = box + r * PITCH;
+            const long g0 = ((long)cy * g.src_w + bx0) * C;  // global float index of box column 0
+            const int shift = (int)(g0 & 3);
+            if (lane == 0) s_shift[r] = (int8_t)shift;
+            const long a0 = g0 - shift;
+            const int nvec = (shift + row_floats + 3) >> 2;
+            const bool row_in = cy >= 0 && cy < g.rot_h;
+            const long row_lo = (long)cy * g.src_w * C, row_hi = row_lo + (long)g.src_w * C;
+            float4 v[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int iv = lane + 32 * u;
+                const long gi = a0 + 4 * iv;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (iv < nvec && row_in) {
+                    if (gi >= row_lo && gi + 4 <= row_hi) {
+                        v[u] = __ldg(reinterpret_cast<const float4 *>(src + gi));
+                    } else {
+                        float *e = reinterpret_cast<float *>(&v[u]);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (gi + k >= row_lo && gi + k < row_hi) e[k] = __ldg(src + gi + k);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int iv = lane + 32 * u;
+                if (iv < nvec) *reinterpret_cast<float4 *>(brow + 4 * iv) = v[u];
+            }
         }
     } else {
+        // ---- scalar staging through the pre map (and the pre-rotate pointwise ops)
+        constexpr int PER_LANE = (kGatherBox * C + 31) / 32;
+        const bool has_pre = g.pw_pre.n > 0;
+        const int row_floats = bw * C;
+        for (int r = w; r < bh; r += 8) {
+            const int cy = by0 + r;
+            const bool row_in = cy >= 0 && cy < g.rot_h;
+            float *brow = box + r * PITCH;
+            if (lane == 0) s_shift[r] = 0;
+            float v[PER_LANE];
 #pragma unroll
-        for (int c = 0; c < C; ++c) acc[c] = fetch(qy, qx, c);
+            for (int u = 0; u < PER_LANE; ++u) {
+                const int j = lane + 32 * u;
+                const int cxp = j / C, c = j - cxp * C;
+                const int cx = bx0 + cxp;
+                v[u] = 0.f;
+                if (j < row_floats && row_in && cx >= 0 && cx < g.rot_w) {
+                    const int sy = g.pre.ay * cy + g.pre.by * cx + g.pre.cy;
+                    const int sx = g.pre.ax * cy + g.pre.bx * cx + g.pre.cx;
+                    v[u] = __ldg(src + ((size_t)sy * g.src_w + sx) * C + c);
+                    if (has_pre) v[u] = pw_apply<C>(g.pw_pre, v[u], c);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PER_LANE; ++u) {
+                const int j = lane + 32 * u;
+                if (j < row_floats) brow[j] = v[u];
+            }
+        }
     }
-    float *o = dst + ((size_t)y * g.out_w + x) * C;
+    __syncthreads();
+
+    const int x = ox0 + lane;
+    if (x >= g.out_w) return;
+    // output pixel (x, y): q = post(x, y); stepping y by 8 moves q by 8 * (post.ay, post.ax)
+    const int y_first = oy0 + w;
+    int qy = g.post.ay * y_first + g.post.by * x + g.post.cy;
+    int qx = g.post.ax * y_first + g.post.bx * x + g.post.cx;
+    const int dqy = 8 * g.post.ay, dqx = 8 * g.post.ax;
+    double xs = qx, ys = qy, dxs = dqx, dys = dqy;
+    if (g.has_rotate) {
+        const double fx = (double)qx - g.rp.cx, fy = (double)qy - g.rp.cy;
+        xs = g.rp.c * fx - g.rp.s * fy + g.rp.cx;
+        ys = g.rp.s * fx + g.rp.c * fy + g.rp.cy;
+        dxs = g.rp.c * dqx - g.rp.s * dqy;
+        dys = g.rp.s * dqx + g.rp.c * dqy;
+    }
 #pragma unroll
-    for (int c = 0; c < C; ++c) o[c] = pw_apply<C>(g.pw_post, acc[c], c);
+    for (int k = 0; k < kGatherTile / 8; ++k) {
+        const int y = y_first + 8 * k;
+        if (y >= g.out_h) break;
+        // recomputing from k keeps every row one rounding away from the direct formula
+        const double xk = xs + k * dxs, yk = ys + k * dys;
+        float acc[C];
+        if (g.has_rotate) {
+            const int ix = __double2int_rd(xk), iy = __double2int_rd(yk);
+            const float dx = (float)(xk - (double)ix), dy = (float)(yk - (double)iy);
+            const int x0 = ix - bx0, y0 = iy - by0;
+            const int x1 = x0 + (dx > 0.f), y1 = y0 + (dy > 0.f);
+            const float *r0 = box + y0 * PITCH + s_shift[y0];
+            const float *r1 = box + y1 * PITCH + s_shift[y1];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float p00 = r0[x0 * C + c], p01 = r0[x1 * C + c];
+                const float p10 = r1[x0 * C + c], p11 = r1[x1 * C + c];
+                const float top = (1.f - dx) * p00 + dx * p01;
+                const float bot = (1.f - dx) * p10 + dx * p11;
+                acc[c] = (1.f - dy) * top + dy * bot;
+            }
+        } else {
+            const int yy = qy + k * dqy - by0, xx = qx + k * dqx - bx0;
+            const float *r0 = box + yy * PITCH + s_shift[yy] + xx * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = r0[c];
+        }
+        pw_apply_tile<C, C>(g.pw_post, acc, 0);
+        float *o = dst + ((size_t)y * g.out_w + x) * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) o[c] = acc[c];
+    }
 }
 
 }  // namespace mpk

@@ -345,13 +345,13 @@ MPStatus mpimg_rotate(MPObjData *obj, void *args)
         RotateParams rp = mp::rotate_params(d.W, d.H, angle);
         dim3 block(32, 8), grid((d.W + 31) / 32, (d.H + 7) / 8);
         if (d.fam == mp::FAM_F64)
-            rotate_bilinear_kernel<double, 1><<<grid, block, 0, s>>>((const double *)obj->device_data, (double *)out, d.W, d.H, rp);
+            rotate_bilinear_kernel<double, 1><<<grid, 256, 0, s>>>((const double *)obj->device_data, (double *)out, d.W, d.H, rp);
         else if (d.C == 1)
-            rotate_bilinear_kernel<float, 1><<<grid, block, 0, s>>>((const float *)obj->device_data, (float *)out, d.W, d.H, rp);
+            rotate_bilinear_kernel<float, 1><<<grid, 256, 0, s>>>((const float *)obj->device_data, (float *)out, d.W, d.H, rp);
         else if (d.C == 3)
-            rotate_bilinear_kernel<float, 3><<<grid, block, 0, s>>>((const float *)obj->device_data, (float *)out, d.W, d.H, rp);
+            rotate_bilinear_kernel<float, 3><<<grid, 256, 0, s>>>((const float *)obj->device_data, (float *)out, d.W, d.H, rp);
         else
-            rotate_bilinear_kernel<float, 4><<<grid, block, 0, s>>>((const float *)obj->device_data, (float *)out, d.W, d.H, rp);
+            rotate_bilinear_kernel<float, 4><<<grid, 256, 0, s>>>((const float *)obj->device_data, (float *)out, d.W, d.H, rp);
     }
     mp::count_launch();
     return finish(obj, s, out, obj->nbytes);
@@ -694,10 +694,18 @@ namespace mp {
 
 void launch_gather_f32(cudaStream_t s, int channels, const GatherParams &g, int n_images)
 {
-    dim3 block(32, 8), grid((g.out_w + 31) / 32, (g.out_h + 7) / 8, n_images);
-    if (channels == 1) gather_f32_kernel<1><<<grid, block, 0, s>>>(g);
-    else if (channels == 3) gather_f32_kernel<3><<<grid, block, 0, s>>>(g);
-    else gather_f32_kernel<4><<<grid, block, 0, s>>>(g);
+    dim3 grid((g.out_w + kGatherTile - 1) / kGatherTile, (g.out_h + kGatherTile - 1) / kGatherTile, n_images);
+    const size_t smem = channels == 1 ? GatherGeom<1>::SMEM : (channels == 3 ? GatherGeom<3>::SMEM : GatherGeom<4>::SMEM);
+    static bool configured = false;
+    if (!configured) {  // 40 KB for C = 4 is under the 48 KB default; set anyway so a larger box stays legal
+        cudaFuncSetAttribute(gather_f32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(gather_f32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(gather_f32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        configured = true;
+    }
+    if (channels == 1) gather_f32_kernel<1><<<grid, 256, smem, s>>>(g);
+    else if (channels == 3) gather_f32_kernel<3><<<grid, 256, smem, s>>>(g);
+    else gather_f32_kernel<4><<<grid, 256, smem, s>>>(g);
     count_launch();
 }
 
