@@ -28,8 +28,12 @@
 
 namespace mpk {
 
-constexpr int kWsRowWarps = kGsQ;             // 10
-constexpr int kWsColWarps = kGsQ;             // 10: 320 threads x 2 columns = 640 floats
+// ROW warps = rows per group.  10:10 with the COLUMN warps is what the register file allows: 21
+// warps put 6 on one SM sub-partition (16 K registers each), which caps a thread at 80 registers
+// and spills the row pass (measured: 11:10 at 80 registers is 8 % slower than 10:10 at 91).
+constexpr int kWsRows = 10;
+constexpr int kWsRowWarps = kWsRows;
+constexpr int kWsColWarps = kGsTW / 64;       // 10: 320 threads x 2 columns = 640 floats
 constexpr int kWsThreads = 32 * (kWsRowWarps + kWsColWarps);
 constexpr int kWsInSlots = 4;                 // rows in flight per ROW warp
 constexpr int kWsGroups = 4;                  // filtered groups in flight between the roles
@@ -39,7 +43,7 @@ struct WsGeom {
     static constexpr int HALO = GsGeom<C, R>::HALO;
     static constexpr int ROW = GsGeom<C, R>::ROW;
     static constexpr size_t IN_BYTES = (size_t)kWsRowWarps * kWsInSlots * ROW * 4;
-    static constexpr size_t H_BYTES = (size_t)kWsGroups * kGsQ * kGsTW * 4;
+    static constexpr size_t H_BYTES = (size_t)kWsGroups * kWsRows * kGsTW * 4;
     static constexpr int N_BARS = kWsRowWarps * kWsInSlots + 2 * kWsGroups;
     static constexpr size_t SMEM = IN_BYTES + H_BYTES + 8 * N_BARS + 64;
 };
@@ -148,7 +152,7 @@ gauss_stream_ws_kernel(const __grid_constant__ GaussStreamParams p)
             const int y1 = min(p.height, y0 + p.chunk_rows);
             const int r_begin = y0 - R;
             const int n_rows = (y1 - y0) + 2 * R;
-            const int n_steps = (n_rows + kGsQ - 1) / kGsQ;
+            const int n_steps = (n_rows + kWsRows - 1) / kWsRows;
             const int gx_start = x0 - G::HALO;
             const int lo = gx_start < 0 ? -gx_start : 0;
             const int hi = min(G::ROW, p.row_elems - gx_start);
@@ -169,12 +173,12 @@ gauss_stream_ws_kernel(const __grid_constant__ GaussStreamParams p)
             // pointer and two compares.
             const int r_first = r_begin + warp;
             const int r_end = min(p.height, r_begin + n_rows);
-            int live_lo = r_first < 0 ? (-r_first + kGsQ - 1) / kGsQ : 0;
-            int live_hi = r_end > r_first ? (r_end - r_first + kGsQ - 1) / kGsQ : 0;
+            int live_lo = r_first < 0 ? (-r_first + kWsRows - 1) / kWsRows : 0;
+            int live_hi = r_end > r_first ? (r_end - r_first + kWsRows - 1) / kWsRows : 0;
             if (live_hi > n_steps) live_hi = n_steps;
             if (live_lo > live_hi) live_lo = live_hi;
-            const float *gptr = src + (long)(r_first + live_lo * kGsQ) * p.row_elems + gx_start + lo;
-            const long gstep = (long)kGsQ * p.row_elems;
+            const float *gptr = src + (long)(r_first + live_lo * kWsRows) * p.row_elems + gx_start + lo;
+            const long gstep = (long)kWsRows * p.row_elems;
             int next_issue = live_lo;  // next live step to issue
 
             auto issue_next = [&]() {  // all lanes keep the counters; lane 0 talks to the TMA unit
@@ -208,7 +212,7 @@ gauss_stream_ws_kernel(const __grid_constant__ GaussStreamParams p)
                 // hand-off ring: wait until the COLUMN warps have drained this group slot
                 const uint32_t gs = group % kWsGroups;
                 mbar_wait(&h_empty[gs], ((group / kWsGroups) & 1u) ^ 1u);
-                float *hrow = hbase + (size_t)gs * (kGsQ * kGsTW);
+                float *hrow = hbase + (size_t)gs * (kWsRows * kGsTW);
 #pragma unroll
                 for (int v = 0; v < kGsPH / 4; ++v)
                     *reinterpret_cast<float4 *>(hrow + 4 * v) =
@@ -239,7 +243,7 @@ gauss_stream_ws_kernel(const __grid_constant__ GaussStreamParams p)
             const int y0 = chunk * p.chunk_rows;
             const int y1 = min(p.height, y0 + p.chunk_rows);
             const int n_rows = (y1 - y0) + 2 * R;
-            const int n_steps = (n_rows + kGsQ - 1) / kGsQ;
+            const int n_steps = (n_rows + kWsRows - 1) / kWsRows;
             // rows [y0, y1) of columns gx, gx+1; the first filtered row completes output row y0 - 2R
             const unsigned n_valid = gx < p.row_elems ? (unsigned)(y1 - y0) : 0u;
             float *base = p.out_tab ? p.out_tab[img] : p.out + (size_t)img * p.image_stride;
@@ -249,9 +253,9 @@ gauss_stream_ws_kernel(const __grid_constant__ GaussStreamParams p)
             for (int step = 0; step < n_steps; ++step) {
                 const uint32_t gs = group % kWsGroups;
                 mbar_wait(&h_full[gs], (group / kWsGroups) & 1u);
-                const float *hrow = s_h + (size_t)gs * kGsQ * kGsTW + 2 * vt;
+                const float *hrow = s_h + (size_t)gs * kWsRows * kGsTW + 2 * vt;
 #pragma unroll
-                for (int q = 0; q < kGsQ; ++q) {
+                for (int q = 0; q < kWsRows; ++q) {
                     const uint64_t v = *reinterpret_cast<const uint64_t *>(hrow + q * kGsTW);
                     const uint64_t o = ffma2(p.ww[R], v, A[0]);
 #pragma unroll

@@ -21,9 +21,14 @@ def _free_port():
 
 
 def _torchrun(nproc, script_args, timeout=600):
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
-           "--master-addr", "127.0.0.1", "--master-port", str(_free_port())] + script_args
-    return subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+    r = None
+    for _ in range(3):      # the probed port can be taken between the probe and the rendezvous: retry
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+               "--master-addr", "127.0.0.1", "--master-port", str(_free_port())] + script_args
+        r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+        if r.returncode == 0:
+            break
+    return r
 
 
 @pytest.mark.timeout(900)
