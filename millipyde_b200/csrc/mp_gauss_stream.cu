@@ -6,8 +6,6 @@
 // (effective radius 11) lands exactly on a bucket.
 #include <cstring>
 
-#include <cstdlib>
-
 #include "kernels/gaussian_stream.cuh"
 #include "kernels/gaussian_stream_ws.cuh"
 #include "mp_internal.h"
@@ -31,49 +29,27 @@ bool gauss_stream_supported(int W, int C, int radius)
     return ((size_t)W * C) % 4 == 0 && (size_t)W * C >= 64 && bucket_for(radius) != 0;
 }
 
-// MILLIPYDE_GAUSS_KERNEL=v2 selects the barrier-per-step kernel (kept for A/B runs);
-// the default is the warp-specialised one.
-static bool use_ws()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("MILLIPYDE_GAUSS_KERNEL");
-        v = (e && strcmp(e, "v2") == 0) ? 0 : 1;
-    }
-    return v == 1;
-}
-
 template <int C, int R>
 static MPStatus launch_cr(int device, cudaStream_t s, GaussStreamParams &p)
 {
-    const bool ws = use_ws();
     const int sms = sm_count(device) ? sm_count(device) : 148;
-    const int ctas_per_sm = ws ? 1 : 2;
-    const size_t smem = ws ? WsGeom<C, R>::SMEM : GsGeom<C, R>::SMEM;
-    static bool configured[2][64] = {};  // per kernel flavour, per device
-    if (device >= 0 && device < 64 && !configured[ws][device]) {
-        if (ws)
-            MP_CUDA_TRY(cudaFuncSetAttribute(gauss_stream_ws_kernel<C, R>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else
-            MP_CUDA_TRY(cudaFuncSetAttribute(gauss_stream_kernel<C, R>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[ws][device] = true;
+    const size_t smem = WsGeom<C, R>::SMEM;
+    static bool configured[64] = {};  // per device
+    if (device >= 0 && device < 64 && !configured[device]) {
+        MP_CUDA_TRY(cudaFuncSetAttribute(gauss_stream_ws_kernel<C, R>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[device] = true;
     }
-    // Row chunks only when the batch alone cannot fill the machine: every extra
-    // chunk re-filters 2R rows.
-    const int slots = ctas_per_sm * sms;
+    // One persistent CTA per SM.  Row chunks only when the batch alone cannot fill the machine:
+    // every extra chunk re-filters 2R rows.
     long items = (long)p.n_images * p.n_strips;
     int chunks = 1;
-    while (items * chunks < 2L * slots && p.height / (chunks * 2) >= 8 * R) chunks *= 2;
+    while (items * chunks < 2L * sms && p.height / (chunks * 2) >= 8 * R) chunks *= 2;
     p.n_chunks = chunks;
     p.chunk_rows = (p.height + chunks - 1) / chunks;
     items *= chunks;
-    const int grid = (int)(items < slots ? items : slots);
-    if (ws)
-        gauss_stream_ws_kernel<C, R><<<grid, kWsThreads, smem, s>>>(p);
-    else
-        gauss_stream_kernel<C, R><<<grid, kGsThreads, smem, s>>>(p);
+    const int grid = (int)(items < sms ? items : sms);
+    gauss_stream_ws_kernel<C, R><<<grid, kWsThreads, smem, s>>>(p);
     count_launch();
     return MILLIPYDE_SUCCESS;
 }

@@ -343,7 +343,7 @@ MPStatus mpimg_rotate(MPObjData *obj, void *args)
             rotate_nearest_kernel<2><<<grid, block, 0, s>>>((const uint32_t *)obj->device_data, (uint32_t *)out, d.W, d.H, rad);
     } else {
         RotateParams rp = mp::rotate_params(d.W, d.H, angle);
-        dim3 block(32, 8), grid((d.W + 31) / 32, (d.H + 7) / 8);
+        dim3 grid((d.W + 31) / 32, (d.H + 7) / 8);
         if (d.fam == mp::FAM_F64)
             rotate_bilinear_kernel<double, 1><<<grid, 256, 0, s>>>((const double *)obj->device_data, (double *)out, d.W, d.H, rp);
         else if (d.C == 1)
@@ -632,6 +632,32 @@ MPStatus launch_gaussian(int device, cudaStream_t s, const Img &d, const void *i
         const int R = 8, tile = 32;
         size_t smem = ((size_t)(tile + 2 * R) * (tile + 2 * R) + (size_t)(tile + 2 * R) * tile) * 4;
         dim3 grid((d.W + tile - 1) / tile, (d.H + tile - 1) / tile);
+        // exact integer form, if every (byte, weight) product agrees with the double rule
+        GaussU8Params ip = {};
+        ip.radius = R;
+        bool exact = true;
+        for (int k = 0; k <= R && exact; ++k) {
+            const double w = gp.w[k];
+            bool found = false;
+            const double scaled = w * 4294967296.0;
+            for (int bump = 0; bump <= 1 && !found; ++bump) {
+                if (!(scaled >= 0 && scaled < 4294967295.0)) break;
+                const uint32_t m = (uint32_t)scaled + (uint32_t)bump;
+                bool ok = true;
+                for (uint32_t b = 0; b < 256 && ok; ++b)
+                    ok = (uint32_t)(((uint64_t)b * m) >> 32) == (uint32_t)(int)(b * w);
+                if (ok) {
+                    ip.m[k] = m;
+                    found = true;
+                }
+            }
+            exact = found;
+        }
+        if (exact) {
+            gauss_rgba8_int_kernel<<<grid, 256, smem, s>>>((const uint32_t *)in, (uint32_t *)out, d.W, d.H, tile, tile, ip);
+            count_launch();
+            return MILLIPYDE_SUCCESS;
+        }
         gauss_rgba8_tile_kernel<<<grid, 256, smem, s>>>((const uint32_t *)in, (uint32_t *)out, d.W, d.H, tile, tile, gp);
         count_launch();
         return MILLIPYDE_SUCCESS;
