@@ -224,10 +224,15 @@ def run_reference(args, dist):
 # --------------------------------------------------------------------------- B200 arm
 def run_b200(args, dist):
     import numpy as np
+    physical_gpu = 0
+    outer = [x for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip() != ""]
     if dist.world > 1:
         # one rank per GPU: this process only ever sees its own device
-        os.environ["CUDA_VISIBLE_DEVICES"] = os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[dist.local] \
-            if os.environ.get("CUDA_VISIBLE_DEVICES") else str(dist.local)
+        mine = outer[dist.local] if len(outer) > dist.local else str(dist.local)
+        os.environ["CUDA_VISIBLE_DEVICES"] = mine
+        physical_gpu = int(mine) if mine.isdigit() else dist.local
+    elif outer and outer[0].isdigit():
+        physical_gpu = int(outer[0])
     from millipyde_b200 import capi
     from millipyde_b200 import engine
 
@@ -271,7 +276,7 @@ def run_b200(args, dist):
         # the public batch call: one Pipeline-style run per device shard
         engine.run_batches(pipe, shards, devices)
 
-    sampler = ClockSampler(dist.local if dist.world > 1 else 0)
+    sampler = ClockSampler(physical_gpu)
     sampler.start()
     t_warm = time.time()
     while True:     # >= W warm-up steps and long enough for the clock sampler to come up
@@ -324,7 +329,16 @@ def run_b200(args, dist):
     if args.no_e2e:
         e2e = {"images_per_s": 0.0, "h2d_bytes": 0, "d2h_bytes": 0, "images": 0}
     else:
-        e2e = engine.e2e_gaussian(devices, args.e2e_images, (H, W, C), SIGMA, steps=max(2, min(args.steps, 3)))
+        # page-locked staging is 2 x 99.5 MB per image per rank: keep the whole job's pinned set bounded
+        n_e2e = args.e2e_images if dist.world <= 2 else max(8, args.e2e_images // 2)
+        e2e = None
+        while e2e is None:
+            try:
+                e2e = engine.e2e_gaussian(devices, n_e2e, (H, W, C), SIGMA, steps=max(2, min(args.steps, 3)))
+            except MemoryError:
+                if n_e2e <= 2:
+                    raise
+                n_e2e //= 2
     e2e_value = dist.sum(e2e["images_per_s"])
 
     line = {

@@ -635,13 +635,14 @@ static PyObject *generator_next(MPGeneratorObject *g)
         return r;
     }
     if (PyList_Size(g->ready) == 0) {
-        /* default look-ahead: one block per device when spreading, else a single item (so a
-         * consumer that stops early has not paid for work it never sees) */
+        /* default look-ahead: one block of THREADS_PER_DEVICE items per device when spreading, two
+         * blocks on a single device -- enough for the executor to batch and overlap, small enough
+         * that a consumer that stops early has paid for at most a few items it never sees */
         long want = g->prefetch;
         if (want <= 0)
             want = (generator_device(g) == DEVICE_LOC_NO_AFFINITY && mpdev_get_device_count() > 1)
                        ? (long)THREADS_PER_DEVICE * mpdev_get_device_count()
-                       : 1;
+                       : 2L * THREADS_PER_DEVICE;
         if (g->max != NO_OUTPUT_MAX && g->produced + want > g->max) want = g->max - g->produced;
         if (want < 1) want = 1;
         if (produce_batch(g, want) < 0) return NULL;
