@@ -14,6 +14,12 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "timeout: per-test time limit (pytest-timeout)")
+    # The native pieces are build artefacts (git-ignored): build them if a fresh checkout has none.
+    # nvcc cross-compiles sm_100a without a GPU; on the GPU box the snapshot already carries them.
+    from millipyde_b200 import build as _build
+    if not (os.path.exists(_build.LIB) and os.path.exists(_build.EXT)):
+        _build.build_all(force=False, verbose=False)
 
 
 @pytest.fixture(scope="session")
