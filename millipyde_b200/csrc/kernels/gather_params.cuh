@@ -8,6 +8,13 @@ struct IndexMap {  // (y', x') = (ay*y + by*x + cy, ax*y + bx*x + cx)
     int ay, by, cy, ax, bx, cx;
 };
 
+// What differs between the images of one batched gather launch when the chain draws random
+// parameters: the angle and the pointwise programs (device memory, one record per image).
+struct GatherVar {
+    RotateParams rp;
+    PwProgram pw_pre, pw_post;
+};
+
 struct GatherParams {
     const float *const *in_tab;
     float *const *out_tab;
@@ -20,6 +27,7 @@ struct GatherParams {
     int has_rotate;
     RotateParams rp;
     PwProgram pw_pre, pw_post;
+    const GatherVar *var_tab;  // per-image records (kernel template TAB = true), else null
 };
 
 

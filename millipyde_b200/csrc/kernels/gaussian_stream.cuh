@@ -36,6 +36,16 @@ struct GaussStreamParams {
     unsigned long long ww[16];   // (w[d], w[d]) packed for fma.rn.f32x2
 };
 
+// Per-image weight sets of a batched launch whose images share the radius bucket but not sigma
+// (Generator streams with random_gaussian).  The table travels in the kernel parameter block, i.e.
+// the constant bank: the image index of a work item is warp-uniform, so the weights still reach the
+// FFMA2s as uniform-register operands.  Image i uses set i % kGsMaxSets (the launcher sends at most
+// kGsMaxSets images per launch when the sets differ).
+constexpr int kGsMaxSets = 64;
+struct GaussWeightSets {
+    unsigned long long ww[kGsMaxSets][14];  // (w[d], w[d]) for d = 0..13
+};
+
 // ---- packed fp32x2 arithmetic (SASS FFMA2 / FMUL2): one issue slot, two FMAs ----
 __device__ __forceinline__ uint64_t pack2(float lo, float hi)
 {

@@ -57,9 +57,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 // A[m] = outputs (2m, 2m+1) fed by taps with an even offset k*C; B[m] = outputs
 // (2m-1, 2m) fed by taps with an odd offset.  Either way the operand is the aligned
 // pair (x[2j], x[2j+1]) as loaded.  out[i] = A-part + B-part.
-template <int C, int R>
-__device__ __forceinline__ void ws_row_pass(const float *__restrict__ win, float (&out)[kGsPH],
-                                            const GaussStreamParams &p)
+// `W` is a small accessor whose operator()(d) yields the packed weight pair of distance d from the
+// constant bank (WsOneSet: the launch's single set; WsSetOf: the work item's image's set).
+struct WsOneSet {
+    const GaussStreamParams &p;
+    __device__ __forceinline__ uint64_t operator()(int d) const { return p.ww[d]; }
+};
+struct WsSetOf {
+    const GaussWeightSets &ws;
+    int set;
+    __device__ __forceinline__ uint64_t operator()(int d) const { return ws.ww[set][d]; }
+};
+
+template <int C, int R, typename W>
+__device__ __forceinline__ void ws_row_pass(const float *__restrict__ win, float (&out)[kGsPH], const W &w)
 {
     constexpr int HALO = GsGeom<C, R>::HALO;
     constexpr int NV = (kGsPH + 2 * HALO) / 4;
@@ -81,10 +92,10 @@ __device__ __forceinline__ void ws_row_pass(const float *__restrict__ win, float
                 const int kc = k * C;
                 const int i0 = 2 * j - HALO - kc;  // output fed by the pair's low half
                 if ((kc & 1) == 0) {
-                    if (i0 >= 0 && i0 < kGsPH) A[i0 / 2] = ffma2(p.ww[k < 0 ? -k : k], e[u], A[i0 / 2]);
+                    if (i0 >= 0 && i0 < kGsPH) A[i0 / 2] = ffma2(w(k < 0 ? -k : k), e[u], A[i0 / 2]);
                 } else {
                     // i0 is odd: the pair feeds outputs (i0, i0 + 1) = B[(i0 + 1) / 2]
-                    if (i0 >= -1 && i0 < kGsPH) B[(i0 + 1) / 2] = ffma2(p.ww[k < 0 ? -k : k], e[u], B[(i0 + 1) / 2]);
+                    if (i0 >= -1 && i0 < kGsPH) B[(i0 + 1) / 2] = ffma2(w(k < 0 ? -k : k), e[u], B[(i0 + 1) / 2]);
                 }
             }
         }
@@ -107,9 +118,8 @@ __device__ __forceinline__ void ws_row_pass(const float *__restrict__ win, float
     }
 }
 
-template <int C, int R>
-__global__ void __launch_bounds__(kWsThreads, 1)
-gauss_stream_ws_kernel(const __grid_constant__ GaussStreamParams p)
+template <int C, int R, bool SETS>
+__device__ __forceinline__ void ws_body(const GaussStreamParams &p, const GaussWeightSets &ws)
 {
     using G = WsGeom<C, R>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -142,11 +152,16 @@ gauss_stream_ws_kernel(const __grid_constant__ GaussStreamParams p)
         uint32_t takes = 0;   // rows consumed so far
         uint32_t group = 0;   // groups produced so far (ring slot and parity)
 
-        for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int img = (int)(item / items_per_image);
-            const int rem = (int)(item - (long)img * items_per_image);
+        int img = 0, rem = (int)blockIdx.x;  // item = img * items_per_image + rem, kept by add/compare only
+        for (long item = blockIdx.x; item < n_items; item += gridDim.x, rem += (int)gridDim.x) {
+            while (rem >= items_per_image) {
+                rem -= items_per_image;
+                ++img;
+            }
             const int chunk = rem / p.n_strips, strip = rem - chunk * p.n_strips;
             const float *__restrict__ src = p.in_tab ? p.in_tab[img] : p.in + (size_t)img * p.image_stride;
+            const WsSetOf w_img{ws, img % kGsMaxSets};
+            const WsOneSet w_one{p};
             const int x0 = strip * kGsTW;
             const int y0 = chunk * p.chunk_rows;
             const int y1 = min(p.height, y0 + p.chunk_rows);
@@ -204,7 +219,8 @@ gauss_stream_ws_kernel(const __grid_constant__ GaussStreamParams p)
                     const uint32_t slot = takes % kWsInSlots;
                     mbar_wait(&my_full[slot], (takes / kWsInSlots) & 1u);
                     ++takes;
-                    ws_row_pass<C, R>(my_in + (size_t)slot * G::ROW + lane * kGsPH, out, p);
+                    if (SETS) ws_row_pass<C, R>(my_in + (size_t)slot * G::ROW + lane * kGsPH, out, w_img);
+                    else ws_row_pass<C, R>(my_in + (size_t)slot * G::ROW + lane * kGsPH, out, w_one);
                 } else {
 #pragma unroll
                     for (int i = 0; i < kGsPH; ++i) out[i] = 0.f;
@@ -235,9 +251,12 @@ gauss_stream_ws_kernel(const __grid_constant__ GaussStreamParams p)
         for (int i = 0; i < 2 * R; ++i) A[i] = 0ull;
         uint32_t group = 0;
 
-        for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int img = (int)(item / items_per_image);
-            const int rem = (int)(item - (long)img * items_per_image);
+        int img = 0, rem = (int)blockIdx.x;
+        for (long item = blockIdx.x; item < n_items; item += gridDim.x, rem += (int)gridDim.x) {
+            while (rem >= items_per_image) {
+                rem -= items_per_image;
+                ++img;
+            }
             const int chunk = rem / p.n_strips, strip = rem - chunk * p.n_strips;
             const int gx = strip * kGsTW + 2 * vt;
             const int y0 = chunk * p.chunk_rows;
@@ -247,6 +266,8 @@ gauss_stream_ws_kernel(const __grid_constant__ GaussStreamParams p)
             // rows [y0, y1) of columns gx, gx+1; the first filtered row completes output row y0 - 2R
             const unsigned n_valid = gx < p.row_elems ? (unsigned)(y1 - y0) : 0u;
             float *base = p.out_tab ? p.out_tab[img] : p.out + (size_t)img * p.image_stride;
+            const int set = SETS ? img % kGsMaxSets : 0;
+            auto w = [&](int d) -> uint64_t { return SETS ? ws.ww[set][d] : p.ww[d]; };
             float *optr = base + ((long)y0 - 2 * R) * p.row_elems + gx;  // only dereferenced when valid
             unsigned rel = (unsigned)(-2 * R);                            // output row - y0, wraps below 0
 
@@ -257,10 +278,10 @@ gauss_stream_ws_kernel(const __grid_constant__ GaussStreamParams p)
 #pragma unroll
                 for (int q = 0; q < kWsRows; ++q) {
                     const uint64_t v = *reinterpret_cast<const uint64_t *>(hrow + q * kGsTW);
-                    const uint64_t o = ffma2(p.ww[R], v, A[0]);
+                    const uint64_t o = ffma2(w(R), v, A[0]);
 #pragma unroll
-                    for (int j = 1; j < 2 * R; ++j) A[j - 1] = ffma2(p.ww[j < R ? R - j : j - R], v, A[j]);
-                    A[2 * R - 1] = fmul2(p.ww[R], v);
+                    for (int j = 1; j < 2 * R; ++j) A[j - 1] = ffma2(w(j < R ? R - j : j - R), v, A[j]);
+                    A[2 * R - 1] = fmul2(w(R), v);
                     if (rel < n_valid) {
                         float o_lo, o_hi;
                         unpack2(o, o_lo, o_hi);
@@ -275,6 +296,22 @@ gauss_stream_ws_kernel(const __grid_constant__ GaussStreamParams p)
             }
         }
     }
+}
+
+template <int C, int R>
+__global__ void __launch_bounds__(kWsThreads, 1)
+gauss_stream_ws_kernel(const __grid_constant__ GaussStreamParams p)
+{
+    // one weight set for the whole launch; the reference below is never read
+    ws_body<C, R, false>(p, *reinterpret_cast<const GaussWeightSets *>(&p));
+}
+
+// Same kernel, weights per image (see GaussWeightSets).
+template <int C, int R>
+__global__ void __launch_bounds__(kWsThreads, 1)
+gauss_stream_ws_sets_kernel(const __grid_constant__ GaussStreamParams p, const __grid_constant__ GaussWeightSets ws)
+{
+    ws_body<C, R, true>(p, ws);
 }
 
 }  // namespace mpk

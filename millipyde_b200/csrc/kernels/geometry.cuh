@@ -231,8 +231,14 @@ rotate_nearest_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
 template <typename T, int C>
 __global__ void __launch_bounds__(256)
 rotate_bilinear_kernel(const T *__restrict__ in, T *__restrict__ out, int width, int height,
-                       RotateParams rp)
+                       RotateParams rp, const T *const *__restrict__ in_tab = nullptr,
+                       T *const *__restrict__ out_tab = nullptr, const RotateParams *__restrict__ rp_tab = nullptr)
 {
+    if (in_tab) {  // batched launch: blockIdx.z selects the image and, if given, its own angle
+        in = in_tab[blockIdx.z];
+        out = out_tab[blockIdx.z];
+        if (rp_tab) rp = rp_tab[blockIdx.z];
+    }
     // a warp covers a 32 x 1 run of output pixels, the block 32 x 8 (measured: 8 x 4 warp patches
     // are slower here -- the stores dominate and want the long runs)
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -306,13 +312,24 @@ struct GatherGeom {
     static constexpr size_t SMEM = (size_t)kGatherBox * PITCH * sizeof(float) + 64;
 };
 
-template <int C>
+template <int C, bool TAB = false>
 __global__ void __launch_bounds__(256)
 gather_f32_kernel(const __grid_constant__ GatherParams g)
 {
     constexpr int PITCH = GatherGeom<C>::PITCH;
     extern __shared__ __align__(16) float box[];  // [bh][PITCH]
     int8_t *s_shift = reinterpret_cast<int8_t *>(box + kGatherBox * PITCH);
+    // TAB: the angle and the pointwise programs are the image's own (GatherVar record in device
+    // memory, copied to shared memory once per block); everything else is common to the launch
+    __shared__ GatherVar s_var;
+    if (TAB) {
+        for (int i = threadIdx.x; i < (int)(sizeof(GatherVar) / 4); i += blockDim.x)
+            reinterpret_cast<int *>(&s_var)[i] = reinterpret_cast<const int *>(g.var_tab + blockIdx.z)[i];
+        __syncthreads();
+    }
+    const RotateParams &rp = TAB ? s_var.rp : g.rp;
+    const PwProgram &pw_pre = TAB ? s_var.pw_pre : g.pw_pre;
+    const PwProgram &pw_post = TAB ? s_var.pw_post : g.pw_post;
     const float *__restrict__ src = g.in_tab ? g.in_tab[blockIdx.z] : g.in;
     float *__restrict__ dst = g.out_tab ? g.out_tab[blockIdx.z] : g.out;
     const int ox0 = blockIdx.x * kGatherTile, oy0 = blockIdx.y * kGatherTile;
@@ -329,9 +346,9 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
         const int qx = g.post.ax * py + g.post.bx * px + g.post.cx;
         double xs = qx, ys = qy;
         if (g.has_rotate) {
-            const double fx = (double)qx - g.rp.cx, fy = (double)qy - g.rp.cy;
-            xs = g.rp.c * fx - g.rp.s * fy + g.rp.cx;
-            ys = g.rp.s * fx + g.rp.c * fy + g.rp.cy;
+            const double fx = (double)qx - rp.cx, fy = (double)qy - rp.cy;
+            xs = rp.c * fx - rp.s * fy + rp.cx;
+            ys = rp.s * fx + rp.c * fy + rp.cy;
         }
         xmin = fmin(xmin, xs); xmax = fmax(xmax, xs);
         ymin = fmin(ymin, ys); ymax = fmax(ymax, ys);
@@ -341,7 +358,7 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
     const int bh = min(__double2int_ru(ymax) + 2 - by0, kGatherBox);
 
     const bool identity_pre = g.pre.ay == 1 && g.pre.by == 0 && g.pre.cy == 0 && g.pre.ax == 0 &&
-                              g.pre.bx == 1 && g.pre.cx == 0 && g.pw_pre.n == 0;
+                              g.pre.bx == 1 && g.pre.cx == 0 && pw_pre.n == 0;
     if (identity_pre) {
         // ---- vector staging
         const int row_floats = bw * C;
@@ -381,7 +398,7 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
     } else {
         // ---- scalar staging through the pre map (and the pre-rotate pointwise ops)
         constexpr int PER_LANE = (kGatherBox * C + 31) / 32;
-        const bool has_pre = g.pw_pre.n > 0;
+        const bool has_pre = pw_pre.n > 0;
         const int row_floats = bw * C;
         for (int r = w; r < bh; r += 8) {
             const int cy = by0 + r;
@@ -399,7 +416,7 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
                     const int sy = g.pre.ay * cy + g.pre.by * cx + g.pre.cy;
                     const int sx = g.pre.ax * cy + g.pre.bx * cx + g.pre.cx;
                     v[u] = __ldg(src + ((size_t)sy * g.src_w + sx) * C + c);
-                    if (has_pre) v[u] = pw_apply<C>(g.pw_pre, v[u], c);
+                    if (has_pre) v[u] = pw_apply<C>(pw_pre, v[u], c);
                 }
             }
 #pragma unroll
@@ -420,11 +437,11 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
     const int dqy = 8 * g.post.ay, dqx = 8 * g.post.ax;
     double xs = qx, ys = qy, dxs = dqx, dys = dqy;
     if (g.has_rotate) {
-        const double fx = (double)qx - g.rp.cx, fy = (double)qy - g.rp.cy;
-        xs = g.rp.c * fx - g.rp.s * fy + g.rp.cx;
-        ys = g.rp.s * fx + g.rp.c * fy + g.rp.cy;
-        dxs = g.rp.c * dqx - g.rp.s * dqy;
-        dys = g.rp.s * dqx + g.rp.c * dqy;
+        const double fx = (double)qx - rp.cx, fy = (double)qy - rp.cy;
+        xs = rp.c * fx - rp.s * fy + rp.cx;
+        ys = rp.s * fx + rp.c * fy + rp.cy;
+        dxs = rp.c * dqx - rp.s * dqy;
+        dys = rp.s * dqx + rp.c * dqy;
     }
 #pragma unroll
     for (int k = 0; k < kGatherTile / 8; ++k) {
@@ -454,7 +471,7 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
 #pragma unroll
             for (int c = 0; c < C; ++c) acc[c] = r0[c];
         }
-        pw_apply_tile<C, C>(g.pw_post, acc, 0);
+        pw_apply_tile<C, C>(pw_post, acc, 0);
         float *o = dst + ((size_t)y * g.out_w + x) * C;
 #pragma unroll
         for (int c = 0; c < C; ++c) o[c] = acc[c];

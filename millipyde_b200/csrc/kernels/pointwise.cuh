@@ -17,16 +17,27 @@ namespace mpk {
 // every element is known from the lane: vector v starts at channel (4v) mod C).  Measured on
 // B200 (tools/stream_peak.cu): this shape reaches 93 % of the copy bandwidth, a thread-contiguous
 // 48-byte chunk only 75 %.
-template <int C>
+//
+// TAB = true: every image of a batched launch has its own program (Generator streams with
+// random_* parameters); the records live in device memory and a block copies its image's record
+// into shared memory once.
+template <int C, bool TAB = false>
 __global__ void __launch_bounds__(256)
 pw_f32_kernel(const float *__restrict__ in, float *__restrict__ out, size_t n,
-              const __grid_constant__ PwProgram prog, const float *const *__restrict__ in_tab = nullptr,
-              float *const *__restrict__ out_tab = nullptr)
+              const __grid_constant__ PwProgram prog_one, const float *const *__restrict__ in_tab = nullptr,
+              float *const *__restrict__ out_tab = nullptr, const PwProgram *__restrict__ prog_tab = nullptr)
 {
     if (in_tab) {  // batched launch: blockIdx.y selects the image
         in = in_tab[blockIdx.y];
         out = out_tab[blockIdx.y];
     }
+    __shared__ PwProgram s_prog;
+    if (TAB) {
+        if (threadIdx.x < sizeof(PwProgram) / 4)
+            reinterpret_cast<int *>(&s_prog)[threadIdx.x] = reinterpret_cast<const int *>(prog_tab + blockIdx.y)[threadIdx.x];
+        __syncthreads();
+    }
+    const PwProgram &prog = TAB ? s_prog : prog_one;
     const size_t nvec = n / 4;
     const int lane = threadIdx.x & 31;
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -66,17 +77,28 @@ pw_f32_kernel(const float *__restrict__ in, float *__restrict__ out, size_t n,
 // its own 1.5 KB of shared memory, each lane then reads ITS four pixels back as three LDS.128
 // (lane pitch 48 B = 3 x 16 B: conflict-free) and the warp stores 32 consecutive float4.
 // C = 4: a vector is a pixel, so loads are coalesced as they are; greys leave as 4-byte stores.
-template <int C>
+// TAB = true: per-image (pre, post) program pairs from device memory, as in pw_f32_kernel.
+template <int C, bool TAB = false>
 __global__ void __launch_bounds__(256)
 grey_f32_kernel(const float *__restrict__ in, float *__restrict__ out, size_t npix,
-                const __grid_constant__ PwProgram pre, const __grid_constant__ PwProgram post,
-                const float *const *__restrict__ in_tab = nullptr, float *const *__restrict__ out_tab = nullptr)
+                const __grid_constant__ PwProgram pre_one, const __grid_constant__ PwProgram post_one,
+                const float *const *__restrict__ in_tab = nullptr, float *const *__restrict__ out_tab = nullptr,
+                const PwProgram *__restrict__ prog_tab = nullptr)  // [image][2] = pre, post
 {
     static_assert(C == 3 || C == 4, "colour input");
     if (in_tab) {
         in = in_tab[blockIdx.y];
         out = out_tab[blockIdx.y];
     }
+    __shared__ PwProgram s_prog[2];
+    if (TAB) {
+        if (threadIdx.x < 2 * sizeof(PwProgram) / 4)
+            reinterpret_cast<int *>(s_prog)[threadIdx.x] =
+                reinterpret_cast<const int *>(prog_tab + 2 * (size_t)blockIdx.y)[threadIdx.x];
+        __syncthreads();
+    }
+    const PwProgram &pre = TAB ? s_prog[0] : pre_one;
+    const PwProgram &post = TAB ? s_prog[1] : post_one;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;

@@ -30,13 +30,15 @@ bool gauss_stream_supported(int W, int C, int radius)
 }
 
 template <int C, int R>
-static MPStatus launch_cr(int device, cudaStream_t s, GaussStreamParams &p)
+static MPStatus launch_cr(int device, cudaStream_t s, GaussStreamParams &p, const GaussWeightSets *sets)
 {
     const int sms = sm_count(device) ? sm_count(device) : 148;
     const size_t smem = WsGeom<C, R>::SMEM;
     static bool configured[64] = {};  // per device
     if (device >= 0 && device < 64 && !configured[device]) {
         MP_CUDA_TRY(cudaFuncSetAttribute(gauss_stream_ws_kernel<C, R>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MP_CUDA_TRY(cudaFuncSetAttribute(gauss_stream_ws_sets_kernel<C, R>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[device] = true;
     }
@@ -49,21 +51,23 @@ static MPStatus launch_cr(int device, cudaStream_t s, GaussStreamParams &p)
     p.chunk_rows = (p.height + chunks - 1) / chunks;
     items *= chunks;
     const int grid = (int)(items < sms ? items : sms);
-    gauss_stream_ws_kernel<C, R><<<grid, kWsThreads, smem, s>>>(p);
+    if (sets) gauss_stream_ws_sets_kernel<C, R><<<grid, kWsThreads, smem, s>>>(p, *sets);
+    else gauss_stream_ws_kernel<C, R><<<grid, kWsThreads, smem, s>>>(p);
     count_launch();
     return MILLIPYDE_SUCCESS;
 }
 
 template <int C>
-static MPStatus launch_c(int device, cudaStream_t s, GaussStreamParams &p, int bucket)
+static MPStatus launch_c(int device, cudaStream_t s, GaussStreamParams &p, int bucket,
+                         const GaussWeightSets *sets = nullptr)
 {
     switch (bucket) {
-        case 3: return launch_cr<C, 3>(device, s, p);
-        case 5: return launch_cr<C, 5>(device, s, p);
-        case 7: return launch_cr<C, 7>(device, s, p);
-        case 9: return launch_cr<C, 9>(device, s, p);
-        case 11: return launch_cr<C, 11>(device, s, p);
-        case 13: return launch_cr<C, 13>(device, s, p);
+        case 3: return launch_cr<C, 3>(device, s, p, sets);
+        case 5: return launch_cr<C, 5>(device, s, p, sets);
+        case 7: return launch_cr<C, 7>(device, s, p, sets);
+        case 9: return launch_cr<C, 9>(device, s, p, sets);
+        case 11: return launch_cr<C, 11>(device, s, p, sets);
+        case 13: return launch_cr<C, 13>(device, s, p, sets);
         default: return MP_ERROR_INVALID_ARGUMENT;
     }
 }
@@ -95,6 +99,42 @@ MPStatus launch_gauss_stream_batch(int device, cudaStream_t s, int H, int W, int
     if (C == 1) return launch_c<1>(device, s, p, bucket);
     if (C == 3) return launch_c<3>(device, s, p, bucket);
     if (C == 4) return launch_c<4>(device, s, p, bucket);
+    return MP_ERROR_UNSUPPORTED_LAYOUT;
+}
+
+int gauss_stream_bucket(int radius) { return bucket_for(radius); }
+
+// n_images <= kGsMaxSets images of one radius bucket, image i filtered with gps[i].
+MPStatus launch_gauss_stream_sets(int device, cudaStream_t s, int H, int W, int C, int n_images,
+                                  const float *const *in_tab, float *const *out_tab,
+                                  const GaussParams<float> *gps)
+{
+    if (n_images < 1 || n_images > kGsMaxSets) return MP_ERROR_INVALID_ARGUMENT;
+    int bucket = 0;
+    for (int i = 0; i < n_images; ++i) {
+        const int b = bucket_for(gps[i].radius);
+        if (!b) return MP_ERROR_INVALID_ARGUMENT;
+        if (b > bucket) bucket = b;
+    }
+    GaussStreamParams p = {};
+    p.in_tab = in_tab;
+    p.out_tab = out_tab;
+    p.n_images = n_images;
+    p.height = H;
+    p.row_elems = W * C;
+    p.n_strips = (p.row_elems + kGsTW - 1) / kGsTW;
+    p.radius = bucket;
+    static thread_local GaussWeightSets sets;  // 7 KB: keep it off the worker's stack frames
+    for (int i = 0; i < n_images; ++i)
+        for (int d = 0; d < 14; ++d) {
+            const float w = d <= gps[i].radius ? gps[i].w[d] : 0.f;
+            unsigned int bits;
+            memcpy(&bits, &w, 4);
+            sets.ww[i][d] = ((unsigned long long)bits << 32) | bits;
+        }
+    if (C == 1) return launch_c<1>(device, s, p, bucket, &sets);
+    if (C == 3) return launch_c<3>(device, s, p, bucket, &sets);
+    if (C == 4) return launch_c<4>(device, s, p, bucket, &sets);
     return MP_ERROR_UNSUPPORTED_LAYOUT;
 }
 

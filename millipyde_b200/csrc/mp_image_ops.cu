@@ -729,7 +729,18 @@ void launch_gather_f32(cudaStream_t s, int channels, const GatherParams &g, int 
         cudaFuncSetAttribute(gather_f32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         configured = true;
     }
-    if (channels == 1) gather_f32_kernel<1><<<grid, 256, smem, s>>>(g);
+    if (g.var_tab) {  // per-image angle / programs
+        static bool configured_tab = false;
+        if (!configured_tab) {
+            cudaFuncSetAttribute(gather_f32_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaFuncSetAttribute(gather_f32_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaFuncSetAttribute(gather_f32_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            configured_tab = true;
+        }
+        if (channels == 1) gather_f32_kernel<1, true><<<grid, 256, smem, s>>>(g);
+        else if (channels == 3) gather_f32_kernel<3, true><<<grid, 256, smem, s>>>(g);
+        else gather_f32_kernel<4, true><<<grid, 256, smem, s>>>(g);
+    } else if (channels == 1) gather_f32_kernel<1><<<grid, 256, smem, s>>>(g);
     else if (channels == 3) gather_f32_kernel<3><<<grid, 256, smem, s>>>(g);
     else gather_f32_kernel<4><<<grid, 256, smem, s>>>(g);
     count_launch();
@@ -741,23 +752,46 @@ namespace mp {
 
 // Batched forms used by the chain executor: n same-shape images through device pointer tables.
 void launch_pw_f32_batch(cudaStream_t s, const Img &d, const PwProgram &prog, const float *const *in_tab,
-                         float *const *out_tab, int n_images)
+                         float *const *out_tab, int n_images, const PwProgram *prog_tab)
 {
     const size_t n = d.npix * d.C;
     size_t want = (n / 4 + 96 * 8 - 1) / (96 * 8);
     dim3 grid((unsigned)(want < 1 ? 1 : want), (unsigned)n_images);
-    if (d.C == 1) pw_f32_kernel<1><<<grid, 256, 0, s>>>(nullptr, nullptr, n, prog, in_tab, out_tab);
+    if (prog_tab) {  // one program per image (device memory)
+        if (d.C == 1) pw_f32_kernel<1, true><<<grid, 256, 0, s>>>(nullptr, nullptr, n, prog, in_tab, out_tab, prog_tab);
+        else if (d.C == 3) pw_f32_kernel<3, true><<<grid, 256, 0, s>>>(nullptr, nullptr, n, prog, in_tab, out_tab, prog_tab);
+        else pw_f32_kernel<4, true><<<grid, 256, 0, s>>>(nullptr, nullptr, n, prog, in_tab, out_tab, prog_tab);
+    } else if (d.C == 1) pw_f32_kernel<1><<<grid, 256, 0, s>>>(nullptr, nullptr, n, prog, in_tab, out_tab);
     else if (d.C == 3) pw_f32_kernel<3><<<grid, 256, 0, s>>>(nullptr, nullptr, n, prog, in_tab, out_tab);
     else pw_f32_kernel<4><<<grid, 256, 0, s>>>(nullptr, nullptr, n, prog, in_tab, out_tab);
     count_launch();
 }
 
 void launch_grey_f32_batch(cudaStream_t s, const Img &d, const PwProgram &pre, const PwProgram &post,
-                           const float *const *in_tab, float *const *out_tab, int n_images)
+                           const float *const *in_tab, float *const *out_tab, int n_images,
+                           const PwProgram *prog_tab)
 {
     dim3 grid((unsigned)grey_grid(d), (unsigned)n_images);
-    if (d.C == 3) grey_f32_kernel<3><<<grid, 256, 0, s>>>(nullptr, nullptr, d.npix, pre, post, in_tab, out_tab);
+    if (prog_tab) {  // [image][2] = (pre, post) per image
+        if (d.C == 3) grey_f32_kernel<3, true><<<grid, 256, 0, s>>>(nullptr, nullptr, d.npix, pre, post, in_tab, out_tab, prog_tab);
+        else grey_f32_kernel<4, true><<<grid, 256, 0, s>>>(nullptr, nullptr, d.npix, pre, post, in_tab, out_tab, prog_tab);
+    } else if (d.C == 3) grey_f32_kernel<3><<<grid, 256, 0, s>>>(nullptr, nullptr, d.npix, pre, post, in_tab, out_tab);
     else grey_f32_kernel<4><<<grid, 256, 0, s>>>(nullptr, nullptr, d.npix, pre, post, in_tab, out_tab);
+    count_launch();
+}
+
+}  // namespace mp
+
+namespace mp {
+
+// Bilinear rotate of n same-shape fp32 images; `rp_tab` (device memory) gives each its own angle.
+void launch_rotate_f32_batch(cudaStream_t s, const Img &d, const RotateParams &rp, const float *const *in_tab,
+                             float *const *out_tab, int n_images, const RotateParams *rp_tab)
+{
+    dim3 grid((d.W + 31) / 32, (d.H + 7) / 8, n_images);
+    if (d.C == 1) rotate_bilinear_kernel<float, 1><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, d.H, rp, in_tab, out_tab, rp_tab);
+    else if (d.C == 3) rotate_bilinear_kernel<float, 3><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, d.H, rp, in_tab, out_tab, rp_tab);
+    else rotate_bilinear_kernel<float, 4><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, d.H, rp, in_tab, out_tab, rp_tab);
     count_launch();
 }
 

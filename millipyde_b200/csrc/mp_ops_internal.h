@@ -47,10 +47,15 @@ MPStatus op_pointwise_f32(MPObjData *obj, const mpk::PwProgram &prog);
 MPStatus op_pointwise_rgba8(MPObjData *obj, const mpk::U8Program &prog);
 MPStatus op_grey_f32(MPObjData *obj, const mpk::PwProgram &pre, const mpk::PwProgram &post);
 
+// The *_tab record tables (device memory, one entry per image) carry per-image parameters for
+// chains with random_* stages; null = the single program / angle passed by value.
 void launch_pw_f32_batch(cudaStream_t s, const Img &d, const mpk::PwProgram &prog, const float *const *in_tab,
-                         float *const *out_tab, int n_images);
+                         float *const *out_tab, int n_images, const mpk::PwProgram *prog_tab = nullptr);
 void launch_grey_f32_batch(cudaStream_t s, const Img &d, const mpk::PwProgram &pre, const mpk::PwProgram &post,
-                           const float *const *in_tab, float *const *out_tab, int n_images);
+                           const float *const *in_tab, float *const *out_tab, int n_images,
+                           const mpk::PwProgram *prog_tab = nullptr);  // [image][2] = pre, post
+void launch_rotate_f32_batch(cudaStream_t s, const Img &d, const mpk::RotateParams &rp, const float *const *in_tab,
+                             float *const *out_tab, int n_images, const mpk::RotateParams *rp_tab = nullptr);
 
 bool fliplr_batch_supported(const Img &d);
 void launch_fliplr_batch(cudaStream_t s, const Img &d, const void *const *in_tab, void *const *out_tab, int n_images);
@@ -64,6 +69,10 @@ void launch_gather_f32(cudaStream_t s, int channels, const mpk::GatherParams &g,
 
 // fp32 roofline path (kernels/gaussian_stream.cuh)
 bool gauss_stream_supported(int W, int C, int radius);
+int gauss_stream_bucket(int radius);  // smallest compiled radius >= radius, 0 if none
+MPStatus launch_gauss_stream_sets(int device, cudaStream_t s, int H, int W, int C, int n_images,
+                                  const float *const *in_tab, float *const *out_tab,
+                                  const mpk::GaussParams<float> *gps);  // n_images <= 64, per-image weights
 MPStatus launch_gauss_stream(int device, cudaStream_t s, const Img &d, const float *in, float *out,
                              const mpk::GaussParams<float> &gp);
 // n_images of one shape in one launch: either a contiguous batch (in/out +

@@ -231,9 +231,8 @@ std::vector<Segment> compile(const std::vector<const Stage *> &ops, mp::Family f
 
 // Per-image realisation of the chain: coin flips (src/gpupipeline.c:380-387) and, for random_*
 // stages, the parameter draws the reference makes inside the gpuimage method.  The result is a
-// list of concrete stages (args point at the stage's own doubles) plus a key that is equal for
-// two images iff they run the same ops with the same parameters.
-void realize(const mp_pipeline *p, std::vector<Stage> *out, std::string *key)
+// list of concrete stages (args point at the stage's own doubles).
+void realize(const mp_pipeline *p, std::vector<Stage> *out)
 {
     const size_t ns = p->stages.size();
     out->clear();
@@ -245,12 +244,8 @@ void realize(const mp_pipeline *p, std::vector<Stage> *out, std::string *key)
             double u = 0;
             if (random_double_in_range(0.0, 1.0, &u) == MILLIPYDE_SUCCESS && u > st.probability) run = false;
         }
-        if (!run) {
-            key->push_back('0');
-            continue;
-        }
+        if (!run) continue;
         if (st.kind != OP_RANDOM) {
-            key->push_back('1');
             out->push_back(st);
             continue;
         }
@@ -275,17 +270,57 @@ void realize(const mp_pipeline *p, std::vector<Stage> *out, std::string *key)
             c.a[1] = draw(r[2], r[3]);
             c.a[2] = draw(r[4], r[5]);
         }
-        char buf[96];
-        snprintf(buf, sizeof buf, "R%.17g,%.17g,%.17g;", c.a[0], c.a[1], c.a[2]);
-        key->append(buf);
         out->push_back(c);
     }
     for (Stage &c : *out)
         if (c.kind != OP_FOREIGN && c.kind != OP_GREY && c.kind != OP_TRANSPOSE && c.kind != OP_FLIPLR) c.args = (void *)c.a;
 }
 
-MPStatus run_gather(const std::vector<MPObjData *> &objs, const Segment &seg, const mp::Img &d, int device,
-                    cudaStream_t s);
+// What decides the KERNEL a segment runs (never its parameter VALUES: those travel as per-image
+// records).  Two images whose current segments have equal signatures and equal layouts share one
+// launch.  The Gaussian adds the radius bucket its sigma falls in; with fusion off, pointwise and
+// Gaussian values are part of the signature too, which restores the reference's one-image,
+// one-op-at-a-time launches.
+std::string signature(const Segment &g)
+{
+    char b[96];
+    switch (g.kind) {
+        case Segment::SINGLE: {
+            const Stage &st = *g.single;
+            if (st.kind == OP_GAUSSIAN) {
+                int bucket = -1;
+                if (st.a[0] > 1e-15 && g_fusion.load()) {
+                    double w[kGaussMaxRadius + 1];
+                    const int r = mp::oracle_weights(st.a[0], w, kGaussMaxRadius);
+                    bucket = mp::gauss_stream_bucket(mp::effective_radius(w, r, ldexp(1.0, -24)));
+                }
+                if (bucket > 0) snprintf(b, sizeof b, "S%d:G%d", (int)st.kind, bucket);
+                else snprintf(b, sizeof b, "S%d:%.17g", (int)st.kind, st.a[0]);
+            } else if (st.kind == OP_FOREIGN) {
+                snprintf(b, sizeof b, "S%d:%p:%p", (int)st.kind, (void *)st.func, st.args);
+            } else if (st.kind == OP_ROTATE && g_fusion.load()) {
+                snprintf(b, sizeof b, "S%d", (int)st.kind);
+            } else {
+                snprintf(b, sizeof b, "S%d:%.17g,%.17g,%.17g", (int)st.kind, st.a[0], st.a[1], st.a[2]);
+            }
+            break;
+        }
+        case Segment::GATHER_F32:
+            snprintf(b, sizeof b, "T%d%d%d", (int)g.flip_pre, (int)g.flip_post, (int)g.has_rotate);
+            break;
+        case Segment::PW_RGBA8: {
+            // composed byte tables are built per program: same program, same launch shape
+            std::string k = "U";
+            k.append((const char *)&g.u8, sizeof g.u8);
+            return k;
+        }
+        default: snprintf(b, sizeof b, "P%d", (int)g.kind); break;
+    }
+    return b;
+}
+
+MPStatus run_gather(const std::vector<MPObjData *> &objs, const std::vector<const Segment *> &segs, const mp::Img &d,
+                    int device, cudaStream_t s);
 
 MPStatus run_segment_on(MPObjData *obj, const Segment &seg)
 {
@@ -298,7 +333,8 @@ MPStatus run_segment_on(MPObjData *obj, const Segment &seg)
             if (!mp::describe(obj, &d) || d.fam != mp::FAM_F32) return MP_ERROR_UNSUPPORTED_LAYOUT;
             if (cudaSetDevice(obj->mem_loc) != cudaSuccess) return MP_ERROR_CUDA_RUNTIME;
             std::vector<MPObjData *> one(1, obj);
-            return run_gather(one, seg, d, obj->mem_loc, mp::stream_of(obj));
+            std::vector<const Segment *> one_seg(1, &seg);
+            return run_gather(one, one_seg, d, obj->mem_loc, mp::stream_of(obj));
         }
         default: return seg.single->func(obj, seg.single->args);
     }
@@ -308,17 +344,25 @@ MPStatus run_segment_on(MPObjData *obj, const Segment &seg)
 // pointer tables (inputs then outputs) uploaded from the page-locked arena, one call of `launch`,
 // then the inputs are retired in stream order.  *handled = false (and nothing changed) if the
 // arena or the pool cannot serve the request.
+//
+// `records` (optional): per-image parameter records, uploaded behind the tables in the same copy;
+// `launch` finds them at g_records (device address), valid for the duration of the call.
+thread_local const void *g_records = nullptr;
+
 template <typename Launch>
 MPStatus run_batched(const std::vector<MPObjData *> &objs, size_t out_bytes, int device, cudaStream_t s,
-                     bool *handled, Launch launch)
+                     bool *handled, Launch launch, const void *records = nullptr, size_t record_bytes = 0)
 {
     *handled = false;
     const size_t n = objs.size();
     Arena &arena = g_arenas[device];
-    void **h_tab = (void **)arena.take(2 * n * sizeof(void *));
+    const size_t tab_bytes = (2 * n * sizeof(void *) + 15) & ~(size_t)15;
+    void **h_tab = (void **)arena.take(tab_bytes + record_bytes);
     if (!h_tab) return MILLIPYDE_SUCCESS;
-    void *d_tab = mp::pool_alloc(device, s, 2 * n * sizeof(void *));
+    void *d_tab = mp::pool_alloc(device, s, tab_bytes + record_bytes);
     if (!d_tab) return MP_ERROR_DEVICE_ALLOC;
+    if (record_bytes) memcpy((char *)h_tab + tab_bytes, records, record_bytes);
+    g_records = record_bytes ? (const char *)d_tab + tab_bytes : nullptr;
     std::vector<void *> fresh(n);
     for (size_t i = 0; i < n; ++i) {
         fresh[i] = mp::pool_alloc(device, s, out_bytes);
@@ -330,7 +374,7 @@ MPStatus run_batched(const std::vector<MPObjData *> &objs, size_t out_bytes, int
         h_tab[i] = objs[i]->device_data;
         h_tab[n + i] = fresh[i];
     }
-    MP_CUDA_TRY(cudaMemcpyAsync(d_tab, h_tab, 2 * n * sizeof(void *), cudaMemcpyHostToDevice, s));
+    MP_CUDA_TRY(cudaMemcpyAsync(d_tab, h_tab, tab_bytes + record_bytes, cudaMemcpyHostToDevice, s));
     MPStatus st = launch((const float *const *)d_tab, (float *const *)((void **)d_tab + n), (int)n);
     cudaError_t e = cudaGetLastError();
     if (st == MILLIPYDE_SUCCESS && e != cudaSuccess) {
@@ -351,24 +395,42 @@ MPStatus run_batched(const std::vector<MPObjData *> &objs, size_t out_bytes, int
     return st;
 }
 
-// One launch for the Gaussian of a whole same-shape fp32 group.
-MPStatus run_gaussian_batch(mp_pipeline *p, const std::vector<MPObjData *> &objs, const mp::Img &d, double sigma,
+constexpr int kMaxSets = 64;  // images per launch_gauss_stream_sets call (kernels/gaussian_stream.cuh: kGsMaxSets)
+
+// One launch for the Gaussian of a whole same-shape fp32 group (`sigmas` all equal), or one launch
+// per 64 images with per-image weight sets when the sigmas were drawn per image (same radius bucket:
+// realize() keyed the group on it).
+MPStatus run_gaussian_batch(const std::vector<MPObjData *> &objs, const mp::Img &d, const std::vector<double> &sigmas,
                             int device, cudaStream_t s, bool *handled)
 {
-    (void)p;
     *handled = false;
-    if (!(sigma > 1e-15) || objs.size() < 2) return MILLIPYDE_SUCCESS;
-    double w[kGaussMaxRadius + 1];
-    int r = mp::oracle_weights(sigma, w, kGaussMaxRadius);
-    int eff = mp::effective_radius(w, r, ldexp(1.0, -24));
-    if (!mp::gauss_stream_supported(d.W, d.C, eff)) return MILLIPYDE_SUCCESS;
-    GaussParams<float> gp = {};
-    gp.radius = eff;
-    for (int k = 0; k <= eff; ++k) gp.w[k] = (float)w[k];
+    const size_t n = objs.size();
+    if (n < 2) return MILLIPYDE_SUCCESS;
+    bool same = true;
+    for (size_t i = 1; i < n; ++i) same = same && sigmas[i] == sigmas[0];
+    std::vector<GaussParams<float>> gps(same ? 1 : n);
+    for (size_t i = 0; i < gps.size(); ++i) {
+        if (!(sigmas[i] > 1e-15)) return MILLIPYDE_SUCCESS;
+        double w[kGaussMaxRadius + 1];
+        const int r = mp::oracle_weights(sigmas[i], w, kGaussMaxRadius);
+        const int eff = mp::effective_radius(w, r, ldexp(1.0, -24));
+        if (!mp::gauss_stream_supported(d.W, d.C, eff)) return MILLIPYDE_SUCCESS;
+        gps[i] = {};
+        gps[i].radius = eff;
+        for (int k = 0; k <= eff; ++k) gps[i].w[k] = (float)w[k];
+    }
     return run_batched(objs, objs[0]->nbytes, device, s, handled,
-                       [&](const float *const *in_tab, float *const *out_tab, int n) {
-                           return mp::launch_gauss_stream_batch(device, s, d.H, d.W, d.C, n, nullptr, nullptr, 0,
-                                                                in_tab, out_tab, gp);
+                       [&](const float *const *in_tab, float *const *out_tab, int m) {
+                           if (same)
+                               return mp::launch_gauss_stream_batch(device, s, d.H, d.W, d.C, m, nullptr, nullptr, 0,
+                                                                    in_tab, out_tab, gps[0]);
+                           for (int off = 0; off < m; off += kMaxSets) {
+                               const int cnt = m - off < kMaxSets ? m - off : kMaxSets;
+                               MPStatus st = mp::launch_gauss_stream_sets(device, s, d.H, d.W, d.C, cnt, in_tab + off,
+                                                                          out_tab + off, gps.data() + off);
+                               if (st != MILLIPYDE_SUCCESS) return st;
+                           }
+                           return (MPStatus)MILLIPYDE_SUCCESS;
                        });
 }
 
@@ -387,26 +449,47 @@ GatherParams gather_params(const Segment &seg, const mp::Img &d)
     return g;
 }
 
-MPStatus run_gather(const std::vector<MPObjData *> &objs, const Segment &seg, const mp::Img &d, int device,
-                    cudaStream_t s)
+// `segs`: one Segment per image (same structure; the angle and the programs may differ) or a single
+// one for all.
+MPStatus run_gather(const std::vector<MPObjData *> &objs, const std::vector<const Segment *> &segs, const mp::Img &d,
+                    int device, cudaStream_t s)
 {
-    GatherParams g = gather_params(seg, d);
-    auto launch = [&](const float *const *in_tab, float *const *out_tab, int n) {
+    const size_t n = objs.size();
+    GatherParams g = gather_params(*segs[0], d);
+    std::vector<GatherVar> vars;
+    if (segs.size() == n && n >= 2) {
+        bool same = true;
+        for (size_t i = 1; i < n && same; ++i)
+            same = segs[i]->angle == segs[0]->angle && !memcmp(&segs[i]->pre, &segs[0]->pre, sizeof(PwProgram)) &&
+                   !memcmp(&segs[i]->post, &segs[0]->post, sizeof(PwProgram));
+        if (!same) {
+            vars.resize(n);
+            for (size_t i = 0; i < n; ++i) {
+                const GatherParams gi = gather_params(*segs[i], d);
+                vars[i].rp = gi.rp;
+                vars[i].pw_pre = gi.pw_pre;
+                vars[i].pw_post = gi.pw_post;
+            }
+        }
+    }
+    auto launch = [&](const float *const *in_tab, float *const *out_tab, int m) {
         g.in_tab = in_tab;
         g.out_tab = out_tab;
-        mp::launch_gather_f32(s, d.C, g, n);
+        g.var_tab = vars.empty() ? nullptr : (const GatherVar *)g_records;
+        mp::launch_gather_f32(s, d.C, g, m);
         return MILLIPYDE_SUCCESS;
     };
-    if (objs.size() >= 2) {
+    if (n >= 2) {
         bool handled = false;
-        MPStatus st = run_batched(objs, objs[0]->nbytes, device, s, &handled, launch);
+        MPStatus st = run_batched(objs, objs[0]->nbytes, device, s, &handled, launch, vars.data(),
+                                  vars.size() * sizeof(GatherVar));
         if (st != MILLIPYDE_SUCCESS || handled) return st;
     }
-    for (MPObjData *o : objs) {  // one image, or the arena was exhausted
+    for (size_t i = 0; i < n; ++i) {  // one image, or the arena was exhausted
+        MPObjData *o = objs[i];
+        g = gather_params(*segs[segs.size() == n ? i : 0], d);
         void *fresh = mp::pool_alloc(device, s, o->nbytes);
         if (!fresh) return MP_ERROR_DEVICE_ALLOC;
-        g.in_tab = nullptr;
-        g.out_tab = nullptr;
         g.in = (const float *)o->device_data;
         g.out = (float *)fresh;
         mp::launch_gather_f32(s, d.C, g, 1);
@@ -422,105 +505,131 @@ MPStatus run_gather(const std::vector<MPObjData *> &objs, const Segment &seg, co
     return MILLIPYDE_SUCCESS;
 }
 
-// All images of `objs` share layout and surviving op list.
-void run_group(mp_pipeline *p, const std::vector<MPObjData *> &objs, const std::vector<const Stage *> &ops,
-               int device, cudaStream_t s)
+// One segment for a group of images that share the layout and the segment's signature; `segs[i]`
+// is image i's own segment.  Parameters that differ between the images (random_* draws) travel as
+// per-image records, so the group is one launch.
+void run_segment_group(mp_pipeline *p, const std::vector<MPObjData *> &objs, const std::vector<const Segment *> &segs,
+                       int device, cudaStream_t s)
 {
-    if (objs.empty() || ops.empty()) return;
-    mp::Img d;
-    const bool known = mp::describe(objs[0], &d);
-    std::vector<Segment> segs = compile(ops, known ? d.fam : mp::FAM_U8_OTHER, known ? d.C : 0);
-    p->segments.fetch_add((int)segs.size());
-    const unsigned long long before = mpdev_launch_count();
-    for (const Segment &seg : segs) {
-        if (seg.kind == Segment::SINGLE && seg.single->kind == OP_GAUSSIAN && g_fusion.load()) {
-            mp::Img cur;
-            if (mp::describe(objs[0], &cur) && cur.fam == mp::FAM_F32) {
-                bool handled = false;
-                MPStatus st = run_gaussian_batch(p, objs, cur, seg.single->a[0], device, s, &handled);
-                note_status(p, st);
-                if (handled) continue;
-            }
-        }
-        if ((seg.kind == Segment::PW_F32 || seg.kind == Segment::GREY_F32) && objs.size() >= 2) {
-            // one launch for the whole group (pointer tables); the grey variant also rewrites headers
-            mp::Img cur;
-            if (mp::describe(objs[0], &cur) && cur.fam == mp::FAM_F32 &&
-                (seg.kind == Segment::PW_F32 || (cur.C >= 3 && objs[0]->ndims == 3))) {
-                cudaSetDevice(device);
-                const bool grey = seg.kind == Segment::GREY_F32;
-                const size_t out_bytes = grey ? cur.npix * 4 : objs[0]->nbytes;
-                bool handled = false;
-                MPStatus st = run_batched(objs, out_bytes, device, s, &handled,
-                                          [&](const float *const *in_tab, float *const *out_tab, int n) {
-                                              if (grey) mp::launch_grey_f32_batch(s, cur, seg.pre, seg.post, in_tab, out_tab, n);
-                                              else mp::launch_pw_f32_batch(s, cur, seg.pre, in_tab, out_tab, n);
-                                              return MILLIPYDE_SUCCESS;
-                                          });
-                note_status(p, st);
-                if (handled) {
-                    if (grey)
-                        for (MPObjData *o : objs) {  // header rewrite of mpimg_color_to_greyscale
-                            o->ndims = 2;
-                            o->type = MP_NPY_FLOAT;
-                            o->dims[2] = cur.W * 4;
-                            o->dims[3] = 4;
-                        }
-                    continue;
-                }
-                if (st != MILLIPYDE_SUCCESS) continue;
-            }
-        }
-        if (seg.kind == Segment::SINGLE && seg.single->kind == OP_FLIPLR && objs.size() >= 2 && g_fusion.load()) {
-            mp::Img cur;
-            if (mp::describe(objs[0], &cur) && mp::fliplr_batch_supported(cur)) {
-                cudaSetDevice(device);
-                bool handled = false;
-                MPStatus st = run_batched(objs, objs[0]->nbytes, device, s, &handled,
-                                          [&](const float *const *in_tab, float *const *out_tab, int n) {
-                                              mp::launch_fliplr_batch(s, cur, (const void *const *)in_tab,
-                                                                      (void *const *)out_tab, n);
-                                              return MILLIPYDE_SUCCESS;
-                                          });
-                note_status(p, st);
-                if (handled || st != MILLIPYDE_SUCCESS) continue;
-            }
-        }
-        if (seg.kind == Segment::SINGLE && seg.single->kind == OP_TRANSPOSE && objs.size() >= 2 && g_fusion.load()) {
-            mp::Img cur;
-            if (mp::describe(objs[0], &cur) && mp::transpose_batch_supported(cur)) {
-                cudaSetDevice(device);
-                bool handled = false;
-                MPStatus st = run_batched(objs, objs[0]->nbytes, device, s, &handled,
-                                          [&](const float *const *in_tab, float *const *out_tab, int n) {
-                                              mp::launch_transpose_batch(s, cur, (const void *const *)in_tab,
-                                                                         (void *const *)out_tab, n);
-                                              return MILLIPYDE_SUCCESS;
-                                          });
-                note_status(p, st);
-                if (handled) {
-                    const int pix_bytes = cur.C * cur.esize;
-                    for (MPObjData *o : objs) {  // header rewrite of mpimg_transpose
-                        o->dims[0] = cur.W;
-                        o->dims[1] = cur.H;
-                        o->dims[o->ndims] = cur.H * pix_bytes;
-                        o->dims[o->ndims + 1] = pix_bytes;
-                    }
-                }
-                if (handled || st != MILLIPYDE_SUCCESS) continue;
-            }
-        }
-        if (seg.kind == Segment::GATHER_F32) {
-            mp::Img cur;
-            if (mp::describe(objs[0], &cur) && cur.fam == mp::FAM_F32) {
-                cudaSetDevice(device);
-                note_status(p, run_gather(objs, seg, cur, device, s));
-                continue;
-            }
-        }
-        for (MPObjData *o : objs) note_status(p, run_segment_on(o, seg));
+    const size_t n = objs.size();
+    if (!n) return;
+    const Segment &seg = *segs[0];
+    mp::Img cur;
+    const bool f32 = mp::describe(objs[0], &cur) && cur.fam == mp::FAM_F32;
+    if (n >= 2) cudaSetDevice(device);
+
+    if (seg.kind == Segment::SINGLE && seg.single->kind == OP_GAUSSIAN && g_fusion.load() && f32) {
+        std::vector<double> sigmas(n);
+        for (size_t i = 0; i < n; ++i) sigmas[i] = segs[i]->single->a[0];
+        bool handled = false;
+        note_status(p, run_gaussian_batch(objs, cur, sigmas, device, s, &handled));
+        if (handled) return;
     }
-    (void)before;
+    if ((seg.kind == Segment::PW_F32 || seg.kind == Segment::GREY_F32) && n >= 2 && f32 &&
+        (seg.kind == Segment::PW_F32 || (cur.C >= 3 && objs[0]->ndims == 3))) {
+        // one launch for the whole group (pointer tables); the grey variant also rewrites headers
+        const bool grey = seg.kind == Segment::GREY_F32;
+        const size_t out_bytes = grey ? cur.npix * 4 : objs[0]->nbytes;
+        std::vector<PwProgram> progs;  // per-image records: [i] (pw) or [2i], [2i+1] (grey)
+        bool same = true;
+        for (size_t i = 1; i < n && same; ++i)
+            same = !memcmp(&segs[i]->pre, &seg.pre, sizeof(PwProgram)) && !memcmp(&segs[i]->post, &seg.post, sizeof(PwProgram));
+        if (!same)
+            for (size_t i = 0; i < n; ++i) {
+                progs.push_back(segs[i]->pre);
+                if (grey) progs.push_back(segs[i]->post);
+            }
+        bool handled = false;
+        MPStatus st = run_batched(
+            objs, out_bytes, device, s, &handled,
+            [&](const float *const *in_tab, float *const *out_tab, int m) {
+                const PwProgram *tab = progs.empty() ? nullptr : (const PwProgram *)g_records;
+                if (grey) mp::launch_grey_f32_batch(s, cur, seg.pre, seg.post, in_tab, out_tab, m, tab);
+                else mp::launch_pw_f32_batch(s, cur, seg.pre, in_tab, out_tab, m, tab);
+                return MILLIPYDE_SUCCESS;
+            },
+            progs.data(), progs.size() * sizeof(PwProgram));
+        note_status(p, st);
+        if (handled) {
+            if (grey)
+                for (MPObjData *o : objs) {  // header rewrite of mpimg_color_to_greyscale
+                    o->ndims = 2;
+                    o->type = MP_NPY_FLOAT;
+                    o->dims[2] = cur.W * 4;
+                    o->dims[3] = 4;
+                }
+            return;
+        }
+        if (st != MILLIPYDE_SUCCESS) return;
+    }
+    if (seg.kind == Segment::SINGLE && seg.single->kind == OP_ROTATE && n >= 2 && f32 && g_fusion.load()) {
+        std::vector<RotateParams> rps;
+        bool same = true;
+        for (size_t i = 1; i < n && same; ++i) same = segs[i]->single->a[0] == seg.single->a[0];
+        if (!same)
+            for (size_t i = 0; i < n; ++i) rps.push_back(mp::rotate_params(cur.W, cur.H, segs[i]->single->a[0]));
+        const RotateParams rp0 = mp::rotate_params(cur.W, cur.H, seg.single->a[0]);
+        bool handled = false;
+        MPStatus st = run_batched(
+            objs, objs[0]->nbytes, device, s, &handled,
+            [&](const float *const *in_tab, float *const *out_tab, int m) {
+                mp::launch_rotate_f32_batch(s, cur, rp0, in_tab, out_tab, m,
+                                            rps.empty() ? nullptr : (const RotateParams *)g_records);
+                return MILLIPYDE_SUCCESS;
+            },
+            rps.data(), rps.size() * sizeof(RotateParams));
+        note_status(p, st);
+        if (handled || st != MILLIPYDE_SUCCESS) return;
+    }
+    if (seg.kind == Segment::SINGLE && seg.single->kind == OP_FLIPLR && n >= 2 && g_fusion.load() &&
+        mp::describe(objs[0], &cur) && mp::fliplr_batch_supported(cur)) {
+        bool handled = false;
+        MPStatus st = run_batched(objs, objs[0]->nbytes, device, s, &handled,
+                                  [&](const float *const *in_tab, float *const *out_tab, int m) {
+                                      mp::launch_fliplr_batch(s, cur, (const void *const *)in_tab,
+                                                              (void *const *)out_tab, m);
+                                      return MILLIPYDE_SUCCESS;
+                                  });
+        note_status(p, st);
+        if (handled || st != MILLIPYDE_SUCCESS) return;
+    }
+    if (seg.kind == Segment::SINGLE && seg.single->kind == OP_TRANSPOSE && n >= 2 && g_fusion.load() &&
+        mp::describe(objs[0], &cur) && mp::transpose_batch_supported(cur)) {
+        bool handled = false;
+        MPStatus st = run_batched(objs, objs[0]->nbytes, device, s, &handled,
+                                  [&](const float *const *in_tab, float *const *out_tab, int m) {
+                                      mp::launch_transpose_batch(s, cur, (const void *const *)in_tab,
+                                                                 (void *const *)out_tab, m);
+                                      return MILLIPYDE_SUCCESS;
+                                  });
+        note_status(p, st);
+        if (handled) {
+            const int pix_bytes = cur.C * cur.esize;
+            for (MPObjData *o : objs) {  // header rewrite of mpimg_transpose
+                o->dims[0] = cur.W;
+                o->dims[1] = cur.H;
+                o->dims[o->ndims] = cur.H * pix_bytes;
+                o->dims[o->ndims + 1] = pix_bytes;
+            }
+        }
+        if (handled || st != MILLIPYDE_SUCCESS) return;
+    }
+    if (seg.kind == Segment::GATHER_F32 && f32) {
+        cudaSetDevice(device);
+        note_status(p, run_gather(objs, segs, cur, device, s));
+        return;
+    }
+    for (size_t i = 0; i < n; ++i) note_status(p, run_segment_on(objs[i], *segs[i]));
+}
+
+// The layout part of a grouping key: images must agree on it to share a launch.
+std::string layout_key(const MPObjData *o)
+{
+    char hdr[64];
+    const int c = o->ndims == 3 ? o->dims[2] : 1;
+    snprintf(hdr, sizeof hdr, "%d:%d:%d:%d:%d|", o->type, o->ndims, o->ndims > 0 ? o->dims[0] : 0,
+             o->ndims > 1 ? o->dims[1] : 0, c);
+    return hdr;
 }
 
 struct ShardTask {
@@ -543,7 +652,7 @@ void shard_worker(void *arg)
 
     Arena &arena = g_arenas[device];
     std::unique_lock<std::mutex> arena_lock(arena.mux);
-    const size_t want = n * sizeof(void *) * 2 * (p->stages.size() + 1) + 4096;
+    const size_t want = n * (sizeof(void *) * 2 + sizeof(GatherVar) + 64) * (p->stages.size() + 1) + 4096;
     if (arena.cap < want) {
         if (arena.base) cudaFreeHost(arena.base);
         arena.base = nullptr;
@@ -561,27 +670,37 @@ void shard_worker(void *arg)
         mpobj_set_stream(o, (void *)batch_stream);
     }
 
-    // 2. coin flips / random draws per image, 3. grouping by (layout, realised stage list)
-    std::map<std::string, std::vector<size_t>> groups;
+    // 2. coin flips / random draws per image, then the fusion pass on what survived
     std::vector<std::vector<Stage>> realized(n);
+    std::vector<std::vector<Segment>> segs(n);
+    size_t rounds = 0;
     for (size_t i = 0; i < n; ++i) {
-        MPObjData *o = t->objs[i];
-        char hdr[64];
-        int c = o->ndims == 3 ? o->dims[2] : 1;
-        snprintf(hdr, sizeof hdr, "%d:%d:%d:%d:%d|", o->type, o->ndims, o->ndims > 0 ? o->dims[0] : 0,
-                 o->ndims > 1 ? o->dims[1] : 0, c);
-        std::string key = hdr;
-        realize(p, &realized[i], &key);
-        groups[key].push_back(i);
+        realize(p, &realized[i]);
+        std::vector<const Stage *> ops;
+        for (const Stage &st : realized[i]) ops.push_back(&st);
+        mp::Img d;
+        const bool known = mp::describe(t->objs[i], &d);
+        segs[i] = compile(ops, known ? d.fam : mp::FAM_U8_OTHER, known ? d.C : 0);
+        if (segs[i].size() > rounds) rounds = segs[i].size();
     }
 
-    // 4. per group: fusion pass + launches
-    for (auto &g : groups) {
-        std::vector<const Stage *> ops;
-        for (const Stage &st : realized[g.second[0]]) ops.push_back(&st);
-        std::vector<MPObjData *> objs;
-        for (size_t i : g.second) objs.push_back(t->objs[i]);
-        run_group(p, objs, ops, device, batch_stream);
+    // 3. round r runs every image's r-th segment; the images of a round are regrouped by (current
+    // layout, segment signature), so images whose coins fell differently part and meet again, and
+    // a chain of random_* stages still costs one launch per (round, kernel), not per image.
+    for (size_t r = 0; r < rounds; ++r) {
+        std::map<std::string, std::vector<size_t>> groups;
+        for (size_t i = 0; i < n; ++i)
+            if (r < segs[i].size()) groups[layout_key(t->objs[i]) + signature(segs[i][r])].push_back(i);
+        for (auto &g : groups) {
+            std::vector<MPObjData *> objs;
+            std::vector<const Segment *> sp;
+            for (size_t i : g.second) {
+                objs.push_back(t->objs[i]);
+                sp.push_back(&segs[i][r]);
+            }
+            run_segment_group(p, objs, sp, device, batch_stream);
+        }
+        p->segments.fetch_add((int)groups.size());
     }
 
     // 5. hand the results on, or finish
@@ -838,8 +957,7 @@ void host_worker(void *arg)
         if (st == MILLIPYDE_SUCCESS) st = mpobj_upload_async(o, t->host_in[i], t->in_bytes);
 
         std::vector<Stage> mine;
-        std::string unused_key;
-        realize(p, &mine, &unused_key);
+        realize(p, &mine);
         std::vector<const Stage *> ops;
         for (const Stage &sg : mine) ops.push_back(&sg);
         if (st == MILLIPYDE_SUCCESS) {

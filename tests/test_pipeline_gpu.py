@@ -137,6 +137,94 @@ def test_probability_is_per_image(mp):
     assert 16 <= n_flip <= 48
 
 
+def _draw(mp, lo, hi):
+    import ctypes
+    v = ctypes.c_double()
+    assert mp.lib.random_double_in_range(lo, hi, ctypes.byref(v)) == 0
+    return v.value
+
+
+def test_random_chain_is_one_launch_per_segment_and_matches_oracle(mp):
+    """Per-image parameter records: 70 images with their own brightness delta, sigma and colour
+    multipliers run as a handful of launches (the Gaussians split by radius bucket and into sets of
+    64), and every image equals the oracle evaluated with ITS draws.  The draws are predicted by
+    replaying the seeded generator in the executor's order (image by image, stage by stage)."""
+    n = 70
+    imgs = [synth.noise_f32(40, 160, 3, 3000 + k) for k in range(n)]
+    chain = [("random_brightness", -.2, .2), ("random_gaussian", .5, 2.),
+             ("random_colorize", .5, 1.5, .5, 1.5, .5, 1.5), ("rgb2grey",), ("random_adjust_gamma", .5, 2., 1., 1.)]
+    mp.lib.mprand_seed(1234)
+    draws = []
+    for _ in range(n):
+        b = _draw(mp, -.2, .2)
+        sg = _draw(mp, .5, 2.)
+        col = (_draw(mp, .5, 1.5), _draw(mp, .5, 1.5), _draw(mp, .5, 1.5))
+        gam = (_draw(mp, .5, 2.), _draw(mp, 1., 1.))
+        draws.append((b, sg, col, gam))
+    mp.lib.mprand_seed(1234)
+    dev = [mp.capi.DeviceImage(a) for a in imgs]
+    ch = mp.engine.Chain(chain, device=0)
+    ch.run(dev)
+    mp.lib.mprand_seed(0)
+    # brightness: 1 launch; Gaussian: <= 5 buckets x 2 sets; colorize+grey+gamma: 1 per bucket group
+    assert ch.last_launches <= 5 * (1 + 2 + 1), ch.last_launches
+    assert ch.last_launches < n
+    for a, d, (b, sg, col, gam) in zip(imgs, dev, draws):
+        want = so.apply_chain(a, [("brightness", b), ("gaussian", sg), ("colorize", *col), ("rgb2grey",),
+                                  ("adjust_gamma", *gam)])
+        got = d.numpy()
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= TOL32
+
+
+@pytest.mark.parametrize("c", [1, 3])
+def test_random_rotate_records_match_eager_rotates(mp, c):
+    """random_rotate alone (direct bilinear kernel, per-image angle table) and inside a gather
+    segment (fliplr + rotate + brightness, per-image GatherVar records) against eager ops with
+    the replayed angles."""
+    n = 9
+    imgs = [synth.noise_f32(48, 64, c, 3100 + k) for k in range(n)]
+    for chain, replay in (
+        ([("random_rotate", 0., 120.)], lambda: [("rotate", _draw(mp, 0., 120.))]),
+        ([("fliplr",), ("random_rotate", 0., 120.), ("random_brightness", -.2, .2)],
+         lambda: [("fliplr",), ("rotate", _draw(mp, 0., 120.)), ("brightness", _draw(mp, -.2, .2))]),
+    ):
+        mp.lib.mprand_seed(4321)
+        eager_chains = [replay() for _ in range(n)]
+        mp.lib.mprand_seed(4321)
+        dev = [mp.capi.DeviceImage(a) for a in imgs]
+        ch = mp.engine.Chain(chain, device=0)
+        ch.run(dev)
+        mp.lib.mprand_seed(0)
+        assert ch.last_launches == 1
+        for a, d, ec in zip(imgs, dev, eager_chains):
+            want = so.apply_chain(a, ec)
+            assert np.abs(d.numpy() - want).max() <= TOL32
+            eager = mp.capi.DeviceImage(a).apply_chain(ec).numpy()
+            assert np.abs(d.numpy() - eager).max() <= 2e-6
+
+
+def test_random_chain_fusion_off_is_image_by_image(mp):
+    """With fusion off the same seeded chain runs one image at a time and agrees with the batched
+    per-image-record run."""
+    n = 6
+    imgs = [synth.noise_f32(32, 96, 3, 3200 + k) for k in range(n)]
+    chain = [("random_gaussian", .5, 2.), ("random_brightness", -.2, .2)]
+    outs = {}
+    for fused in (1, 0):
+        mp.lib.mppipe_set_fusion(fused)
+        mp.lib.mprand_seed(555)
+        dev = [mp.capi.DeviceImage(a) for a in imgs]
+        ch = mp.engine.Chain(chain, device=0)
+        ch.run(dev)
+        outs[fused] = ([d.numpy() for d in dev], ch.last_launches)
+    mp.lib.mppipe_set_fusion(1)
+    mp.lib.mprand_seed(0)
+    assert outs[0][1] == 2 * n and outs[1][1] < outs[0][1]
+    for f, u in zip(outs[1][0], outs[0][0]):
+        assert np.array_equal(f, u)
+
+
 def test_ragged_batch(mp):
     shapes = [(40, 64, 3), (97, 131, 3), (40, 64, 3), (33, 20, 1), (64, 64, 4)]
     imgs = [synth.noise_f32(h, w, c, 500 + i) for i, (h, w, c) in enumerate(shapes)]
