@@ -293,12 +293,19 @@ namespace mpk {
 // which IS the rotate's cval = 0 rule.  The four corner reads per output sample hit shared memory.
 //
 // The kernel is issue-bound, so instructions are what is optimised:
-//  * staging moves 16-byte vectors: each box row is copied from the 16-byte-aligned address at or
-//    below its first float, and the row's alignment shift (0..3 floats) is remembered per row;
-//    vectors that straddle the image row's ends take a masked scalar path.  (Maps with a flip
-//    before the rotate, or pointwise ops before it, use the scalar staging loop.)
+//  * staging is done by the TMA unit: one 1-D bulk copy per box row, issued by the lanes of warp 0
+//    (a lane owns rows lane and lane + 32), all completing on one mbarrier.  A row's copy starts at
+//    the 16-byte boundary at or below its first float and ends at the one at or above its last;
+//    image rows are whole vectors (checked: otherwise the scalar path stages), so neither leaves
+//    the row and the alignment shift (0..3 floats) is the same for every row of the box.  Only
+//    tiles whose box leaves the image zero anything, and only outside the copies' destinations.
+//    (Maps with a flip or pointwise ops BEFORE the rotate use the scalar staging loop.)
 //  * source coordinates: one fp64 affine evaluation per thread, then fp64 adds down the column;
-//    floor is cvt.rmi, ceil is "floor + (frac > 0)", the blend runs in fp32.
+//    floor is cvt.rmi, the blend runs in fp32.  The second corner is always the next pixel / next
+//    row (weight exactly 0 when the coordinate is an integer; the box reaches ceil(max) + 1, so it
+//    is staged), which makes the four corners one base address plus immediates.
+//  * the thread's four pixels are blended first and the post-rotate pointwise program runs once
+//    over all of them (its op decode is per program, not per pixel).
 constexpr int kGatherTile = 32;
 constexpr int kGatherBox = 50;  // >= 32 * sqrt(2) + 4
 
@@ -309,7 +316,7 @@ struct GatherGeom {
     static constexpr int ROW_MAX = (kGatherBox * C + 3 + 3) / 4 * 4;
     static constexpr int PITCH = C == 1 ? 68 : (C == 3 ? 164 : 212);
     static_assert(PITCH >= ROW_MAX && PITCH % 4 == 0, "pitch");
-    static constexpr size_t SMEM = (size_t)kGatherBox * PITCH * sizeof(float) + 64;
+    static constexpr size_t SMEM = (size_t)kGatherBox * PITCH * sizeof(float);
 };
 
 template <int C, bool TAB = false>
@@ -317,16 +324,21 @@ __global__ void __launch_bounds__(256)
 gather_f32_kernel(const __grid_constant__ GatherParams g)
 {
     constexpr int PITCH = GatherGeom<C>::PITCH;
+    constexpr int NPX = kGatherTile / 8;  // output pixels per thread
     extern __shared__ __align__(16) float box[];  // [bh][PITCH]
-    int8_t *s_shift = reinterpret_cast<int8_t *>(box + kGatherBox * PITCH);
     // TAB: the angle and the pointwise programs are the image's own (GatherVar record in device
     // memory, copied to shared memory once per block); everything else is common to the launch
     __shared__ GatherVar s_var;
+    __shared__ uint64_t s_bar;
     if (TAB) {
         for (int i = threadIdx.x; i < (int)(sizeof(GatherVar) / 4); i += blockDim.x)
             reinterpret_cast<int *>(&s_var)[i] = reinterpret_cast<const int *>(g.var_tab + blockIdx.z)[i];
-        __syncthreads();
     }
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     const RotateParams &rp = TAB ? s_var.rp : g.rp;
     const PwProgram &pw_pre = TAB ? s_var.pw_pre : g.pw_pre;
     const PwProgram &pw_post = TAB ? s_var.pw_post : g.pw_post;
@@ -356,55 +368,67 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
     const int bx0 = __double2int_rd(xmin) - 1, by0 = __double2int_rd(ymin) - 1;
     const int bw = min(__double2int_ru(xmax) + 2 - bx0, kGatherBox);
     const int bh = min(__double2int_ru(ymax) + 2 - by0, kGatherBox);
+    const int row_floats = bw * C;
 
     const bool identity_pre = g.pre.ay == 1 && g.pre.by == 0 && g.pre.cy == 0 && g.pre.ax == 0 &&
                               g.pre.bx == 1 && g.pre.cx == 0 && pw_pre.n == 0;
-    if (identity_pre) {
-        // ---- vector staging
-        const int row_floats = bw * C;
-        for (int r = w; r < bh; r += 8) {
+    const bool rows_aligned = ((g.src_w * C) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    int shift = 0;  // floats between a staged row's start and box column 0 (same for every row)
+    if (identity_pre && rows_aligned) {
+        // ---- TMA staging
+        const long row_len = (long)g.src_w * C;
+        shift = (int)(((long)bx0 * C) & 3);  // two's complement: right for bx0 < 0 too; row_len % 4 == 0
+        const int want = (shift + row_floats + 3) & ~3;  // staged floats of a row: [0, want)
+        // box row r holds global floats [b0, b0 + want) of image row by0 + r; [c_lo, c_hi) of it exist
+        auto row_span = [&](int r, int &c_lo, int &c_hi, long &gsrc) {
             const int cy = by0 + r;
-            float *brow = box + r * PITCH;
-            const long g0 = ((long)cy * g.src_w + bx0) * C;  // global float index of box column 0
-            const int shift = (int)(g0 & 3);
-            if (lane == 0) s_shift[r] = (int8_t)shift;
-            const long a0 = g0 - shift;
-            const int nvec = (shift + row_floats + 3) >> 2;
-            const bool row_in = cy >= 0 && cy < g.rot_h;
-            const long row_lo = (long)cy * g.src_w * C, row_hi = row_lo + (long)g.src_w * C;
-            float4 v[2];
+            const long row_lo = (long)cy * row_len;
+            const long b0 = row_lo + (long)bx0 * C - shift;
+            const long a = b0 > row_lo ? b0 : row_lo;  // all multiples of 4
+            const long e = b0 + want < row_lo + row_len ? b0 + want : row_lo + row_len;
+            const bool row_in = cy >= 0 && cy < g.rot_h && e > a;
+            c_lo = row_in ? (int)(a - b0) : 0;
+            c_hi = row_in ? (int)(e - b0) : 0;
+            gsrc = a;
+        };
+        if (w == 0) {
+            uint32_t bytes = 0;
+            int lo[2], hi[2];
+            long gs[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                const int iv = lane + 32 * u;
-                const long gi = a0 + 4 * iv;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (iv < nvec && row_in) {
-                    if (gi >= row_lo && gi + 4 <= row_hi) {
-                        v[u] = __ldg(reinterpret_cast<const float4 *>(src + gi));
-                    } else {
-                        float *e = reinterpret_cast<float *>(&v[u]);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (gi + k >= row_lo && gi + k < row_hi) e[k] = __ldg(src + gi + k);
-                    }
-                }
+                lo[u] = hi[u] = 0;
+                if (lane + 32 * u < bh) row_span(lane + 32 * u, lo[u], hi[u], gs[u]);
+                bytes += (uint32_t)(hi[u] - lo[u]) * 4u;
             }
+            mbar_expect_tx(&s_bar, bytes);  // arrive + expect: the barrier counts the 32 lanes
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int iv = lane + 32 * u;
-                if (iv < nvec) *reinterpret_cast<float4 *>(brow + 4 * iv) = v[u];
+            for (int u = 0; u < 2; ++u)
+                if (hi[u] > lo[u])
+                    bulk_g2s(box + (lane + 32 * u) * PITCH + lo[u], src + gs[u], (uint32_t)(hi[u] - lo[u]) * 4u, &s_bar);
+        }
+        // tiles whose box leaves the image zero what the copies do not cover
+        const bool interior = by0 >= 0 && by0 + bh <= g.rot_h && (long)bx0 * C - shift >= 0 &&
+                              (long)bx0 * C - shift + want <= row_len;
+        if (!interior) {
+            for (int r = w; r < bh; r += 8) {
+                int lo, hi;
+                long gs;
+                row_span(r, lo, hi, gs);
+                float *brow = box + r * PITCH;
+                for (int c = lane; c < want; c += 32)
+                    if (c < lo || c >= hi) brow[c] = 0.f;
             }
         }
+        mbar_wait(&s_bar, 0);
     } else {
         // ---- scalar staging through the pre map (and the pre-rotate pointwise ops)
         constexpr int PER_LANE = (kGatherBox * C + 31) / 32;
         const bool has_pre = pw_pre.n > 0;
-        const int row_floats = bw * C;
         for (int r = w; r < bh; r += 8) {
             const int cy = by0 + r;
             const bool row_in = cy >= 0 && cy < g.rot_h;
             float *brow = box + r * PITCH;
-            if (lane == 0) s_shift[r] = 0;
             float v[PER_LANE];
 #pragma unroll
             for (int u = 0; u < PER_LANE; ++u) {
@@ -432,8 +456,8 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
     if (x >= g.out_w) return;
     // output pixel (x, y): q = post(x, y); stepping y by 8 moves q by 8 * (post.ay, post.ax)
     const int y_first = oy0 + w;
-    int qy = g.post.ay * y_first + g.post.by * x + g.post.cy;
-    int qx = g.post.ax * y_first + g.post.bx * x + g.post.cx;
+    const int qy = g.post.ay * y_first + g.post.by * x + g.post.cy;
+    const int qx = g.post.ax * y_first + g.post.bx * x + g.post.cx;
     const int dqy = 8 * g.post.ay, dqx = 8 * g.post.ax;
     double xs = qx, ys = qy, dxs = dqx, dys = dqy;
     if (g.has_rotate) {
@@ -443,38 +467,40 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
         dxs = rp.c * dqx - rp.s * dqy;
         dys = rp.s * dqx + rp.c * dqy;
     }
+    const float *origin = box + shift - by0 * PITCH - bx0 * C;  // box address of source pixel (0, 0)
+    float acc[NPX * C];
 #pragma unroll
-    for (int k = 0; k < kGatherTile / 8; ++k) {
-        const int y = y_first + 8 * k;
-        if (y >= g.out_h) break;
-        // recomputing from k keeps every row one rounding away from the direct formula
-        const double xk = xs + k * dxs, yk = ys + k * dys;
-        float acc[C];
-        if (g.has_rotate) {
+    for (int k = 0; k < NPX; ++k) {
+        if (y_first + 8 * k >= g.out_h) {  // past the bottom edge: its footprint is not in the box
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[k * C + c] = 0.f;
+        } else if (g.has_rotate) {
+            // recomputing from k keeps every row one rounding away from the direct formula
+            const double xk = xs + k * dxs, yk = ys + k * dys;
             const int ix = __double2int_rd(xk), iy = __double2int_rd(yk);
             const float dx = (float)(xk - (double)ix), dy = (float)(yk - (double)iy);
-            const int x0 = ix - bx0, y0 = iy - by0;
-            const int x1 = x0 + (dx > 0.f), y1 = y0 + (dy > 0.f);
-            const float *r0 = box + y0 * PITCH + s_shift[y0];
-            const float *r1 = box + y1 * PITCH + s_shift[y1];
+            const float *c00 = origin + iy * PITCH + ix * C;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                const float p00 = r0[x0 * C + c], p01 = r0[x1 * C + c];
-                const float p10 = r1[x0 * C + c], p11 = r1[x1 * C + c];
-                const float top = (1.f - dx) * p00 + dx * p01;
-                const float bot = (1.f - dx) * p10 + dx * p11;
-                acc[c] = (1.f - dy) * top + dy * bot;
+                const float top = (1.f - dx) * c00[c] + dx * c00[C + c];
+                const float bot = (1.f - dx) * c00[PITCH + c] + dx * c00[PITCH + C + c];
+                acc[k * C + c] = (1.f - dy) * top + dy * bot;
             }
         } else {
-            const int yy = qy + k * dqy - by0, xx = qx + k * dqx - bx0;
-            const float *r0 = box + yy * PITCH + s_shift[yy] + xx * C;
+            const float *c00 = origin + (qy + k * dqy) * PITCH + (qx + k * dqx) * C;
 #pragma unroll
-            for (int c = 0; c < C; ++c) acc[c] = r0[c];
+            for (int c = 0; c < C; ++c) acc[k * C + c] = c00[c];
         }
-        pw_apply_tile<C, C>(pw_post, acc, 0);
-        float *o = dst + ((size_t)y * g.out_w + x) * C;
+    }
+    pw_apply_tile<C, NPX * C>(pw_post, acc, 0);
 #pragma unroll
-        for (int c = 0; c < C; ++c) o[c] = acc[c];
+    for (int k = 0; k < NPX; ++k) {
+        const int y = y_first + 8 * k;
+        if (y < g.out_h) {
+            float *o = dst + ((size_t)y * g.out_w + x) * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) o[c] = acc[k * C + c];
+        }
     }
 }
 
