@@ -177,6 +177,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "r"(parity)
         : "memory");
 }
+// The same wait for callers whose sibling CTAs on the SM have work to issue meanwhile: the thread
+// may be suspended up to `hint_ns` per probe instead of re-probing at once.
+__device__ __forceinline__ void mbar_wait_suspend(uint64_t *bar, uint32_t parity, uint32_t hint_ns)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP_S:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra WAIT_DONE_S;\n"
+        "bra WAIT_LOOP_S;\n"
+        "WAIT_DONE_S:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity), "r"(hint_ns)
+        : "memory");
+}
 // global -> shared 1-D bulk copy through the TMA unit; bytes % 16 == 0, both sides 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {

@@ -320,7 +320,7 @@ struct GatherGeom {
 };
 
 template <int C, bool TAB = false>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 gather_f32_kernel(const __grid_constant__ GatherParams g)
 {
     constexpr int PITCH = GatherGeom<C>::PITCH;
@@ -348,23 +348,25 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
     const int ox1 = min(ox0 + kGatherTile, g.out_w) - 1, oy1 = min(oy0 + kGatherTile, g.out_h) - 1;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 
-    // footprint of the tile in the rotate's space (after the post map): the map is affine, so its
-    // extremes are at the tile corners
-    double xmin = 1e30, xmax = -1e30, ymin = 1e30, ymax = -1e30;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int px = (k & 1) ? ox1 : ox0, py = (k & 2) ? oy1 : oy0;
-        const int qy = g.post.ay * py + g.post.by * px + g.post.cy;
-        const int qx = g.post.ax * py + g.post.bx * px + g.post.cx;
-        double xs = qx, ys = qy;
-        if (g.has_rotate) {
-            const double fx = (double)qx - rp.cx, fy = (double)qy - rp.cy;
-            xs = rp.c * fx - rp.s * fy + rp.cx;
-            ys = rp.s * fx + rp.c * fy + rp.cy;
-        }
-        xmin = fmin(xmin, xs); xmax = fmax(xmax, xs);
-        ymin = fmin(ymin, ys); ymax = fmax(ymax, ys);
+    // footprint of the tile in the rotate's space (after the post map): both maps are affine, so the
+    // image of the tile is a parallelogram around the image of its centre, and its bounding box has
+    // half-extents |M| * (half-extents of the tile) -- a dozen fp64 operations instead of mapping
+    // the four corners and reducing them
+    const double hx = 0.5 * (ox1 - ox0), hy = 0.5 * (oy1 - oy0);
+    const double pcx = ox0 + hx, pcy = oy0 + hy;
+    const double qcy = g.post.ay * pcy + g.post.by * pcx + g.post.cy;
+    const double qcx = g.post.ax * pcy + g.post.bx * pcx + g.post.cx;
+    const double qhy = abs(g.post.ay) * hy + abs(g.post.by) * hx;
+    const double qhx = abs(g.post.ax) * hy + abs(g.post.bx) * hx;
+    double xc = qcx, yc = qcy, ex = qhx, ey = qhy;
+    if (g.has_rotate) {
+        const double fx = qcx - rp.cx, fy = qcy - rp.cy;
+        xc = rp.c * fx - rp.s * fy + rp.cx;
+        yc = rp.s * fx + rp.c * fy + rp.cy;
+        ex = fabs(rp.c) * qhx + fabs(rp.s) * qhy;
+        ey = fabs(rp.s) * qhx + fabs(rp.c) * qhy;
     }
+    const double xmin = xc - ex, xmax = xc + ex, ymin = yc - ey, ymax = yc + ey;
     const int bx0 = __double2int_rd(xmin) - 1, by0 = __double2int_rd(ymin) - 1;
     const int bw = min(__double2int_ru(xmax) + 2 - bx0, kGatherBox);
     const int bh = min(__double2int_ru(ymax) + 2 - by0, kGatherBox);
@@ -374,53 +376,45 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
                               g.pre.bx == 1 && g.pre.cx == 0 && pw_pre.n == 0;
     const bool rows_aligned = ((g.src_w * C) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
     int shift = 0;  // floats between a staged row's start and box column 0 (same for every row)
-    if (identity_pre && rows_aligned) {
-        // ---- TMA staging
-        const long row_len = (long)g.src_w * C;
-        shift = (int)(((long)bx0 * C) & 3);  // two's complement: right for bx0 < 0 too; row_len % 4 == 0
+    const bool tma = identity_pre && rows_aligned;
+    if (tma) {
+        // ---- TMA staging.  Column arithmetic is per row and in floats, so 32 bits do.
+        const int row_len = g.src_w * C;
+        shift = (bx0 * C) & 3;  // two's complement: right for bx0 < 0 too; row_len % 4 == 0
         const int want = (shift + row_floats + 3) & ~3;  // staged floats of a row: [0, want)
-        // box row r holds global floats [b0, b0 + want) of image row by0 + r; [c_lo, c_hi) of it exist
-        auto row_span = [&](int r, int &c_lo, int &c_hi, long &gsrc) {
-            const int cy = by0 + r;
-            const long row_lo = (long)cy * row_len;
-            const long b0 = row_lo + (long)bx0 * C - shift;
-            const long a = b0 > row_lo ? b0 : row_lo;  // all multiples of 4
-            const long e = b0 + want < row_lo + row_len ? b0 + want : row_lo + row_len;
-            const bool row_in = cy >= 0 && cy < g.rot_h && e > a;
-            c_lo = row_in ? (int)(a - b0) : 0;
-            c_hi = row_in ? (int)(e - b0) : 0;
-            gsrc = a;
-        };
+        const int col0 = bx0 * C - shift;                // image-row float held by box-row float 0
+        // the part [c_lo, c_hi) of every box row that exists in the image (multiples of 4)
+        const int c_lo = col0 < 0 ? -col0 : 0;
+        const int c_hi = want < row_len - col0 ? want : row_len - col0;
+        // box rows [r_lo, r_hi) lie inside the image
+        const int r_lo = by0 < 0 ? -by0 : 0;
+        const int r_hi = bh < g.rot_h - by0 ? bh : g.rot_h - by0;
+        const bool any = c_hi > c_lo && r_hi > r_lo;
         if (w == 0) {
             uint32_t bytes = 0;
-            int lo[2], hi[2];
-            long gs[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                lo[u] = hi[u] = 0;
-                if (lane + 32 * u < bh) row_span(lane + 32 * u, lo[u], hi[u], gs[u]);
-                bytes += (uint32_t)(hi[u] - lo[u]) * 4u;
+                const int r = lane + 32 * u;
+                if (any && r >= r_lo && r < r_hi) bytes += (uint32_t)(c_hi - c_lo) * 4u;
             }
             mbar_expect_tx(&s_bar, bytes);  // arrive + expect: the barrier counts the 32 lanes
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
-                if (hi[u] > lo[u])
-                    bulk_g2s(box + (lane + 32 * u) * PITCH + lo[u], src + gs[u], (uint32_t)(hi[u] - lo[u]) * 4u, &s_bar);
-        }
-        // tiles whose box leaves the image zero what the copies do not cover
-        const bool interior = by0 >= 0 && by0 + bh <= g.rot_h && (long)bx0 * C - shift >= 0 &&
-                              (long)bx0 * C - shift + want <= row_len;
-        if (!interior) {
-            for (int r = w; r < bh; r += 8) {
-                int lo, hi;
-                long gs;
-                row_span(r, lo, hi, gs);
-                float *brow = box + r * PITCH;
-                for (int c = lane; c < want; c += 32)
-                    if (c < lo || c >= hi) brow[c] = 0.f;
+            for (int u = 0; u < 2; ++u) {
+                const int r = lane + 32 * u;
+                if (any && r >= r_lo && r < r_hi)
+                    bulk_g2s(box + r * PITCH + c_lo, src + ((long)(by0 + r) * row_len + col0 + c_lo),
+                             (uint32_t)(c_hi - c_lo) * 4u, &s_bar);
             }
         }
-        mbar_wait(&s_bar, 0);
+        // tiles whose box leaves the image zero what the copies do not cover
+        if (!any || c_lo > 0 || c_hi < want || r_lo > 0 || r_hi < bh) {
+            for (int r = w; r < bh; r += 8) {
+                float *brow = box + r * PITCH;
+                const bool row_in = any && r >= r_lo && r < r_hi;
+                for (int c = lane; c < want; c += 32)
+                    if (!row_in || c < c_lo || c >= c_hi) brow[c] = 0.f;
+            }
+        }
     } else {
         // ---- scalar staging through the pre map (and the pre-rotate pointwise ops)
         constexpr int PER_LANE = (kGatherBox * C + 31) / 32;
@@ -450,10 +444,10 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
             }
         }
     }
-    __syncthreads();
+    // (the TMA path waits for its copies after the coordinate set-up below)
+    if (!tma) __syncthreads();
 
     const int x = ox0 + lane;
-    if (x >= g.out_w) return;
     // output pixel (x, y): q = post(x, y); stepping y by 8 moves q by 8 * (post.ay, post.ax)
     const int y_first = oy0 + w;
     const int qy = g.post.ay * y_first + g.post.by * x + g.post.cy;
@@ -467,6 +461,11 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
         dxs = rp.c * dqx - rp.s * dqy;
         dys = rp.s * dqx + rp.c * dqy;
     }
+    if (tma) {
+        mbar_wait_suspend(&s_bar, 0, 2000);
+        __syncthreads();  // the zero fill of edge tiles
+    }
+    if (x >= g.out_w) return;
     const float *origin = box + shift - by0 * PITCH - bx0 * C;  // box address of source pixel (0, 0)
     float acc[NPX * C];
 #pragma unroll
