@@ -223,22 +223,15 @@ rotate_nearest_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
 // skimage.transform.rotate defaults (order=1, mode='constant', cval=0, centre
 // (W/2-0.5, H/2-0.5)).  Source coordinates in fp64 (fp32 would carry ~2.4e-4 px
 // at x ~ 3840, 24x the tolerance), blend in the image's precision.  Each corner
-// is the pixel if inside, else 0.  A warp covers a 32 x 1 run of output pixels
-// and a block a 32 x 8 patch, so the four-corner gathers of neighbouring lanes
-// fall in the same few 128-byte lines and are served by L1 after the first
-// touch (the read-only path, __ldg).
-
+// is the pixel if inside, else 0.  This direct form (a warp covers a 32 x 1 run of
+// output pixels, corners through the read-only path) serves the fp64 greyscale
+// layout; fp32 images go through the tile-staged gather_f32_kernel below, whose
+// loads are coalesced at every angle.
 template <typename T, int C>
 __global__ void __launch_bounds__(256)
 rotate_bilinear_kernel(const T *__restrict__ in, T *__restrict__ out, int width, int height,
-                       RotateParams rp, const T *const *__restrict__ in_tab = nullptr,
-                       T *const *__restrict__ out_tab = nullptr, const RotateParams *__restrict__ rp_tab = nullptr)
+                       RotateParams rp)
 {
-    if (in_tab) {  // batched launch: blockIdx.z selects the image and, if given, its own angle
-        in = in_tab[blockIdx.z];
-        out = out_tab[blockIdx.z];
-        if (rp_tab) rp = rp_tab[blockIdx.z];
-    }
     // a warp covers a 32 x 1 run of output pixels, the block 32 x 8 (measured: 8 x 4 warp patches
     // are slower here -- the stores dominate and want the long runs)
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);

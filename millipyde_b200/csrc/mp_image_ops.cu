@@ -343,15 +343,23 @@ MPStatus mpimg_rotate(MPObjData *obj, void *args)
             rotate_nearest_kernel<2><<<grid, block, 0, s>>>((const uint32_t *)obj->device_data, (uint32_t *)out, d.W, d.H, rad);
     } else {
         RotateParams rp = mp::rotate_params(d.W, d.H, angle);
-        dim3 grid((d.W + 31) / 32, (d.H + 7) / 8);
-        if (d.fam == mp::FAM_F64)
+        if (d.fam == mp::FAM_F64) {
+            dim3 grid((d.W + 31) / 32, (d.H + 7) / 8);
             rotate_bilinear_kernel<double, 1><<<grid, 256, 0, s>>>((const double *)obj->device_data, (double *)out, d.W, d.H, rp);
-        else if (d.C == 1)
-            rotate_bilinear_kernel<float, 1><<<grid, 256, 0, s>>>((const float *)obj->device_data, (float *)out, d.W, d.H, rp);
-        else if (d.C == 3)
-            rotate_bilinear_kernel<float, 3><<<grid, 256, 0, s>>>((const float *)obj->device_data, (float *)out, d.W, d.H, rp);
-        else
-            rotate_bilinear_kernel<float, 4><<<grid, 256, 0, s>>>((const float *)obj->device_data, (float *)out, d.W, d.H, rp);
+        } else {
+            // fp32: the tile-staged gather (kernels/geometry.cuh) with identity index maps and no
+            // pointwise programs -- its loads are coalesced at every angle
+            GatherParams g = {};
+            g.in = (const float *)obj->device_data;
+            g.out = (float *)out;
+            g.out_h = g.rot_h = d.H;
+            g.out_w = g.rot_w = g.src_w = d.W;
+            g.post = g.pre = IndexMap{1, 0, 0, 0, 1, 0};
+            g.has_rotate = 1;
+            g.rp = rp;
+            mp::launch_gather_f32(s, d.C, g, 1);
+            return finish(obj, s, out, obj->nbytes);
+        }
     }
     mp::count_launch();
     return finish(obj, s, out, obj->nbytes);
@@ -783,17 +791,6 @@ void launch_grey_f32_batch(cudaStream_t s, const Img &d, const PwProgram &pre, c
 }  // namespace mp
 
 namespace mp {
-
-// Bilinear rotate of n same-shape fp32 images; `rp_tab` (device memory) gives each its own angle.
-void launch_rotate_f32_batch(cudaStream_t s, const Img &d, const RotateParams &rp, const float *const *in_tab,
-                             float *const *out_tab, int n_images, const RotateParams *rp_tab)
-{
-    dim3 grid((d.W + 31) / 32, (d.H + 7) / 8, n_images);
-    if (d.C == 1) rotate_bilinear_kernel<float, 1><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, d.H, rp, in_tab, out_tab, rp_tab);
-    else if (d.C == 3) rotate_bilinear_kernel<float, 3><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, d.H, rp, in_tab, out_tab, rp_tab);
-    else rotate_bilinear_kernel<float, 4><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, d.H, rp, in_tab, out_tab, rp_tab);
-    count_launch();
-}
 
 }  // namespace mp
 

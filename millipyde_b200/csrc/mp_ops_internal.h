@@ -54,8 +54,6 @@ void launch_pw_f32_batch(cudaStream_t s, const Img &d, const mpk::PwProgram &pro
 void launch_grey_f32_batch(cudaStream_t s, const Img &d, const mpk::PwProgram &pre, const mpk::PwProgram &post,
                            const float *const *in_tab, float *const *out_tab, int n_images,
                            const mpk::PwProgram *prog_tab = nullptr);  // [image][2] = pre, post
-void launch_rotate_f32_batch(cudaStream_t s, const Img &d, const mpk::RotateParams &rp, const float *const *in_tab,
-                             float *const *out_tab, int n_images, const mpk::RotateParams *rp_tab = nullptr);
 
 bool fliplr_batch_supported(const Img &d);
 void launch_fliplr_batch(cudaStream_t s, const Img &d, const void *const *in_tab, void *const *out_tab, int n_images);

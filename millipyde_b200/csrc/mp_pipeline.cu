@@ -171,7 +171,7 @@ std::vector<Segment> compile(const std::vector<const Stage *> &ops, mp::Family f
                 }
                 ++j;
             }
-            if (geometric && j - i >= 2) {
+            if (geometric && (j - i >= 2 || seg.has_rotate)) {  // a lone rotate is a gather too
                 out.push_back(seg);
                 i = j;
                 continue;
@@ -561,25 +561,6 @@ void run_segment_group(mp_pipeline *p, const std::vector<MPObjData *> &objs, con
             return;
         }
         if (st != MILLIPYDE_SUCCESS) return;
-    }
-    if (seg.kind == Segment::SINGLE && seg.single->kind == OP_ROTATE && n >= 2 && f32 && g_fusion.load()) {
-        std::vector<RotateParams> rps;
-        bool same = true;
-        for (size_t i = 1; i < n && same; ++i) same = segs[i]->single->a[0] == seg.single->a[0];
-        if (!same)
-            for (size_t i = 0; i < n; ++i) rps.push_back(mp::rotate_params(cur.W, cur.H, segs[i]->single->a[0]));
-        const RotateParams rp0 = mp::rotate_params(cur.W, cur.H, seg.single->a[0]);
-        bool handled = false;
-        MPStatus st = run_batched(
-            objs, objs[0]->nbytes, device, s, &handled,
-            [&](const float *const *in_tab, float *const *out_tab, int m) {
-                mp::launch_rotate_f32_batch(s, cur, rp0, in_tab, out_tab, m,
-                                            rps.empty() ? nullptr : (const RotateParams *)g_records);
-                return MILLIPYDE_SUCCESS;
-            },
-            rps.data(), rps.size() * sizeof(RotateParams));
-        note_status(p, st);
-        if (handled || st != MILLIPYDE_SUCCESS) return;
     }
     if (seg.kind == Segment::SINGLE && seg.single->kind == OP_FLIPLR && n >= 2 && g_fusion.load() &&
         mp::describe(objs[0], &cur) && mp::fliplr_batch_supported(cur)) {
