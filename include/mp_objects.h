@@ -35,6 +35,13 @@ void mpobj_dealloc_device_data(MPObjData *obj);
 /* Deep copy (possibly cross-device). src/millipyde_objects.cpp:98-120 */
 MPObjData *mpobj_clone_data(MPObjData *obj, int device_id, int stream_id);
 
+/* Header copy that BORROWS obj's device buffer (same device): the input of mppipe_run_views and of
+ * nothing else -- the executor reads the borrowed buffer in the chain's first launch and gives the
+ * view a buffer of its own, which saves the clone's extra pass over the image (the Generator's
+ * "clone, then augment", src/gpugenerator.c:236-247).  Never run an eager op on a view or free it
+ * while it still borrows; mppipe_run_views leaves no borrowed buffer behind. */
+MPObjData *mpobj_view_data(MPObjData *obj);
+
 /* ---- new entry points -------------------------------------------------- */
 
 /* D2H straight into caller memory (e.g. a numpy buffer); waits for completion. */

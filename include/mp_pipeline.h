@@ -48,6 +48,11 @@ void mppipe_connect(MPPipeline *from, MPPipeline *to);
  * involved are idle.  Objects are mutated in place like the eager ops do. */
 MPStatus mppipe_run(MPPipeline *p, MPObjData **objs, int n);
 
+/* mppipe_run for views made by mpobj_view_data (all on the pipeline's device): the first launch
+ * that touches an image reads the borrowed buffer and writes the view's own; a view no stage
+ * touched is deep-copied.  On return every view owns its buffer (or holds none, on error). */
+MPStatus mppipe_run_views(MPPipeline *p, MPObjData **views, int n);
+
 /* Asynchronous halves of mppipe_run, for callers that drive several pipelines at once. */
 MPStatus mppipe_submit(MPPipeline *p, MPObjData **objs, int n);
 MPStatus mppipe_wait(MPPipeline *p);

@@ -126,6 +126,7 @@ SYMBOLS = {
     "mpobj_change_device": (None, [_OBJ, C.c_int]),
     "mpobj_dealloc_device_data": (None, [_OBJ]),
     "mpobj_clone_data": (_OBJ, [_OBJ, C.c_int, C.c_int]),
+    "mpobj_view_data": (_OBJ, [_OBJ]),
     "mpobj_copy_to_host_into": (C.c_int, [_OBJ, C.c_void_p, C.c_size_t]),
     "mpobj_upload_async": (C.c_int, [_OBJ, C.c_void_p, C.c_size_t]),
     "mpobj_download_async": (C.c_int, [_OBJ, C.c_void_p, C.c_size_t]),
@@ -181,6 +182,7 @@ SYMBOLS = {
     "mppipe_set_device": (None, [C.c_void_p, C.c_int]),
     "mppipe_connect": (None, [C.c_void_p, C.c_void_p]),
     "mppipe_run": (C.c_int, [C.c_void_p, C.POINTER(_OBJ), C.c_int]),
+    "mppipe_run_views": (C.c_int, [C.c_void_p, C.POINTER(_OBJ), C.c_int]),
     "mppipe_submit": (C.c_int, [C.c_void_p, C.POINTER(_OBJ), C.c_int]),
     "mppipe_wait": (C.c_int, [C.c_void_p]),
     "mppipe_run_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t,
@@ -319,6 +321,13 @@ class DeviceImage:
         p = lib().mpobj_clone_data(self.ptr, dev, stream)
         if not p:
             raise MillipydeError(57, "mpobj_clone_data")
+        return DeviceImage(_ptr=p)
+
+    def view(self) -> "DeviceImage":
+        """Header copy borrowing this image's buffer: input of Chain.run_views only."""
+        p = lib().mpobj_view_data(self.ptr)
+        if not p:
+            raise MillipydeError(57, "mpobj_view_data")
         return DeviceImage(_ptr=p)
 
     def to_device(self, device: int) -> "DeviceImage":

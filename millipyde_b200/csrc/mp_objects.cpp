@@ -215,6 +215,19 @@ MPObjData *mpobj_clone_data(MPObjData *obj, int device_id, int stream_id)
     return c;
 }
 
+MPObjData *mpobj_view_data(MPObjData *obj)
+{
+    if (!obj || !obj->device_data || mp::ensure_initialized() != MILLIPYDE_SUCCESS) return NULL;
+    MPObjData *c = (MPObjData *)malloc(sizeof(MPObjData));
+    if (!c) return NULL;
+    *c = *obj;
+    c->pinned = MP_FALSE;
+    int slots = obj->ndims < 3 ? 3 : obj->ndims;
+    c->dims = (int *)calloc(2 * (size_t)slots, sizeof(int));
+    memcpy(c->dims, obj->dims, sizeof(int) * 2 * (size_t)obj->ndims);
+    return c;  // device_data and stream are obj's: the view is ordered after obj's pending work
+}
+
 MPObjData *mpobj_create(const void *host, int ndims, const long *shape, int typenum)
 {
     if (mp::ensure_initialized() != MILLIPYDE_SUCCESS) return NULL;

@@ -9,6 +9,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "mp_devices.h"
@@ -349,6 +350,36 @@ MPStatus run_segment_on(MPObjData *obj, const Segment &seg)
 // `launch` finds them at g_records (device address), valid for the duration of the call.
 thread_local const void *g_records = nullptr;
 
+// Views (mpobj_view_data) whose buffer still belongs to someone else, for the shard this worker
+// thread is running.  The launch that first rewrites such an image must not free its input.
+thread_local std::unordered_set<MPObjData *> *g_borrowed = nullptr;
+
+// Retire the buffer an image held before a launch gave it a fresh one.
+void release_input(int device, cudaStream_t s, MPObjData *o)
+{
+    if (g_borrowed && g_borrowed->erase(o)) return;  // not ours to free
+    mp::pool_free(device, s, o->device_data);
+}
+
+// Give a still-borrowing view a buffer of its own (deep copy) before anything frees or mutates it.
+MPStatus materialize(int device, cudaStream_t s, MPObjData *o)
+{
+    if (!g_borrowed || !g_borrowed->count(o)) return MILLIPYDE_SUCCESS;
+    g_borrowed->erase(o);
+    void *fresh = mp::pool_alloc(device, s, o->nbytes);
+    if (!fresh) {
+        o->device_data = NULL;
+        return MP_ERROR_DEVICE_ALLOC;
+    }
+    cudaError_t e = cudaMemcpyAsync(fresh, o->device_data, o->nbytes, cudaMemcpyDeviceToDevice, s);
+    o->device_data = fresh;
+    if (e != cudaSuccess) {
+        mp::record_cuda_error(e, "cudaMemcpyAsync(view)", __FILE__, __LINE__);
+        return MP_ERROR_CUDA_RUNTIME;
+    }
+    return MILLIPYDE_SUCCESS;
+}
+
 template <typename Launch>
 MPStatus run_batched(const std::vector<MPObjData *> &objs, size_t out_bytes, int device, cudaStream_t s,
                      bool *handled, Launch launch, const void *records = nullptr, size_t record_bytes = 0)
@@ -383,7 +414,7 @@ MPStatus run_batched(const std::vector<MPObjData *> &objs, size_t out_bytes, int
     }
     for (size_t i = 0; i < n; ++i) {
         if (st == MILLIPYDE_SUCCESS) {
-            mp::pool_free(device, s, objs[i]->device_data);
+            release_input(device, s, objs[i]);
             objs[i]->device_data = fresh[i];
             objs[i]->nbytes = out_bytes;
         } else {
@@ -499,7 +530,7 @@ MPStatus run_gather(const std::vector<MPObjData *> &objs, const std::vector<cons
             mp::pool_free(device, s, fresh);
             return MP_ERROR_CUDA_RUNTIME;
         }
-        mp::pool_free(device, s, o->device_data);
+        release_input(device, s, o);
         o->device_data = fresh;
     }
     return MILLIPYDE_SUCCESS;
@@ -600,7 +631,14 @@ void run_segment_group(mp_pipeline *p, const std::vector<MPObjData *> &objs, con
         note_status(p, run_gather(objs, segs, cur, device, s));
         return;
     }
-    for (size_t i = 0; i < n; ++i) note_status(p, run_segment_on(objs[i], *segs[i]));
+    for (size_t i = 0; i < n; ++i) {
+        if (segs[i]->kind != Segment::GATHER_F32) {  // eager ops free their input: own it first
+            MPStatus st = materialize(device, s, objs[i]);
+            note_status(p, st);
+            if (st != MILLIPYDE_SUCCESS) continue;
+        }
+        note_status(p, run_segment_on(objs[i], *segs[i]));
+    }
 }
 
 // The layout part of a grouping key: images must agree on it to share a launch.
@@ -617,9 +655,10 @@ struct ShardTask {
     mp_pipeline *pipe;
     std::vector<MPObjData *> objs;
     int device;
+    bool views;  // objs borrow their buffers (mppipe_run_views)
 };
 
-void submit_shard(mp_pipeline *p, std::vector<MPObjData *> objs, int device);
+void submit_shard(mp_pipeline *p, std::vector<MPObjData *> objs, int device, bool views = false);
 
 void shard_worker(void *arg)
 {
@@ -642,6 +681,10 @@ void shard_worker(void *arg)
         else (void)cudaGetLastError();
     }
     arena.used = 0;
+
+    std::unordered_set<MPObjData *> borrowed;
+    if (t->views) borrowed.insert(t->objs.begin(), t->objs.end());
+    g_borrowed = t->views ? &borrowed : nullptr;
 
     // 1. bring every object onto this device and onto the shard's stream
     for (size_t i = 0; i < n; ++i) {
@@ -684,6 +727,12 @@ void shard_worker(void *arg)
         p->segments.fetch_add((int)groups.size());
     }
 
+    // 4b. a view no segment rewrote still borrows: deep-copy it
+    if (t->views) {
+        for (size_t i = 0; i < n; ++i) note_status(p, materialize(device, batch_stream, t->objs[i]));
+        g_borrowed = nullptr;
+    }
+
     // 5. hand the results on, or finish
     if (p->receiver) {
         // the receiver's worker orders itself after this stream through the objects' events
@@ -704,14 +753,14 @@ void shard_worker(void *arg)
     delete t;
 }
 
-void submit_shard(mp_pipeline *p, std::vector<MPObjData *> objs, int device)
+void submit_shard(mp_pipeline *p, std::vector<MPObjData *> objs, int device, bool views)
 {
     if (objs.empty()) return;
     {
         std::lock_guard<std::mutex> lk(p->mux);
         p->in_flight.push_back(device);
     }
-    ShardTask *t = new ShardTask{p, std::move(objs), device};
+    ShardTask *t = new ShardTask{p, std::move(objs), device, views};
     mpdev_submit_work(device, shard_worker, t);
 }
 
@@ -795,7 +844,22 @@ void mppipe_connect(MPPipeline *self, MPPipeline *receiver)
     self->receiver = receiver;
 }
 
-MPStatus mppipe_submit(MPPipeline *p, MPObjData **objs, int n)
+static MPStatus submit_impl(MPPipeline *p, MPObjData **objs, int n, bool views);
+
+MPStatus mppipe_submit(MPPipeline *p, MPObjData **objs, int n) { return submit_impl(p, objs, n, false); }
+
+MPStatus mppipe_run_views(MPPipeline *p, MPObjData **views, int n)
+{
+    MPStatus st = submit_impl(p, views, n, true);
+    if (st != MILLIPYDE_SUCCESS) {  // nothing ran: the views must not keep (and later free) what they borrow
+        for (int i = 0; views && i < n; ++i)
+            if (views[i]) views[i]->device_data = NULL;
+        return st;
+    }
+    return mppipe_wait(p);
+}
+
+static MPStatus submit_impl(MPPipeline *p, MPObjData **objs, int n, bool views)
 {
     if (!p || n < 0 || (n > 0 && !objs)) return MP_ERROR_INVALID_ARGUMENT;
     MPStatus st = mp::ensure_initialized();
@@ -813,6 +877,13 @@ MPStatus mppipe_submit(MPPipeline *p, MPObjData **objs, int n)
             device = mpdev_get_recommended_device();
         }
     }
+    if (views) {
+        // a view stays where the buffer it borrows lives: one shard, on that device
+        if (cycle && n > 0 && objs[0]) device = objs[0]->mem_loc;
+        cycle = false;
+        for (int i = 0; i < n; ++i)
+            if (!objs[i] || !objs[i]->device_data || objs[i]->mem_loc != device) return MP_ERROR_INVALID_ARGUMENT;
+    }
     if (!mpdev_is_valid_device(device)) return GPUPIPELINE_ERROR_UNUSABLE_DEVICE;
     p->cycled = cycle;
     for (mp_pipeline *q = p->receiver; q; q = q->receiver)
@@ -826,7 +897,7 @@ MPStatus mppipe_submit(MPPipeline *p, MPObjData **objs, int n)
         if (objs[i]) shards[cur].push_back(objs[i]);
         if (cycle && ((i + 1) % THREADS_PER_DEVICE == 0)) cur = mpdev_get_next_device(cur);
     }
-    for (auto &kv : shards) submit_shard(p, std::move(kv.second), kv.first);
+    for (auto &kv : shards) submit_shard(p, std::move(kv.second), kv.first, views);
     return MILLIPYDE_SUCCESS;
 }
 

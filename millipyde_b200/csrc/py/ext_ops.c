@@ -565,11 +565,22 @@ static int produce_batch(MPGeneratorObject *g, long count)
     PyObject *batch = PyList_New(0);
     MPObjData **objs = (MPObjData **)calloc((size_t)count, sizeof(MPObjData *));
     int dev = bound != DEVICE_LOC_NO_AFFINITY ? bound : mpdev_get_recommended_device();
+    /* One device and every input already there: hand the executor VIEWS of the inputs instead of
+     * clones.  The chain's first launch then reads the input itself and writes the output's own
+     * buffer, which saves the clone's pass over every image (mppipe_run_views). */
+    int use_views = bound != DEVICE_LOC_NO_AFFINITY || ndev == 1;
+    for (Py_ssize_t k = 0; use_views && k < n_in; ++k) {
+        MPObjData *o = ((MPArrayObject *)PyList_GetItem(g->inputs, k))->obj;
+        if (!o || !o->device_data || o->mem_loc != dev) use_views = 0;
+    }
     for (long k = 0; k < count; ++k) {
         PyObject *input = PyList_GetItem(g->inputs, (g->produced + k) % n_in);
         /* the executor assigns image k to device block k / THREADS_PER_DEVICE: clone it there */
-        PyObject *c = mpext_clone((MPArrayObject *)input, dev, 0);
+        PyObject *c = use_views ? mpext_wrap_obj(Py_TYPE(input), mpobj_view_data(((MPArrayObject *)input)->obj))
+                                : mpext_clone((MPArrayObject *)input, dev, 0);
         if (!c) {
+            if (use_views) /* the views made so far still borrow: they must not free the inputs' buffers */
+                for (long j = 0; j < k; ++j) objs[j]->device_data = NULL;
             Py_DECREF(batch);
             free(objs);
             return -1;
@@ -582,7 +593,7 @@ static int produce_batch(MPGeneratorObject *g, long count)
     }
     MPStatus st;
     Py_BEGIN_ALLOW_THREADS
-    st = mppipe_run(g->pipe, objs, (int)count);
+    st = use_views ? mppipe_run_views(g->pipe, objs, (int)count) : mppipe_run(g->pipe, objs, (int)count);
     Py_END_ALLOW_THREADS
     free(objs);
     if (st != MILLIPYDE_SUCCESS) {

@@ -54,6 +54,10 @@ class Chain:
     def run(self, images) -> None:
         capi.check(capi.lib().mppipe_run(self.ptr, self._objs(images), len(images)), "mppipe_run")
 
+    def run_views(self, views) -> None:
+        """`views` = [img.view() ...]: the sources stay untouched, every view ends up owning its result."""
+        capi.check(capi.lib().mppipe_run_views(self.ptr, self._objs(views), len(views)), "mppipe_run_views")
+
     def submit(self, images) -> None:
         self._pending = self._objs(images)
         capi.check(capi.lib().mppipe_submit(self.ptr, self._pending, len(images)), "mppipe_submit")

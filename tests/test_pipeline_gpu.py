@@ -225,6 +225,37 @@ def test_random_chain_fusion_off_is_image_by_image(mp):
         assert np.array_equal(f, u)
 
 
+def test_views_leave_sources_untouched_and_own_their_results(mp):
+    """mppipe_run_views (the Generator's clone-free path): sources unchanged, results == the same
+    chain on deep clones, for chains whose first segment is batched, eager, or absent."""
+    imgs = [synth.noise_f32(48, 64, 3, 3300 + k) for k in range(5)]
+    u8 = [synth.rgba8(32, 48, 3400 + k) for k in range(3)]
+    cases = [
+        (imgs, [("brightness", 0.1), ("gaussian", 1.0)]),                 # batched first segment
+        (imgs, [("rotate", 20.0), ("rgb2grey",)]),                        # gather first
+        (imgs, [("fliplr", {"probability": 0.5}), ("transpose", {"probability": 0.5})]),  # some images untouched
+        (imgs, []),                                                       # nothing runs: deep copy
+        (u8, [("adjust_gamma", 2.0, 1.0), ("rgb2grey",)]),                # eager reference-layout ops
+    ]
+    for arrays, chain in cases:
+        src = [mp.capi.DeviceImage(a) for a in arrays]
+        mp.lib.mprand_seed(31)
+        clones = [d.clone() for d in src]
+        mp.engine.Chain(chain, device=0).run(clones)
+        mp.lib.mprand_seed(31)
+        views = [d.view() for d in src]
+        mp.engine.Chain(chain, device=0).run_views(views)
+        mp.lib.mprand_seed(0)
+        for a, d, c, v in zip(arrays, src, clones, views):
+            assert np.array_equal(d.numpy(), a)                # source untouched
+            assert v.obj.device_data != d.obj.device_data      # the view owns a buffer of its own
+            assert np.array_equal(v.numpy(), c.numpy())
+        for v in views:
+            v.close()
+        for d in src:                                          # and the sources are still alive
+            assert d.numpy().shape == arrays[0].shape
+
+
 def test_ragged_batch(mp):
     shapes = [(40, 64, 3), (97, 131, 3), (40, 64, 3), (33, 20, 1), (64, 64, 4)]
     imgs = [synth.noise_f32(h, w, c, 500 + i) for i, (h, w, c) in enumerate(shapes)]
