@@ -195,4 +195,136 @@ gauss_rgba8_int_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ o
     }
 }
 
+// ---------------------------------------------------------------- RGBA8, fp32 chain form
+// The same rule -- sum over the taps of (int)(byte * w), horizontally, then vertically on the
+// horizontal result, alpha := 0xff -- with ONE instruction per tap and channel pair.  A running sum
+// t = 2^23 + n (n the integer accumulated so far) is an fp32 whose ulp is 1, so
+//     t' = fma.rm(b, w, t)                    (round toward -inf)
+// is exactly 2^23 + n + floor(b * w): the product is exact inside the FMA, t is an integer, and the
+// round-down lands on the integer below.  The host verifies floor(b * (float)w) == (int)(b * w)
+// for all 256 bytes x 9 weights of the sigma at hand before launching (else the integer kernel
+// above runs).  Packed as fma.rm.f32x2 over the (r, g) and (b, -) halves of a pixel, a tap costs two
+// issue slots per pixel instead of twelve.
+//
+// Tile: 32 x 48 output pixels per CTA.  Staging converts the 48 x 64 input pixels to float4 once
+// (alpha dropped).  Pass 1: thread = (input row, run of 8 pixels), lanes on consecutive rows -- the
+// row pitch of 49 float4 spreads them over the banks.  Pass 2: thread = (column, run of 6 rows),
+// lanes on consecutive columns, so shared loads and the 4-byte global stores are contiguous.
+constexpr int kU8R = 8;               // the reference's radius (17 taps), src/millipyde_image.cpp:744
+constexpr int kU8TW = 32, kU8TH = 48;
+constexpr int kU8InW = kU8TW + 2 * kU8R, kU8InH = kU8TH + 2 * kU8R;  // 48 x 64
+constexpr int kU8PitchIn = kU8InW + 1, kU8PitchH = kU8TW + 1;        // in float4 units
+constexpr size_t kU8Smem = ((size_t)kU8InH * kU8PitchIn + (size_t)kU8InH * kU8PitchH) * 16;
+
+struct GaussU8ChainParams {
+    unsigned long long ww[kU8R + 1];  // ((float)w[d], (float)w[d]) packed
+};
+
+__device__ __forceinline__ uint64_t ffma2_rm(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t d;
+    asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+__global__ void __launch_bounds__(256, 2)
+gauss_rgba8_chain_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int width, int height,
+                         const __grid_constant__ GaussU8ChainParams gp)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *s_in = reinterpret_cast<float4 *>(smem_raw);                 // [64][49]
+    float4 *s_h = s_in + kU8InH * kU8PitchIn;                            // [64][33]
+    const int x0 = blockIdx.x * kU8TW, y0 = blockIdx.y * kU8TH;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr float kM = 8388608.f;  // 2^23
+    const uint64_t m2 = ((uint64_t)__float_as_uint(kM) << 32) | __float_as_uint(kM);
+
+    // ---- staging: 64 rows x 48 pixels = 12 per thread, row-major over the threads (a row is 192
+    // contiguous bytes).  All twelve loads are issued before the first conversion.
+    {
+        constexpr int PER = kU8InH * kU8InW / 256;
+        static_assert(PER * 256 == kU8InH * kU8InW, "whole pixels per thread");
+        uint32_t v[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int idx = tid + 256 * u;
+            const int r = idx / kU8InW, j = idx - r * kU8InW;
+            const int gy = y0 - kU8R + r, gx = x0 - kU8R + j;
+            v[u] = 0;
+            if (gy >= 0 && gy < height && gx >= 0 && gx < width) v[u] = __ldg(in + (size_t)gy * width + gx);
+        }
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int idx = tid + 256 * u;
+            const int r = idx / kU8InW, j = idx - r * kU8InW;
+            s_in[r * kU8PitchIn + j] = make_float4((float)(v[u] & 0xff), (float)((v[u] >> 8) & 0xff),
+                                                   (float)((v[u] >> 16) & 0xff), 0.f);
+        }
+    }
+    __syncthreads();
+
+    // ---- pass 1 (rows): thread = (row, run of 8 output pixels)
+    {
+        const int row = (warp & 1) * 32 + lane, run = warp >> 1;
+        const float4 *src = s_in + row * kU8PitchIn + 8 * run;
+        uint64_t a_lo[8], a_hi[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a_lo[i] = a_hi[i] = m2;
+#pragma unroll
+        for (int j = 0; j < 8 + 2 * kU8R; ++j) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(src + j);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = j - i - kU8R;  // tap index of input j for output i
+                if (k >= -kU8R && k <= kU8R) {
+                    const uint64_t w = gp.ww[k < 0 ? -k : k];
+                    a_lo[i] = ffma2_rm(v.x, w, a_lo[i]);
+                    a_hi[i] = ffma2_rm(v.y, w, a_hi[i]);
+                }
+            }
+        }
+        float4 *dst = s_h + row * kU8PitchH + 8 * run;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float r = __uint_as_float((uint32_t)a_lo[i]), g = __uint_as_float((uint32_t)(a_lo[i] >> 32));
+            const float b = __uint_as_float((uint32_t)a_hi[i]);
+            dst[i] = make_float4(r - kM, g - kM, b - kM, 0.f);  // exact: integers below 256
+        }
+    }
+    __syncthreads();
+
+    // ---- pass 2 (columns): thread = (column, run of 6 output rows)
+    {
+        const int col = lane, run = warp;
+        const float4 *src = s_h + (6 * run) * kU8PitchH + col;
+        uint64_t a_lo[6], a_hi[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) a_lo[i] = a_hi[i] = m2;
+#pragma unroll
+        for (int j = 0; j < 6 + 2 * kU8R; ++j) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(src + j * kU8PitchH);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const int k = j - i - kU8R;
+                if (k >= -kU8R && k <= kU8R) {
+                    const uint64_t w = gp.ww[k < 0 ? -k : k];
+                    a_lo[i] = ffma2_rm(v.x, w, a_lo[i]);
+                    a_hi[i] = ffma2_rm(v.y, w, a_hi[i]);
+                }
+            }
+        }
+        const int gx = x0 + col;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int gy = y0 + 6 * run + i;
+            if (gx < width && gy < height) {
+                // t = 2^23 + n: the low mantissa byte IS n
+                const uint32_t r = (uint32_t)a_lo[i] & 0xff, g = (uint32_t)(a_lo[i] >> 32) & 0xff;
+                const uint32_t b = (uint32_t)a_hi[i] & 0xff;
+                out[(size_t)gy * width + gx] = 0xff000000u | (b << 16) | (g << 8) | r;
+            }
+        }
+    }
+}
+
 }  // namespace mpk

@@ -661,6 +661,38 @@ MPStatus launch_gaussian(int device, cudaStream_t s, const Img &d, const void *i
             }
             exact = found;
         }
+        // fp32 chain form (one FFMA2.RM per tap and channel pair), if floor(b * (float)w) agrees with
+        // the double rule for every byte and tap; b * wf is exact in double (8 x 24 bits)
+        GaussU8ChainParams cp = {};
+        bool chain_ok = true;
+        for (int k = 0; k <= R && chain_ok; ++k) {
+            bool found = false;
+            for (int nudge = 0; nudge < 3 && !found; ++nudge) {
+                float wf = (float)gp.w[k];
+                if (nudge == 1) wf = nextafterf(wf, 1.f);
+                if (nudge == 2) wf = nextafterf(wf, 0.f);
+                bool ok = true;
+                for (int b = 0; b < 256 && ok; ++b) ok = (int)floor((double)b * (double)wf) == (int)(b * gp.w[k]);
+                if (ok) {
+                    uint32_t bits;
+                    memcpy(&bits, &wf, 4);
+                    cp.ww[k] = ((unsigned long long)bits << 32) | bits;
+                    found = true;
+                }
+            }
+            chain_ok = found;
+        }
+        if (chain_ok) {
+            static bool configured = false;
+            if (!configured) {
+                cudaFuncSetAttribute(gauss_rgba8_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kU8Smem);
+                configured = true;
+            }
+            dim3 cgrid((d.W + kU8TW - 1) / kU8TW, (d.H + kU8TH - 1) / kU8TH);
+            gauss_rgba8_chain_kernel<<<cgrid, 256, kU8Smem, s>>>((const uint32_t *)in, (uint32_t *)out, d.W, d.H, cp);
+            count_launch();
+            return MILLIPYDE_SUCCESS;
+        }
         if (exact) {
             gauss_rgba8_int_kernel<<<grid, 256, smem, s>>>((const uint32_t *)in, (uint32_t *)out, d.W, d.H, tile, tile, ip);
             count_launch();
