@@ -257,34 +257,53 @@ __device__ __forceinline__ unsigned u8_apply(const U8Op &op, unsigned v, int ch)
     }
 }
 
+// The composed byte tables of a program: lut[ch][v] = ops applied in order to byte v of channel ch.
+// Built once per distinct program (the launcher caches the 768-byte result per device), so the
+// double-precision pow of the gamma rule is paid 768 times in total, not 768 times per CTA.
+__global__ void __launch_bounds__(256)
+u8_lut_kernel(uint8_t *__restrict__ lut, const __grid_constant__ U8Program prog)
+{
+    const int ch = blockIdx.x;
+    unsigned v = threadIdx.x;
+    for (int i = 0; i < prog.n; ++i) v = u8_apply(prog.ops[i], v, ch);
+    lut[ch * 256 + threadIdx.x] = (uint8_t)v;
+}
+
+// Four 16-byte vectors per thread, 256 apart, so every warp access is 512 contiguous bytes and a
+// CTA streams 16 KB; many small CTAs keep more bytes in flight than a short persistent grid.
+constexpr int kU8PwVecs = 4;
+
 __global__ void __launch_bounds__(256)
 pw_rgba8_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t npix,
-                const __grid_constant__ U8Program prog)
+                const uint8_t *__restrict__ lut_g)
 {
-    __shared__ uint8_t lut[3][256];
-    for (int e = threadIdx.x; e < 768; e += blockDim.x) {
-        int ch = e >> 8;
-        unsigned v = e & 255;
-        for (int i = 0; i < prog.n; ++i) v = u8_apply(prog.ops[i], v, ch);
-        lut[ch][e & 255] = (uint8_t)v;
-    }
+    __shared__ __align__(16) uint8_t lut[3][256];
+    if (threadIdx.x < 192)
+        reinterpret_cast<uint32_t *>(&lut[0][0])[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t *>(lut_g) + threadIdx.x);
     __syncthreads();
     auto map = [&](uint32_t w) -> uint32_t {
         return (w & 0xff000000u) | ((uint32_t)lut[2][(w >> 16) & 0xff] << 16) |
                ((uint32_t)lut[1][(w >> 8) & 0xff] << 8) | lut[0][w & 0xff];
     };
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t ngroups = npix / 4;
-    for (size_t g = tid; g < ngroups; g += stride) {
-        uint4 px = ld_stream(reinterpret_cast<const uint4 *>(in) + g);
-        px.x = map(px.x);
-        px.y = map(px.y);
-        px.z = map(px.z);
-        px.w = map(px.w);
-        st_stream(reinterpret_cast<uint4 *>(out) + g, px);
+    const size_t base = (size_t)blockIdx.x * (256 * kU8PwVecs) + threadIdx.x;
+    uint4 px[kU8PwVecs];
+#pragma unroll
+    for (int u = 0; u < kU8PwVecs; ++u)
+        if (base + 256 * u < ngroups) px[u] = ld_stream(reinterpret_cast<const uint4 *>(in) + base + 256 * u);
+#pragma unroll
+    for (int u = 0; u < kU8PwVecs; ++u)
+        if (base + 256 * u < ngroups) {
+            px[u].x = map(px[u].x);
+            px[u].y = map(px[u].y);
+            px[u].z = map(px[u].z);
+            px[u].w = map(px[u].w);
+            st_stream(reinterpret_cast<uint4 *>(out) + base + 256 * u, px[u]);
+        }
+    if (blockIdx.x == 0 && threadIdx.x < (npix & 3)) {  // the last npix % 4 pixels
+        const size_t p = ngroups * 4 + threadIdx.x;
+        out[p] = map(in[p]);
     }
-    for (size_t p = ngroups * 4 + tid; p < npix; p += stride) out[p] = map(in[p]);
 }
 
 }  // namespace mpk

@@ -9,6 +9,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
 
 #include "kernels/gaussian_tile.cuh"
 #include "kernels/geometry.cuh"
@@ -396,15 +399,58 @@ static MPStatus pointwise_f64(MPObjData *obj, const mp::Img &d, cudaStream_t s, 
     return finish(obj, s, out, obj->nbytes);
 }
 
+// Device-resident byte tables per (device, program), built on first use and kept: programs are few
+// (an Operation's arguments) and a table is 768 bytes.  Beyond kLutCacheMax distinct programs
+// (e.g. a stream of random_* draws) tables are built into a stream-ordered temporary instead.
+static const uint8_t *u8_lut_for(int device, cudaStream_t s, const U8Program &prog, void **temp)
+{
+    static std::mutex mux;
+    static std::map<std::string, const uint8_t *> cache[64];
+    constexpr size_t kLutCacheMax = 256;
+    *temp = nullptr;
+    std::string key((const char *)&prog, sizeof prog);
+    if (device >= 0 && device < 64) {
+        std::lock_guard<std::mutex> lk(mux);
+        auto it = cache[device].find(key);
+        if (it != cache[device].end()) return it->second;
+        if (cache[device].size() < kLutCacheMax) {
+            uint8_t *lut = nullptr;
+            if (cudaMalloc((void **)&lut, 768) == cudaSuccess) {
+                u8_lut_kernel<<<3, 256, 0, s>>>(lut, prog);
+                mp::count_launch();
+                cudaStreamSynchronize(s);  // once per program: other streams may use the table next
+                cache[device][key] = lut;
+                return lut;
+            }
+            (void)cudaGetLastError();
+        }
+    }
+    uint8_t *lut = (uint8_t *)mp::pool_alloc(device, s, 768);
+    if (!lut) return nullptr;
+    u8_lut_kernel<<<3, 256, 0, s>>>(lut, prog);
+    mp::count_launch();
+    *temp = lut;
+    return lut;
+}
+
 static MPStatus pointwise_rgba8(MPObjData *obj, const mp::Img &d, cudaStream_t s, const U8Program &prog)
 {
     if (prog.n == 0) return MILLIPYDE_SUCCESS;
     void *out;
     MPStatus st = fresh(obj, s, obj->nbytes, &out);
     if (st != MILLIPYDE_SUCCESS) return st;
-    pw_rgba8_kernel<<<mp::grid_for(obj->mem_loc, d.npix / 4 + 1, 256), 256, 0, s>>>(
-        (const uint32_t *)obj->device_data, (uint32_t *)out, d.npix, prog);
+    void *temp = nullptr;
+    const uint8_t *lut = u8_lut_for(obj->mem_loc, s, prog, &temp);
+    if (!lut) {
+        mp::pool_free(obj->mem_loc, s, out);
+        return MP_ERROR_DEVICE_ALLOC;
+    }
+    const size_t ngroups = d.npix / 4;
+    const size_t blocks = (ngroups + 256 * kU8PwVecs - 1) / (256 * kU8PwVecs);
+    pw_rgba8_kernel<<<(unsigned)(blocks ? blocks : 1), 256, 0, s>>>((const uint32_t *)obj->device_data, (uint32_t *)out,
+                                                                d.npix, lut);
     mp::count_launch();
+    if (temp) mp::pool_free(obj->mem_loc, s, temp);
     return finish(obj, s, out, obj->nbytes);
 }
 
