@@ -198,6 +198,20 @@ void *pool_alloc(int device_id, cudaStream_t stream, size_t nbytes)
     return p;
 }
 
+void *pool_alloc_on(int pool_device, cudaStream_t stream, size_t nbytes)
+{
+    void *p = nullptr;
+    if (nbytes == 0) nbytes = 16;
+    cudaMemPool_t pool;
+    cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, pool_device);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&p, nbytes, pool, stream);
+    if (e != cudaSuccess) {
+        record_cuda_error(e, "cudaMallocFromPoolAsync", __FILE__, __LINE__);
+        return nullptr;
+    }
+    return p;
+}
+
 void pool_free(int device_id, cudaStream_t stream, void *ptr)
 {
     (void)device_id;

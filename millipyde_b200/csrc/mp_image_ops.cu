@@ -729,10 +729,10 @@ MPStatus launch_gaussian(int device, cudaStream_t s, const Img &d, const void *i
             chain_ok = found;
         }
         if (chain_ok) {
-            static bool configured = false;
-            if (!configured) {
+            static bool configured[64] = {};  // the attribute is per device
+            if (device >= 0 && device < 64 && !configured[device]) {
                 cudaFuncSetAttribute(gauss_rgba8_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kU8Smem);
-                configured = true;
+                configured[device] = true;
             }
             dim3 cgrid((d.W + kU8TW - 1) / kU8TW, (d.H + kU8TH - 1) / kU8TH);
             gauss_rgba8_chain_kernel<<<cgrid, 256, kU8Smem, s>>>((const uint32_t *)in, (uint32_t *)out, d.W, d.H, cp);
@@ -808,21 +808,8 @@ void launch_gather_f32(cudaStream_t s, int channels, const GatherParams &g, int 
 {
     dim3 grid((g.out_w + kGatherTile - 1) / kGatherTile, (g.out_h + kGatherTile - 1) / kGatherTile, n_images);
     const size_t smem = channels == 1 ? GatherGeom<1>::SMEM : (channels == 3 ? GatherGeom<3>::SMEM : GatherGeom<4>::SMEM);
-    static bool configured = false;
-    if (!configured) {  // 40 KB for C = 4 is under the 48 KB default; set anyway so a larger box stays legal
-        cudaFuncSetAttribute(gather_f32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(gather_f32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(gather_f32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        configured = true;
-    }
+    static_assert(GatherGeom<4>::SMEM <= 48 * 1024, "fits the default dynamic shared memory limit on every device");
     if (g.var_tab) {  // per-image angle / programs
-        static bool configured_tab = false;
-        if (!configured_tab) {
-            cudaFuncSetAttribute(gather_f32_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            cudaFuncSetAttribute(gather_f32_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            cudaFuncSetAttribute(gather_f32_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            configured_tab = true;
-        }
         if (channels == 1) gather_f32_kernel<1, true><<<grid, 256, smem, s>>>(g);
         else if (channels == 3) gather_f32_kernel<3, true><<<grid, 256, smem, s>>>(g);
         else gather_f32_kernel<4, true><<<grid, 256, smem, s>>>(g);

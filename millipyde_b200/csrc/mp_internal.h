@@ -24,6 +24,10 @@ cudaStream_t device_stream(int device_id, int index);
 // with the release threshold lifted, so steady state never calls the OS).
 void *pool_alloc(int device_id, cudaStream_t stream, size_t nbytes);
 void pool_free(int device_id, cudaStream_t stream, void *ptr);
+// Block from `pool_device`'s pool, allocated in the order of `stream`, which may belong to ANOTHER
+// device that has access to the pool (every pool grants its peers access at start-up): a producer
+// kernel can then write its result straight into the consumer device's memory over NVLink.
+void *pool_alloc_on(int pool_device, cudaStream_t stream, size_t nbytes);
 
 // The stream an op should use for `obj`: obj->stream, or the device's stream 0
 // when a foreign caller left it NULL.

@@ -354,6 +354,11 @@ thread_local const void *g_records = nullptr;
 // thread is running.  The launch that first rewrites such an image must not free its input.
 thread_local std::unordered_set<MPObjData *> *g_borrowed = nullptr;
 
+// Device whose pool the outputs of the current batched launch come from: the shard's own device,
+// or -- for the last segment of a chain that hands its images to a pipeline on another device -- the
+// RECEIVER's, so the producer kernel itself moves the result over NVLink (no copy pass afterwards).
+thread_local int g_out_device = -1;
+
 // Retire the buffer an image held before a launch gave it a fresh one.
 void release_input(int device, cudaStream_t s, MPObjData *o)
 {
@@ -394,9 +399,10 @@ MPStatus run_batched(const std::vector<MPObjData *> &objs, size_t out_bytes, int
     if (!d_tab) return MP_ERROR_DEVICE_ALLOC;
     if (record_bytes) memcpy((char *)h_tab + tab_bytes, records, record_bytes);
     g_records = record_bytes ? (const char *)d_tab + tab_bytes : nullptr;
+    const int out_device = g_out_device >= 0 ? g_out_device : device;
     std::vector<void *> fresh(n);
     for (size_t i = 0; i < n; ++i) {
-        fresh[i] = mp::pool_alloc(device, s, out_bytes);
+        fresh[i] = out_device == device ? mp::pool_alloc(device, s, out_bytes) : mp::pool_alloc_on(out_device, s, out_bytes);
         if (!fresh[i]) {
             for (size_t k = 0; k < i; ++k) mp::pool_free(device, s, fresh[k]);
             mp::pool_free(device, s, d_tab);
@@ -417,6 +423,7 @@ MPStatus run_batched(const std::vector<MPObjData *> &objs, size_t out_bytes, int
             release_input(device, s, objs[i]);
             objs[i]->device_data = fresh[i];
             objs[i]->nbytes = out_bytes;
+            objs[i]->mem_loc = out_device;
         } else {
             mp::pool_free(device, s, fresh[i]);
         }
@@ -651,14 +658,18 @@ std::string layout_key(const MPObjData *o)
     return hdr;
 }
 
+constexpr size_t kHandoffChunk = 32;  // images per hand-off chunk of a cross-device pipeline pair
+
 struct ShardTask {
     mp_pipeline *pipe;
     std::vector<MPObjData *> objs;
     int device;
     bool views;  // objs borrow their buffers (mppipe_run_views)
+    cudaEvent_t after = nullptr;  // work of the sending shard that wrote into this device's memory
 };
 
-void submit_shard(mp_pipeline *p, std::vector<MPObjData *> objs, int device, bool views = false);
+void submit_shard(mp_pipeline *p, std::vector<MPObjData *> objs, int device, bool views = false,
+                  cudaEvent_t after = nullptr);
 
 void shard_worker(void *arg)
 {
@@ -682,6 +693,10 @@ void shard_worker(void *arg)
     }
     arena.used = 0;
 
+    if (t->after) {  // the sender's kernels wrote some of these images straight into this device's memory
+        cudaStreamWaitEvent(batch_stream, t->after, 0);
+        cudaEventDestroy(t->after);
+    }
     std::unordered_set<MPObjData *> borrowed;
     if (t->views) borrowed.insert(t->objs.begin(), t->objs.end());
     g_borrowed = t->views ? &borrowed : nullptr;
@@ -694,50 +709,92 @@ void shard_worker(void *arg)
         mpobj_set_stream(o, (void *)batch_stream);
     }
 
-    // 2. coin flips / random draws per image, then the fusion pass on what survived
-    std::vector<std::vector<Stage>> realized(n);
-    std::vector<std::vector<Segment>> segs(n);
-    size_t rounds = 0;
-    for (size_t i = 0; i < n; ++i) {
-        realize(p, &realized[i]);
-        std::vector<const Stage *> ops;
-        for (const Stage &st : realized[i]) ops.push_back(&st);
-        mp::Img d;
-        const bool known = mp::describe(t->objs[i], &d);
-        segs[i] = compile(ops, known ? d.fam : mp::FAM_U8_OTHER, known ? d.C : 0);
-        if (segs[i].size() > rounds) rounds = segs[i].size();
-    }
-
-    // 3. round r runs every image's r-th segment; the images of a round are regrouped by (current
-    // layout, segment signature), so images whose coins fell differently part and meet again, and
-    // a chain of random_* stages still costs one launch per (round, kernel), not per image.
-    for (size_t r = 0; r < rounds; ++r) {
-        std::map<std::string, std::vector<size_t>> groups;
-        for (size_t i = 0; i < n; ++i)
-            if (r < segs[i].size()) groups[layout_key(t->objs[i]) + signature(segs[i][r])].push_back(i);
-        for (auto &g : groups) {
-            std::vector<MPObjData *> objs;
-            std::vector<const Segment *> sp;
-            for (size_t i : g.second) {
-                objs.push_back(t->objs[i]);
-                sp.push_back(&segs[i][r]);
-            }
-            run_segment_group(p, objs, sp, device, batch_stream);
+    // A chain that hands its images to a pipeline on ANOTHER device writes the result of each
+    // image's last segment straight into that device's memory (batched launches only; whatever
+    // stays here is moved by the receiver with cudaMemcpyPeerAsync as before).
+    const int remote = (p->receiver && p->receiver->device != device && mpdev_is_valid_device(p->receiver->device) &&
+                        g_fusion.load() && (mpdev_can_use_peer(device, p->receiver->device) != 0))
+                           ? p->receiver->device
+                           : -1;
+    // With a receiver on another device the shard goes through in chunks: while this device works
+    // on chunk k + 1 the receiver already has chunk k (its launches are still whole-chunk launches).
+    const size_t chunk = (remote >= 0 && n > 2 * kHandoffChunk) ? kHandoffChunk : (n ? n : 1);
+    for (size_t c0 = 0; c0 < n; c0 += chunk) {
+        const size_t c1 = c0 + chunk < n ? c0 + chunk : n;
+        // 2. coin flips / random draws per image, then the fusion pass on what survived
+        std::vector<std::vector<Stage>> realized(n);
+        std::vector<std::vector<Segment>> segs(n);
+        size_t rounds = 0;
+        for (size_t i = c0; i < c1; ++i) {
+            realize(p, &realized[i]);
+            std::vector<const Stage *> ops;
+            for (const Stage &st : realized[i]) ops.push_back(&st);
+            mp::Img d;
+            const bool known = mp::describe(t->objs[i], &d);
+            segs[i] = compile(ops, known ? d.fam : mp::FAM_U8_OTHER, known ? d.C : 0);
+            if (segs[i].size() > rounds) rounds = segs[i].size();
         }
-        p->segments.fetch_add((int)groups.size());
-    }
 
-    // 4b. a view no segment rewrote still borrows: deep-copy it
-    if (t->views) {
-        for (size_t i = 0; i < n; ++i) note_status(p, materialize(device, batch_stream, t->objs[i]));
-        g_borrowed = nullptr;
-    }
+        // 3. round r runs every image's r-th segment; the images of a round are regrouped by (current
+        // layout, segment signature), so images whose coins fell differently part and meet again, and
+        // a chain of random_* stages still costs one launch per (round, kernel), not per image.
+        for (size_t r = 0; r < rounds; ++r) {
+            std::map<std::string, std::vector<size_t>> groups;
+            for (size_t i = c0; i < c1; ++i)
+                if (r < segs[i].size()) {
+                    const bool last = remote >= 0 && r + 1 == segs[i].size();
+                    groups[layout_key(t->objs[i]) + signature(segs[i][r]) + (last ? "|L" : "")].push_back(i);
+                }
+            for (auto &g : groups) {
+                std::vector<MPObjData *> objs;
+                std::vector<const Segment *> sp;
+                for (size_t i : g.second) {
+                    objs.push_back(t->objs[i]);
+                    sp.push_back(&segs[i][r]);
+                }
+                const bool last = remote >= 0 && r + 1 == segs[g.second[0]].size();
+                g_out_device = last ? remote : -1;
+                run_segment_group(p, objs, sp, device, batch_stream);
+                g_out_device = -1;
+            }
+            p->segments.fetch_add((int)groups.size());
+        }
 
-    // 5. hand the results on, or finish
-    if (p->receiver) {
-        // the receiver's worker orders itself after this stream through the objects' events
-        submit_shard(p->receiver, t->objs, p->receiver->device);
+        // 4b. a view no segment rewrote still borrows: deep-copy it
+        if (t->views)
+            for (size_t i = c0; i < c1; ++i) note_status(p, materialize(device, batch_stream, t->objs[i]));
+
+        // 5. hand the results on, or finish
+        if (p->receiver) {
+            // Images still here: the receiver's worker orders itself after this stream through the
+            // objects' events and moves them.  Images already written into the receiver's memory: one
+            // event for the whole shard, and they are handed over as belonging to its stream.
+            cudaEvent_t after = nullptr;
+            if (remote >= 0) {
+                bool any = false;
+                for (size_t i = c0; i < c1; ++i) any = any || (t->objs[i]->mem_loc == remote && t->objs[i]->device_data);
+                if (any) {
+                    cudaSetDevice(device);
+                    if (cudaEventCreateWithFlags(&after, cudaEventDisableTiming) == cudaSuccess &&
+                        cudaEventRecord(after, batch_stream) == cudaSuccess) {
+                        for (size_t i = c0; i < c1; ++i)
+                            if (t->objs[i]->mem_loc == remote) t->objs[i]->stream = (void *)mp::device_stream(remote, 1);
+                    } else {
+                        (void)cudaGetLastError();
+                        if (after) cudaEventDestroy(after);
+                        after = nullptr;
+                        cudaStreamSynchronize(batch_stream);  // no event: hand over finished work
+                        for (size_t i = c0; i < c1; ++i)
+                            if (t->objs[i]->mem_loc == remote) t->objs[i]->stream = (void *)mp::device_stream(remote, 1);
+                    }
+                }
+            }
+            submit_shard(p->receiver, std::vector<MPObjData *>(t->objs.begin() + c0, t->objs.begin() + c1),
+                         p->receiver->device, false, after);
+        }
     }
+    if (t->views) g_borrowed = nullptr;
+
     cudaError_t e = cudaStreamSynchronize(batch_stream);
     if (e != cudaSuccess) {
         mp::record_cuda_error(e, "cudaStreamSynchronize(shard)", __FILE__, __LINE__);
@@ -753,14 +810,14 @@ void shard_worker(void *arg)
     delete t;
 }
 
-void submit_shard(mp_pipeline *p, std::vector<MPObjData *> objs, int device, bool views)
+void submit_shard(mp_pipeline *p, std::vector<MPObjData *> objs, int device, bool views, cudaEvent_t after)
 {
     if (objs.empty()) return;
     {
         std::lock_guard<std::mutex> lk(p->mux);
         p->in_flight.push_back(device);
     }
-    ShardTask *t = new ShardTask{p, std::move(objs), device, views};
+    ShardTask *t = new ShardTask{p, std::move(objs), device, views, after};
     mpdev_submit_work(device, shard_worker, t);
 }
 

@@ -1,0 +1,157 @@
+#!/usr/bin/env python
+"""Throughput of BASELINE configs 3, 4 and 5 (the headline config 1 is bench.py).
+
+  config 3   fused chain rotate 30 -> fliplr -> gamma 1.5 -> gaussian 2 on 1024 x 1920x1080 RGB fp32, one GPU
+  config 4   Generator random-augmentation stream, 65536 outputs of 1024x1024 RGB fp32 in total, sharded
+             over the ranks (strong scaling): `python -m torch.distributed.run --nproc-per-node N ...`
+  config 5   Pipeline pairs: (rgb2grey, transpose) on GPU 2k -> connect_to -> (gaussian 2, rotate 30) on
+             GPU 2k+1 with the NVLink peer hand-off, all pairs of the box at once, ONE process
+
+    python tools/bench_configs.py config3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 \
+        tools/bench_configs.py config4
+    python tools/bench_configs.py config5 [--pairs 4]
+
+Every mode prints one JSON line (rank 0).  Times are wall clock around a device-wide synchronise on both
+sides, max over ranks.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+from bench import Dist  # gloo barrier / max over ranks
+
+
+def bind_rank_gpu(dist):
+    if dist.world > 1:
+        outer = [x for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip() != ""]
+        os.environ["CUDA_VISIBLE_DEVICES"] = outer[dist.local] if len(outer) > dist.local else str(dist.local)
+
+
+def config3(args, dist):
+    from millipyde_b200 import capi, engine
+    capi.initialize()
+    L = capi.lib()
+    n = args.images or 1024
+    rng = np.random.default_rng(3)
+    seeds = [capi.DeviceImage(rng.random((1080, 1920, 3), dtype=np.float32)) for _ in range(4)]
+    chain = engine.Chain([("rotate", 30.0), ("fliplr",), ("adjust_gamma", 1.5, 1.0), ("gaussian", 2.0)], device=0)
+    best = None
+    for rep in range(args.reps + 1):
+        imgs = [seeds[k % 4].clone() for k in range(n)]
+        L.mpdev_synchronize()
+        t0 = time.perf_counter()
+        chain.run(imgs)
+        L.mpdev_synchronize()
+        dt = time.perf_counter() - t0
+        if rep:  # rep 0 warms the pool
+            best = dt if best is None else min(best, dt)
+        launches = chain.last_launches
+        for d in imgs:
+            d.close()
+    nbytes = 2 * 1080 * 1920 * 12
+    return {"config": 3, "workload": "rotate30+fliplr+gamma1.5+gaussian2, 1920x1080 RGB fp32", "images": n,
+            "images/s": round(n / best, 1), "us_per_image": round(best / n * 1e6, 2), "launches_per_batch": int(launches),
+            "one_round_trip_GB/s": round(n * nbytes / best / 1e9, 1)}
+
+
+def config4(args, dist):
+    import millipyde_b200
+    mp = millipyde_b200.load_extension()
+    total = args.images or 65536
+    mine = total // dist.world
+    rng = np.random.default_rng(4000)
+    base = [mp.gpuimage(rng.random((1024, 1024, 3), dtype=np.float32)) for _ in range(6)]
+    ops = [mp.Operation("transpose", probability=.2), mp.Operation("fliplr", probability=.2),
+           mp.Operation("random_brightness", -.2, .2), mp.Operation("random_gaussian", .5, 2.),
+           mp.Operation("random_colorize", [.5, 1.5], [.5, 1.5], [.5, 1.5], probability=.3),
+           mp.Operation("rgb2grey", probability=.3), mp.Operation("random_rotate", 0., 120., probability=.5)]
+    mp.seed(4 + dist.rank)
+    pre = args.prefetch
+    g = mp.Generator(base, ops, outputs=mine + pre, prefetch=pre, device=0)
+    for _ in range(pre):  # warm the pool
+        next(g)
+    mp.synchronize()
+    l0 = mp.launch_count()
+    dist.barrier()
+    t0 = time.perf_counter()
+    k = 0
+    for _ in g:
+        k += 1
+    mp.synchronize()
+    dt = dist.max(time.perf_counter() - t0)
+    produced = dist.sum(float(k))
+    launches = dist.sum(float(mp.launch_count() - l0))
+    return {"config": 4, "workload": "Generator random-augmentation stream, 1024x1024 RGB fp32", "n_gpus": dist.world,
+            "outputs": int(produced), "prefetch": pre, "images/s": round(produced / dt, 1),
+            "launches_per_image": round(launches / produced, 3), "scaling": "strong"}
+
+
+def config5(args, dist):
+    from millipyde_b200 import capi, engine
+    ndev = capi.initialize()
+    L = capi.lib()
+    pairs = min(args.pairs, ndev // 2)
+    if pairs < 1:
+        raise SystemExit("config 5 needs at least 2 GPUs in this process")
+    n = args.images or 256  # images per pair per run
+    rng = np.random.default_rng(5)
+    host = [rng.random((1080, 1920, 3), dtype=np.float32) for _ in range(2)]
+    firsts, seconds, seeds = [], [], []
+    for p in range(pairs):
+        a = engine.Chain([("rgb2grey",), ("transpose",)], device=2 * p)
+        b = engine.Chain([("gaussian", 2.0), ("rotate", 30.0)], device=2 * p + 1)
+        L.mppipe_connect(a.ptr, b.ptr)
+        firsts.append(a)
+        seconds.append(b)
+        seeds.append([capi.DeviceImage(h).to_device(2 * p) for h in host])
+    best = None
+    for rep in range(args.reps + 1):
+        batches = [[seeds[p][k % 2].clone(2 * p) for k in range(n)] for p in range(pairs)]
+        L.mpdev_synchronize_all()
+        t0 = time.perf_counter()
+        for p in range(pairs):
+            firsts[p].submit(batches[p])
+        for p in range(pairs):
+            firsts[p].wait()
+        L.mpdev_synchronize_all()
+        dt = time.perf_counter() - t0
+        if rep:
+            best = dt if best is None else min(best, dt)
+        where = {b[0].device for b in batches}
+        shape = batches[0][0].shape
+        for b in batches:
+            for d in b:
+                d.close()
+    moved = 1080 * 1920 * 4  # the grey fp32 image crosses NVLink once
+    return {"config": 5, "workload": "(rgb2grey, transpose) on GPU 2k -> (gaussian 2, rotate 30) on GPU 2k+1, "
+            "1920x1080 RGB fp32 in, NVLink peer hand-off", "pairs": pairs, "n_gpus": 2 * pairs, "images_per_pair": n,
+            "images/s": round(pairs * n / best, 1), "result_shape": list(shape), "result_devices": sorted(where),
+            "nvlink_GB/s_per_pair": round(n * moved / best / 1e9, 1)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("mode", choices=["config3", "config4", "config5"])
+    ap.add_argument("--images", type=int, default=0)
+    ap.add_argument("--prefetch", type=int, default=256)
+    ap.add_argument("--pairs", type=int, default=4)
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    dist = Dist()
+    bind_rank_gpu(dist)
+    out = {"config3": config3, "config4": config4, "config5": config5}[args.mode](args, dist)
+    if dist.rank == 0:
+        print(json.dumps(out), flush=True)
+    dist.close()
+
+
+if __name__ == "__main__":
+    main()
