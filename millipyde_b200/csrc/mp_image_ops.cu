@@ -675,6 +675,22 @@ static MPStatus launch_tile(cudaStream_t s, const Img &d, const void *in, void *
     return MILLIPYDE_SUCCESS;
 }
 
+// fp64 greyscale with a compiled radius (8 or 16); false if the radius has no instance.
+template <int R, bool CLAMP0>
+static void launch_f64_fixed(int device, cudaStream_t s, const Img &d, const void *in, void *out,
+                             const GaussParams<double> &gp)
+{
+    using G = GaussF64Geom<R>;
+    static bool configured[64] = {};  // the attribute is per device
+    if (device >= 0 && device < 64 && !configured[device]) {
+        cudaFuncSetAttribute(gauss_f64_kernel<R, CLAMP0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+        configured[device] = true;
+    }
+    dim3 grid((d.W + G::TW - 1) / G::TW, (d.H + G::TH - 1) / G::TH);
+    gauss_f64_kernel<R, CLAMP0><<<grid, 256, G::SMEM, s>>>((const double *)in, (double *)out, d.W, d.H, gp);
+    count_launch();
+}
+
 MPStatus launch_gaussian(int device, cudaStream_t s, const Img &d, const void *in, void *out, double sigma,
                          bool ref_rule)
 {
@@ -753,9 +769,18 @@ MPStatus launch_gaussian(int device, cudaStream_t s, const Img &d, const void *i
         if (ref_rule) {
             gp.radius = 8;
             reference_weights(sigma, gp.w);
-            return launch_tile<double, 1, true>(s, d, in, out, gp);
+            launch_f64_fixed<8, true>(device, s, d, in, out, gp);
+            return MILLIPYDE_SUCCESS;
         }
         gp.radius = oracle_weights(sigma, gp.w, kGaussMaxRadius);
+        if (gp.radius == 16) {  // sigma = 2 under the oracle rule (truncate = 8)
+            launch_f64_fixed<16, false>(device, s, d, in, out, gp);
+            return MILLIPYDE_SUCCESS;
+        }
+        if (gp.radius == 8) {
+            launch_f64_fixed<8, false>(device, s, d, in, out, gp);
+            return MILLIPYDE_SUCCESS;
+        }
         return launch_tile<double, 1, false>(s, d, in, out, gp);
     }
     // fp32: scipy weights, evaluated over the effective support only
