@@ -42,11 +42,24 @@ static MPStatus launch_cr(int device, cudaStream_t s, GaussStreamParams &p, cons
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[device] = true;
     }
-    // One persistent CTA per SM.  Row chunks only when the batch alone cannot fill the machine:
-    // every extra chunk re-filters 2R rows.
+    // One persistent CTA per SM.  An item is (image, strip, row chunk); the number of row chunks is
+    // the one that wastes least: more chunks fill the last wave of CTAs better, but every chunk
+    // re-filters 2R halo rows.  useful(c) = rows / (rows + 2R c)  x  items c / (waves(c) sms).
     long items = (long)p.n_images * p.n_strips;
     int chunks = 1;
-    while (items * chunks < 2L * sms && p.height / (chunks * 2) >= 8 * R) chunks *= 2;
+    {
+        double best = 0;
+        const int c_max = p.height / (4 * R) > 1 ? p.height / (4 * R) : 1;
+        for (int c = 1; c <= c_max && c <= 64; ++c) {
+            const long it = items * c;
+            const long waves = (it + sms - 1) / sms;
+            const double useful = (double)p.height / (p.height + 2.0 * R * c) * (double)it / (double)(waves * sms);
+            if (useful > best * 1.02) {  // prefer fewer chunks unless the gain is real
+                best = useful;
+                chunks = c;
+            }
+        }
+    }
     p.n_chunks = chunks;
     p.chunk_rows = (p.height + chunks - 1) / chunks;
     items *= chunks;
