@@ -1,0 +1,269 @@
+// Separable Gaussian, fp32 HWC, streaming kernel (v4): the column pass on the tensor cores.
+//
+// gaussian_stream_ws.cuh is bound by the fp32 FMA pipe: 2 x (2R+1) FMAs per sample put the pipe and
+// HBM at the same throughput, and the pipe never runs at 100 %.  Here the ROW warps (unchanged:
+// private TMA ring, FFMA2 horizontal filter, hand-off ring) keep the FMA pipe to themselves and the
+// COLUMN warps run the vertical filter as small banded matrix products on the otherwise idle tensor
+// pipe (mma.sync.m16n8k8 tf32, SASS HMMA.1688.F32.TF32), which halves the FMA-pipe load.
+//
+// The product.  Filtered rows arrive in 8-row chunks (chunk s = rows f in [8s, 8s+8) of the item);
+// output rows are produced in 8-row blocks (block b = rows o in [8b, 8b+8)); out[o] = sum_f
+// w[|f - o - R|] F[f] touches the NCH = (7 + 2R)/8 + 1 chunks b .. b+NCH-1.  One MMA computes, for a
+// 16-column tile,
+//     D[16 columns x 8 output rows] += A[16 columns x 8 chunk rows] . B_j[8 chunk rows x 8 output rows]
+// with B_j[k][n] = w[|8j + k - n - R|] (zero outside the support), j = s - b = the block's age.
+// A chunk is loaded ONCE and multiplied into the NCH live blocks; like the FMA version's sliding
+// accumulators the destination of the first MMA is the neighbour (acc[j+1] = A . B_j + acc[j]), so
+// nothing rotates.  The block of age NCH-1 is complete and leaves as 8-byte streaming stores.
+//
+// Precision.  tf32 carries 11 significant bits, so both operands are split, x = hi + lo with
+// hi = x & 0xffffe000 (exact), and the product is hi.hi (one tf32 MMA) + lo.hi + hi.lo.  The two
+// correction products are 2^-10 of the result and need 11 bits themselves, which fp16 has: they are
+// ONE m16n8k16 fp16 MMA whose K dimension is the concatenation [lo(A) | hi(A)] x [hi(B) ; lo(B)].
+// Everything accumulates in fp32.  Dropped: lo.lo and the rounding of the lo parts, each < 2^-21
+// relative -- ~3e-7 absolute on [0,1] images against the fp64 oracle (contract 1e-5).  The fp16
+// operands limit the kernel to |sample| < 65504 (an fp32 *image*; the FMA-pipe kernel has no limit).
+//
+// Fragment mapping (g = lane >> 2, t = lane & 3).  MMA row m <-> tile column: m = g -> column 2g,
+// m = g + 8 -> column 2g + 1, so a thread's A operands (a0, a1) and (a2, a3) are two LDS.64 from ring
+// rows t and t + 4, and its results (c0, c2) / (c1, c3) are column pairs of output rows 2t / 2t + 1.
+// The ring's row pitch is 648 floats (= 8 mod 32): the LDS.64 of a half-warp hit 32 distinct banks.
+#pragma once
+#include "gaussian_stream_ws.cuh"
+
+namespace mpk {
+
+using MmK = WsK<true>;                          // 12 ROW warps (12-row groups), 8 COLUMN warps
+constexpr int kMmPitch = kGsTW + 8;            // hand-off ring row pitch in floats
+constexpr int kMmRing = MmK::groups * MmK::rows;   // 48 rows = 4 groups of 12 = 6 chunks of 8
+constexpr int kMmTiles = kGsTW / 16 / MmK::col_warps;  // 16-column tiles per COLUMN warp (5)
+constexpr int kMmThreads = MmK::threads;       // 640
+// Registers: the kernel is compiled for 96 per thread (640 threads) and that allocation is the
+// CTA's pool.  The 12 ROW warps (warpgroups 0-2) hand 16 each back (setmaxnreg.dec 80), the 8 COLUMN
+// warps (warpgroups 3-4) take them (setmaxnreg.inc 120): 12*80 + 8*120 = 20*96.
+constexpr int kMmRowRegs = 80;
+constexpr int kMmColRegs = 120;
+
+template <int C, int R>
+struct MmGeom {
+    static constexpr int NCH = (7 + 2 * R) / 8 + 1;   // chunks an output block spans
+    static constexpr size_t IN_BYTES = (size_t)MmK::row_warps * MmK::in_slots * GsGeom<C, R>::ROW * 4;
+    static constexpr size_t H_BYTES = (size_t)kMmRing * kMmPitch * 4;
+    static constexpr int N_BARS = MmK::row_warps * MmK::in_slots + 2 * MmK::groups;
+    static constexpr size_t SMEM = IN_BYTES + H_BYTES + 8 * N_BARS + 64;
+};
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1,
+                                         const float (&c)[4])
+{
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+        "{%10,%11,%12,%13};"
+        : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c[0]), "f"(c[1]), "f"(c[2]),
+          "f"(c[3]));
+}
+
+// m16n8k16, fp16 operands, fp32 accumulate (SASS HMMA.16816.F32): the two correction products of a
+// (tile, block) pair in one instruction, K slots 0..7 = lo(A) x hi(B), 8..15 = hi(A) x lo(B).
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1,
+                                        const float (&c)[4])
+{
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+        "{%10,%11,%12,%13};"
+        : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c[0]), "f"(c[1]), "f"(c[2]),
+          "f"(c[3]));
+}
+// (x, y) -> packed f16x2 with x in the low half: the K slot pair (2t, 2t + 1) of one MMA operand
+__device__ __forceinline__ uint32_t pack_f16(float x, float y)
+{
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
+    return r;
+}
+__device__ __forceinline__ float2 lds_f2(const float *p)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(smem_addr(p)));
+    return v;
+}
+
+template <int C, int R, bool SETS>
+__device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussWeightSets &ws)
+{
+    using G = MmGeom<C, R>;
+    constexpr int NCH = G::NCH;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *s_in = reinterpret_cast<float *>(smem_raw);                 // [12 warps][3 slots][ROW]
+    float *s_h = reinterpret_cast<float *>(smem_raw + G::IN_BYTES);    // [48 rows][648]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + G::IN_BYTES + G::H_BYTES);
+    uint64_t *in_full = bars;
+    uint64_t *h_full = bars + MmK::row_warps * MmK::in_slots;
+    uint64_t *h_empty = h_full + MmK::groups;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < MmK::row_warps * MmK::in_slots; ++i) mbar_init(&in_full[i], 1);
+        for (int g = 0; g < MmK::groups; ++g) {
+            mbar_init(&h_full[g], MmK::row_warps);
+            mbar_init(&h_empty[g], MmK::col_warps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();  // the only CTA-wide barrier
+
+    if (warp < MmK::row_warps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMmRowRegs));
+        ws_row_role<C, R, SETS, kMmPitch, true>(p, ws, s_in, s_h, in_full, h_full, h_empty, warp, lane);
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kMmColRegs));
+
+    // ================================================================ COLUMN warp
+    const int items_per_image = p.n_strips * p.n_chunks;
+    const long n_items = (long)p.n_images * items_per_image;
+    const int wc = warp - MmK::row_warps;   // 0..7: columns [80 wc, 80 wc + 80) of the strip
+    const int g = lane >> 2, t = lane & 3;
+    const float *ring = s_h + t * kMmPitch + wc * (16 * kMmTiles) + 2 * g;
+
+    uint32_t waited = 0;     // groups of the hand-off ring waited for so far (all items)
+    uint32_t released = 0;   // groups handed back so far
+
+    int img = 0, rem = (int)blockIdx.x;
+    for (long item = blockIdx.x; item < n_items; item += gridDim.x, rem += (int)gridDim.x) {
+        while (rem >= items_per_image) {
+            rem -= items_per_image;
+            ++img;
+        }
+        const int chunk = rem / p.n_strips, strip = rem - chunk * p.n_strips;
+        const int y0 = chunk * p.chunk_rows;
+        const int y1 = min(p.height, y0 + p.chunk_rows);
+        const int n_rows = (y1 - y0) + 2 * R;
+        const int n_chunks8 = ws_steps<true>(n_rows) / 4 * (kMmRing / 8);
+        const unsigned n_valid = (unsigned)(y1 - y0);
+        const int gx = strip * kGsTW + wc * (16 * kMmTiles) + 2 * g;   // this thread's column pair, tile 0
+        float *base = p.out_tab ? p.out_tab[img] : p.out + (size_t)img * p.image_stride;
+
+        // B fragments of this item's weight set.  tf32 product: bh[j] = hi(B_j[t][g]), hi(B_j[t+4][g]);
+        // fp16 correction product: bc[j][0] = (B_j[t][g], B_j[t+4][g]) against lo(A), bc[j][1] = the
+        // lo parts of the same two weights against hi(A).
+        uint32_t bh[NCH][2], bc[NCH][2];
+        {
+            const int set = SETS ? img % kGsMaxSets : 0;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+                float w[2], wl[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    int d = 8 * j + t + 4 * h - g - R;
+                    d = d < 0 ? -d : d;
+                    w[h] = 0.f;
+                    if (d <= R) w[h] = SETS ? __uint_as_float((uint32_t)ws.ww[set][d]) : p.w[d];
+                    bh[j][h] = __float_as_uint(w[h]) & 0xffffe000u;
+                    wl[h] = w[h] - __uint_as_float(bh[j][h]);
+                    asm volatile("" : "+r"(bh[j][h]));   // keep it: re-deriving it per chunk costs an indexed LDC
+                }
+                bc[j][0] = pack_f16(w[0], w[1]);
+                bc[j][1] = pack_f16(wl[0], wl[1]);
+                asm volatile("" : "+r"(bc[j][0]), "+r"(bc[j][1]));
+            }
+        }
+
+        // acc[tile][j - 1] = partial sums of the block that has seen j chunks, j = 1 .. NCH-1
+        float acc[kMmTiles][NCH - 1][4];
+#pragma unroll
+        for (int q = 0; q < kMmTiles; ++q)
+#pragma unroll
+            for (int j = 0; j < NCH - 1; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[q][j][e] = 0.f;
+
+        const uint32_t item_g0 = waited;   // == released: items are whole turns of the ring
+        int ring_row = 0;                  // (c % 6) * 8
+        // output rows 2t, 2t + 1 of the block that completes with chunk c: rows 8 (c - NCH + 1) + ...
+        int orow = -8 * (NCH - 1) + 2 * t;
+        float *optr = base + ((long)y0 + orow) * p.row_elems + gx;   // only dereferenced when valid
+
+        for (int c = 0; c < n_chunks8; ++c) {
+            const uint32_t need = item_g0 + (uint32_t)(8 * c + 7) / MmK::rows + 1u;
+            while (waited < need) {
+                mbar_wait(&h_full[waited % MmK::groups], (waited / MmK::groups) & 1u);
+                ++waited;
+            }
+            const float *rp = ring + ring_row * kMmPitch;
+            const bool rows0 = (unsigned)orow < n_valid, rows1 = (unsigned)(orow + 1) < n_valid;
+            // the chunk's samples of all tiles first: the loads queue behind the ROW warps' window
+            // reads on the shared-memory pipe, so they are issued before any of them is needed
+            float2 raw[kMmTiles][2];
+#pragma unroll
+            for (int q = 0; q < kMmTiles; ++q) {
+                raw[q][0] = lds_f2(rp + 16 * q);
+                raw[q][1] = lds_f2(rp + 4 * kMmPitch + 16 * q);
+            }
+#pragma unroll
+            for (int q = 0; q < kMmTiles; ++q) {
+                const float2 v0 = raw[q][0], v1 = raw[q][1];
+                const float a[4] = {v0.x, v0.y, v1.x, v1.y};   // (row t | t+4) x (column 2g | 2g+1)
+                uint32_t ah[4];
+                float al[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    ah[e] = __float_as_uint(a[e]) & 0xffffe000u;
+                    al[e] = a[e] - __uint_as_float(ah[e]);
+                }
+                // correction operand: K slots (2t, 2t+1) = lo parts of rows (t, t+4), (2t+8, 2t+9) = hi parts
+                const uint32_t ac[4] = {pack_f16(al[0], al[2]), pack_f16(al[1], al[3]),
+                                        pack_f16(__uint_as_float(ah[0]), __uint_as_float(ah[2])),
+                                        pack_f16(__uint_as_float(ah[1]), __uint_as_float(ah[3]))};
+                // first MMA of every live block: destination is the next age
+                float nxt[NCH][4];   // nxt[j] = block of age j + 1 after this chunk (nxt[NCH-1] is complete)
+                const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = NCH - 1; j >= 0; --j) {
+                    if (j == 0) mma_f16(nxt[0], ac, bc[0][0], bc[0][1], zero);
+                    else mma_f16(nxt[j], ac, bc[j][0], bc[j][1], acc[q][j - 1]);
+                }
+#pragma unroll
+                for (int j = NCH - 1; j >= 0; --j) mma_tf32(nxt[j], ah, bh[j][0], bh[j][1], nxt[j]);
+#pragma unroll
+                for (int j = 0; j < NCH - 1; ++j)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[q][j][e] = nxt[j][e];
+                if (gx + 16 * q < p.row_elems) {
+                    if (rows0) __stcs(reinterpret_cast<float2 *>(optr + 16 * q), make_float2(nxt[NCH - 1][0], nxt[NCH - 1][2]));
+                    if (rows1)
+                        __stcs(reinterpret_cast<float2 *>(optr + p.row_elems + 16 * q),
+                               make_float2(nxt[NCH - 1][1], nxt[NCH - 1][3]));
+                }
+            }
+            orow += 8;
+            optr += 8l * p.row_elems;
+            ring_row = ring_row == kMmRing - 8 ? 0 : ring_row + 8;
+            // hand back every group whose 12 rows are now consumed
+            const uint32_t done = item_g0 + (uint32_t)(8 * (c + 1)) / MmK::rows;
+            if (released < done) {
+                __syncwarp();   // every lane has read the chunk
+                while (released < done) {
+                    if (lane == 0) mbar_arrive(&h_empty[released % MmK::groups]);
+                    ++released;
+                }
+            }
+        }
+    }
+}
+
+template <int C, int R>
+__global__ void __launch_bounds__(kMmThreads, 1)
+gauss_stream_mma_kernel(const __grid_constant__ GaussStreamParams p)
+{
+    mm_body<C, R, false>(p, *reinterpret_cast<const GaussWeightSets *>(&p));
+}
+
+template <int C, int R>
+__global__ void __launch_bounds__(kMmThreads, 1)
+gauss_stream_mma_sets_kernel(const __grid_constant__ GaussStreamParams p, const __grid_constant__ GaussWeightSets ws)
+{
+    mm_body<C, R, true>(p, ws);
+}
+
+}  // namespace mpk

@@ -38,6 +38,18 @@ constexpr int kWsThreads = 32 * (kWsRowWarps + kWsColWarps);
 constexpr int kWsInSlots = 4;                 // rows in flight per ROW warp
 constexpr int kWsGroups = 4;                  // filtered groups in flight between the roles
 
+// The same numbers per kernel flavour: the FMA-column kernel (this file) splits the CTA 10:10, the
+// tensor-core-column kernel (gaussian_stream_mma.cuh) 12:8 on warpgroup boundaries (setmaxnreg).
+template <bool MMA>
+struct WsK {
+    static constexpr int rows = MMA ? 12 : kWsRows;          // rows per group = ROW warps
+    static constexpr int row_warps = rows;
+    static constexpr int col_warps = MMA ? 8 : kWsColWarps;
+    static constexpr int in_slots = MMA ? 3 : kWsInSlots;
+    static constexpr int groups = kWsGroups;
+    static constexpr int threads = 32 * (row_warps + col_warps);
+};
+
 template <int C, int R>
 struct WsGeom {
     static constexpr int HALO = GsGeom<C, R>::HALO;
@@ -118,6 +130,123 @@ __device__ __forceinline__ void ws_row_pass(const float *__restrict__ win, float
     }
 }
 
+// Steps (10-row groups) a work item takes.  The tensor-core column pass (gaussian_stream_mma.cuh)
+// consumes the hand-off ring in 8-row chunks and finishes an output block NCH - 1 chunks after its
+// first row arrived, so there an item is padded by 7 rows and rounded up to a whole turn of the
+// 40-row ring (4 groups = 5 chunks): every item starts on ring row 0 with all barriers in phase.
+template <bool MMA>
+__device__ __forceinline__ int ws_steps(int n_rows)
+{
+    using K = WsK<MMA>;
+    if (!MMA) return (n_rows + K::rows - 1) / K::rows;
+    return ((n_rows + 7 + K::rows - 1) / K::rows + 3) & ~3;
+}
+
+// The ROW-warp role: private TMA ring -> horizontal filter -> hand-off ring (row pitch PITCH floats).
+template <int C, int R, bool SETS, int PITCH, bool MMA>
+__device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const GaussWeightSets &ws, float *s_in,
+                                            float *s_h, uint64_t *in_full, uint64_t *h_full, uint64_t *h_empty,
+                                            int warp, int lane)
+{
+    using G = WsGeom<C, R>;
+    using K = WsK<MMA>;
+    const int items_per_image = p.n_strips * p.n_chunks;
+    const long n_items = (long)p.n_images * items_per_image;
+    // =============================================================== ROW warp
+    float *my_in = s_in + (size_t)warp * K::in_slots * G::ROW;
+    uint64_t *my_full = in_full + warp * K::in_slots;
+    uint32_t loads = 0;   // rows issued so far by this warp (slot = loads % 3, parity from the count)
+    uint32_t takes = 0;   // rows consumed so far
+    uint32_t group = 0;   // groups produced so far (ring slot and parity)
+
+    int img = 0, rem = (int)blockIdx.x;  // item = img * items_per_image + rem, kept by add/compare only
+    for (long item = blockIdx.x; item < n_items; item += gridDim.x, rem += (int)gridDim.x) {
+        while (rem >= items_per_image) {
+            rem -= items_per_image;
+            ++img;
+        }
+        const int chunk = rem / p.n_strips, strip = rem - chunk * p.n_strips;
+        const float *__restrict__ src = p.in_tab ? p.in_tab[img] : p.in + (size_t)img * p.image_stride;
+        const WsSetOf w_img{ws, img % kGsMaxSets};
+        const WsOneSet w_one{p};
+        const int x0 = strip * kGsTW;
+        const int y0 = chunk * p.chunk_rows;
+        const int y1 = min(p.height, y0 + p.chunk_rows);
+        const int r_begin = y0 - R;
+        const int n_rows = (y1 - y0) + 2 * R;
+        const int n_steps = ws_steps<MMA>(n_rows);
+        const int gx_start = x0 - G::HALO;
+        const int lo = gx_start < 0 ? -gx_start : 0;
+        const int hi = min(G::ROW, p.row_elems - gx_start);
+        const uint32_t row_bytes = (uint32_t)(hi - lo) * 4u;
+
+        // every load this warp issued has been consumed: its ring is quiescent
+        if (lo > 0 || hi < G::ROW) {
+            for (int i = lane; i < K::in_slots * G::ROW; i += 32) {
+                const int col = i % G::ROW;
+                if (col < lo || col >= hi) my_in[i] = 0.f;
+            }
+            fence_proxy_async();
+        }
+        __syncwarp();
+
+        // This warp's rows are r_begin + warp + 10*step.  Steps [live_lo, live_hi) are the ones
+        // whose row lies inside the image and the item; everything per step is then a running
+        // pointer and two compares.
+        const int r_first = r_begin + warp;
+        const int r_end = min(p.height, r_begin + n_rows);
+        int live_lo = r_first < 0 ? (-r_first + K::rows - 1) / K::rows : 0;
+        int live_hi = r_end > r_first ? (r_end - r_first + K::rows - 1) / K::rows : 0;
+        if (live_hi > n_steps) live_hi = n_steps;
+        if (live_lo > live_hi) live_lo = live_hi;
+        const float *gptr = src + (long)(r_first + live_lo * K::rows) * p.row_elems + gx_start + lo;
+        const long gstep = (long)K::rows * p.row_elems;
+        int next_issue = live_lo;  // next live step to issue
+
+        auto issue_next = [&]() {  // all lanes keep the counters; lane 0 talks to the TMA unit
+            const uint32_t slot = loads % K::in_slots;
+            if (lane == 0) {
+                mbar_expect_tx(&my_full[slot], row_bytes);
+                bulk_g2s(my_in + (size_t)slot * G::ROW + lo, gptr, row_bytes, &my_full[slot]);
+            }
+            gptr += gstep;
+            ++loads;
+            ++next_issue;
+        };
+        // prologue: up to K::in_slots - 1 rows in flight before the first one is consumed
+        for (int s = 0; s < K::in_slots - 1 && next_issue < live_hi; ++s) issue_next();
+
+        float *hbase = s_h + (size_t)warp * PITCH + lane * kGsPH;
+        for (int step = 0; step < n_steps; ++step) {
+            const bool live = step >= live_lo && step < live_hi;
+            float out[kGsPH];
+            if (live) {
+                // the slot consumed in the previous live step is free again: keep the ring full
+                if (next_issue < live_hi) issue_next();
+                const uint32_t slot = takes % K::in_slots;
+                mbar_wait(&my_full[slot], (takes / K::in_slots) & 1u);
+                ++takes;
+                if (SETS) ws_row_pass<C, R>(my_in + (size_t)slot * G::ROW + lane * kGsPH, out, w_img);
+                else ws_row_pass<C, R>(my_in + (size_t)slot * G::ROW + lane * kGsPH, out, w_one);
+            } else {
+#pragma unroll
+                for (int i = 0; i < kGsPH; ++i) out[i] = 0.f;
+            }
+            // hand-off ring: wait until the COLUMN warps have drained this group slot
+            const uint32_t gs = group % K::groups;
+            mbar_wait(&h_empty[gs], ((group / K::groups) & 1u) ^ 1u);
+            float *hrow = hbase + (size_t)gs * (K::rows * PITCH);
+#pragma unroll
+            for (int v = 0; v < kGsPH / 4; ++v)
+                *reinterpret_cast<float4 *>(hrow + 4 * v) =
+                    make_float4(out[4 * v], out[4 * v + 1], out[4 * v + 2], out[4 * v + 3]);
+            __syncwarp();  // all lanes' stores and window reads are done
+            if (lane == 0) mbar_arrive(&h_full[gs]);
+            ++group;
+        }
+    }
+}
+
 template <int C, int R, bool SETS>
 __device__ __forceinline__ void ws_body(const GaussStreamParams &p, const GaussWeightSets &ws)
 {
@@ -145,99 +274,7 @@ __device__ __forceinline__ void ws_body(const GaussStreamParams &p, const GaussW
     const long n_items = (long)p.n_images * items_per_image;
 
     if (warp < kWsRowWarps) {
-        // =============================================================== ROW warp
-        float *my_in = s_in + (size_t)warp * kWsInSlots * G::ROW;
-        uint64_t *my_full = in_full + warp * kWsInSlots;
-        uint32_t loads = 0;   // rows issued so far by this warp (slot = loads % 3, parity from the count)
-        uint32_t takes = 0;   // rows consumed so far
-        uint32_t group = 0;   // groups produced so far (ring slot and parity)
-
-        int img = 0, rem = (int)blockIdx.x;  // item = img * items_per_image + rem, kept by add/compare only
-        for (long item = blockIdx.x; item < n_items; item += gridDim.x, rem += (int)gridDim.x) {
-            while (rem >= items_per_image) {
-                rem -= items_per_image;
-                ++img;
-            }
-            const int chunk = rem / p.n_strips, strip = rem - chunk * p.n_strips;
-            const float *__restrict__ src = p.in_tab ? p.in_tab[img] : p.in + (size_t)img * p.image_stride;
-            const WsSetOf w_img{ws, img % kGsMaxSets};
-            const WsOneSet w_one{p};
-            const int x0 = strip * kGsTW;
-            const int y0 = chunk * p.chunk_rows;
-            const int y1 = min(p.height, y0 + p.chunk_rows);
-            const int r_begin = y0 - R;
-            const int n_rows = (y1 - y0) + 2 * R;
-            const int n_steps = (n_rows + kWsRows - 1) / kWsRows;
-            const int gx_start = x0 - G::HALO;
-            const int lo = gx_start < 0 ? -gx_start : 0;
-            const int hi = min(G::ROW, p.row_elems - gx_start);
-            const uint32_t row_bytes = (uint32_t)(hi - lo) * 4u;
-
-            // every load this warp issued has been consumed: its ring is quiescent
-            if (lo > 0 || hi < G::ROW) {
-                for (int i = lane; i < kWsInSlots * G::ROW; i += 32) {
-                    const int col = i % G::ROW;
-                    if (col < lo || col >= hi) my_in[i] = 0.f;
-                }
-                fence_proxy_async();
-            }
-            __syncwarp();
-
-            // This warp's rows are r_begin + warp + 10*step.  Steps [live_lo, live_hi) are the ones
-            // whose row lies inside the image and the item; everything per step is then a running
-            // pointer and two compares.
-            const int r_first = r_begin + warp;
-            const int r_end = min(p.height, r_begin + n_rows);
-            int live_lo = r_first < 0 ? (-r_first + kWsRows - 1) / kWsRows : 0;
-            int live_hi = r_end > r_first ? (r_end - r_first + kWsRows - 1) / kWsRows : 0;
-            if (live_hi > n_steps) live_hi = n_steps;
-            if (live_lo > live_hi) live_lo = live_hi;
-            const float *gptr = src + (long)(r_first + live_lo * kWsRows) * p.row_elems + gx_start + lo;
-            const long gstep = (long)kWsRows * p.row_elems;
-            int next_issue = live_lo;  // next live step to issue
-
-            auto issue_next = [&]() {  // all lanes keep the counters; lane 0 talks to the TMA unit
-                const uint32_t slot = loads % kWsInSlots;
-                if (lane == 0) {
-                    mbar_expect_tx(&my_full[slot], row_bytes);
-                    bulk_g2s(my_in + (size_t)slot * G::ROW + lo, gptr, row_bytes, &my_full[slot]);
-                }
-                gptr += gstep;
-                ++loads;
-                ++next_issue;
-            };
-            // prologue: up to kWsInSlots - 1 rows in flight before the first one is consumed
-            for (int s = 0; s < kWsInSlots - 1 && next_issue < live_hi; ++s) issue_next();
-
-            float *hbase = s_h + (size_t)warp * kGsTW + lane * kGsPH;
-            for (int step = 0; step < n_steps; ++step) {
-                const bool live = step >= live_lo && step < live_hi;
-                float out[kGsPH];
-                if (live) {
-                    // the slot consumed in the previous live step is free again: keep the ring full
-                    if (next_issue < live_hi) issue_next();
-                    const uint32_t slot = takes % kWsInSlots;
-                    mbar_wait(&my_full[slot], (takes / kWsInSlots) & 1u);
-                    ++takes;
-                    if (SETS) ws_row_pass<C, R>(my_in + (size_t)slot * G::ROW + lane * kGsPH, out, w_img);
-                    else ws_row_pass<C, R>(my_in + (size_t)slot * G::ROW + lane * kGsPH, out, w_one);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < kGsPH; ++i) out[i] = 0.f;
-                }
-                // hand-off ring: wait until the COLUMN warps have drained this group slot
-                const uint32_t gs = group % kWsGroups;
-                mbar_wait(&h_empty[gs], ((group / kWsGroups) & 1u) ^ 1u);
-                float *hrow = hbase + (size_t)gs * (kWsRows * kGsTW);
-#pragma unroll
-                for (int v = 0; v < kGsPH / 4; ++v)
-                    *reinterpret_cast<float4 *>(hrow + 4 * v) =
-                        make_float4(out[4 * v], out[4 * v + 1], out[4 * v + 2], out[4 * v + 3]);
-                __syncwarp();  // all lanes' stores and window reads are done
-                if (lane == 0) mbar_arrive(&h_full[gs]);
-                ++group;
-            }
-        }
+        ws_row_role<C, R, SETS, kGsTW, false>(p, ws, s_in, s_h, in_full, h_full, h_empty, warp, lane);
     } else {
         // ============================================================ COLUMN warp
         // A[j] is the partial sum of output row (r - R + j) when filtered row r arrives.  Row r

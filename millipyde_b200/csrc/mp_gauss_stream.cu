@@ -4,10 +4,12 @@
 // instantiated for a few radii and a request uses the smallest bucket that
 // holds its effective radius (weights beyond the radius are zero).  sigma = 2
 // (effective radius 11) lands exactly on a bucket.
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels/gaussian_stream.cuh"
 #include "kernels/gaussian_stream_ws.cuh"
+#include "kernels/gaussian_stream_mma.cuh"
 #include "mp_internal.h"
 #include "mp_ops_internal.h"
 
@@ -29,17 +31,37 @@ bool gauss_stream_supported(int W, int C, int radius)
     return ((size_t)W * C) % 4 == 0 && (size_t)W * C >= 64 && bucket_for(radius) != 0;
 }
 
+// Which column pass a launch uses: the tensor-core one (gaussian_stream_mma.cuh) wherever it is
+// instantiated (an output block spans at most 4 chunks: R <= 11), unless MILLIPYDE_GAUSS_COLUMN=fma
+// asks for the FMA-pipe kernel (A/B measurements; the two agree to ~1e-6, not bit for bit).
+static bool use_mma_column()
+{
+    static const bool on = [] {
+        const char *e = getenv("MILLIPYDE_GAUSS_COLUMN");
+        return !(e && strcmp(e, "fma") == 0);
+    }();
+    return on;
+}
+
 template <int C, int R>
 static MPStatus launch_cr(int device, cudaStream_t s, GaussStreamParams &p, const GaussWeightSets *sets)
 {
     const int sms = sm_count(device) ? sm_count(device) : 148;
-    const size_t smem = WsGeom<C, R>::SMEM;
+    constexpr bool kHasMma = MmGeom<C, R>::NCH <= 4;
+    const bool mma = kHasMma && use_mma_column();
+    const size_t smem = mma ? MmGeom<C, R>::SMEM : WsGeom<C, R>::SMEM;
     static bool configured[64] = {};  // per device
     if (device >= 0 && device < 64 && !configured[device]) {
         MP_CUDA_TRY(cudaFuncSetAttribute(gauss_stream_ws_kernel<C, R>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsGeom<C, R>::SMEM));
         MP_CUDA_TRY(cudaFuncSetAttribute(gauss_stream_ws_sets_kernel<C, R>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsGeom<C, R>::SMEM));
+        if constexpr (kHasMma) {
+            MP_CUDA_TRY(cudaFuncSetAttribute(gauss_stream_mma_kernel<C, R>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmGeom<C, R>::SMEM));
+            MP_CUDA_TRY(cudaFuncSetAttribute(gauss_stream_mma_sets_kernel<C, R>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmGeom<C, R>::SMEM));
+        }
         configured[device] = true;
     }
     // One persistent CTA per SM.  An item is (image, strip, row chunk); the number of row chunks is
@@ -64,6 +86,14 @@ static MPStatus launch_cr(int device, cudaStream_t s, GaussStreamParams &p, cons
     p.chunk_rows = (p.height + chunks - 1) / chunks;
     items *= chunks;
     const int grid = (int)(items < sms ? items : sms);
+    if constexpr (kHasMma) {
+        if (mma) {
+            if (sets) gauss_stream_mma_sets_kernel<C, R><<<grid, kMmThreads, smem, s>>>(p, *sets);
+            else gauss_stream_mma_kernel<C, R><<<grid, kMmThreads, smem, s>>>(p);
+            count_launch();
+            return MILLIPYDE_SUCCESS;
+        }
+    }
     if (sets) gauss_stream_ws_sets_kernel<C, R><<<grid, kWsThreads, smem, s>>>(p, *sets);
     else gauss_stream_ws_kernel<C, R><<<grid, kWsThreads, smem, s>>>(p);
     count_launch();
