@@ -4,6 +4,9 @@
 // Replaces PyGPUPipeline_run / gpupipeline_run_sequence / gpupipeline_send_input
 // (src/gpupipeline.c:234-403) and the serial Generator loop
 // (src/gpugenerator.c:203-281).  See include/mp_pipeline.h for the contract.
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -63,12 +66,16 @@ OpKind classify(MPFunc f, size_t *arg_bytes)
 
 bool is_pointwise(OpKind k) { return k == OP_BRIGHTNESS || k == OP_GAMMA || k == OP_COLORIZE; }
 
-// Per-device page-locked arena for pointer tables: grows, is reused by every run
-// on that device, and is only touched by that run's worker under `mux`.
+// Per-device page-locked arenas for pointer tables.  A shard's worker owns one arena of the device's
+// ring while it enqueues (under the device's `enqueue` mutex, which also keeps the launches of two
+// shards from interleaving on the stream) and lets go of the mutex before it waits for the device,
+// so the next shard's host work overlaps this shard's kernels.  `done` marks the end of the last
+// shard that used the arena: it is what that shard's worker waits on, and what guards reuse.
 struct Arena {
-    std::mutex mux;
     char *base = nullptr;
     size_t cap = 0, used = 0;
+    cudaEvent_t done = nullptr;
+    bool in_use = false;   // `done` has been recorded and not yet waited for by a new owner
     void *take(size_t bytes)
     {
         bytes = (bytes + 63) & ~(size_t)63;
@@ -78,7 +85,14 @@ struct Arena {
         return p;
     }
 };
-Arena g_arenas[64];
+constexpr int kArenaRing = 2;
+struct DeviceArenas {
+    std::mutex enqueue;
+    Arena ring[kArenaRing];
+    unsigned next = 0;
+};
+DeviceArenas g_arenas[64];
+thread_local Arena *g_arena = nullptr;   // the arena of the shard this worker thread is enqueueing
 
 }  // namespace
 
@@ -93,6 +107,12 @@ struct mp_pipeline {
     std::mutex mux;
     std::vector<int> in_flight;
     bool cycled = false;
+    // shards of this pipeline submitted and not yet finished; mppipe_wait of a pipeline with a fixed
+    // device waits for this to reach zero instead of draining the whole device, so two pipelines can
+    // keep one device busy back to back (submit B, wait A, submit A, wait B, ...)
+    int pending = 0;
+    bool soft_wait = false;
+    std::condition_variable cv;
 };
 
 namespace {
@@ -391,9 +411,8 @@ MPStatus run_batched(const std::vector<MPObjData *> &objs, size_t out_bytes, int
 {
     *handled = false;
     const size_t n = objs.size();
-    Arena &arena = g_arenas[device];
     const size_t tab_bytes = (2 * n * sizeof(void *) + 15) & ~(size_t)15;
-    void **h_tab = (void **)arena.take(tab_bytes + record_bytes);
+    void **h_tab = g_arena ? (void **)g_arena->take(tab_bytes + record_bytes) : nullptr;
     if (!h_tab) return MILLIPYDE_SUCCESS;
     void *d_tab = mp::pool_alloc(device, s, tab_bytes + record_bytes);
     if (!d_tab) return MP_ERROR_DEVICE_ALLOC;
@@ -679,10 +698,16 @@ void shard_worker(void *arg)
     const size_t n = t->objs.size();
     cudaSetDevice(device);
     cudaStream_t batch_stream = mp::device_stream(device, 1);
-    const unsigned long long launches0 = mpdev_launch_count();
+    // MILLIPYDE_TRACE=1: one stderr line per shard with the host time spent enqueueing it and the time
+    // spent waiting for the device afterwards (tells host-bound batches from device-bound ones)
+    static const bool trace = [] { const char *e = getenv("MILLIPYDE_TRACE"); return e && *e && *e != '0'; }();
+    const auto t_start = std::chrono::steady_clock::now();
 
-    Arena &arena = g_arenas[device];
-    std::unique_lock<std::mutex> arena_lock(arena.mux);
+    DeviceArenas &da = g_arenas[device];
+    std::unique_lock<std::mutex> enqueue_lock(da.enqueue);
+    Arena &arena = da.ring[da.next++ % kArenaRing];
+    const unsigned long long launches0 = mpdev_launch_count();
+    if (arena.in_use) cudaEventSynchronize(arena.done);   // its previous shard's copies have been read
     const size_t want = n * (sizeof(void *) * 2 + sizeof(GatherVar) + 64) * (p->stages.size() + 1) + 4096;
     if (arena.cap < want) {
         if (arena.base) cudaFreeHost(arena.base);
@@ -691,7 +716,12 @@ void shard_worker(void *arg)
         if (cudaHostAlloc((void **)&arena.base, want * 2, cudaHostAllocPortable) == cudaSuccess) arena.cap = want * 2;
         else (void)cudaGetLastError();
     }
+    if (!arena.done && cudaEventCreateWithFlags(&arena.done, cudaEventDisableTiming) != cudaSuccess) {
+        (void)cudaGetLastError();
+        arena.done = nullptr;
+    }
     arena.used = 0;
+    g_arena = &arena;
 
     if (t->after) {  // the sender's kernels wrote some of these images straight into this device's memory
         cudaStreamWaitEvent(batch_stream, t->after, 0);
@@ -795,7 +825,22 @@ void shard_worker(void *arg)
     }
     if (t->views) g_borrowed = nullptr;
 
-    cudaError_t e = cudaStreamSynchronize(batch_stream);
+    // Everything is enqueued: mark the end, let the next shard of this device start enqueueing, and
+    // wait for OUR work only (the stream may already hold the next shard's).
+    g_arena = nullptr;
+    const unsigned long long launched = mpdev_launch_count() - launches0;
+    cudaEvent_t done = arena.done;
+    arena.in_use = done && cudaEventRecord(done, batch_stream) == cudaSuccess;
+    const bool have_done = arena.in_use;
+    enqueue_lock.unlock();
+    const auto t_enqueued = std::chrono::steady_clock::now();
+    cudaError_t e = have_done ? cudaEventSynchronize(done) : cudaStreamSynchronize(batch_stream);
+    if (trace) {
+        const auto t_done = std::chrono::steady_clock::now();
+        fprintf(stderr, "[millipyde] shard dev=%d images=%zu enqueue=%.3f ms wait=%.3f ms\n", device, n,
+                std::chrono::duration<double, std::milli>(t_enqueued - t_start).count(),
+                std::chrono::duration<double, std::milli>(t_done - t_enqueued).count());
+    }
     if (e != cudaSuccess) {
         mp::record_cuda_error(e, "cudaStreamSynchronize(shard)", __FILE__, __LINE__);
         note_status(p, MP_ERROR_CUDA_RUNTIME);
@@ -806,8 +851,13 @@ void shard_worker(void *arg)
             t->objs[i]->stream = (void *)mp::device_stream(device, 0);  // idle: no event needed
         }
     }
-    p->launches.fetch_add(mpdev_launch_count() - launches0);
+    p->launches.fetch_add(launched);
     delete t;
+    {
+        std::lock_guard<std::mutex> lk(p->mux);
+        --p->pending;
+    }
+    p->cv.notify_all();
 }
 
 void submit_shard(mp_pipeline *p, std::vector<MPObjData *> objs, int device, bool views, cudaEvent_t after)
@@ -816,6 +866,7 @@ void submit_shard(mp_pipeline *p, std::vector<MPObjData *> objs, int device, boo
     {
         std::lock_guard<std::mutex> lk(p->mux);
         p->in_flight.push_back(device);
+        ++p->pending;
     }
     ShardTask *t = new ShardTask{p, std::move(objs), device, views, after};
     mpdev_submit_work(device, shard_worker, t);
@@ -943,6 +994,7 @@ static MPStatus submit_impl(MPPipeline *p, MPObjData **objs, int n, bool views)
     }
     if (!mpdev_is_valid_device(device)) return GPUPIPELINE_ERROR_UNUSABLE_DEVICE;
     p->cycled = cycle;
+    p->soft_wait = !cycle;
     for (mp_pipeline *q = p->receiver; q; q = q->receiver)
         if (!mpdev_is_valid_device(q->device)) q->device = device;
 
@@ -963,6 +1015,13 @@ MPStatus mppipe_wait(MPPipeline *p)
     if (!p) return MP_ERROR_INVALID_ARGUMENT;
     if (p->cycled) {
         mpdev_hard_synchronize_all();
+    } else if (p->soft_wait) {
+        // every shard's worker returns only after its device work is complete, and a sender registers
+        // its receiver's shards before it finishes: own shards first, then down the chain
+        for (mp_pipeline *q = p; q; q = q->receiver) {
+            std::unique_lock<std::mutex> lk(q->mux);
+            q->cv.wait(lk, [q] { return q->pending == 0; });
+        }
     } else {
         // own device first, then down the receiver chain: by the time a device's pool is
         // drained its workers have enqueued their hand-offs (src/gpupipeline.c:293-306)
@@ -1140,6 +1199,7 @@ extern "C" MPStatus mppipe_run_host(MPPipeline *p, const void *const *host_in, v
     }
     if (!mpdev_is_valid_device(device)) return GPUPIPELINE_ERROR_UNUSABLE_DEVICE;
     p->cycled = cycle;
+    p->soft_wait = false;   // host_worker tasks are not counted in `pending`
 
     std::map<int, std::vector<int>> shards;
     int cur = device;
