@@ -91,18 +91,35 @@ def cpu_baseline(n_images: int):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock, power and throttle reasons of one GPU sampled DURING the timed region: NVML in a
+    thread every 5 ms when pynvml is importable (a 250 ms timed region gets ~50 samples), else
+    `nvidia-smi -lms 100`."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.rows = []          # (arrival time, fields)
+        self.rows = []          # (arrival time, sm MHz, max MHz, watts, set of reasons)
         self.window = None      # (t0, t1) of the timed region
         self.proc = None
         self.gpu = gpu_index
         self.thread = None
+        self.stop_flag = False
+        self.how = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.how = "NVML every 5 ms"
+            self.thread = threading.Thread(target=self._pump_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
@@ -110,46 +127,66 @@ class ClockSampler:
         except OSError:
             self.proc = None
             return
-        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.how = "nvidia-smi -lms 100"
+        self.thread = threading.Thread(target=self._pump_smi, daemon=True)
         self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+    def _pump_nvml(self):
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                watts = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.time(), sm, self.max_sm, watts, {k for k, b in bits.items() if mask & b}))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons, power = [], 0, set(), 0.0
-        rows = self.rows
-        if self.window:
-            inside = [x for x in rows if self.window[0] <= x[0] <= self.window[1] + 0.15]
-            # a timed region shorter than the sampling period: fall back to every sample taken
-            # since the warm-up started (the GPU was under the same load throughout)
-            rows = inside if len(inside) >= 3 else rows
-        for _, r in rows:
+    def _pump_smi(self):
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
             if len(r) < 9:
                 continue
             try:
-                sm.append(float(r[1]))
-                mx = max(mx, float(r[2]))
-                power = max(power, float(r[3]))
+                names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+                self.rows.append((time.time(), float(r[1]), float(r[2]), float(r[3]),
+                                  {n for n, v in zip(names, r[5:9]) if v.lower().startswith("active")}))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        # median of the upper half: the samples taken while the kernels were running
-        busy = sm[len(sm) // 2:] if sm else []
-        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx or None,
-                "power_w_max": power, "samples": len(sm), "reasons": sorted(reasons),
-                "note": "nvidia-smi -lms 100 from warm-up to the end of the timed region; median of the busy half"}
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        if self.thread and self.nv:
+            self.thread.join(timeout=1)
+        if not self.how:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML, no nvidia-smi"]}
+        rows = self.rows
+        scope = "warm-up + timed region"
+        if self.window:
+            inside = [x for x in rows if self.window[0] <= x[0] <= self.window[1]]
+            # a timed region shorter than the sampling period: fall back to every sample taken
+            # since the warm-up started (the GPU was under the same load throughout)
+            if len(inside) >= 3:
+                rows, scope = inside, "timed region only"
+        sm = sorted(r[1] for r in rows)
+        reasons = set().union(*[r[4] for r in rows]) if rows else set()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": max((r[2] for r in rows), default=None),
+                "power_w_max": max((r[3] for r in rows), default=0.0),
+                "power_w_median": sorted(r[3] for r in rows)[len(rows) // 2] if rows else None,
+                "samples": len(sm), "reasons": sorted(reasons),
+                "note": f"{self.how}, {scope}; sm_mhz = median"}
 
 
 # --------------------------------------------------------------------------- dist

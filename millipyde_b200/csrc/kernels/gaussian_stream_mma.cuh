@@ -38,6 +38,9 @@ constexpr int kMmPitch = kGsTW + 8;            // hand-off ring row pitch in flo
 constexpr int kMmRing = MmK::groups * MmK::rows;   // 48 rows = 4 groups of 12 = 6 chunks of 8
 constexpr int kMmTiles = kGsTW / 16 / MmK::col_warps;  // 16-column tiles per COLUMN warp (5)
 constexpr int kMmThreads = MmK::threads;       // 640
+// Output staging: 8 rows x 80 floats per COLUMN warp at a pitch of 88 floats (= 24 mod 32: rows
+// t and 4+t of the four t's of a half-warp start 8 banks apart, so its 8-byte stores do not conflict).
+constexpr int kMmStagePitch = 88;
 // Registers: the kernel is compiled for 96 per thread (640 threads) and that allocation is the
 // CTA's pool.  The 12 ROW warps (warpgroups 0-2) hand 16 each back (setmaxnreg.dec 80), the 8 COLUMN
 // warps (warpgroups 3-4) take them (setmaxnreg.inc 120): 12*80 + 8*120 = 20*96.
@@ -49,8 +52,9 @@ struct MmGeom {
     static constexpr int NCH = (7 + 2 * R) / 8 + 1;   // chunks an output block spans
     static constexpr size_t IN_BYTES = (size_t)MmK::row_warps * MmK::in_slots * GsGeom<C, R>::ROW * 4;
     static constexpr size_t H_BYTES = (size_t)kMmRing * kMmPitch * 4;
+    static constexpr size_t STAGE_BYTES = (size_t)MmK::col_warps * 8 * kMmStagePitch * 4;
     static constexpr int N_BARS = MmK::row_warps * MmK::in_slots + 2 * MmK::groups;
-    static constexpr size_t SMEM = IN_BYTES + H_BYTES + 8 * N_BARS + 64;
+    static constexpr size_t SMEM = IN_BYTES + H_BYTES + STAGE_BYTES + 8 * N_BARS + 64;
 };
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1,
@@ -81,6 +85,23 @@ __device__ __forceinline__ uint32_t pack_f16(float x, float y)
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
     return r;
 }
+// shared -> global 1-D bulk copy through the TMA unit (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void sts_f2(float *p, float x, float y)
+{
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(smem_addr(p)), "f"(x), "f"(y) : "memory");
+}
 __device__ __forceinline__ float2 lds_f2(const float *p)
 {
     float2 v;
@@ -96,7 +117,8 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_in = reinterpret_cast<float *>(smem_raw);                 // [12 warps][3 slots][ROW]
     float *s_h = reinterpret_cast<float *>(smem_raw + G::IN_BYTES);    // [48 rows][648]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + G::IN_BYTES + G::H_BYTES);
+    float *s_stage = reinterpret_cast<float *>(smem_raw + G::IN_BYTES + G::H_BYTES);   // [8 warps][8 rows][88]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + G::IN_BYTES + G::H_BYTES + G::STAGE_BYTES);
     uint64_t *in_full = bars;
     uint64_t *h_full = bars + MmK::row_warps * MmK::in_slots;
     uint64_t *h_empty = h_full + MmK::groups;
@@ -122,9 +144,13 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
     // ================================================================ COLUMN warp
     const int items_per_image = p.n_strips * p.n_chunks;
     const long n_items = (long)p.n_images * items_per_image;
-    const int wc = warp - MmK::row_warps;   // 0..7: columns [80 wc, 80 wc + 80) of the strip
+    // 0..7: columns [80 wc, 80 wc + 80) of the strip; read from lane 0 so that the compiler knows it
+    // is warp-uniform (the bulk-store addresses then live in uniform registers)
+    const int wc = __shfl_sync(0xffffffffu, warp, 0) - MmK::row_warps;
     const int g = lane >> 2, t = lane & 3;
     const float *ring = s_h + t * kMmPitch + wc * (16 * kMmTiles) + 2 * g;
+    float *stage = s_stage + wc * (8 * kMmStagePitch);              // this warp's staging rows
+    float *my_stage = stage + t * kMmStagePitch + 2 * g;           // block row 2t (row 2t+1: 4 rows further)
 
     uint32_t waited = 0;     // groups of the hand-off ring waited for so far (all items)
     uint32_t released = 0;   // groups handed back so far
@@ -141,7 +167,6 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
         const int n_rows = (y1 - y0) + 2 * R;
         const int n_chunks8 = ws_steps<true>(n_rows) / 4 * (kMmRing / 8);
         const unsigned n_valid = (unsigned)(y1 - y0);
-        const int gx = strip * kGsTW + wc * (16 * kMmTiles) + 2 * g;   // this thread's column pair, tile 0
         float *base = p.out_tab ? p.out_tab[img] : p.out + (size_t)img * p.image_stride;
 
         // B fragments of this item's weight set.  tf32 product: bh[j] = hi(B_j[t][g]), hi(B_j[t+4][g]);
@@ -180,9 +205,15 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
 
         const uint32_t item_g0 = waited;   // == released: items are whole turns of the ring
         int ring_row = 0;                  // (c % 6) * 8
-        // output rows 2t, 2t + 1 of the block that completes with chunk c: rows 8 (c - NCH + 1) + ...
-        int orow = -8 * (NCH - 1) + 2 * t;
-        float *optr = base + ((long)y0 + orow) * p.row_elems + gx;   // only dereferenced when valid
+        // Output.  The block that completes with chunk c is rows ob .. ob+7, ob = 8 (c - NCH + 1).  Its
+        // 8 x 80 samples are staged in the warp's own shared-memory rows and leave as eight 320-byte
+        // TMA bulk stores (SASS UBLKCP.G.S) issued by lane 0: a direct store of the accumulator
+        // fragments touches 4 rows x 32 bytes per half-warp and costs 4x the shared/L1 data-pipe
+        // wavefronts.  Thread (g, t) holds block rows 2t and 2t+1; they are staged in rows t and 4+t.
+        int ob = -8 * (NCH - 1);
+        const int gx0 = strip * kGsTW + wc * (16 * kMmTiles);     // first column of the warp's slice
+        const int cols = min(16 * kMmTiles, p.row_elems - gx0);    // <= 0: the slice is outside the image
+        float *gdst = base + ((long)y0 + ob) * p.row_elems + gx0;  // block row 0; only used when valid
 
         for (int c = 0; c < n_chunks8; ++c) {
             const uint32_t need = item_g0 + (uint32_t)(8 * c + 7) / MmK::rows + 1u;
@@ -191,7 +222,6 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
                 ++waited;
             }
             const float *rp = ring + ring_row * kMmPitch;
-            const bool rows0 = (unsigned)orow < n_valid, rows1 = (unsigned)(orow + 1) < n_valid;
             // the chunk's samples of all tiles first: the loads queue behind the ROW warps' window
             // reads on the shared-memory pipe, so they are issued before any of them is needed
             float2 raw[kMmTiles][2];
@@ -229,27 +259,37 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
                 for (int j = 0; j < NCH - 1; ++j)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) acc[q][j][e] = nxt[j][e];
-                if (gx + 16 * q < p.row_elems) {
-                    if (rows0) __stcs(reinterpret_cast<float2 *>(optr + 16 * q), make_float2(nxt[NCH - 1][0], nxt[NCH - 1][2]));
-                    if (rows1)
-                        __stcs(reinterpret_cast<float2 *>(optr + p.row_elems + 16 * q),
-                               make_float2(nxt[NCH - 1][1], nxt[NCH - 1][3]));
+                if (q == 0) {
+                    // the previous block's bulk stores have read the staging rows (a chunk ago: no wait
+                    // in practice); only lane 0 has groups, the others fall through
+                    bulk_wait_read<0>();
+                    __syncwarp();
                 }
+                sts_f2(my_stage + 16 * q, nxt[NCH - 1][0], nxt[NCH - 1][2]);                        // block row 2t
+                sts_f2(my_stage + 4 * kMmStagePitch + 16 * q, nxt[NCH - 1][1], nxt[NCH - 1][3]);   // block row 2t + 1
             }
-            orow += 8;
-            optr += 8l * p.row_elems;
+            // hand back every group whose 12 rows are now consumed (the MMAs above used every sample)
             ring_row = ring_row == kMmRing - 8 ? 0 : ring_row + 8;
-            // hand back every group whose 12 rows are now consumed
             const uint32_t done = item_g0 + (uint32_t)(8 * (c + 1)) / MmK::rows;
-            if (released < done) {
-                __syncwarp();   // every lane has read the chunk
-                while (released < done) {
-                    if (lane == 0) mbar_arrive(&h_empty[released % MmK::groups]);
-                    ++released;
+            fence_proxy_async();   // the staged rows are read by the async proxy
+            __syncwarp();          // every lane has read the chunk and staged its part of the block
+            if (lane == 0) {
+                while (released < done) mbar_arrive(&h_empty[released++ % MmK::groups]);
+                if (cols > 0) {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+                        if ((unsigned)(ob + r) < n_valid)
+                            bulk_s2g(gdst + (long)r * p.row_elems, stage + ((r >> 1) + 4 * (r & 1)) * kMmStagePitch,
+                                     (uint32_t)cols * 4u);
                 }
+                bulk_commit();
             }
+            released = done;
+            ob += 8;
+            gdst += 8l * p.row_elems;
         }
     }
+    if (lane == 0) bulk_wait_read<0>();   // shared memory stays valid until the last stores have read it
 }
 
 template <int C, int R>

@@ -45,7 +45,7 @@ struct WsK {
     static constexpr int rows = MMA ? 12 : kWsRows;          // rows per group = ROW warps
     static constexpr int row_warps = rows;
     static constexpr int col_warps = MMA ? 8 : kWsColWarps;
-    static constexpr int in_slots = MMA ? 3 : kWsInSlots;
+    static constexpr int in_slots = MMA ? 2 : kWsInSlots;   // MMA: the third slot's room stages the output
     static constexpr int groups = kWsGroups;
     static constexpr int threads = 32 * (row_warps + col_warps);
 };
