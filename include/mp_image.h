@@ -84,6 +84,22 @@ int mpimg_get_semantics(void);
  * the oracle's nominal radius int(8*sigma+0.5). */
 int mpimg_gaussian_effective_radius(double sigma, int *full);
 
+/*
+ * Column pass of the fp32 streaming Gaussian (new; a tuning and A/B-test switch, not a
+ * semantics switch -- both forms meet the 1e-5 contract and differ by ~1e-6):
+ *   MP_GAUSS_COLUMN_MMA (default)  vertical filter on the tensor cores: split-precision
+ *       tf32 + fp16-correction mma.sync products, output through TMA bulk stores
+ *       (kernels/gaussian_stream_mma.cuh; effective radius <= 11, |sample| < 65504).
+ *   MP_GAUSS_COLUMN_FMA  vertical filter on the fp32 FMA pipe
+ *       (kernels/gaussian_stream_ws.cuh; every radius bucket, no range limit).
+ * The default can also be chosen with the environment variable
+ * MILLIPYDE_GAUSS_COLUMN=mma|fma, read on first use.
+ */
+#define MP_GAUSS_COLUMN_MMA 0
+#define MP_GAUSS_COLUMN_FMA 1
+void mpimg_set_gauss_column(int mode);
+int mpimg_get_gauss_column(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,6 +119,8 @@ SYMBOLS = {
     "mpimg_func_from_name": (C.c_void_p, [C.c_char_p, C.POINTER(C.c_size_t)]),
     "mpimg_set_semantics": (None, [C.c_int]),
     "mpimg_get_semantics": (C.c_int, []),
+    "mpimg_set_gauss_column": (None, [C.c_int]),
+    "mpimg_get_gauss_column": (C.c_int, []),
     "mpimg_gaussian_effective_radius": (C.c_int, [C.c_double, C.POINTER(C.c_int)]),
     # mp_objects.h
     "mpobj_copy_from_host": (None, [_OBJ, C.c_void_p, C.c_size_t]),

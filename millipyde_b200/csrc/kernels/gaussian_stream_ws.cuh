@@ -224,7 +224,8 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
                 // the slot consumed in the previous live step is free again: keep the ring full
                 if (next_issue < live_hi) issue_next();
                 const uint32_t slot = takes % K::in_slots;
-                mbar_wait(&my_full[slot], (takes / K::in_slots) & 1u);
+                if (MMA) mbar_wait_suspend(&my_full[slot], (takes / K::in_slots) & 1u, 2000u);
+                else mbar_wait(&my_full[slot], (takes / K::in_slots) & 1u);
                 ++takes;
                 if (SETS) ws_row_pass<C, R>(my_in + (size_t)slot * G::ROW + lane * kGsPH, out, w_img);
                 else ws_row_pass<C, R>(my_in + (size_t)slot * G::ROW + lane * kGsPH, out, w_one);
@@ -234,7 +235,8 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
             }
             // hand-off ring: wait until the COLUMN warps have drained this group slot
             const uint32_t gs = group % K::groups;
-            mbar_wait(&h_empty[gs], ((group / K::groups) & 1u) ^ 1u);
+            if (MMA) mbar_wait_suspend(&h_empty[gs], ((group / K::groups) & 1u) ^ 1u, 2000u);
+            else mbar_wait(&h_empty[gs], ((group / K::groups) & 1u) ^ 1u);
             float *hrow = hbase + (size_t)gs * (K::rows * PITCH);
 #pragma unroll
             for (int v = 0; v < kGsPH / 4; ++v)

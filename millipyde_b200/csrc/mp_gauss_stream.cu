@@ -4,12 +4,14 @@
 // instantiated for a few radii and a request uses the smallest bucket that
 // holds its effective radius (weights beyond the radius are zero).  sigma = 2
 // (effective radius 11) lands exactly on a bucket.
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
 #include "kernels/gaussian_stream.cuh"
 #include "kernels/gaussian_stream_ws.cuh"
 #include "kernels/gaussian_stream_mma.cuh"
+#include "mp_image.h"
 #include "mp_internal.h"
 #include "mp_ops_internal.h"
 
@@ -32,15 +34,19 @@ bool gauss_stream_supported(int W, int C, int radius)
 }
 
 // Which column pass a launch uses: the tensor-core one (gaussian_stream_mma.cuh) wherever it is
-// instantiated (an output block spans at most 4 chunks: R <= 11), unless MILLIPYDE_GAUSS_COLUMN=fma
-// asks for the FMA-pipe kernel (A/B measurements; the two agree to ~1e-6, not bit for bit).
+// instantiated (an output block spans at most 4 chunks: R <= 11), unless mpimg_set_gauss_column /
+// MILLIPYDE_GAUSS_COLUMN=fma asks for the FMA-pipe kernel (A/B measurements and parity tests; the
+// two agree to ~1e-6, not bit for bit).
+static std::atomic<int> g_column{-1};
 static bool use_mma_column()
 {
-    static const bool on = [] {
+    int m = g_column.load(std::memory_order_relaxed);
+    if (m < 0) {
         const char *e = getenv("MILLIPYDE_GAUSS_COLUMN");
-        return !(e && strcmp(e, "fma") == 0);
-    }();
-    return on;
+        m = (e && strcmp(e, "fma") == 0) ? MP_GAUSS_COLUMN_FMA : MP_GAUSS_COLUMN_MMA;
+        g_column.store(m);
+    }
+    return m == MP_GAUSS_COLUMN_MMA;
 }
 
 template <int C, int R>
@@ -188,3 +194,11 @@ MPStatus launch_gauss_stream(int device, cudaStream_t s, const Img &d, const flo
 }
 
 }  // namespace mp
+
+extern "C" {
+void mpimg_set_gauss_column(int mode)
+{
+    mp::g_column.store(mode == MP_GAUSS_COLUMN_FMA ? MP_GAUSS_COLUMN_FMA : MP_GAUSS_COLUMN_MMA);
+}
+int mpimg_get_gauss_column(void) { return mp::use_mma_column() ? MP_GAUSS_COLUMN_MMA : MP_GAUSS_COLUMN_FMA; }
+}

@@ -106,6 +106,50 @@ def test_f32_gaussian(capi, c, sigma):
         assert np.abs(got - want).max() <= TOL32, (shape, sigma)
 
 
+# The streaming kernels (W*C % 4 == 0, W*C >= 64) in both column-pass forms -- tensor-core (MMA,
+# the default) and FMA-pipe -- on shapes that exercise every boundary of their tiling: heights
+# around the 8-row chunk / 12-row group / 48-row ring sizes, strips that end inside an 80-column
+# slice or a 16-column tile, more than one strip, every radius bucket (sigma 0.4 .. 2.0; 2.3 has
+# effective radius 13 and always takes the FMA-pipe kernel).
+STREAM_SHAPES = [(1, 64), (7, 16), (8, 84), (9, 161), (23, 200), (48, 160), (49, 321), (100, 644), (131, 1284)]
+
+
+@pytest.mark.parametrize("column", ["mma", "fma"])
+@pytest.mark.parametrize("c", CHANNELS)
+def test_f32_streaming_gaussian_shapes(capi, c, column):
+    L = capi.lib()
+    L.mpimg_set_gauss_column(1 if column == "fma" else 0)
+    try:
+        for k, (h, w) in enumerate(STREAM_SHAPES):
+            if (w * c) % 4 or w * c < 64:
+                w = (w + 3) // 4 * 4
+            a = synth.noise_f32(h, w, c, 7000 + 10 * k + c)
+            for sigma in (2.0, 0.4, 1.1):
+                got = dev(capi, a).apply("gaussian", sigma).numpy()
+                assert np.abs(got - so.gaussian(a, sigma)).max() <= TOL32, (h, w, c, sigma, column)
+        a = synth.smooth_f32(300, 700, c)
+        for sigma in (0.7, 1.5, 2.0, 2.3):
+            got = dev(capi, a).apply("gaussian", sigma).numpy()
+            assert np.abs(got - so.gaussian(a, sigma)).max() <= TOL32, (c, sigma, column)
+    finally:
+        L.mpimg_set_gauss_column(0)
+
+
+def test_f32_streaming_gaussian_column_forms_agree(capi):
+    """Tensor-core and FMA-pipe column passes on the same input: the split-precision products cost
+    well under 1e-6, and out-of-range rows/columns are exact zeros' worth in both."""
+    L = capi.lib()
+    a = synth.noise_f32(211, 800, 3, 7100)
+    outs = {}
+    for mode in (0, 1):
+        L.mpimg_set_gauss_column(mode)
+        outs[mode] = dev(capi, a).apply("gaussian", 2.0).numpy()
+    L.mpimg_set_gauss_column(0)
+    assert L.mpimg_get_gauss_column() == 0
+    assert np.abs(outs[0] - outs[1]).max() <= 1e-6
+    assert np.abs(outs[0].astype(np.float64) - so.gaussian(a, 2.0)).max() <= 2e-6
+
+
 def test_f32_gaussian_edge_cases(capi):
     a = synth.noise_f32(5, 7, 3, 1)                 # smaller than the kernel support
     assert np.abs(dev(capi, a).apply("gaussian", 2.0).numpy() - so.gaussian(a, 2.0)).max() <= TOL32
