@@ -20,7 +20,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from millipyde_b200 import capi, engine  # noqa: E402
 
-PEAK = 6456.2
+_PEAKS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+PEAK = json.load(open(_PEAKS))["hbm_gbs"] if os.path.exists(_PEAKS) else 6650.0
 if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
     PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 

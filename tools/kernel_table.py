@@ -65,7 +65,8 @@ def run():
 
 def parse(csv_path, plan_path):
     import csv
-    peak = 6456.2
+    peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = json.load(open(peaks))["hbm_gbs"] if os.path.exists(peaks) else 6650.0
     rows = [r for r in csv.reader(open(csv_path)) if len(r) > 10 and r[0].isdigit()]
     # one record per launch id with its three metrics
     launches = {}
