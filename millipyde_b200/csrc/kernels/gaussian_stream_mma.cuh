@@ -232,43 +232,67 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
                 raw[q][0] = lds_f2(rp + 16 * q);
                 raw[q][1] = lds_f2(rp + 4 * kMmPitch + 16 * q);
             }
+            // Tiles go through in pairs: the correction MMAs of both tiles, then the tf32 MMAs of both,
+            // so the two dependent MMAs of a (tile, block) are 8 tensor instructions apart.
 #pragma unroll
-            for (int q = 0; q < kMmTiles; ++q) {
-                const float2 v0 = raw[q][0], v1 = raw[q][1];
-                const float a[4] = {v0.x, v0.y, v1.x, v1.y};   // (row t | t+4) x (column 2g | 2g+1)
-                uint32_t ah[4];
-                float al[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    ah[e] = __float_as_uint(a[e]) & 0xffffe000u;
-                    al[e] = a[e] - __uint_as_float(ah[e]);
-                }
-                // correction operand: K slots (2t, 2t+1) = lo parts of rows (t, t+4), (2t+8, 2t+9) = hi parts
-                const uint32_t ac[4] = {pack_f16(al[0], al[2]), pack_f16(al[1], al[3]),
-                                        pack_f16(__uint_as_float(ah[0]), __uint_as_float(ah[2])),
-                                        pack_f16(__uint_as_float(ah[1]), __uint_as_float(ah[3]))};
-                // first MMA of every live block: destination is the next age
-                float nxt[NCH][4];   // nxt[j] = block of age j + 1 after this chunk (nxt[NCH-1] is complete)
+            for (int q0 = 0; q0 < kMmTiles; q0 += 2) {
+                constexpr int kPair = 2;
+                uint32_t ah[kPair][4], ac[kPair][4];
+                float nxt[kPair][NCH][4];   // nxt[.][j] = block of age j + 1 after this chunk (NCH-1: complete)
                 const float zero[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int j = NCH - 1; j >= 0; --j) {
-                    if (j == 0) mma_f16(nxt[0], ac, bc[0][0], bc[0][1], zero);
-                    else mma_f16(nxt[j], ac, bc[j][0], bc[j][1], acc[q][j - 1]);
+                for (int u = 0; u < kPair; ++u) {
+                    const int q = q0 + u;
+                    if (q >= kMmTiles) continue;
+                    const float2 v0 = raw[q][0], v1 = raw[q][1];
+                    const float a[4] = {v0.x, v0.y, v1.x, v1.y};   // (row t | t+4) x (column 2g | 2g+1)
+                    float al[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        ah[u][e] = __float_as_uint(a[e]) & 0xffffe000u;
+                        al[e] = a[e] - __uint_as_float(ah[u][e]);
+                    }
+                    // correction operand: K slots (2t, 2t+1) = lo parts of rows (t, t+4), (2t+8, 2t+9) = hi parts
+                    ac[u][0] = pack_f16(al[0], al[2]);
+                    ac[u][1] = pack_f16(al[1], al[3]);
+                    ac[u][2] = pack_f16(__uint_as_float(ah[u][0]), __uint_as_float(ah[u][2]));
+                    ac[u][3] = pack_f16(__uint_as_float(ah[u][1]), __uint_as_float(ah[u][3]));
+                }
+                // first MMA of every live block: destination is the next age
+#pragma unroll
+                for (int u = 0; u < kPair; ++u) {
+                    const int q = q0 + u;
+                    if (q >= kMmTiles) continue;
+#pragma unroll
+                    for (int j = NCH - 1; j >= 0; --j) {
+                        if (j == 0) mma_f16(nxt[u][0], ac[u], bc[0][0], bc[0][1], zero);
+                        else mma_f16(nxt[u][j], ac[u], bc[j][0], bc[j][1], acc[q][j - 1]);
+                    }
                 }
 #pragma unroll
-                for (int j = NCH - 1; j >= 0; --j) mma_tf32(nxt[j], ah, bh[j][0], bh[j][1], nxt[j]);
+                for (int u = 0; u < kPair; ++u) {
+                    const int q = q0 + u;
+                    if (q >= kMmTiles) continue;
 #pragma unroll
-                for (int j = 0; j < NCH - 1; ++j)
+                    for (int j = NCH - 1; j >= 0; --j) mma_tf32(nxt[u][j], ah[u], bh[j][0], bh[j][1], nxt[u][j]);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) acc[q][j][e] = nxt[j][e];
-                if (q == 0) {
+                    for (int j = 0; j < NCH - 1; ++j)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[q][j][e] = nxt[u][j][e];
+                }
+                if (q0 == 0) {
                     // the previous block's bulk stores have read the staging rows (a chunk ago: no wait
                     // in practice); only lane 0 has groups, the others fall through
                     bulk_wait_read<0>();
                     __syncwarp();
                 }
-                sts_f2(my_stage + 16 * q, nxt[NCH - 1][0], nxt[NCH - 1][2]);                        // block row 2t
-                sts_f2(my_stage + 4 * kMmStagePitch + 16 * q, nxt[NCH - 1][1], nxt[NCH - 1][3]);   // block row 2t + 1
+#pragma unroll
+                for (int u = 0; u < kPair; ++u) {
+                    const int q = q0 + u;
+                    if (q >= kMmTiles) continue;
+                    sts_f2(my_stage + 16 * q, nxt[u][NCH - 1][0], nxt[u][NCH - 1][2]);                        // block row 2t
+                    sts_f2(my_stage + 4 * kMmStagePitch + 16 * q, nxt[u][NCH - 1][1], nxt[u][NCH - 1][3]);   // block row 2t + 1
+                }
             }
             // hand back every group whose 12 rows are now consumed (the MMAs above used every sample)
             ring_row = ring_row == kMmRing - 8 ? 0 : ring_row + 8;
