@@ -171,13 +171,76 @@ static PyObject *hostify_tuple(PyObject *seq)
     return out;
 }
 
-/* __array_function__(func, types, args, kwargs): numpy functions run on host
- * copies, as src/gpuarray.c:194-226 (dispatching them to the device kernels is
- * listed under "next" in SURVEY.md 8f). */
+/* numpy functions that ARE one of the device operators: np.fliplr(img) and
+ * np.transpose(img) [2-D, or HWC with axes=(1, 0, 2)] run the CUDA kernel on a device-side copy and
+ * return a new object of the caller's type -- no D2H, no CPU work; the source is not modified (numpy
+ * functions do not mutate).  Returns a new reference, or NULL with *handled = 0 when the call is not
+ * one of these (other function, other axes, layout the operator does not take). */
+static PyObject *device_function(MPArrayObject *self, PyObject *func, PyObject *fargs, PyObject *fkw, int *handled)
+{
+    *handled = 0;
+    if (!self->obj || !self->obj->device_data || !PyTuple_Check(fargs) || PyTuple_GET_SIZE(fargs) < 1 ||
+        PyTuple_GET_ITEM(fargs, 0) != (PyObject *)self)
+        return NULL;
+    PyObject *name = PyObject_GetAttrString(func, "__name__");
+    if (!name) {
+        PyErr_Clear();
+        return NULL;
+    }
+    const char *fn = PyUnicode_Check(name) ? PyUnicode_AsUTF8(name) : NULL;
+    MPFunc op = NULL;
+    const Py_ssize_t nargs = PyTuple_GET_SIZE(fargs);
+    const int has_kw = fkw && fkw != Py_None && PyDict_Check(fkw) && PyDict_Size(fkw) > 0;
+    if (fn && strcmp(fn, "fliplr") == 0 && nargs == 1 && !has_kw && self->obj->ndims >= 2) {
+        op = mpimg_fliplr;
+    } else if (fn && strcmp(fn, "transpose") == 0 && nargs <= 2) {
+        PyObject *axes = nargs == 2 ? PyTuple_GET_ITEM(fargs, 1) : NULL;
+        if (has_kw) {
+            PyObject *k = PyDict_GetItemString(fkw, "axes");
+            if (k && PyDict_Size(fkw) == 1 && !axes) axes = k;
+            else axes = Py_Ellipsis; /* anything else: not ours */
+        }
+        const int nd = self->obj->ndims;
+        if (!axes || axes == Py_None) {
+            if (nd == 2) op = mpimg_transpose;   /* numpy reverses ALL axes: ours only for 2-D */
+        } else if (PyTuple_Check(axes) && PyTuple_GET_SIZE(axes) == nd && (nd == 2 || nd == 3)) {
+            long want[3] = {1, 0, 2};
+            int same = 1;
+            for (int i = 0; i < nd; ++i) {
+                PyObject *a = PyTuple_GET_ITEM(axes, i);
+                if (!PyLong_Check(a) || PyLong_AsLong(a) != want[i]) same = 0;
+            }
+            if (same) op = mpimg_transpose;
+        }
+    }
+    Py_DECREF(name);
+    if (!op) return NULL;
+    MPArrayObject *copy = (MPArrayObject *)mpext_clone(self, self->obj->mem_loc, 0);
+    if (!copy) {
+        PyErr_Clear();
+        return NULL;
+    }
+    MPStatus st;
+    Py_BEGIN_ALLOW_THREADS
+    st = op(copy->obj, NULL);
+    Py_END_ALLOW_THREADS
+    if (st != MILLIPYDE_SUCCESS) { /* e.g. an integer gpuarray: the host path below handles it */
+        Py_DECREF(copy);
+        return NULL;
+    }
+    *handled = 1;
+    return (PyObject *)copy;
+}
+
+/* __array_function__(func, types, args, kwargs): device operators where numpy's function is one
+ * (above), everything else on host copies as src/gpuarray.c:194-226. */
 static PyObject *array_function(MPArrayObject *self, PyObject *args, PyObject *kwds)
 {
     PyObject *func, *types, *fargs, *fkw;
     if (!PyArg_ParseTuple(args, "OOOO", &func, &types, &fargs, &fkw)) return NULL;
+    int handled = 0;
+    PyObject *on_device = device_function(self, func, fargs, fkw, &handled);
+    if (handled) return on_device;
     PyObject *host_args = hostify_tuple(fargs);
     if (!host_args) return NULL;
     PyObject *res = PyObject_Call(func, host_args, (fkw == Py_None) ? NULL : fkw);

@@ -91,6 +91,22 @@ def test_connected_fp32_chain_config5_shape():
         assert np.abs(np.array(d) - so.apply_chain(a, chain)).max() <= 1e-5
 
 
+def test_gaussian_writes_into_the_receivers_memory():
+    """The sender's LAST segment writes straight into the receiving device's pool; when that segment
+    is the streaming Gaussian its outputs leave through TMA bulk stores over NVLink.  Enough images
+    for the chunked hand-off (> 2 x 32) and a shape with a partial last strip."""
+    imgs = [synth.noise_f32(75, 250, 3, 6000 + k) for k in range(70)]
+    dev = [mp.gpuimage(a) for a in imgs]
+    pa = mp.Pipeline(dev, [mp.Operation("adjust_gamma", 1.5, 1), mp.Operation("gaussian", 2)], device=0)
+    pb = mp.Pipeline([], [mp.Operation("fliplr")], device=1)
+    pa.connect_to(pb)
+    pa.run()
+    chain = [("adjust_gamma", 1.5, 1.0), ("gaussian", 2.0), ("fliplr",)]
+    for a, d in zip(imgs, dev):
+        assert d.device == 1
+        assert np.abs(np.array(d) - so.apply_chain(a, chain)).max() <= 1e-5
+
+
 def test_pipeline_spreads_over_all_devices():
     n = 4 * mp.DEVICE_COUNT + 3
     imgs = [synth.noise_f32(64, 640, 3, 100 + k) for k in range(n)]

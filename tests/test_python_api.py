@@ -184,6 +184,31 @@ def test_create_gpuarray_round_trips():
 
 
 @gpu
+def test_np_functions_that_are_device_operators_stay_on_the_device():
+    """np.fliplr / np.transpose of a gpuimage run the CUDA kernels on a device-side copy and return a
+    gpuimage; the source is untouched; anything numpy defines differently (3-D
+    transpose without axes reverses ALL axes) still takes the host path with numpy's semantics."""
+    from tests import synth
+    a = synth.noise_f32(37, 52, 3, 42)
+    g = mp.gpuimage(a)
+    f = np.fliplr(g)
+    assert type(f) is mp.gpuimage and np.array_equal(np.array(f), np.fliplr(a))
+    t = np.transpose(g, (1, 0, 2))
+    assert type(t) is mp.gpuimage and t.shape == (52, 37, 3) and np.array_equal(np.array(t), np.transpose(a, (1, 0, 2)))
+    t = np.transpose(g, axes=(1, 0, 2))
+    assert type(t) is mp.gpuimage and np.array_equal(np.array(t), np.transpose(a, (1, 0, 2)))
+    assert np.array_equal(np.array(g), a)                                   # numpy functions do not mutate
+    host = np.transpose(g)                                                  # numpy: axes reversed -> (3, 52, 37)
+    assert isinstance(host, np.ndarray) and np.array_equal(host, np.transpose(a))
+    grey = synth.noise_f32(20, 33, 1, 43).astype(np.float64)
+    t2 = np.transpose(mp.gpuimage(grey))
+    assert type(t2) is mp.gpuimage and np.array_equal(np.array(t2), grey.T)
+    rgba = np.random.default_rng(5).integers(0, 256, (16, 24, 4), dtype=np.uint8)
+    assert np.array_equal(np.array(np.fliplr(mp.gpuimage(rgba))), np.fliplr(rgba))
+    assert isinstance(np.flipud(g), np.ndarray)                             # not a device operator: host
+
+
+@gpu
 def test_np_function_protocol():
     lst = [[1, 2, 3], [4, 5, 6], [7, 8, 9]]
     want = np.transpose(np.array(lst))
