@@ -51,6 +51,8 @@ MPStatus mpobj_copy_to_host_into(MPObjData *obj, void *dst, size_t nbytes);
  * enqueue the copy on obj->stream and return; the caller syncs the stream. */
 MPStatus mpobj_upload_async(MPObjData *obj, const void *src, size_t nbytes);
 MPStatus mpobj_download_async(MPObjData *obj, void *dst, size_t nbytes);
+/* Wait until everything enqueued for the object (operators, the copies above) has completed. */
+MPStatus mpobj_synchronize(MPObjData *obj);
 
 /* Build / destroy a whole MPObjData from C (what src/gpuarray.c:82-114 does
  * inline): shape has ndims entries, strides are derived (C order). `host` may

@@ -132,6 +132,7 @@ SYMBOLS = {
     "mpobj_copy_to_host_into": (C.c_int, [_OBJ, C.c_void_p, C.c_size_t]),
     "mpobj_upload_async": (C.c_int, [_OBJ, C.c_void_p, C.c_size_t]),
     "mpobj_download_async": (C.c_int, [_OBJ, C.c_void_p, C.c_size_t]),
+    "mpobj_synchronize": (C.c_int, [_OBJ]),
     "mpobj_create": (_OBJ, [C.c_void_p, C.c_int, C.POINTER(C.c_long), C.c_int]),
     "mpobj_destroy": (None, [_OBJ]),
     "mpobj_set_stream": (None, [_OBJ, C.c_void_p]),

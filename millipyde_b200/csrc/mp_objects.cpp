@@ -107,6 +107,15 @@ MPStatus mpobj_copy_to_host_into(MPObjData *obj, void *dst, size_t nbytes)
     return MILLIPYDE_SUCCESS;
 }
 
+MPStatus mpobj_synchronize(MPObjData *obj)
+{
+    if (!obj) return MP_ERROR_INVALID_ARGUMENT;
+    if (!obj->device_data || obj->mem_loc < 0) return MILLIPYDE_SUCCESS;
+    MP_CUDA_TRY(cudaSetDevice(obj->mem_loc));
+    MP_CUDA_TRY(cudaStreamSynchronize(mp::stream_of(obj)));
+    return MILLIPYDE_SUCCESS;
+}
+
 // mem_loc is left alone: nothing moves, the host gets a copy (millipyde_objects.cpp:39).
 void *mpobj_copy_to_host(MPObjData *obj)
 {

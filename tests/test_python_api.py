@@ -366,6 +366,29 @@ def test_generator_random_augmentation_stream(so):
 
 
 @gpu
+def test_generator_host_outputs_are_page_locked_recycled_and_never_aliased(so):
+    """return_to_host=True downloads a batch's outputs together into recycled page-locked ndarrays:
+    every output a consumer still holds must keep its own contents while later batches reuse the
+    blocks of the ones it dropped."""
+    from tests import synth
+    base = [mp.gpuimage(synth.noise_f32(48, 64, 3, 4100 + k)) for k in range(3)]
+    want = [np.fliplr(np.array(b)) for b in base]
+    g = mp.Generator(base, [mp.Operation("fliplr")], return_to_host=True, outputs=40, prefetch=4, device=0)
+    kept = []
+    for i, out in enumerate(g):
+        assert isinstance(out, np.ndarray) and out.flags.c_contiguous and out.flags.writeable
+        assert np.array_equal(out, want[i % 3])
+        if i % 2 == 0:
+            kept.append((i, out))          # half of the outputs stay alive, the others free their block
+        else:
+            out[...] = -1.0                # scribbling on a dropped output must not reach anyone else
+    assert len(kept) == 20
+    for i, out in kept:
+        assert np.array_equal(out, want[i % 3])
+    assert len({out.ctypes.data for _, out in kept}) == len(kept)
+
+
+@gpu
 def test_gaussian_and_gamma(charlie_small, so):
     grey = so.rgb2grey(charlie_small)
     d = mp.gpuimage(charlie_small)

@@ -75,7 +75,7 @@ def config4(args, dist):
            mp.Operation("rgb2grey", probability=.3), mp.Operation("random_rotate", 0., 120., probability=.5)]
     mp.seed(4 + dist.rank)
     pre = args.prefetch
-    g = mp.Generator(base, ops, outputs=mine + pre, prefetch=pre, device=0)
+    g = mp.Generator(base, ops, outputs=mine + pre, prefetch=pre, device=0, return_to_host=args.to_host)
     for _ in range(pre):  # warm the pool
         next(g)
     mp.synchronize()
@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--prefetch", type=int, default=256)
     ap.add_argument("--pairs", type=int, default=4)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--to-host", action="store_true", help="config 4: return_to_host=True (PCIe-bound)")
     args = ap.parse_args()
     dist = Dist()
     bind_rank_gpu(dist)
