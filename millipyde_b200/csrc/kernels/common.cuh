@@ -193,6 +193,25 @@ __device__ __forceinline__ void mbar_wait_suspend(uint64_t *bar, uint32_t parity
         "r"(parity), "r"(hint_ns)
         : "memory");
 }
+// The wait for role hand-offs that are expected to block for a while: a non-blocking probe, then a
+// plain timed sleep.  try_wait with a suspend hint compiles to TRYWAIT + NANOSLEEP.SYNCS, which any
+// mbarrier traffic of the CTA wakes up again (11 wake-ups per wait measured); every probe is issue
+// slots and energy, and the sustained Gaussian is power-capped.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, uint32_t sleep_ns)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP_Z:\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE_Z;\n"
+        "nanosleep.u32 %2;\n"
+        "bra WAIT_LOOP_Z;\n"
+        "WAIT_DONE_Z:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity), "r"(sleep_ns)
+        : "memory");
+}
 // global -> shared 1-D bulk copy through the TMA unit; bytes % 16 == 0, both sides 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {

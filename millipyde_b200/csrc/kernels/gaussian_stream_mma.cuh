@@ -41,8 +41,6 @@ constexpr int kMmThreads = MmK::threads;       // 640
 // Output staging: 8 rows x 80 floats per COLUMN warp at a pitch of 88 floats (= 24 mod 32: rows
 // t and 4+t of the four t's of a half-warp start 8 banks apart, so its 8-byte stores do not conflict).
 constexpr int kMmStagePitch = 88;
-// Role hand-off waits may suspend the warp this long per probe instead of spinning on the issue port.
-constexpr uint32_t kMmWaitNs = 2000;
 // Registers: the kernel is compiled for 96 per thread (640 threads) and that allocation is the
 // CTA's pool.  The 12 ROW warps (warpgroups 0-2) hand 16 each back (setmaxnreg.dec 80), the 8 COLUMN
 // warps (warpgroups 3-4) take them (setmaxnreg.inc 120): 12*80 + 8*120 = 20*96.
@@ -220,7 +218,7 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
         for (int c = 0; c < n_chunks8; ++c) {
             const uint32_t need = item_g0 + (uint32_t)(8 * c + 7) / MmK::rows + 1u;
             while (waited < need) {
-                mbar_wait_suspend(&h_full[waited % MmK::groups], (waited / MmK::groups) & 1u, kMmWaitNs);
+                ws_wait(&h_full[waited % MmK::groups], (waited / MmK::groups) & 1u, p.wait_sleep_ns);
                 ++waited;
             }
             const float *rp = ring + ring_row * kMmPitch;

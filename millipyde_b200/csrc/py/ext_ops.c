@@ -563,8 +563,8 @@ static PyObject *produce_one_python(MPGeneratorObject *g, long index)
  * (full PCIe rate, one wait per batch).  The page-locked blocks are recycled: the ndarray's base
  * object is a capsule whose destructor hands the block back to a small cache, so a steady stream
  * of same-sized outputs allocates nothing. */
-#define MP_PIN_CACHE_SLOTS 64
-#define MP_PIN_CACHE_BYTES ((size_t)2 << 30)
+#define MP_PIN_CACHE_SLOTS 1024
+#define MP_PIN_CACHE_BYTES ((size_t)8 << 30) /* a look-ahead of 256 outputs of 12.6 MB is 3.2 GB */
 typedef struct {
     void *p;
     size_t bytes;
