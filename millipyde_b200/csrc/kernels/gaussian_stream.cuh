@@ -32,7 +32,6 @@ struct GaussStreamParams {
     int chunk_rows;              // rows per work item
     int n_chunks;
     int radius;                  // actual radius (<= R); w[d] = 0 beyond it
-    unsigned wait_sleep_ns;      // tensor-core flavour: sleep between probes of a blocked hand-off wait (0: try_wait hint)
     float w[16];
     unsigned long long ww[16];   // (w[d], w[d]) packed for fma.rn.f32x2
 };

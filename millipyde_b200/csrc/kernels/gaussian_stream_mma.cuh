@@ -123,7 +123,9 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
     uint64_t *h_full = bars + MmK::row_warps * MmK::in_slots;
     uint64_t *h_empty = h_full + MmK::groups;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the warp index is read from lane 0 so that the compiler knows it is warp-uniform: ring slots,
+    // barrier and bulk-copy addresses then live in uniform registers (UBLKCP without R2UR loops)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < MmK::row_warps * MmK::in_slots; ++i) mbar_init(&in_full[i], 1);
         for (int g = 0; g < MmK::groups; ++g) {
@@ -144,9 +146,7 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
     // ================================================================ COLUMN warp
     const int items_per_image = p.n_strips * p.n_chunks;
     const long n_items = (long)p.n_images * items_per_image;
-    // 0..7: columns [80 wc, 80 wc + 80) of the strip; read from lane 0 so that the compiler knows it
-    // is warp-uniform (the bulk-store addresses then live in uniform registers)
-    const int wc = __shfl_sync(0xffffffffu, warp, 0) - MmK::row_warps;
+    const int wc = warp - MmK::row_warps;   // 0..7: columns [80 wc, 80 wc + 80) of the strip
     const int g = lane >> 2, t = lane & 3;
     const float *ring = s_h + t * kMmPitch + wc * (16 * kMmTiles) + 2 * g;
     float *stage = s_stage + wc * (8 * kMmStagePitch);              // this warp's staging rows
@@ -218,7 +218,7 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
         for (int c = 0; c < n_chunks8; ++c) {
             const uint32_t need = item_g0 + (uint32_t)(8 * c + 7) / MmK::rows + 1u;
             while (waited < need) {
-                ws_wait(&h_full[waited % MmK::groups], (waited / MmK::groups) & 1u, p.wait_sleep_ns);
+                mbar_wait_sleep(&h_full[waited % MmK::groups], (waited / MmK::groups) & 1u, kWsSleepNs);
                 ++waited;
             }
             const float *rp = ring + ring_row * kMmPitch;

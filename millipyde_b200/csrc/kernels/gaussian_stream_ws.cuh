@@ -37,7 +37,7 @@ constexpr int kWsColWarps = kGsTW / 64;       // 10: 320 threads x 2 columns = 6
 constexpr int kWsThreads = 32 * (kWsRowWarps + kWsColWarps);
 constexpr int kWsInSlots = 4;                 // rows in flight per ROW warp
 constexpr int kWsGroups = 4;                  // filtered groups in flight between the roles
-constexpr uint32_t kWsSleepNs = 100;          // default sleep between probes of a blocked hand-off wait (MMA flavour)
+constexpr uint32_t kWsSleepNs = 100;          // sleep between probes of a blocked hand-off wait (MMA flavour)
 
 // The same numbers per kernel flavour: the FMA-column kernel (this file) splits the CTA 10:10, the
 // tensor-core-column kernel (gaussian_stream_mma.cuh) 12:8 on warpgroup boundaries (setmaxnreg).
@@ -60,14 +60,6 @@ struct WsGeom {
     static constexpr int N_BARS = kWsRowWarps * kWsInSlots + 2 * kWsGroups;
     static constexpr size_t SMEM = IN_BYTES + H_BYTES + 8 * N_BARS + 64;
 };
-
-// Hand-off wait of the tensor-core flavour: timed sleeps between probes, or (sleep_ns == 0, kept for
-// A/B runs: MILLIPYDE_GAUSS_SLEEP_NS=0) try_wait with a suspend hint.
-__device__ __forceinline__ void ws_wait(uint64_t *bar, uint32_t parity, uint32_t sleep_ns)
-{
-    if (sleep_ns) mbar_wait_sleep(bar, parity, sleep_ns);
-    else mbar_wait_suspend(bar, parity, 2000u);
-}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
@@ -233,7 +225,7 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
                 // the slot consumed in the previous live step is free again: keep the ring full
                 if (next_issue < live_hi) issue_next();
                 const uint32_t slot = takes % K::in_slots;
-                if (MMA) ws_wait(&my_full[slot], (takes / K::in_slots) & 1u, p.wait_sleep_ns);
+                if (MMA) mbar_wait_sleep(&my_full[slot], (takes / K::in_slots) & 1u, kWsSleepNs);
                 else mbar_wait(&my_full[slot], (takes / K::in_slots) & 1u);
                 ++takes;
                 if (SETS) ws_row_pass<C, R>(my_in + (size_t)slot * G::ROW + lane * kGsPH, out, w_img);
@@ -244,7 +236,7 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
             }
             // hand-off ring: wait until the COLUMN warps have drained this group slot
             const uint32_t gs = group % K::groups;
-            if (MMA) ws_wait(&h_empty[gs], ((group / K::groups) & 1u) ^ 1u, p.wait_sleep_ns);
+            if (MMA) mbar_wait_sleep(&h_empty[gs], ((group / K::groups) & 1u) ^ 1u, kWsSleepNs);
             else mbar_wait(&h_empty[gs], ((group / K::groups) & 1u) ^ 1u);
             float *hrow = hbase + (size_t)gs * (K::rows * PITCH);
 #pragma unroll

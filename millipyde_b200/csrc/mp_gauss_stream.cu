@@ -55,11 +55,6 @@ static MPStatus launch_cr(int device, cudaStream_t s, GaussStreamParams &p, cons
     const int sms = sm_count(device) ? sm_count(device) : 148;
     constexpr bool kHasMma = MmGeom<C, R>::NCH <= 4;
     const bool mma = kHasMma && use_mma_column();
-    static const unsigned sleep_ns = [] {
-        const char *e = getenv("MILLIPYDE_GAUSS_SLEEP_NS");
-        return e && *e ? (unsigned)atoi(e) : kWsSleepNs;
-    }();
-    p.wait_sleep_ns = sleep_ns;
     const size_t smem = mma ? MmGeom<C, R>::SMEM : WsGeom<C, R>::SMEM;
     static bool configured[64] = {};  // per device
     if (device >= 0 && device < 64 && !configured[device]) {
