@@ -1,4 +1,6 @@
 // Separable Gaussian, fp32 HWC, streaming kernel (v4): the column pass on the tensor cores.
+// Reference: the two-pass choreography of src/millipyde_image.cpp:725-789 (_gaussian_greyscale) and
+// its kernels :146-244, under the oracle rule (scipy weights, radius int(8 sigma + 0.5)).
 //
 // gaussian_stream_ws.cuh is bound by the fp32 FMA pipe: 2 x (2R+1) FMAs per sample put the pipe and
 // HBM at the same throughput, and the pipe never runs at 100 %.  Here the ROW warps (unchanged:
@@ -14,7 +16,9 @@
 // with B_j[k][n] = w[|8j + k - n - R|] (zero outside the support), j = s - b = the block's age.
 // A chunk is loaded ONCE and multiplied into the NCH live blocks; like the FMA version's sliding
 // accumulators the destination of the first MMA is the neighbour (acc[j+1] = A . B_j + acc[j]), so
-// nothing rotates.  The block of age NCH-1 is complete and leaves as 8-byte streaming stores.
+// nothing rotates.  The block of age NCH-1 is complete: it is staged in shared memory and leaves as
+// TMA bulk stores (cp.async.bulk shared -> global), because accumulator fragments are row-scattered
+// and a direct STG.64 costs 4x the L1 data-pipe wavefronts.
 //
 // Precision.  tf32 carries 11 significant bits, so both operands are split, x = hi + lo with
 // hi = x & 0xffffe000 (exact), and the product is hi.hi (one tf32 MMA) + lo.hi + hi.lo.  The two
