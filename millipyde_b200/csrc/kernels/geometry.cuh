@@ -95,29 +95,34 @@ transpose_tma_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out
     }
 }
 
-// One-word pixels (fp32 greyscale, packed RGBA8): 64 x 64 tiles and a skewed shared-memory layout.
-// With 4-byte pixels the 32 x 32 tile above is 4 KB -- too little in flight per CTA to cover the TMA
-// round trip (50 % of the HBM peak) -- and its gather conflicts 4-way: a warp reads rows 4q + e for
-// q = 0..7 of columns r..r+3, and any 16-byte-aligned row pitch P puts rows 4 apart 16 banks apart at
-// best.  Here row y lands at y * 96 + 4 * ((y >> 2) & 7) words: rows 4q + e of a warp start 4 banks
-// apart, the 4 columns fill the gaps, every LDS.32 of the gather hits 32 distinct banks, and 16 KB per
-// CTA are in flight.  Stores are unchanged: 8 consecutive lanes write 128 contiguous bytes of one
-// output row.  Same contract as transpose_tma_kernel<1> (W % 4 == 0 and H % 4 == 0).
-constexpr int kT64 = 64;
+// One- and two-word pixels (fp32 greyscale, packed RGBA8; fp64 greyscale): 64-word x 64-row tiles
+// and a skewed shared-memory layout.  With 4-byte pixels the 32 x 32 tile above is 4 KB -- too little
+// in flight per CTA to cover the TMA round trip (50 % of the HBM peak) -- and its gather conflicts
+// 4-way: a warp reads rows 4q + e for q = 0..7 of columns r..r+3, and any 16-byte-aligned row pitch
+// puts rows 4 apart 16 banks apart at best.  Here row y lands at y * 96 + 4 * ((y >> S) & 7) words
+// (S = 2 for one-word pixels, 1 for two-word pixels): the rows a warp gathers from start 4 banks
+// apart, its columns fill the gaps, every LDS.32 (K = 1) / LDS.64 (K = 2) hits distinct banks, and
+// 16 KB per CTA are in flight.  Stores are unchanged: 8 consecutive lanes write 128 contiguous bytes
+// of one output row.  Same contract as transpose_tma_kernel<K> ((W*K) % 4 == 0 and (H*K) % 4 == 0).
+constexpr int kT64Rows = 64;
 constexpr int kT64Pitch = 96;
+template <int K>
 __global__ void __launch_bounds__(256)
 transpose_tma64_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int width, int height,
                        const uint32_t *const *__restrict__ in_tab = nullptr,
                        uint32_t *const *__restrict__ out_tab = nullptr)
 {
-    __shared__ __align__(128) uint32_t tile[kT64 * kT64Pitch];
+    static_assert(K == 1 || K == 2, "one- and two-word pixels");
+    constexpr int TX = 64 / K;            // tile width in pixels (64 words)
+    constexpr int S = K == 1 ? 2 : 1;     // rows per output vector = 4 / K = 1 << S
+    __shared__ __align__(128) uint32_t tile[kT64Rows * kT64Pitch];
     __shared__ __align__(8) uint64_t bar;
     if (in_tab) {
         in = in_tab[blockIdx.z];
         out = out_tab[blockIdx.z];
     }
-    const int x0 = blockIdx.x * kT64, y0 = blockIdx.y * kT64;
-    const int tw = min(kT64, width - x0), th = min(kT64, height - y0);
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * kT64Rows;
+    const int tw = min(TX, width - x0), th = min(kT64Rows, height - y0);
     const int tid = threadIdx.x;
     if (tid == 0) {
         mbar_init(&bar, 1);
@@ -125,25 +130,34 @@ transpose_tma64_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ o
     }
     __syncthreads();
     if (tid < 32) {
-        const uint32_t row_bytes = (uint32_t)tw * 4u;
+        const uint32_t row_bytes = (uint32_t)tw * K * 4u;
         if (tid == 0) mbar_expect_tx(&bar, row_bytes * (uint32_t)th);
         __syncwarp();
         for (int y = tid; y < th; y += 32)
-            bulk_g2s(tile + y * kT64Pitch + 4 * ((y >> 2) & 7), in + ((size_t)(y0 + y) * width + x0), row_bytes, &bar);
+            bulk_g2s(tile + y * kT64Pitch + 4 * ((y >> S) & 7), in + ((size_t)(y0 + y) * width + x0) * K, row_bytes,
+                     &bar);
         if (tid == 0) mbar_wait(&bar, 0);   // one poller; the other warps park at the barrier below
     }
     __syncthreads();
-    // output row (x0 + r) holds pixels y0 .. y0+th-1 = th / 4 vectors; a warp handles 8 vectors of 4 rows
-    const int vpr = th / 4;
+    // output row (x0 + r) holds pixels y0 .. y0+th-1 = th * K / 4 vectors; a warp handles 8 vectors of 4 rows
+    const int vpr = th * K / 4;
     const int q_groups = (vpr + 7) / 8;
     for (int i = tid; i < 8 * tw * q_groups; i += 256) {
         const int q_lo = i & 7, t2 = i >> 3;
         const int q_hi = t2 / tw, r = t2 - q_hi * tw;
         const int q = 8 * q_hi + q_lo;
         if (q >= vpr) continue;
-        const uint32_t *src = tile + (4 * q) * kT64Pitch + 4 * q_lo + r;   // row 4q: skew 4 * (q & 7)
-        const uint4 v = make_uint4(src[0], src[kT64Pitch], src[2 * kT64Pitch], src[3 * kT64Pitch]);
-        st_stream(reinterpret_cast<uint4 *>(out + ((size_t)(x0 + r) * height + y0)) + q, v);
+        // vector q = input rows (q << S) .. ((q + 1) << S) - 1, all with skew 4 * (q & 7)
+        const uint32_t *src = tile + (q << S) * kT64Pitch + 4 * q_lo + r * K;
+        uint4 v;
+        if (K == 1) {
+            v = make_uint4(src[0], src[kT64Pitch], src[2 * kT64Pitch], src[3 * kT64Pitch]);
+        } else {
+            const uint2 a = *reinterpret_cast<const uint2 *>(src);
+            const uint2 b = *reinterpret_cast<const uint2 *>(src + kT64Pitch);
+            v = make_uint4(a.x, a.y, b.x, b.y);
+        }
+        st_stream(reinterpret_cast<uint4 *>(out + ((size_t)(x0 + r) * height + y0) * K) + q, v);
     }
 }
 

@@ -177,10 +177,15 @@ template <int K>
 static void launch_transpose(const void *in, void *out, int W, int H, cudaStream_t s)
 {
     dim3 grid((W + 31) / 32, (H + 31) / 32);
-    if (K == 1 && W % 4 == 0 && H % 4 == 0)
-        transpose_tma64_kernel<<<dim3((W + 63) / 64, (H + 63) / 64), 256, 0, s>>>((const uint32_t *)in,
-                                                                                 (uint32_t *)out, W, H);
-    else if (((size_t)W * K) % 4 == 0 && ((size_t)H * K) % 4 == 0)
+    if constexpr (K <= 2) {
+        if (((size_t)W * K) % 4 == 0 && ((size_t)H * K) % 4 == 0) {
+            constexpr int TX = 64 / K;
+            transpose_tma64_kernel<K><<<dim3((W + TX - 1) / TX, (H + 63) / 64), 256, 0, s>>>(
+                (const uint32_t *)in, (uint32_t *)out, W, H);
+            return;
+        }
+    }
+    if (((size_t)W * K) % 4 == 0 && ((size_t)H * K) % 4 == 0)
         transpose_tma_kernel<K><<<grid, 256, 0, s>>>((const uint32_t *)in, (uint32_t *)out, W, H);
     else
         transpose_kernel<K><<<grid, 256, 0, s>>>((const uint32_t *)in, (uint32_t *)out, W, H);
@@ -928,10 +933,13 @@ void launch_transpose_batch(cudaStream_t s, const Img &d, const void *const *in_
     uint32_t *const *ot = (uint32_t *const *)out_tab;
     switch (K) {
         case 1:
-            transpose_tma64_kernel<<<dim3((d.W + 63) / 64, (d.H + 63) / 64, n_images), 256, 0, s>>>(nullptr, nullptr, d.W,
-                                                                                                  d.H, it, ot);
+            transpose_tma64_kernel<1><<<dim3((d.W + 63) / 64, (d.H + 63) / 64, n_images), 256, 0, s>>>(
+                nullptr, nullptr, d.W, d.H, it, ot);
             break;
-        case 2: transpose_tma_kernel<2><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, d.H, it, ot); break;
+        case 2:
+            transpose_tma64_kernel<2><<<dim3((d.W + 31) / 32, (d.H + 63) / 64, n_images), 256, 0, s>>>(
+                nullptr, nullptr, d.W, d.H, it, ot);
+            break;
         case 3: transpose_tma_kernel<3><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, d.H, it, ot); break;
         default: transpose_tma_kernel<4><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, d.H, it, ot); break;
     }

@@ -106,6 +106,22 @@ def test_f32_gaussian(capi, c, sigma):
         assert np.abs(got - want).max() <= TOL32, (shape, sigma)
 
 
+@pytest.mark.parametrize("dtype", ["f32", "f64", "rgba8"])
+def test_transpose_skewed_tile_kernel_shapes(capi, dtype):
+    """One- and two-word pixels take the 64-row skewed-layout TMA transpose: full tiles, partial
+    tiles on either edge, images smaller than a tile, several tiles per axis -- bit-exact."""
+    rng = np.random.default_rng(8100)
+    for h, w in [(64, 64), (4, 8), (68, 132), (200, 36), (130, 258), (256, 320), (540, 96)]:
+        if dtype == "rgba8":
+            a = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+            want = np.transpose(a, (1, 0, 2))
+        else:
+            a = rng.random((h, w)).astype(np.float32 if dtype == "f32" else np.float64)
+            want = a.T
+        got = dev(capi, a).apply("transpose").numpy()
+        assert got.shape == want.shape and np.array_equal(got, want), (dtype, h, w)
+
+
 # The streaming kernels (W*C % 4 == 0, W*C >= 64) in both column-pass forms -- tensor-core (MMA,
 # the default) and FMA-pipe -- on shapes that exercise every boundary of their tiling: heights
 # around the 8-row chunk / 12-row group / 48-row ring sizes, strips that end inside an 80-column
