@@ -77,8 +77,9 @@ transpose_tma_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out
         __syncwarp();
         if (tid < th)
             bulk_g2s(tile + tid * P, in + ((size_t)(y0 + tid) * width + x0) * K, row_bytes, &bar);
+        if (tid == 0) mbar_wait(&bar, 0);   // one poller; the other warps park at the barrier below
     }
-    mbar_wait(&bar, 0);
+    __syncthreads();
     // output row (x0 + r) holds pixels y0 .. y0+th-1: th*K words, written as th*K/4 vectors
     const int vec_per_row = th * K / 4;
     for (int i = tid; i < tw * vec_per_row; i += 256) {
