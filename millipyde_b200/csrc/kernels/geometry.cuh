@@ -366,25 +366,30 @@ namespace mpk {
 //    is staged), which makes the four corners one base address plus immediates.
 //  * the thread's four pixels are blended first and the post-rotate pointwise program runs once
 //    over all of them (its op decode is per program, not per pixel).
-constexpr int kGatherTile = 32;
-constexpr int kGatherBox = 50;  // >= 32 * sqrt(2) + 4
+constexpr int kGatherTile = 32;      // tile width in output pixels (one per lane)
+constexpr int kGatherBox = 50;       // box edge of a 32 x 32 tile: >= 32 * sqrt(2) + 4
+constexpr int kGatherTileTall = 64;  // single-channel images: 32 x 64 tiles (a 32 x 32 x 4-byte tile is too little
+constexpr int kGatherBoxTall = 76;   // work per CTA to amortise the set-up); box >= sqrt(32^2 + 64^2) + 4
 
-template <int C>
+template <int C, int TH = kGatherTile>
 struct GatherGeom {
+    static constexpr int BOX = TH == kGatherTile ? kGatherBox : kGatherBoxTall;
     // floats per staged row: box width * C plus up to 3 floats of alignment shift, rounded to a
     // vector, plus a skew that keeps PITCH % 32 in {4, 20} so rows spread over the banks
-    static constexpr int ROW_MAX = (kGatherBox * C + 3 + 3) / 4 * 4;
-    static constexpr int PITCH = C == 1 ? 68 : (C == 3 ? 164 : 212);
+    static constexpr int ROW_MAX = (BOX * C + 3 + 3) / 4 * 4;
+    static constexpr int PITCH = TH == kGatherTile ? (C == 1 ? 68 : (C == 3 ? 164 : 212)) : (C == 1 ? 84 : ROW_MAX + 4);
     static_assert(PITCH >= ROW_MAX && PITCH % 4 == 0, "pitch");
-    static constexpr size_t SMEM = (size_t)kGatherBox * PITCH * sizeof(float);
+    static_assert(TH == kGatherTile || TH == kGatherTileTall, "tile heights");
+    static constexpr size_t SMEM = (size_t)BOX * PITCH * sizeof(float);
 };
 
-template <int C, bool TAB = false>
+template <int C, bool TAB = false, int TH = kGatherTile>
 __global__ void __launch_bounds__(256, 6)
 gather_f32_kernel(const __grid_constant__ GatherParams g)
 {
-    constexpr int PITCH = GatherGeom<C>::PITCH;
-    constexpr int NPX = kGatherTile / 8;  // output pixels per thread
+    constexpr int PITCH = GatherGeom<C, TH>::PITCH;
+    constexpr int BOX = GatherGeom<C, TH>::BOX;
+    constexpr int NPX = TH / 8;  // output pixels per thread
     extern __shared__ __align__(16) float box[];  // [bh][PITCH]
     // TAB: the angle and the pointwise programs are the image's own (GatherVar record in device
     // memory, copied to shared memory once per block); everything else is common to the launch
@@ -404,8 +409,8 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
     const PwProgram &pw_post = TAB ? s_var.pw_post : g.pw_post;
     const float *__restrict__ src = g.in_tab ? g.in_tab[blockIdx.z] : g.in;
     float *__restrict__ dst = g.out_tab ? g.out_tab[blockIdx.z] : g.out;
-    const int ox0 = blockIdx.x * kGatherTile, oy0 = blockIdx.y * kGatherTile;
-    const int ox1 = min(ox0 + kGatherTile, g.out_w) - 1, oy1 = min(oy0 + kGatherTile, g.out_h) - 1;
+    const int ox0 = blockIdx.x * kGatherTile, oy0 = blockIdx.y * TH;
+    const int ox1 = min(ox0 + kGatherTile, g.out_w) - 1, oy1 = min(oy0 + TH, g.out_h) - 1;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 
     // footprint of the tile in the rotate's space (after the post map): both maps are affine, so the
@@ -428,8 +433,8 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
     }
     const double xmin = xc - ex, xmax = xc + ex, ymin = yc - ey, ymax = yc + ey;
     const int bx0 = __double2int_rd(xmin) - 1, by0 = __double2int_rd(ymin) - 1;
-    const int bw = min(__double2int_ru(xmax) + 2 - bx0, kGatherBox);
-    const int bh = min(__double2int_ru(ymax) + 2 - by0, kGatherBox);
+    const int bw = min(__double2int_ru(xmax) + 2 - bx0, BOX);
+    const int bh = min(__double2int_ru(ymax) + 2 - by0, BOX);
     const int row_floats = bw * C;
 
     const bool identity_pre = g.pre.ay == 1 && g.pre.by == 0 && g.pre.cy == 0 && g.pre.ax == 0 &&
@@ -453,13 +458,13 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
         if (w == 0) {
             uint32_t bytes = 0;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < (BOX + 31) / 32; ++u) {
                 const int r = lane + 32 * u;
                 if (any && r >= r_lo && r < r_hi) bytes += (uint32_t)(c_hi - c_lo) * 4u;
             }
             mbar_expect_tx(&s_bar, bytes);  // arrive + expect: the barrier counts the 32 lanes
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < (BOX + 31) / 32; ++u) {
                 const int r = lane + 32 * u;
                 if (any && r >= r_lo && r < r_hi)
                     bulk_g2s(box + r * PITCH + c_lo, src + ((long)(by0 + r) * row_len + col0 + c_lo),
@@ -477,7 +482,7 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
         }
     } else {
         // ---- scalar staging through the pre map (and the pre-rotate pointwise ops)
-        constexpr int PER_LANE = (kGatherBox * C + 31) / 32;
+        constexpr int PER_LANE = (BOX * C + 31) / 32;
         const bool has_pre = pw_pre.n > 0;
         for (int r = w; r < bh; r += 8) {
             const int cy = by0 + r;

@@ -839,14 +839,18 @@ namespace mp {
 
 void launch_gather_f32(cudaStream_t s, int channels, const GatherParams &g, int n_images)
 {
-    dim3 grid((g.out_w + kGatherTile - 1) / kGatherTile, (g.out_h + kGatherTile - 1) / kGatherTile, n_images);
-    const size_t smem = channels == 1 ? GatherGeom<1>::SMEM : (channels == 3 ? GatherGeom<3>::SMEM : GatherGeom<4>::SMEM);
-    static_assert(GatherGeom<4>::SMEM <= 48 * 1024, "fits the default dynamic shared memory limit on every device");
+    // single-channel images use 32 x 64 tiles: a 32 x 32 tile of 4-byte pixels is too little work per CTA
+    const int th = channels == 1 ? kGatherTileTall : kGatherTile;
+    dim3 grid((g.out_w + kGatherTile - 1) / kGatherTile, (g.out_h + th - 1) / th, n_images);
+    const size_t smem = channels == 1 ? GatherGeom<1, kGatherTileTall>::SMEM
+                                      : (channels == 3 ? GatherGeom<3>::SMEM : GatherGeom<4>::SMEM);
+    static_assert(GatherGeom<4>::SMEM <= 48 * 1024 && GatherGeom<1, kGatherTileTall>::SMEM <= 48 * 1024,
+                  "fits the default dynamic shared memory limit on every device");
     if (g.var_tab) {  // per-image angle / programs
-        if (channels == 1) gather_f32_kernel<1, true><<<grid, 256, smem, s>>>(g);
+        if (channels == 1) gather_f32_kernel<1, true, kGatherTileTall><<<grid, 256, smem, s>>>(g);
         else if (channels == 3) gather_f32_kernel<3, true><<<grid, 256, smem, s>>>(g);
         else gather_f32_kernel<4, true><<<grid, 256, smem, s>>>(g);
-    } else if (channels == 1) gather_f32_kernel<1><<<grid, 256, smem, s>>>(g);
+    } else if (channels == 1) gather_f32_kernel<1, false, kGatherTileTall><<<grid, 256, smem, s>>>(g);
     else if (channels == 3) gather_f32_kernel<3><<<grid, 256, smem, s>>>(g);
     else gather_f32_kernel<4><<<grid, 256, smem, s>>>(g);
     count_launch();
