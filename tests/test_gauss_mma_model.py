@@ -1,0 +1,193 @@
+"""CPU models of the two pieces of the tensor-core Gaussian column pass
+(millipyde_b200/csrc/kernels/gaussian_stream_mma.cuh) that can be checked without a GPU:
+
+  * the arithmetic: banded 8-row-chunk x 8-row-block products with the MMA fragment layouts of
+    mma.sync.m16n8k8 / m16n8k16, the hi/lo operand split (tf32 product + one fp16 correction
+    product whose K dimension concatenates [lo(A) | hi(A)] x [hi(B) ; lo(B)]) and fp32
+    accumulation -- against the plain fp64 column filter;
+  * the hand-off protocol: ROW warps produce 12-row groups into a 48-row ring, COLUMN warps
+    consume 8-row chunks; the `need` / `done` formulas must never let a chunk be read before
+    its rows exist nor a ring row be overwritten before its chunk was consumed, and every item
+    must end with the ring empty and the barriers in phase.
+
+The GPU parity tests (tests/test_ops_gpu.py::test_f32_streaming_gaussian_*) check the kernel
+itself; these pin the design it implements."""
+import numpy as np
+import pytest
+
+ROWS_PER_GROUP, GROUPS, CHUNK = 12, 4, 8          # WsK<true>::rows, ::groups; chunk rows
+RING = ROWS_PER_GROUP * GROUPS                    # 48
+
+
+def nch(radius):
+    return (7 + 2 * radius) // 8 + 1              # MmGeom::NCH
+
+
+def steps(n_rows):
+    """ws_steps<true>: 12-row groups an item takes (padded by 7 rows, whole turns of the ring)."""
+    return ((n_rows + 7 + ROWS_PER_GROUP - 1) // ROWS_PER_GROUP + 3) & ~3
+
+
+# ------------------------------------------------------------------ arithmetic
+def tf32_hi(x):
+    """hi = x & 0xffffe000 on the fp32 bit pattern (what the kernel feeds the tf32 MMA)."""
+    return (np.asarray(x, np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def mma(a_frag, b_frag, c_frag, k):
+    """D = A.B + C for one warp with the PTX fragment layouts (m16n8k8 tf32: k = 8, two A columns
+    and one B row per register; m16n8k16 f16: k = 16, register pairs hold K slots (2t, 2t+1)).
+    Products and sums in fp32, as the tensor core accumulates."""
+    A = np.zeros((16, k), np.float32)
+    B = np.zeros((k, 8), np.float32)
+    C = np.zeros((16, 8), np.float32)
+    for lane in range(32):
+        g, t = lane >> 2, lane & 3
+        if k == 8:
+            A[g, t], A[g + 8, t], A[g, t + 4], A[g + 8, t + 4] = a_frag[lane]
+            B[t, g], B[t + 4, g] = b_frag[lane]
+        else:
+            (A[g, 2 * t], A[g, 2 * t + 1]), (A[g + 8, 2 * t], A[g + 8, 2 * t + 1]) = a_frag[lane][0], a_frag[lane][1]
+            (A[g, 2 * t + 8], A[g, 2 * t + 9]), (A[g + 8, 2 * t + 8], A[g + 8, 2 * t + 9]) = a_frag[lane][2], a_frag[lane][3]
+            (B[2 * t, g], B[2 * t + 1, g]), (B[2 * t + 8, g], B[2 * t + 9, g]) = b_frag[lane][0], b_frag[lane][1]
+        C[g, 2 * t], C[g, 2 * t + 1], C[g + 8, 2 * t], C[g + 8, 2 * t + 1] = c_frag[lane]
+    D = (A.astype(np.float64) @ B.astype(np.float64)).astype(np.float32) + C
+    out = np.zeros((32, 4), np.float32)
+    for lane in range(32):
+        g, t = lane >> 2, lane & 3
+        out[lane] = D[g, 2 * t], D[g, 2 * t + 1], D[g + 8, 2 * t], D[g + 8, 2 * t + 1]
+    return out
+
+
+def column_pass_model(F, w, radius, n_valid):
+    """One 16-column tile of one item: F[f][col] filtered rows (fp32), w[d] weights (fp32)."""
+    R, N = radius, nch(radius)
+    n_chunks = steps(n_valid + 2 * R) // 4 * (RING // CHUNK)
+    F = np.vstack([F, np.zeros((n_chunks * CHUNK - F.shape[0], 16), np.float32)])
+    f16 = lambda x: np.float32(np.float16(x))
+    bh = np.zeros((N, 32, 2), np.float32)        # tf32 operand: hi(B_j[t][g]), hi(B_j[t+4][g])
+    bc = np.zeros((N, 32, 2, 2), np.float32)     # fp16 operand: (w, w) pair and (w_lo, w_lo) pair
+    for j in range(N):
+        for lane in range(32):
+            g, t = lane >> 2, lane & 3
+            ws = []
+            for h in range(2):
+                d = abs(8 * j + t + 4 * h - g - R)
+                ws.append(np.float32(w[d]) if d <= R else np.float32(0))
+            bh[j, lane] = [tf32_hi(x) for x in ws]
+            bc[j, lane, 0] = [f16(x) for x in ws]
+            bc[j, lane, 1] = [f16(np.float32(x) - tf32_hi(x)) for x in ws]
+    acc = np.zeros((N - 1, 32, 4), np.float32)
+    got = np.full((n_valid, 16), np.nan, np.float32)
+    for c in range(n_chunks):
+        ah = np.zeros((32, 4), np.float32)
+        ac = np.zeros((32, 4, 2), np.float32)
+        for lane in range(32):
+            g, t = lane >> 2, lane & 3
+            a = np.array([F[8 * c + t, 2 * g], F[8 * c + t, 2 * g + 1], F[8 * c + t + 4, 2 * g], F[8 * c + t + 4, 2 * g + 1]],
+                         np.float32)
+            hi = tf32_hi(a)
+            lo = a - hi
+            ah[lane] = hi
+            ac[lane] = [(f16(lo[0]), f16(lo[2])), (f16(lo[1]), f16(lo[3])), (f16(hi[0]), f16(hi[2])), (f16(hi[1]), f16(hi[3]))]
+        nxt = np.zeros((N, 32, 4), np.float32)
+        for j in range(N - 1, -1, -1):
+            base = np.zeros((32, 4), np.float32) if j == 0 else acc[j - 1]
+            nxt[j] = mma(ac, bc[j], base, 16)
+            nxt[j] = mma(ah, bh[j], nxt[j], 8)
+        acc[:] = nxt[:N - 1]
+        ob = 8 * (c - (N - 1))
+        for lane in range(32):
+            g, t = lane >> 2, lane & 3
+            for e, row in ((0, ob + 2 * t), (1, ob + 2 * t + 1)):
+                if 0 <= row < n_valid:
+                    got[row, 2 * g], got[row, 2 * g + 1] = nxt[N - 1, lane, e], nxt[N - 1, lane, e + 2]
+    return got
+
+
+@pytest.mark.parametrize("radius,n_valid", [(11, 37), (11, 8), (9, 21), (7, 40), (5, 13), (3, 1)])
+def test_split_precision_banded_products_match_the_fp64_filter(radius, n_valid):
+    rng = np.random.default_rng(100 + radius)
+    sigma = radius / 5.5
+    x = np.arange(-radius, radius + 1)
+    full = np.exp(-0.5 * (x / sigma) ** 2)
+    full /= full.sum()
+    w = full[radius:].astype(np.float32)                       # w[d], like GaussParams<float>
+    F = rng.random((n_valid + 2 * radius, 16), dtype=np.float32)
+    got = column_pass_model(F, w, radius, n_valid)
+    want = np.zeros((n_valid, 16))
+    for o in range(n_valid):
+        for f in range(o, o + 2 * radius + 1):
+            want[o] += float(w[abs(f - o - radius)]) * F[f].astype(np.float64)
+    assert not np.isnan(got).any()
+    # dropped lo.lo term and the rounding of the lo parts: each below 2^-21 of the result
+    assert np.abs(got - want).max() <= 1e-6
+
+
+def test_split_is_exact_and_corrections_fit_fp16():
+    rng = np.random.default_rng(7)
+    a = rng.random(10000, dtype=np.float32)
+    hi = tf32_hi(a)
+    lo = a - hi
+    assert np.array_equal((hi.astype(np.float64) + lo.astype(np.float64)).astype(np.float32), a)
+    assert np.all(np.abs(lo) <= np.abs(a) * 2.0 ** -10)
+    assert np.array_equal(np.float16(hi).astype(np.float32), hi)       # 11 significant bits: exact in fp16
+    assert np.all(np.abs(np.float16(lo).astype(np.float32) - lo) <= np.maximum(np.abs(lo) * 2.0 ** -11, 2.0 ** -25))
+
+
+# ------------------------------------------------------------------ hand-off protocol
+def simulate_item(n_rows, producer_lead):
+    """Replay one work item.  Returns the number of chunks consumed.  `producer_lead` bounds how far
+    the producers run ahead when they could (0 = as late as the consumer allows, large = as early
+    as the ring allows), to exercise both extremes of the schedule."""
+    n_steps = steps(n_rows)
+    n_chunks = n_steps // 4 * (RING // CHUNK)
+    assert n_steps % GROUPS == 0 and n_chunks * CHUNK == n_steps * ROWS_PER_GROUP >= n_rows + 7
+    produced = 0            # groups written (rows [12 g, 12 g + 12) of the item)
+    released = 0            # groups handed back by the consumer
+    waited = 0
+    owner = [None] * RING   # item row currently held by each ring row
+    for c in range(n_chunks):
+        need = (8 * c + 7) // ROWS_PER_GROUP + 1
+        # the producers write group g only once its ring slot was released (they block on empty[g % 4]
+        # otherwise): g - released < GROUPS
+        target = min(n_steps, need + producer_lead, released + GROUPS)
+        assert target >= need, "deadlock: the consumer waits for a group the producers may not write yet"
+        while produced < target:
+            for r in range(ROWS_PER_GROUP):
+                row = produced * ROWS_PER_GROUP + r
+                owner[row % RING] = row
+            produced += 1
+        while waited < need:
+            assert waited < produced
+            waited += 1
+        for r in range(8 * c, 8 * c + 8):                       # the chunk's rows are the item's rows
+            assert owner[r % RING] == r, "chunk read before / after its rows were in the ring"
+        done = (8 * (c + 1)) // ROWS_PER_GROUP
+        assert done <= waited
+        released = max(released, done)
+    assert released == waited == n_steps                         # ring empty, barriers in phase
+    # every output row's support is inside chunks the schedule delivers before the item ends
+    return n_chunks
+
+
+@pytest.mark.parametrize("lead", [0, 1, 2, 100])
+def test_ring_protocol_never_reads_early_or_overwrites_late(lead):
+    for radius in (3, 5, 7, 9, 11):
+        for n_valid in list(range(1, 60)) + [135, 540, 1080, 2160]:
+            n_rows = n_valid + 2 * radius
+            n_chunks = simulate_item(n_rows, lead)
+            last_block = (n_valid - 1) // 8
+            assert last_block + nch(radius) - 1 < n_chunks, "an output block would complete after the item ends"
+
+
+def test_producer_can_always_make_progress():
+    """Deadlock freedom: at the moment the consumer waits for group `need - 1`, the producers are
+    allowed to write it (its ring slot has been released)."""
+    for n_rows in range(1, 400):
+        n_steps = steps(n_rows)
+        released = 0
+        for c in range(n_steps // 4 * (RING // CHUNK)):
+            need = (8 * c + 7) // ROWS_PER_GROUP + 1
+            assert (need - 1) - released < GROUPS
+            released = (8 * (c + 1)) // ROWS_PER_GROUP
