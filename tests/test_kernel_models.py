@@ -1,4 +1,4 @@
-"""CPU models of the two pieces of the tensor-core Gaussian column pass
+"""CPU models of device-side designs that can be checked without a GPU: the two pieces of the tensor-core Gaussian column pass
 (millipyde_b200/csrc/kernels/gaussian_stream_mma.cuh) that can be checked without a GPU:
 
   * the arithmetic: banded 8-row-chunk x 8-row-block products with the MMA fragment layouts of
@@ -191,3 +191,37 @@ def test_producer_can_always_make_progress():
             need = (8 * c + 7) // ROWS_PER_GROUP + 1
             assert (need - 1) - released < GROUPS
             released = (8 * (c + 1)) // ROWS_PER_GROUP
+
+
+# ------------------------------------------------------------------ skewed transpose layout
+def test_skewed_transpose_layout_is_conflict_free_and_tma_aligned():
+    """transpose_tma64_kernel<K> (kernels/geometry.cuh): row y of a tile lands at
+    y * 96 + 4 * ((y >> S) & 7) words.  Every warp-wide LDS.32 (K = 1) and every half-warp of an
+    LDS.64 (K = 2) of the gather must hit distinct banks, rows must stay inside the pitch, and every
+    bulk-copy destination must be 16-byte aligned."""
+    pitch = 96
+    for K, S in ((1, 2), (2, 1)):
+        tx = 64 // K
+        for y in range(64):
+            start = y * pitch + 4 * ((y >> S) & 7)
+            assert (start * 4) % 16 == 0 and 4 * ((y >> S) & 7) + 64 <= pitch
+        for tw in (tx, tx - 4, 8, 4):                      # full and partial tile widths (multiples of 4 / K ... even)
+            vpr = 64 * K // 4
+            for i0 in range(0, 8 * tw * ((vpr + 7) // 8), 32):
+                lanes = []
+                for i in range(i0, i0 + 32):
+                    q_lo, t2 = i & 7, i >> 3
+                    q_hi, r = divmod(t2, tw)
+                    q = 8 * q_hi + q_lo
+                    if q < vpr:
+                        lanes.append(((q << S) * pitch + 4 * q_lo + r * K, q, r))
+                if K == 1:
+                    for e in range(4):                     # the four LDS.32 of a thread: rows 4q + e
+                        banks = [(a + e * pitch) % 32 for a, _, _ in lanes]
+                        assert len(set(banks)) == len(banks), (K, tw, i0, e)
+                else:
+                    for half in (lanes[:16], lanes[16:]):  # LDS.64: 16 lanes x 2 banks per wavefront
+                        for e in range(2):
+                            banks = [b for a, _, _ in half for b in ((a + e * pitch) % 32, (a + e * pitch + 1) % 32)]
+                            assert len(set(banks)) == len(banks), (K, tw, i0, e)
+                            assert all(a % 2 == 0 for a, _, _ in half)
