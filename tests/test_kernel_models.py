@@ -1,5 +1,6 @@
-"""CPU models of device-side designs that can be checked without a GPU: the two pieces of the tensor-core Gaussian column pass
-(millipyde_b200/csrc/kernels/gaussian_stream_mma.cuh) that can be checked without a GPU:
+"""CPU models of device-side designs that can be checked without a GPU.
+
+Tensor-core Gaussian column pass (millipyde_b200/csrc/kernels/gaussian_stream_mma.cuh):
 
   * the arithmetic: banded 8-row-chunk x 8-row-block products with the MMA fragment layouts of
     mma.sync.m16n8k8 / m16n8k16, the hi/lo operand split (tf32 product + one fp16 correction
@@ -10,8 +11,11 @@
     its rows exist nor a ring row be overwritten before its chunk was consumed, and every item
     must end with the ring empty and the barriers in phase.
 
-The GPU parity tests (tests/test_ops_gpu.py::test_f32_streaming_gaussian_*) check the kernel
-itself; these pin the design it implements."""
+Skewed transpose (kernels/geometry.cuh, transpose_tma64_kernel): bank-conflict freedom of the
+gather and 16-byte alignment of the bulk-copy destinations.
+
+The GPU parity tests (tests/test_ops_gpu.py) check the kernels themselves; these pin the designs
+they implement."""
 import numpy as np
 import pytest
 
