@@ -50,21 +50,22 @@ transpose_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, in
 // OUTPUT row (4 x LDS.32) and writes them as one 16-byte store, so the store side moves 128-bit
 // vectors too.  Many small CTAs (12.8 KB of shared memory each for RGB fp32) overlap each other's
 // copy latency.  Images of a batch are addressed through pointer tables (blockIdx.z).
-template <int K>
+// TH = rows per tile: 64 for three- and four-word pixels (24-33 KB in flight per CTA).
+template <int K, int TH = 32>
 __global__ void __launch_bounds__(256)
 transpose_tma_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int width, int height,
                      const uint32_t *const *__restrict__ in_tab = nullptr,
                      uint32_t *const *__restrict__ out_tab = nullptr)
 {
     constexpr int P = 32 * K + 4;
-    __shared__ __align__(128) uint32_t tile[32 * P];
+    __shared__ __align__(128) uint32_t tile[TH * P];
     __shared__ __align__(8) uint64_t bar;
     if (in_tab) {
         in = in_tab[blockIdx.z];
         out = out_tab[blockIdx.z];
     }
-    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
-    const int tw = min(32, width - x0), th = min(32, height - y0);
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * TH;
+    const int tw = min(32, width - x0), th = min(TH, height - y0);
     const int tid = threadIdx.x;
     if (tid == 0) {
         mbar_init(&bar, 1);
@@ -75,8 +76,8 @@ transpose_tma_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out
         const uint32_t row_bytes = (uint32_t)tw * K * 4u;
         if (tid == 0) mbar_expect_tx(&bar, row_bytes * (uint32_t)th);
         __syncwarp();
-        if (tid < th)
-            bulk_g2s(tile + tid * P, in + ((size_t)(y0 + tid) * width + x0) * K, row_bytes, &bar);
+        for (int y = tid; y < th; y += 32)
+            bulk_g2s(tile + y * P, in + ((size_t)(y0 + y) * width + x0) * K, row_bytes, &bar);
         if (tid == 0) mbar_wait(&bar, 0);   // one poller; the other warps park at the barrier below
     }
     __syncthreads();

@@ -186,7 +186,8 @@ static void launch_transpose(const void *in, void *out, int W, int H, cudaStream
         }
     }
     if (((size_t)W * K) % 4 == 0 && ((size_t)H * K) % 4 == 0)
-        transpose_tma_kernel<K><<<grid, 256, 0, s>>>((const uint32_t *)in, (uint32_t *)out, W, H);
+        transpose_tma_kernel<K, 64><<<dim3((W + 31) / 32, (H + 63) / 64), 256, 0, s>>>((const uint32_t *)in,
+                                                                                      (uint32_t *)out, W, H);
     else
         transpose_kernel<K><<<grid, 256, 0, s>>>((const uint32_t *)in, (uint32_t *)out, W, H);
 }
@@ -932,7 +933,6 @@ void launch_transpose_batch(cudaStream_t s, const Img &d, const void *const *in_
                             int n_images)
 {
     const int K = words_per_pixel(d);
-    dim3 grid((d.W + 31) / 32, (d.H + 31) / 32, n_images);
     const uint32_t *const *it = (const uint32_t *const *)in_tab;
     uint32_t *const *ot = (uint32_t *const *)out_tab;
     switch (K) {
@@ -944,8 +944,14 @@ void launch_transpose_batch(cudaStream_t s, const Img &d, const void *const *in_
             transpose_tma64_kernel<2><<<dim3((d.W + 31) / 32, (d.H + 63) / 64, n_images), 256, 0, s>>>(
                 nullptr, nullptr, d.W, d.H, it, ot);
             break;
-        case 3: transpose_tma_kernel<3><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, d.H, it, ot); break;
-        default: transpose_tma_kernel<4><<<grid, 256, 0, s>>>(nullptr, nullptr, d.W, d.H, it, ot); break;
+        case 3:
+            transpose_tma_kernel<3, 64><<<dim3((d.W + 31) / 32, (d.H + 63) / 64, n_images), 256, 0, s>>>(
+                nullptr, nullptr, d.W, d.H, it, ot);
+            break;
+        default:
+            transpose_tma_kernel<4, 64><<<dim3((d.W + 31) / 32, (d.H + 63) / 64, n_images), 256, 0, s>>>(
+                nullptr, nullptr, d.W, d.H, it, ot);
+            break;
     }
     count_launch();
 }

@@ -10,7 +10,8 @@ from millipyde_b200 import capi, engine
 capi.initialize()
 rng = np.random.default_rng(0)
 for shape, dt, n in [((1024, 1024), np.float32, 32), ((2160, 3840, 4), np.uint8, 8), ((1080, 1920), np.float32, 64),
-                     ((2160, 3840), np.float64, 8)]:
+                     ((2160, 3840), np.float64, 8),
+                     ((2160, 3840, 3), np.float32, 8), ((1080, 1920, 4), np.float32, 16)]:
     img = rng.integers(0, 256, shape, dtype=np.uint8) if dt == np.uint8 else rng.random(shape).astype(dt)
     seed = capi.DeviceImage(img)
     batch = [seed.clone() for _ in range(n)]
