@@ -79,6 +79,17 @@ void mppipe_set_fusion(int enabled);
 int mppipe_get_fusion(void);
 
 /* Kernel launches and fused segments issued by the most recent run of `p` (all devices). */
+/* Host-only "explain" (new; needs no GPU): the segments the fusion pass compiles the chain into for
+ * an image of numpy type `typenum` with `channels` channels when every stage runs (probabilities are
+ * ignored; random_* stages draw their parameters from the seeded source like a real run).  Writes a
+ * ';'-separated description into buf, one token per segment = one HBM round trip per image:
+ *   pw(op,...)            fused fp32 pointwise program      u8(op,...)   composed RGBA8 byte tables
+ *   grey(pre|post)        rgb2grey with the pointwise ops it absorbed
+ *   gather(flip,rotate,flip;pre|post)   fliplr / rotate / pointwise ops in one gather pass
+ *   op                    an operator run on its own (transpose, gaussian, foreign, ...)
+ * Returns the number of segments, or -1 (bad arguments / buffer too small). */
+int mppipe_plan(const MPPipeline *p, int typenum, int channels, char *buf, int cap);
+
 unsigned long long mppipe_last_launches(const MPPipeline *p);
 int mppipe_last_segments(const MPPipeline *p);
 

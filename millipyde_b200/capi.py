@@ -190,6 +190,7 @@ SYMBOLS = {
     "mppipe_wait": (C.c_int, [C.c_void_p]),
     "mppipe_run_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t,
                                   C.POINTER(MPHostResult), C.c_int, C.c_int, C.POINTER(C.c_long), C.c_int]),
+    "mppipe_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int]),
     "mppipe_set_fusion": (None, [C.c_int]),
     "mppipe_get_fusion": (C.c_int, []),
     "mppipe_last_launches": (C.c_ulonglong, [C.c_void_p]),

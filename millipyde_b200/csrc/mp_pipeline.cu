@@ -1052,6 +1052,59 @@ MPStatus mppipe_run(MPPipeline *p, MPObjData **objs, int n)
     return mppipe_wait(p);
 }
 
+int mppipe_plan(const MPPipeline *p, int typenum, int channels, char *buf, int cap)
+{
+    if (!p || !buf || cap < 1 || channels < 1) return -1;
+    mp::Family fam;
+    switch (typenum) {
+        case MP_NPY_UBYTE: fam = channels == 4 ? mp::FAM_RGBA8 : mp::FAM_U8_OTHER; break;
+        case MP_NPY_DOUBLE: fam = channels == 1 ? mp::FAM_F64 : mp::FAM_F64_OTHER; break;
+        case MP_NPY_FLOAT:
+            if (channels != 1 && channels != 3 && channels != 4) return -1;
+            fam = mp::FAM_F32;
+            break;
+        default: return -1;
+    }
+    mp_pipeline all = {};   // the same stages with every coin forced to "run"
+    all.stages = p->stages;
+    for (Stage &st : all.stages) st.probability = -1;
+    std::vector<Stage> realized;
+    realize(&all, &realized);
+    std::vector<const Stage *> ops;
+    for (const Stage &st : realized) ops.push_back(&st);
+    const std::vector<Segment> segs = compile(ops, fam, channels);
+    static const char *const kOp[] = {"rgb2grey", "transpose", "gaussian", "fliplr", "rotate", "brightness",
+                                      "adjust_gamma", "colorize", "random", "foreign", "null"};
+    static const char *const kPw[] = {"none", "brightness", "adjust_gamma", "colorize"};
+    auto prog = [](const PwProgram &g) {
+        std::string t;
+        for (int i = 0; i < g.n; ++i) t += (i ? "," : "") + std::string(kPw[g.ops[i].kind & 3]);
+        return t;
+    };
+    std::string out;
+    for (const Segment &g : segs) {
+        if (!out.empty()) out += ";";
+        switch (g.kind) {
+            case Segment::SINGLE: out += kOp[g.single->kind]; break;
+            case Segment::PW_F32: out += "pw(" + prog(g.pre) + ")"; break;
+            case Segment::GREY_F32: out += "grey(" + prog(g.pre) + "|" + prog(g.post) + ")"; break;
+            case Segment::PW_RGBA8: {
+                std::string t;
+                for (int i = 0; i < g.u8.n; ++i) t += (i ? "," : "") + std::string(kPw[g.u8.ops[i].kind & 3]);
+                out += "u8(" + t + ")";
+                break;
+            }
+            case Segment::GATHER_F32:
+                out += std::string("gather(") + (g.flip_pre ? "fliplr" : "-") + "," + (g.has_rotate ? "rotate" : "-") + "," +
+                       (g.flip_post ? "fliplr" : "-") + ";" + prog(g.pre) + "|" + prog(g.post) + ")";
+                break;
+        }
+    }
+    if ((int)out.size() + 1 > cap) return -1;
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return (int)segs.size();
+}
+
 void mppipe_set_fusion(int enabled) { g_fusion.store(enabled ? 1 : 0); }
 int mppipe_get_fusion(void) { return g_fusion.load(); }
 unsigned long long mppipe_last_launches(const MPPipeline *p) { return p ? p->launches.load() : 0; }
