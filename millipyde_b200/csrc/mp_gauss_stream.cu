@@ -88,8 +88,11 @@ static MPStatus launch_cr(int device, cudaStream_t s, GaussStreamParams &p, cons
             }
         }
     }
-    p.n_chunks = chunks;
     p.chunk_rows = (p.height + chunks - 1) / chunks;
+    // rounding the chunk height up can leave the last chunks empty (770 rows in 64 chunks of 13 end
+    // at chunk 59): count the chunks that start inside the image, every item must own at least one row
+    chunks = (p.height + p.chunk_rows - 1) / p.chunk_rows;
+    p.n_chunks = chunks;
     items *= chunks;
     const int grid = (int)(items < sms ? items : sms);
     if constexpr (kHasMma) {
