@@ -49,7 +49,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step")
-    ap.add_argument("--e2e-images", type=int, default=32, help="images per e2e step")
+    ap.add_argument("--e2e-images", type=int, default=16, help="images per GPU per e2e step (the same at every N)")
+    ap.add_argument("--in-process", action="store_true",
+                    help="one process drives --gpus N devices: headline workload + multi-device checks, one JSON line")
+    ap.add_argument("--no-in-process", action="store_true", help="under torchrun: skip rank 0's one-process leg")
     ap.add_argument("--cpu-images", type=int, default=0, help="images in the CPU sample (0 = one per core)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (profiling runs only)")
@@ -63,7 +66,7 @@ def _cpu_one(seed):
     rng = np.random.default_rng(seed)
     img = rng.random((H, W, C), dtype=np.float32)      # input generation is not part of the timed path
     t0 = time.perf_counter()
-    out = so.gaussian(img, SIGMA)
+    out = so.gaussian(img, SIGMA, keep_float32=True)   # skimage 0.18 keeps float32 images in float32
     dt = time.perf_counter() - t0
     return os.getpid(), dt, float(out[H // 2, W // 2, 0])
 
@@ -85,7 +88,7 @@ def cpu_baseline(n_images: int):
         per_worker[pid] = per_worker.get(pid, 0.0) + dt
     busy = max(per_worker.values())
     return {"value": n / busy, "unit": "images/s", "cores": procs, "kind": "port",
-            "sample": f"{n} of the step's images, scipy.ndimage.gaussian_filter(sigma=2, truncate=8, "
+            "sample": f"{n} of the step's images, scipy.ndimage.gaussian_filter(float32, sigma=2, truncate=8, "
                       f"mode=constant) per image, {procs} processes in parallel, busiest worker {busy:.2f}s"}
 
 
@@ -259,10 +262,233 @@ def run_reference(args, dist):
 
 
 # --------------------------------------------------------------------------- B200 arm
+class Resident:
+    """The device-resident leg's data on a set of devices: `batch` noise images per device (uploaded
+    once, never written again) and two sets of *views* that receive the results.  A step =
+    `Pipeline` over one view set: every launch reads the fixed noise inputs and writes fresh output
+    buffers (mppipe_submit_views), so the timed data is `rng.random` noise in every step -- not
+    the n-th blur of itself."""
+
+    def __init__(self, capi, engine, devices, batch, seeds):
+        self.capi, self.engine, self.devices, self.batch = capi, engine, devices, batch
+        L = capi.lib()
+        self.inputs, self.views, self.pipes = [], [[], []], [[], []]
+        for d in devices:
+            L.mpdev_set_target_device(d)
+            base = [capi.DeviceImage(s) for s in seeds]
+            self.inputs.append([base[k % len(base)].clone(device=d) for k in range(batch)])
+            for b in base:
+                b.close()
+        L.mpdev_set_target_device(capi.DEVICE_LOC_NO_AFFINITY)
+        L.mpdev_synchronize_all()
+        for s in range(2):
+            for di, d in enumerate(devices):
+                self.views[s].append([im.view() for im in self.inputs[di]])
+                self.pipes[s].append(engine.Chain([("gaussian", SIGMA)], device=d))
+        self.ran = [False, False]        # the set's views own results (must be re-armed before reuse)
+        self.in_flight = [False, False]
+        self.last_set = 0
+
+    def _wait(self, s):
+        if self.in_flight[s]:
+            for ch in self.pipes[s]:
+                ch.wait()
+            self.in_flight[s] = False
+
+    def run_steps(self, n):
+        """n steps, step k on view set k % 2; the host prepares step k+1 (re-arming 256 views, pool
+        allocations, pointer tables, the launch) while the device runs step k.  Returns when the
+        last step's work is complete."""
+        for k in range(n):
+            s = k % 2
+            self._wait(s)               # the set's previous pass is complete
+            if self.ran[s]:
+                for di in range(len(self.devices)):
+                    for v, src in zip(self.views[s][di], self.inputs[di]):
+                        v.rebind(src)   # previous result back to the pool, borrow the noise input again
+            for ch, vs in zip(self.pipes[s], self.views[s]):
+                ch.submit_views(vs)
+            self.in_flight[s] = True
+            self.ran[s] = True
+            self.last_set = s
+        self._wait(0)
+        self._wait(1)
+
+    def close(self):
+        self._wait(0)
+        self._wait(1)
+        for s in range(2):
+            for vs in self.views[s]:
+                for v in vs:
+                    if self.ran[s]:
+                        v.rebind(None)
+                    else:
+                        v.obj.device_data = None    # never ran: still borrowing, nothing of its own
+                    v.close()
+            for ch in self.pipes[s]:
+                ch.close()
+        for imgs in self.inputs:
+            for i in imgs:
+                i.close()
+        self.views, self.pipes, self.inputs = [[], []], [[], []], []
+
+
+def parity_check(res, seeds):
+    """Download one image from the middle of the last timed launch and compare the WHOLE 4K frame
+    with the oracle (scipy.ndimage.gaussian_filter in float64 on the same noise image)."""
+    import numpy as np
+    from oracle import skimage_oracle as so
+    k = res.batch // 2
+    got = res.views[res.last_set][0][k].numpy()
+    want = so.gaussian(seeds[k % len(seeds)], SIGMA)
+    err = float(np.abs(got.astype(np.float64) - want).max())
+    border = float(np.abs(got[-12:].astype(np.float64) - want[-12:]).max())
+    return {"image": k, "of_launch_of": res.batch, "frame": list(got.shape), "max_abs_err": err,
+            "max_abs_err_bottom_12_rows": border, "tol": 1e-5, "ok": bool(err <= 1e-5),
+            "oracle": "scipy.ndimage.gaussian_filter(float64, sigma=2, truncate=8, mode=constant)"}
+
+
+def e2e_leg(capi, engine, devices, per_dev, steps, dist):
+    """Host buffers in, host buffers out through the public call (Pipeline over host arrays,
+    mppipe_run_host): per_dev page-locked noise images per device are uploaded, blurred and
+    downloaded, all inside the timed region.  One untimed pass first; every timed step starts at a
+    barrier and costs the slowest rank's wall time; the value is images / MEAN step time."""
+    import numpy as np
+    import threading
+    rng = np.random.default_rng(4000 + dist.rank)
+    chains, ins, outs = [], [], []
+    for d in devices:
+        chains.append(engine.Chain([("gaussian", SIGMA)], device=d))
+        a = [engine.pinned_empty((H, W, C), np.float32) for _ in range(per_dev)]
+        for k, x in enumerate(a):
+            if k < 2:
+                x[...] = rng.random((H, W, C), dtype=np.float32)
+            else:
+                x[...] = a[k % 2]
+        ins.append(a)
+        outs.append([engine.pinned_empty((H, W, C), np.float32) for _ in range(per_dev)])
+
+    def one_pass():
+        ths = [threading.Thread(target=ch.run_host, args=(i, o)) for ch, i, o in zip(chains, ins, outs)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+
+    one_pass()
+    times = []
+    for _ in range(steps):
+        dist.barrier()
+        t0 = time.perf_counter()
+        one_pass()
+        times.append(dist.max(time.perf_counter() - t0))
+    # the result that came back is the blur of what went in (full frame, one image)
+    from oracle import skimage_oracle as so
+    err = float(np.abs(outs[0][0].astype(np.float64) - so.gaussian(np.array(ins[0][0]), SIGMA)).max()) \
+        if dist.rank == 0 else 0.0
+    for group in ins + outs:
+        for a in group:
+            engine.pinned_free(a)
+    for ch in chains:
+        ch.close()
+    images = dist.sum(float(per_dev * len(devices)))
+    nbytes = int(images) * H * W * C * 4
+    mean_t = sum(times) / len(times)
+    return {"value": images / mean_t, "unit": "images/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+            "images_per_step": int(images), "images_per_gpu_per_step": per_dev, "steps": steps,
+            "step_s": {"mean": mean_t, "min": min(times), "max": max(times)},
+            "host_result_max_abs_err": err,
+            "note": "pinned host -> device -> blur -> pinned host, copies in the timed region; mean of steps, "
+                    "slowest rank per step, one untimed pass first"}
+
+
+def multi_device_check(capi, engine, ndev):
+    """What the one-process N-device mode adds over N ranks, on small images against the oracle:
+    (a) a connected pipeline pair across two devices (BASELINE config 5's hand-off: grey+transpose
+    on device 0 -> gaussian+rotate on device 1, the sender's last kernel writing into the receiver's
+    memory over NVLink), (b) Pipeline.run() without a device: blocks of 4 images round-robin over
+    every device (src/gpupipeline.c:267-283)."""
+    import numpy as np
+    from oracle import skimage_oracle as so
+    L = capi.lib()
+    rng = np.random.default_rng(5000)
+    out = {}
+    # (a)
+    imgs = [rng.random((120, 640, 3), dtype=np.float32) for _ in range(6)]
+    dev = [capi.DeviceImage(a) for a in imgs]
+    pa = engine.Chain([("rgb2grey",), ("transpose",)], device=0)
+    pb = engine.Chain([("gaussian", 2.0), ("rotate", 30.0)], device=1)
+    pa.connect_to(pb)
+    pa.run(dev)
+    chain = [("rgb2grey",), ("transpose",), ("gaussian", 2.0), ("rotate", 30.0)]
+    err = max(float(np.abs(d.numpy() - so.apply_chain(a, chain)).max()) for a, d in zip(imgs, dev))
+    out["pair_handoff"] = {"max_abs_err": err, "landed_on": sorted({d.device for d in dev}), "ok": err <= 1e-5 and {d.device for d in dev} == {1}}
+    for d in dev:
+        d.close()
+    # (b)
+    n = 4 * ndev + 3
+    imgs = [rng.random((64, 640, 3), dtype=np.float32) for _ in range(n)]
+    L.mpdev_set_target_device(0)
+    dev = [capi.DeviceImage(a) for a in imgs]
+    L.mpdev_set_target_device(capi.DEVICE_LOC_NO_AFFINITY)
+    engine.Chain([("gaussian", 2.0), ("fliplr",)]).run(dev)
+    used = sorted({d.device for d in dev})
+    err = max(float(np.abs(d.numpy() - so.apply_chain(a, [("gaussian", 2.0), ("fliplr",)])).max())
+              for a, d in zip(imgs, dev))
+    out["cycling_run"] = {"images": n, "devices_used": used, "max_abs_err": err,
+                          "ok": err <= 1e-5 and used == list(range(ndev))}
+    for d in dev:
+        d.close()
+    out["ok"] = all(v["ok"] for v in out.values())
+    return out
+
+
+def timed_resident(capi, engine, args, dist, devices, batch, seeds, physical_gpu):
+    """Warm up, then time exactly args.steps steps with CUDA events on the launching streams."""
+    L = capi.lib()
+    res = Resident(capi, engine, devices, batch, seeds)
+    sampler = ClockSampler(physical_gpu)
+    sampler.start()
+    try:
+        t_warm = time.time()
+        while True:     # >= W warm-up steps and long enough for the clock sampler to come up
+            res.run_steps(max(args.warmup, 3))
+            L.mpdev_synchronize_all()
+            if time.time() - t_warm > 1.0:
+                break
+        dist.barrier()
+        L.mpdev_synchronize_all()
+        t_region0 = time.time()
+        launches0 = L.mpdev_launch_count()
+        evs = [(L.mpdev_event_create(d), L.mpdev_event_create(d)) for d in devices]
+        t0 = time.perf_counter()
+        for (e0, _), d in zip(evs, devices):
+            L.mpdev_event_record(e0, L.mpdev_get_stream(d, 1))   # stream 1: where Pipeline shards launch
+        res.run_steps(args.steps)       # returns when the last step's work is complete
+        for (_, e1), d in zip(evs, devices):
+            L.mpdev_event_record(e1, L.mpdev_get_stream(d, 1))
+        dev_ms = max(L.mpdev_event_elapsed_ms(e0, e1) for e0, e1 in evs)
+        L.mpdev_synchronize_all()
+        wall_ms = (time.perf_counter() - t0) * 1000.0
+        launches = L.mpdev_launch_count() - launches0
+        dist.barrier()
+        sampler.window = (t_region0, time.time())
+    except Exception:
+        sampler.stop()
+        res.close()
+        raise
+    clocks = sampler.stop()
+    for e0, e1 in evs:
+        L.mpdev_event_destroy(e0)
+        L.mpdev_event_destroy(e1)
+    return res, dev_ms, wall_ms, int(launches), clocks
+
+
 def run_b200(args, dist):
     import numpy as np
     physical_gpu = 0
-    outer = [x for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip() != ""]
+    outer_env = os.environ.get("CUDA_VISIBLE_DEVICES")
+    outer = [x for x in (outer_env or "").split(",") if x.strip() != ""]
     if dist.world > 1:
         # one rank per GPU: this process only ever sees its own device
         mine = outer[dist.local] if len(outer) > dist.local else str(dist.local)
@@ -286,81 +512,31 @@ def run_b200(args, dist):
     else:
         hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
 
-    # ---- batch: a few distinct host images, replicated on the device -------------
+    # ---- batch: fixed noise inputs + two output sets per GPU ----------------------
     free_b, total_b = ctypes.c_size_t(), ctypes.c_size_t()
     L.mpdev_mem_info(0, ctypes.byref(free_b), ctypes.byref(total_b))
     img_bytes = H * W * C * 4
     batch = args.batch
-    # inputs + outputs of one step live together (the op is out-of-place into pool memory)
-    # Two resident batches per GPU, processed alternately (step k works on batch k % 2): the host
-    # prepares step k + 1 (pool allocations, pointer tables, launch) while the device runs step k.
-    n_sets = 2
-    while batch > 8 and 2.2 * n_sets * batch * img_bytes > free_b.value:
+    while batch > 8 and 3.3 * batch * img_bytes > free_b.value:   # inputs + 2 output sets + slack
         batch //= 2
     rng = np.random.default_rng(2000)
-    seeds = [rng.random((H, W, C), dtype=np.float32) for _ in range(2)]
-    shard_sets = [[] for _ in range(n_sets)]
-    for d in devices:
-        L.mpdev_set_target_device(d)
-        base = [capi.DeviceImage(s) for s in seeds]
-        for shards in shard_sets:
-            shards.append([base[k % len(base)].clone(device=d) for k in range(batch)])
-        for b in base:
-            b.close()
-    L.mpdev_set_target_device(capi.DEVICE_LOC_NO_AFFINITY)
-    L.mpdev_synchronize_all()
-
-    # one Pipeline per (batch, device): Pipeline.run() = submit + wait, here issued one step ahead
-    pipes = [[engine.Chain([("gaussian", SIGMA)], device=d) for d in devices] for _ in range(n_sets)]
-    in_flight = [False] * n_sets
-
-    def drain():
-        for k in range(n_sets):
-            if in_flight[k]:
-                for ch in pipes[k]:
-                    ch.wait()
-                in_flight[k] = False
-
-    def run_steps(n):
-        for k in range(n):
-            s = k % n_sets
-            if in_flight[s]:      # this batch's previous pass must be complete before the next one
-                for ch in pipes[s]:
-                    ch.wait()
-            for ch, imgs in zip(pipes[s], shard_sets[s]):
-                ch.submit(imgs)
-            in_flight[s] = True
-        drain()
-
-    sampler = ClockSampler(physical_gpu)
-    sampler.start()
-    t_warm = time.time()
-    while True:     # >= W warm-up steps and long enough for the clock sampler to come up
-        run_steps(max(args.warmup, 3))
-        L.mpdev_synchronize_all()
-        if time.time() - t_warm > 1.0:
+    seeds = [rng.random((H, W, C), dtype=np.float32) for _ in range(4)]
+    shrunk = []
+    while True:
+        try:
+            res, dev_ms, wall_ms, launches, clocks = timed_resident(capi, engine, args, dist, devices, batch, seeds,
+                                                                    physical_gpu)
             break
-    dist.barrier()
-    L.mpdev_synchronize_all()
-    t_region0 = time.time()
-    launches0 = L.mpdev_launch_count()
-    evs = [(L.mpdev_event_create(d), L.mpdev_event_create(d)) for d in devices]
-    t0 = time.perf_counter()
-    for (e0, _), d in zip(evs, devices):
-        L.mpdev_event_record(e0, engine.timing_stream(d))
-    run_steps(args.steps)       # returns when the last step's work is complete
-    for (_, e1), d in zip(evs, devices):
-        L.mpdev_event_record(e1, engine.timing_stream(d))
-    dev_ms = max(L.mpdev_event_elapsed_ms(e0, e1) for e0, e1 in evs)
-    L.mpdev_synchronize_all()
-    wall_ms = (time.perf_counter() - t0) * 1000.0
-    launches = L.mpdev_launch_count() - launches0
-    dist.barrier()
-    sampler.window = (t_region0, time.time())
-    clocks = sampler.stop()
-    for e0, e1 in evs:
-        L.mpdev_event_destroy(e0)
-        L.mpdev_event_destroy(e1)
+        except capi.MillipydeError as e:
+            # out of device memory (another tenant on the GPU, a smaller part): halve the batch, say so
+            if e.status != 57 or batch <= 8 or dist.world > 1:
+                raise
+            shrunk.append(batch)
+            batch //= 2
+            L.mpdev_trim_pools()
+
+    parity = parity_check(res, seeds) if dist.rank == 0 else None
+    res.close()
 
     dev_ms = dist.max(dev_ms)
     images_per_step = dist.sum(float(batch * len(devices)))
@@ -368,60 +544,107 @@ def run_b200(args, dist):
     value = images_per_step / (ms_per_step / 1000.0)
 
     # roofline of the dominant kernel (the Gaussian): launches run back to back on the timing
-    # stream, so average launch duration = device time / launches on this rank
+    # stream, so average launch duration = device time / launches per device
     kern_launches = max(1, launches // max(1, len(devices)))
-    avg_launch_ms = (dev_ms if dist.world == 1 else dev_ms) / kern_launches
+    avg_launch_ms = dev_ms / kern_launches
     images_per_launch = batch * args.steps / kern_launches
     achieved = images_per_launch * ALGO_BYTES_PER_IMAGE / (avg_launch_ms / 1000.0) / 1e9
+    full = ctypes.c_int()
+    eff_radius = L.mpimg_gaussian_effective_radius(SIGMA, ctypes.byref(full))
+    column = "mma" if L.mpimg_get_gauss_column() == 0 else "fma"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": _ncu_traffic(images_per_launch),
-                "kernel": ("gauss_stream_ws_kernel<3,11>" if os.environ.get("MILLIPYDE_GAUSS_COLUMN") == "fma"
-                           else "gauss_stream_mma_kernel<3,11>"), "peak_source": peak_src,
+                "traffic_source": "committed ncu --set full capture (profiles/gauss_stream_dram.json), per image x images per launch",
+                "kernel": f"gauss_stream_{'mma' if column == 'mma' else 'ws'}_kernel<3,{eff_radius}>",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": images_per_launch * ALGO_BYTES_PER_IMAGE,
                 "avg_launch_ms": avg_launch_ms}
 
     # ---- e2e: host buffers in, host buffers out ----------------------------------
     if args.no_e2e:
-        e2e = {"images_per_s": 0.0, "h2d_bytes": 0, "d2h_bytes": 0, "images": 0}
+        e2e = {"value": 0.0, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     else:
-        # page-locked staging is 2 x 99.5 MB per image per rank: keep the whole job's pinned set bounded
-        n_e2e = args.e2e_images if dist.world <= 2 else max(8, args.e2e_images // 2)
-        e2e = None
-        while e2e is None:
-            try:
-                e2e = engine.e2e_gaussian(devices, n_e2e, (H, W, C), SIGMA, steps=max(2, min(args.steps, 3)))
-            except MemoryError:
-                if n_e2e <= 2:
-                    raise
-                n_e2e //= 2
-    e2e_value = dist.sum(e2e["images_per_s"])
+        e2e = e2e_leg(capi, engine, devices, args.e2e_images, max(3, min(args.steps, 5)), dist)
 
     line = {
         "metric": "augmented images/sec (4K RGB fp32 pipeline)", "value": value, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "images_per_gpu_per_step": batch, "image_shape": [H, W, C],
-                   "sigma": SIGMA, "effective_radius": 11, "l2": "inputs (25.5 GB/GPU per step) far exceed the 126 MB L2",
-                   "batches": "2 resident batches per GPU, alternating; the host enqueues step k+1 while step k runs",
+                   "sigma": SIGMA, "effective_radius": eff_radius,
+                   "l2": "inputs (25.5 GB/GPU per step) far exceed the 126 MB L2",
+                   "inputs": "fixed rng.random noise images, never written; every step reads them and writes fresh "
+                             "output buffers (views), two output sets alternating so the host enqueues step k+1 "
+                             "while step k runs",
                    "parallelism": f"{args.gpus} GPU(s), images sharded, no collective",
                    "launcher": "torchrun ranks" if dist.world > 1 else "one process"},
-        "roofline": roofline,
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(dist.sum(float(e2e["h2d_bytes"]))),
-                "d2h_bytes_per_step": int(dist.sum(float(e2e["d2h_bytes"]))),
-                "images_per_step": int(dist.sum(float(e2e["images"]))),
-                "note": "pinned host -> device -> blur -> pinned host, copies in the timed region"},
+        "roofline": roofline, "e2e": e2e, "parity_check": parity,
         "gpu_launches": int(launches), "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
     }
+    if shrunk:
+        line["config"]["batch_halved_after_oom_at"] = shrunk
     if dist.rank == 0 and not args.no_cpu and args.gpus == 1:
         line["cpu_baseline"] = cpu_baseline(args.cpu_images)
     elif dist.rank == 0:
         line["cpu_baseline"] = None
+
+    # ---- the one-process N-device mode, beside the ranks number --------------------
+    if dist.world > 1 and not args.no_in_process:
+        # every rank lets go of its device memory, then rank 0 runs ONE process that drives all N
+        # devices (the reference's own operating mode, src/gpupipeline.c:266-309) and checks the
+        # multi-device semantics against the oracle
+        L.mpdev_trim_pools()
+        dist.barrier()
+        if dist.rank == 0:
+            env = dict(os.environ)
+            if outer_env is None:
+                env.pop("CUDA_VISIBLE_DEVICES", None)
+            else:
+                env["CUDA_VISIBLE_DEVICES"] = outer_env
+            for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+                env.pop(k, None)
+            cmd = [sys.executable, os.path.abspath(__file__), "--in-process", "--gpus", str(args.gpus),
+                   "--steps", str(min(args.steps, 10)), "--warmup", str(args.warmup), "--batch", str(batch)]
+            try:
+                r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+                rows = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                line["in_process"] = json.loads(rows[-1]) if rows else {"error": (r.stderr or "no output")[-400:]}
+            except Exception as e:   # the ranks number stands on its own
+                line["in_process"] = {"error": repr(e)[:400]}
+            line["multi_device_check"] = "ok" if line["in_process"].get("multi_device_check", {}).get("ok") else "failed"
+        dist.barrier()
     if dist.rank == 0:
         print(json.dumps(line), flush=True)
-    for shards in shard_sets:
-        for imgs in shards:
-            for i in imgs:
-                i.close()
+
+
+def run_in_process(args):
+    """`--in-process --gpus N` (what rank 0 spawns under torchrun, and usable by hand): ONE process
+    with N visible devices runs the headline workload sharded over them by the library's own
+    device table and worker pools, then the multi-device checks."""
+    import numpy as np
+    from millipyde_b200 import capi, engine
+
+    class Solo:
+        rank, world, local = 0, 1, 0
+        def barrier(self): pass
+        def max(self, x): return x
+        def sum(self, x): return x
+    ndev = capi.initialize()
+    if args.gpus > ndev:
+        print(json.dumps({"error": f"{args.gpus} devices asked for, {ndev} visible"}), flush=True)
+        return
+    devices = list(range(args.gpus))
+    rng = np.random.default_rng(2000)
+    seeds = [rng.random((H, W, C), dtype=np.float32) for _ in range(4)]
+    res, dev_ms, wall_ms, launches, clocks = timed_resident(capi, engine, args, Solo(), devices, args.batch, seeds, 0)
+    res.close()
+    capi.lib().mpdev_trim_pools()
+    images = args.batch * len(devices)
+    out = {"launcher": "one process", "n_devices": len(devices), "images_per_step": images,
+           "value": images / (dev_ms / args.steps / 1000.0), "unit": "images/s", "ms_per_step": dev_ms / args.steps,
+           "wall_ms_per_step": wall_ms / args.steps, "steps": args.steps, "gpu_launches": launches,
+           "multi_device_check": multi_device_check(capi, engine, len(devices)) if len(devices) >= 2 else None}
+    print(json.dumps(out), flush=True)
 
 
 def _ncu_traffic(images_per_launch):
@@ -438,9 +661,14 @@ def _ncu_traffic(images_per_launch):
 
 def main():
     args = parse()
+    if args.in_process:
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+            os.environ.pop(k, None)
     dist = Dist()
     try:
-        if args.impl == "reference":
+        if args.in_process:
+            run_in_process(args)
+        elif args.impl == "reference":
             run_reference(args, dist)
         else:
             run_b200(args, dist)

@@ -9,9 +9,11 @@
  * outside millipyde_workers.cpp touches them).
  *
  * B200 differences behind the same calls: every stream (index 0 included) is a
- * non-blocking stream; peer access is enabled once for all ordered pairs at
- * init (NVSwitch: uniform), pool memory is made peer-accessible; no
- * cudaDeviceReset during the P2P probe.
+ * non-blocking stream; a device's context, streams and pool are set up by the
+ * first call that uses it (a one-GPU job on an 8-GPU box owns one context);
+ * peer access and pool access are granted per ordered pair by the first
+ * hand-off that needs them (mpdev_can_use_peer answers "yes" by making it so);
+ * no cudaDeviceReset during the P2P probe.
  */
 #ifndef MP_B200_DEVICES_H
 #define MP_B200_DEVICES_H
@@ -70,6 +72,9 @@ MPStatus mpdev_mem_info(int device_id, size_t *free_bytes, size_t *total_bytes);
 int mpdev_sm_count(int device_id);
 /* write > L2-size bytes so the next timed launch starts cold */
 void mpdev_flush_l2(int device_id, void *stream);
+/* Hand the unused part of every device pool back to the driver (the pools otherwise keep every
+ * freed block: release threshold = never).  For a process that stays alive but is done with the GPU. */
+void mpdev_trim_pools(void);
 /* number of kernels this library launched since load (all threads) */
 unsigned long long mpdev_launch_count(void);
 

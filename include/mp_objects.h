@@ -42,6 +42,13 @@ MPObjData *mpobj_clone_data(MPObjData *obj, int device_id, int stream_id);
  * while it still borrows; mppipe_run_views leaves no borrowed buffer behind. */
 MPObjData *mpobj_view_data(MPObjData *obj);
 
+/* Re-arm a view for another mppipe_run_views / mppipe_submit_views pass over `src`: the buffer the
+ * view owns from its previous pass (if any) goes back to the pool in stream order and the view
+ * borrows src's buffer and header again.  src == NULL only returns the buffer (the view then holds
+ * none and may be destroyed).  Call it on a view that owns its buffer or holds none -- never on one
+ * that still borrows.  A Generator epoch over fixed inputs is: rebind, submit, wait, read, repeat. */
+void mpobj_view_rebind(MPObjData *view, MPObjData *src);
+
 /* ---- new entry points -------------------------------------------------- */
 
 /* D2H straight into caller memory (e.g. a numpy buffer); waits for completion. */

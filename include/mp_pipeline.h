@@ -53,8 +53,10 @@ MPStatus mppipe_run(MPPipeline *p, MPObjData **objs, int n);
  * touched is deep-copied.  On return every view owns its buffer (or holds none, on error). */
 MPStatus mppipe_run_views(MPPipeline *p, MPObjData **views, int n);
 
-/* Asynchronous halves of mppipe_run, for callers that drive several pipelines at once. */
+/* Asynchronous halves of mppipe_run / mppipe_run_views, for callers that drive several pipelines
+ * at once (submit B; wait A; submit A; wait B; ...). */
 MPStatus mppipe_submit(MPPipeline *p, MPObjData **objs, int n);
+MPStatus mppipe_submit_views(MPPipeline *p, MPObjData **views, int n);
 MPStatus mppipe_wait(MPPipeline *p);
 
 /* Layout of one result of mppipe_run_host. */

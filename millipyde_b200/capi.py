@@ -129,6 +129,7 @@ SYMBOLS = {
     "mpobj_dealloc_device_data": (None, [_OBJ]),
     "mpobj_clone_data": (_OBJ, [_OBJ, C.c_int, C.c_int]),
     "mpobj_view_data": (_OBJ, [_OBJ]),
+    "mpobj_view_rebind": (None, [_OBJ, _OBJ]),
     "mpobj_copy_to_host_into": (C.c_int, [_OBJ, C.c_void_p, C.c_size_t]),
     "mpobj_upload_async": (C.c_int, [_OBJ, C.c_void_p, C.c_size_t]),
     "mpobj_download_async": (C.c_int, [_OBJ, C.c_void_p, C.c_size_t]),
@@ -177,6 +178,7 @@ SYMBOLS = {
     "mpdev_mem_info": (C.c_int, [C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "mpdev_sm_count": (C.c_int, [C.c_int]),
     "mpdev_flush_l2": (None, [C.c_int, C.c_void_p]),
+    "mpdev_trim_pools": (None, []),
     "mpdev_launch_count": (C.c_ulonglong, []),
     # mp_pipeline.h
     "mppipe_create": (C.c_void_p, [C.POINTER(MPRunnable), C.c_int, C.c_int]),
@@ -187,6 +189,7 @@ SYMBOLS = {
     "mppipe_run": (C.c_int, [C.c_void_p, C.POINTER(_OBJ), C.c_int]),
     "mppipe_run_views": (C.c_int, [C.c_void_p, C.POINTER(_OBJ), C.c_int]),
     "mppipe_submit": (C.c_int, [C.c_void_p, C.POINTER(_OBJ), C.c_int]),
+    "mppipe_submit_views": (C.c_int, [C.c_void_p, C.POINTER(_OBJ), C.c_int]),
     "mppipe_wait": (C.c_int, [C.c_void_p]),
     "mppipe_run_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t,
                                   C.POINTER(MPHostResult), C.c_int, C.c_int, C.POINTER(C.c_long), C.c_int]),
@@ -333,6 +336,12 @@ class DeviceImage:
         if not p:
             raise MillipydeError(57, "mpobj_view_data")
         return DeviceImage(_ptr=p)
+
+    def rebind(self, src: "DeviceImage | None") -> "DeviceImage":
+        """Re-arm a view (mpobj_view_rebind): its previous result goes back to the pool, it borrows
+        `src` again.  src=None only returns the buffer."""
+        lib().mpobj_view_rebind(self.ptr, src.ptr if src is not None else None)
+        return self
 
     def to_device(self, device: int) -> "DeviceImage":
         lib().mpobj_change_device(self.ptr, device)

@@ -4,8 +4,9 @@
 // Replaces src/millipyde_devices.cpp (device table :13-17, init :49-115,
 // teardown :122-149, selection :227-323, sync :350-398, P2P probe :424-458)
 // and src/millipyde_workers.cpp (FIFO pool).  Re-designed for an 8-GPU NVSwitch
-// box: every stream non-blocking, peer access + pool access enabled once for all
-// ordered pairs, no device resets, allocation through cudaMallocAsync pools.
+// box: every stream non-blocking; contexts, streams and pool set-up per device on
+// first use, peer access + pool access per ordered pair on first hand-off; no
+// device resets; allocation through cudaMallocAsync pools.
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -39,9 +40,20 @@ struct mp_event {
 
 namespace {
 
+// One entry per visible device.  Only what needs no CUDA context is filled in at
+// start-up (SM count, clock, the worker pool); the context, the five streams and
+// the pool configuration are created by the first caller that really uses the
+// device (`ready`), and peer access is granted pair by pair when a hand-off asks
+// for it (`mp::ensure_peer`).  A process that only ever touches one GPU of an
+// 8-GPU box therefore owns one context and no peer mappings -- the reference
+// creates streams on every device and probes every pair (with device resets) at
+// import, src/millipyde_devices.cpp:49-115, :424-458.
 struct Device {
     bool valid = false;
+    std::once_flag ready_once;
+    std::atomic<bool> ready{false};
     cudaStream_t streams[DEVICE_STREAM_COUNT] = {};
+    cudaMemPool_t mempool = nullptr;
     work_pool *pool = nullptr;
     int sm_count = 0;
     double perf_metric = 0;  // clockRate x SM count, millipyde_devices.cpp:515-536
@@ -49,8 +61,12 @@ struct Device {
     size_t flush_bytes = 0;
 };
 
-std::vector<Device> g_devices;
-std::vector<char> g_peer;  // g_peer[a * n + b] = a can reach b
+Device *g_devices = nullptr;   // array of g_count entries (Device holds a once_flag: not movable)
+int g_count = 0;
+// g_peer[a * n + b]: 0 = not asked yet, 1 = a reaches b's memory (peer access + pool access on),
+// 2 = the hardware offers no path
+std::vector<char> g_peer;
+std::mutex g_peer_mux;
 bool g_any_peer = false;
 std::atomic<int> g_target{DEVICE_LOC_NO_AFFINITY};
 int g_recommended = 0;
@@ -60,13 +76,36 @@ std::atomic<bool> g_initialized{false};
 
 thread_local char t_last_error[512] = "";
 
-MPStatus init_streams(int id)
+inline bool in_range(int id) { return id >= 0 && id < g_count; }
+
+// Context + streams + pool set-up of one device, once.  Leaves the caller's current device alone.
+bool make_ready(int id)
 {
+    if (!in_range(id) || !g_devices[id].valid) return false;
     Device &d = g_devices[id];
-    MP_CUDA_TRY(cudaSetDevice(id));
-    for (int s = 0; s < DEVICE_STREAM_COUNT; ++s)
-        MP_CUDA_TRY(cudaStreamCreateWithFlags(&d.streams[s], cudaStreamNonBlocking));
-    return MILLIPYDE_SUCCESS;
+    if (d.ready.load(std::memory_order_acquire)) return true;
+    std::call_once(d.ready_once, [&d, id] {
+        int prev = -1;
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        bool ok = cudaSetDevice(id) == cudaSuccess;
+        for (int s = 0; ok && s < DEVICE_STREAM_COUNT; ++s)
+            ok = cudaStreamCreateWithFlags(&d.streams[s], cudaStreamNonBlocking) == cudaSuccess;
+        // Keep freed blocks in the pool: steady state never returns memory to the
+        // driver, so alloc/free are pure stream-ordered bookkeeping.
+        if (ok && cudaDeviceGetDefaultMemPool(&d.mempool, id) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(d.mempool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            d.mempool = nullptr;
+        }
+        if (!ok) {
+            mp::record_cuda_error(cudaGetLastError(), "device set-up", __FILE__, __LINE__);
+            d.valid = false;
+        }
+        if (prev >= 0 && prev != id) cudaSetDevice(prev);
+        d.ready.store(ok, std::memory_order_release);
+    });
+    return d.ready.load(std::memory_order_acquire);
 }
 
 MPStatus do_initialize()
@@ -76,30 +115,21 @@ MPStatus do_initialize()
         (void)cudaGetLastError();
         return DEV_ERROR_DEVICE_COUNT;
     }
-    g_devices.assign(count, Device());
+    g_devices = new Device[count];
+    g_count = count;
     g_peer.assign((size_t)count * count, 0);
 
     double best = -1;
     for (int i = 0; i < count; ++i) {
         Device &d = g_devices[i];
-        cudaDeviceProp props;
-        if (cudaSetDevice(i) != cudaSuccess || cudaGetDeviceProperties(&props, i) != cudaSuccess) {
+        int khz = 0, sms = 0;   // attribute queries need no context on device i
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, i) != cudaSuccess ||
+            cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, i) != cudaSuccess) {
             (void)cudaGetLastError();
             continue;  // DEV_WARN_BAD_DEVICE: skipped by mpdev_get_next_device
         }
-        int khz = 0;
-        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, i);
-        d.sm_count = props.multiProcessorCount;
-        d.perf_metric = (double)khz * props.multiProcessorCount;
-        if (init_streams(i) != MILLIPYDE_SUCCESS) continue;
-
-        // Keep freed blocks in the pool: steady state never returns memory to the
-        // driver, so alloc/free are pure stream-ordered bookkeeping.
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, i) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
+        d.sm_count = sms;
+        d.perf_metric = (double)khz * sms;
         d.valid = true;
         if (d.perf_metric > best) {
             best = d.perf_metric;
@@ -108,50 +138,34 @@ MPStatus do_initialize()
     }
     if (best < 0) return DEV_ERROR_DEVICE_COUNT;
 
-    // Peer access for every ordered pair (uniform over NVSwitch).
-    for (int a = 0; a < count; ++a) {
-        if (!g_devices[a].valid) continue;
-        cudaSetDevice(a);
-        cudaMemPool_t pool_a = nullptr;
-        cudaDeviceGetDefaultMemPool(&pool_a, a);
-        for (int b = 0; b < count; ++b) {
-            if (a == b || !g_devices[b].valid) continue;
+    // is there any peer path at all?  (a capability query: enables nothing, creates no context)
+    for (int a = 0; a < count && !g_any_peer; ++a)
+        for (int b = 0; b < count && !g_any_peer; ++b) {
             int ok = 0;
-            if (cudaDeviceCanAccessPeer(&ok, a, b) != cudaSuccess || !ok) {
-                (void)cudaGetLastError();
-                continue;
-            }
-            cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
-            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
-                (void)cudaGetLastError();
-                continue;
-            }
-            (void)cudaGetLastError();
-            g_peer[(size_t)a * count + b] = 1;
-            g_any_peer = true;
-            // let device a's kernels and copies touch pool memory that lives on b
-            cudaMemPool_t pool_b = nullptr;
-            if (cudaDeviceGetDefaultMemPool(&pool_b, b) == cudaSuccess) {
-                cudaMemAccessDesc desc = {};
-                desc.location.type = cudaMemLocationTypeDevice;
-                desc.location.id = a;
-                desc.flags = cudaMemAccessFlagsProtReadWrite;
-                if (cudaMemPoolSetAccess(pool_b, &desc, 1) != cudaSuccess) (void)cudaGetLastError();
-            }
+            if (a != b && g_devices[a].valid && g_devices[b].valid &&
+                cudaDeviceCanAccessPeer(&ok, a, b) == cudaSuccess && ok)
+                g_any_peer = true;
         }
-    }
+    (void)cudaGetLastError();
 
     for (int i = 0; i < count; ++i) {
         if (!g_devices[i].valid) continue;
         MPStatus st = mpwrk_create_work_pool(&g_devices[i].pool, THREADS_PER_DEVICE);
         if (st != MILLIPYDE_SUCCESS) return st;
     }
-    cudaSetDevice(g_recommended);
     g_initialized.store(true);
+    // the recommended device is the one eager ops land on: have it ready (and current) now
+    if (!make_ready(g_recommended)) return DEV_ERROR_DEVICE_COUNT;
+    cudaSetDevice(g_recommended);
+
+    // MILLIPYDE_EAGER_PEER=1 (diagnostics): the round-1 behaviour, every ordered pair up front
+    const char *eager = getenv("MILLIPYDE_EAGER_PEER");
+    if (eager && *eager && *eager != '0')
+        for (int a = 0; a < count; ++a)
+            for (int b = 0; b < count; ++b)
+                if (a != b) mp::ensure_peer(a, b);
     return MILLIPYDE_SUCCESS;
 }
-
-inline bool in_range(int id) { return id >= 0 && id < (int)g_devices.size(); }
 
 }  // namespace
 
@@ -173,9 +187,44 @@ MPStatus ensure_initialized()
     return g_init_status;
 }
 
+bool device_ready(int device_id) { return make_ready(device_id); }
+
+// Let device `a` (its kernels and copy engines) reach memory that lives on `b`: peer access a -> b
+// and read/write access for `a` on b's pool.  Granted on first request, remembered per ordered pair.
+bool ensure_peer(int a, int b)
+{
+    if (!in_range(a) || !in_range(b)) return false;
+    if (a == b) return true;
+    std::lock_guard<std::mutex> lk(g_peer_mux);
+    char &state = g_peer[(size_t)a * g_count + b];
+    if (state) return state == 1;
+    state = 2;
+    int ok = 0;
+    if (cudaDeviceCanAccessPeer(&ok, a, b) != cudaSuccess || !ok) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    if (!make_ready(a) || !make_ready(b)) return false;
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    cudaSetDevice(a);
+    cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+    (void)cudaGetLastError();
+    if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaMemAccessDesc desc = {};
+        desc.location.type = cudaMemLocationTypeDevice;
+        desc.location.id = a;
+        desc.flags = cudaMemAccessFlagsProtReadWrite;
+        if (g_devices[b].mempool && cudaMemPoolSetAccess(g_devices[b].mempool, &desc, 1) == cudaSuccess) state = 1;
+        else (void)cudaGetLastError();
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    return state == 1;
+}
+
 cudaStream_t device_stream(int device_id, int index)
 {
-    if (!in_range(device_id) || index < 0 || index >= DEVICE_STREAM_COUNT) return nullptr;
+    if (index < 0 || index >= DEVICE_STREAM_COUNT || !make_ready(device_id)) return nullptr;
     return g_devices[device_id].streams[index];
 }
 
@@ -185,31 +234,46 @@ cudaStream_t stream_of(const MPObjData *obj)
     return device_stream(obj->mem_loc, 0);
 }
 
-void *pool_alloc(int device_id, cudaStream_t stream, size_t nbytes)
+// Stream-ordered block from `pool_device`'s pool.  On out-of-memory the pool's cached blocks may
+// be what is in the way (the release threshold is "never"): drain the device, hand the unused part
+// of the pool back to the driver and try once more before reporting the failure.
+static void *alloc_from(int pool_device, cudaStream_t stream, size_t nbytes, const char *what, int line)
 {
     void *p = nullptr;
     if (nbytes == 0) nbytes = 16;
-    cudaError_t e = cudaMallocAsync(&p, nbytes, stream);
-    if (e != cudaSuccess) {
-        record_cuda_error(e, "cudaMallocAsync", __FILE__, __LINE__);
+    if (!make_ready(pool_device) || !g_devices[pool_device].mempool) {
+        record_cuda_error(cudaErrorInvalidDevice, what, __FILE__, line);
         return nullptr;
     }
-    (void)device_id;
+    cudaMemPool_t pool = g_devices[pool_device].mempool;
+    cudaError_t e = cudaMallocFromPoolAsync(&p, nbytes, pool, stream);
+    if (e == cudaErrorMemoryAllocation) {
+        (void)cudaGetLastError();
+        int prev = -1;
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        cudaSetDevice(pool_device);
+        cudaDeviceSynchronize();
+        cudaMemPoolTrimTo(pool, 0);
+        if (prev >= 0 && prev != pool_device) cudaSetDevice(prev);
+        (void)cudaGetLastError();
+        e = cudaMallocFromPoolAsync(&p, nbytes, pool, stream);
+    }
+    if (e != cudaSuccess) {
+        record_cuda_error(e, what, __FILE__, line);
+        return nullptr;
+    }
     return p;
 }
 
+void *pool_alloc(int device_id, cudaStream_t stream, size_t nbytes)
+{
+    return alloc_from(device_id, stream, nbytes, "cudaMallocFromPoolAsync", __LINE__);
+}
+
+// `stream` may belong to ANOTHER device: access to the pool is granted to it here if it was not yet.
 void *pool_alloc_on(int pool_device, cudaStream_t stream, size_t nbytes)
 {
-    void *p = nullptr;
-    if (nbytes == 0) nbytes = 16;
-    cudaMemPool_t pool;
-    cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, pool_device);
-    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&p, nbytes, pool, stream);
-    if (e != cudaSuccess) {
-        record_cuda_error(e, "cudaMallocFromPoolAsync", __FILE__, __LINE__);
-        return nullptr;
-    }
-    return p;
+    return alloc_from(pool_device, stream, nbytes, "cudaMallocFromPoolAsync(peer)", __LINE__);
 }
 
 void pool_free(int device_id, cudaStream_t stream, void *ptr)
@@ -235,7 +299,7 @@ MPStatus mpdev_initialize(void) { return mp::ensure_initialized(); }
 void mpdev_teardown(void)
 {
     if (!g_initialized.exchange(false)) return;
-    for (size_t i = 0; i < g_devices.size(); ++i) {
+    for (int i = 0; i < g_count; ++i) {
         Device &d = g_devices[i];
         if (!d.valid) continue;
         if (d.pool) {
@@ -244,7 +308,7 @@ void mpdev_teardown(void)
         }
         // Unlike millipyde_devices.cpp:139 no cudaDeviceReset: the context may be
         // shared with other libraries in the process.  Streams and pools die with it.
-        if (cudaSetDevice((int)i) == cudaSuccess) cudaDeviceSynchronize();
+        if (d.ready.load() && cudaSetDevice(i) == cudaSuccess) cudaDeviceSynchronize();
         d.valid = false;
     }
 }
@@ -253,14 +317,17 @@ void mpdev_teardown(void)
 // millipyde_devices.cpp:156-159); this one answers the question asked.
 MPBool mpdev_peer_to_peer_supported(void) { return g_any_peer ? MP_TRUE : MP_FALSE; }
 
+// "Can `device` work on memory that lives on `peer`?"  Answering yes makes it so: the pair's peer
+// access and pool access are granted here, on first request (millipyde_devices.cpp:161-167 reads a
+// matrix filled at import).
 MPBool mpdev_can_use_peer(int device, int peer)
 {
     if (!in_range(device) || !in_range(peer)) return MP_FALSE;
-    if (device == peer) return MP_TRUE;
-    return g_peer[(size_t)device * g_devices.size() + peer] ? MP_TRUE : MP_FALSE;
+    if (!g_devices[device].valid || !g_devices[peer].valid) return MP_FALSE;
+    return mp::ensure_peer(device, peer) ? MP_TRUE : MP_FALSE;
 }
 
-int mpdev_get_device_count(void) { return (int)g_devices.size(); }
+int mpdev_get_device_count(void) { return g_count; }
 
 MPBool mpdev_is_valid_device(int id) { return in_range(id) && g_devices[id].valid ? MP_TRUE : MP_FALSE; }
 
@@ -276,6 +343,7 @@ void mpdev_hard_synchronize(int device_id)
 {
     if (!mpdev_is_valid_device(device_id)) return;
     mpwrk_work_wait(g_devices[device_id].pool);
+    if (!g_devices[device_id].ready.load()) return;  // never used: no context to drain (or to create)
     MP_CUDA_WARN(cudaSetDevice(device_id));
     MP_CUDA_WARN(cudaDeviceSynchronize());
 }
@@ -283,21 +351,24 @@ void mpdev_hard_synchronize(int device_id)
 void mpdev_hard_synchronize_all(void)
 {
     // drain every pool first so hand-offs between devices have all been enqueued
-    for (size_t i = 0; i < g_devices.size(); ++i)
+    for (int i = 0; i < g_count; ++i)
         if (g_devices[i].valid) mpwrk_work_wait(g_devices[i].pool);
-    for (size_t i = 0; i < g_devices.size(); ++i)
-        if (g_devices[i].valid) mpdev_hard_synchronize((int)i);
+    for (int i = 0; i < g_count; ++i)
+        if (g_devices[i].valid) mpdev_hard_synchronize(i);
 }
 
 void mpdev_synchronize(void) { MP_CUDA_WARN(cudaDeviceSynchronize()); }
 
 void mpdev_synchronize_all(void)
 {
-    for (size_t i = 0; i < g_devices.size(); ++i) {
-        if (!g_devices[i].valid) continue;
-        MP_CUDA_WARN(cudaSetDevice((int)i));
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    for (int i = 0; i < g_count; ++i) {
+        if (!g_devices[i].valid || !g_devices[i].ready.load()) continue;
+        MP_CUDA_WARN(cudaSetDevice(i));
         MP_CUDA_WARN(cudaDeviceSynchronize());
     }
+    if (prev >= 0) cudaSetDevice(prev);
 }
 
 // Device.__exit__ calls this after an exception (src/device.c:60-65).  The
@@ -305,7 +376,7 @@ void mpdev_synchronize_all(void)
 // the device is drained, the error state cleared and the streams re-created.
 void mpdev_reset(int device_id)
 {
-    if (!mpdev_is_valid_device(device_id)) return;
+    if (!mpdev_is_valid_device(device_id) || !g_devices[device_id].ready.load()) return;
     MP_CUDA_WARN(cudaSetDevice(device_id));
     cudaDeviceSynchronize();
     (void)cudaGetLastError();
@@ -333,7 +404,7 @@ int mpdev_get_alternative_device(int device_id)
 {
     int alt = DEVICE_LOC_NO_AFFINITY;
     double best = 0;
-    for (int i = 0; i < (int)g_devices.size(); ++i) {
+    for (int i = 0; i < g_count; ++i) {
         if (i == device_id || !g_devices[i].valid) continue;
         if (g_devices[i].perf_metric > best) {
             best = g_devices[i].perf_metric;
@@ -345,7 +416,7 @@ int mpdev_get_alternative_device(int device_id)
 
 int mpdev_get_next_device(int device_id)
 {
-    int n = (int)g_devices.size();
+    int n = g_count;
     for (int i = 0; i < n; ++i) {
         int id = (i + 1 + device_id) % n;
         if (g_devices[id].valid) return id;
@@ -506,6 +577,21 @@ void mpdev_flush_l2(int device_id, void *stream)
         }
     }
     MP_CUDA_WARN(cudaMemsetAsync(d.flush_buf, 0, d.flush_bytes, (cudaStream_t)stream));
+}
+
+void mpdev_trim_pools(void)
+{
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    for (int i = 0; i < g_count; ++i) {
+        Device &d = g_devices[i];
+        if (!d.valid || !d.ready.load() || !d.mempool) continue;
+        if (cudaSetDevice(i) != cudaSuccess) continue;
+        cudaDeviceSynchronize();
+        MP_CUDA_WARN(cudaMemPoolTrimTo(d.mempool, 0));
+    }
+    (void)cudaGetLastError();
+    if (prev >= 0) cudaSetDevice(prev);
 }
 
 unsigned long long mpdev_launch_count(void) { return mp::g_launch_count.load(); }

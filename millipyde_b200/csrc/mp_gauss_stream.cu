@@ -56,8 +56,9 @@ static MPStatus launch_cr(int device, cudaStream_t s, GaussStreamParams &p, cons
     constexpr bool kHasMma = MmGeom<C, R>::NCH <= 4;
     const bool mma = kHasMma && use_mma_column();
     const size_t smem = mma ? MmGeom<C, R>::SMEM : WsGeom<C, R>::SMEM;
-    static bool configured[64] = {};  // per device
-    if (device >= 0 && device < 64 && !configured[device]) {
+    // per device and per instantiation; two workers racing here both set the same attributes
+    static std::atomic<bool> configured[64] = {};
+    if (device >= 0 && device < 64 && !configured[device].load(std::memory_order_acquire)) {
         MP_CUDA_TRY(cudaFuncSetAttribute(gauss_stream_ws_kernel<C, R>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsGeom<C, R>::SMEM));
         MP_CUDA_TRY(cudaFuncSetAttribute(gauss_stream_ws_sets_kernel<C, R>,
@@ -68,7 +69,7 @@ static MPStatus launch_cr(int device, cudaStream_t s, GaussStreamParams &p, cons
             MP_CUDA_TRY(cudaFuncSetAttribute(gauss_stream_mma_sets_kernel<C, R>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmGeom<C, R>::SMEM));
         }
-        configured[device] = true;
+        configured[device].store(true, std::memory_order_release);
     }
     // One persistent CTA per SM.  An item is (image, strip, row chunk); the number of row chunks is
     // the one that wastes least: more chunks fill the last wave of CTAs better, but every chunk

@@ -18,15 +18,22 @@ void record_cuda_error(cudaError_t err, const char *expr, const char *file, int 
 // Lazily runs mpdev_initialize() once; returns its status.
 MPStatus ensure_initialized();
 
+// Streams of a device; the first call for a device creates its context, its five streams and
+// configures its pool (devices nobody uses cost nothing).  nullptr for an invalid device.
 cudaStream_t device_stream(int device_id, int index);
+bool device_ready(int device_id);
+
+// Grant device `a` access to memory living on `b` (peer access a -> b plus read/write access on b's
+// pool), on first request per ordered pair.  false: no hardware path.
+bool ensure_peer(int a, int b);
 
 // Per-device stream-ordered pool (cudaMallocAsync on the device's default pool
 // with the release threshold lifted, so steady state never calls the OS).
 void *pool_alloc(int device_id, cudaStream_t stream, size_t nbytes);
 void pool_free(int device_id, cudaStream_t stream, void *ptr);
 // Block from `pool_device`'s pool, allocated in the order of `stream`, which may belong to ANOTHER
-// device that has access to the pool (every pool grants its peers access at start-up): a producer
-// kernel can then write its result straight into the consumer device's memory over NVLink.
+// device that has been granted access to the pool (mp::ensure_peer(stream's device, pool_device)):
+// a producer kernel can then write its result straight into the consumer device's memory over NVLink.
 void *pool_alloc_on(int pool_device, cudaStream_t stream, size_t nbytes);
 
 // The stream an op should use for `obj`: obj->stream, or the device's stream 0

@@ -147,7 +147,9 @@ void mpobj_change_device(MPObjData *obj, int new_dev)
     int old_dev = obj->mem_loc;
     if (old_dev == new_dev || obj->device_data == NULL) return;
     if (!mpdev_is_valid_device(new_dev)) return;
-    if (!mpdev_can_use_peer(old_dev, new_dev) && !mpdev_can_use_peer(new_dev, old_dev)) {
+    // the copy runs on the source device's stream and writes the destination device's pool memory
+    const bool fwd = mpdev_can_use_peer(old_dev, new_dev), back = mpdev_can_use_peer(new_dev, old_dev);
+    if (!fwd && !back) {
         // cudaMemcpyPeerAsync still works (staged through the host) -- slower, not fatal.
         static bool warned = false;
         if (!warned) {
@@ -214,9 +216,12 @@ MPObjData *mpobj_clone_data(MPObjData *obj, int device_id, int stream_id)
             if (obj->mem_loc == device_id)
                 MP_CUDA_WARN(cudaMemcpyAsync(c->device_data, obj->device_data, c->nbytes,
                                              cudaMemcpyDeviceToDevice, cs));
-            else
+            else {
+                // runs on the clone's stream (device_id) and reads the source device's pool memory
+                (void)mpdev_can_use_peer(device_id, obj->mem_loc);
                 MP_CUDA_WARN(cudaMemcpyPeerAsync(c->device_data, device_id, obj->device_data,
                                                  obj->mem_loc, c->nbytes, cs));
+            }
             // the source may not be freed/overwritten before the copy has read it
             chain_streams(device_id, cs, src_stream);
         }
@@ -235,6 +240,18 @@ MPObjData *mpobj_view_data(MPObjData *obj)
     c->dims = (int *)calloc(2 * (size_t)slots, sizeof(int));
     memcpy(c->dims, obj->dims, sizeof(int) * 2 * (size_t)obj->ndims);
     return c;  // device_data and stream are obj's: the view is ordered after obj's pending work
+}
+
+void mpobj_view_rebind(MPObjData *view, MPObjData *src)
+{
+    if (!view) return;
+    mpobj_dealloc_device_data(view);   // stream-ordered: whatever still reads the old result finishes first
+    if (!src || !src->device_data) return;
+    int *dims = view->dims;            // room for three dimensions (mpobj_view_data)
+    *view = *src;
+    view->dims = dims;
+    view->pinned = MP_FALSE;
+    if (src->ndims <= 3) memcpy(dims, src->dims, sizeof(int) * 2 * (size_t)src->ndims);
 }
 
 MPObjData *mpobj_create(const void *host, int ndims, const long *shape, int typenum)

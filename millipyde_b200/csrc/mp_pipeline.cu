@@ -956,14 +956,20 @@ static MPStatus submit_impl(MPPipeline *p, MPObjData **objs, int n, bool views);
 
 MPStatus mppipe_submit(MPPipeline *p, MPObjData **objs, int n) { return submit_impl(p, objs, n, false); }
 
-MPStatus mppipe_run_views(MPPipeline *p, MPObjData **views, int n)
+MPStatus mppipe_submit_views(MPPipeline *p, MPObjData **views, int n)
 {
     MPStatus st = submit_impl(p, views, n, true);
     if (st != MILLIPYDE_SUCCESS) {  // nothing ran: the views must not keep (and later free) what they borrow
         for (int i = 0; views && i < n; ++i)
             if (views[i]) views[i]->device_data = NULL;
-        return st;
     }
+    return st;
+}
+
+MPStatus mppipe_run_views(MPPipeline *p, MPObjData **views, int n)
+{
+    MPStatus st = mppipe_submit_views(p, views, n);
+    if (st != MILLIPYDE_SUCCESS) return st;
     return mppipe_wait(p);
 }
 

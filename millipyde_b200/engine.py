@@ -62,6 +62,10 @@ class Chain:
         self._pending = self._objs(images)
         capi.check(capi.lib().mppipe_submit(self.ptr, self._pending, len(images)), "mppipe_submit")
 
+    def submit_views(self, views) -> None:
+        self._pending = self._objs(views)
+        capi.check(capi.lib().mppipe_submit_views(self.ptr, self._pending, len(views)), "mppipe_submit_views")
+
     def wait(self) -> None:
         capi.check(capi.lib().mppipe_wait(self.ptr), "mppipe_wait")
 
@@ -124,72 +128,3 @@ def pinned_free(arr: np.ndarray) -> None:
     p = _PINNED.pop(arr.ctypes.data, None)
     if p:
         capi.lib().mphost_free_pinned(p)
-
-
-# ---------------------------------------------------------------------------- bench helpers
-def timing_stream(device: int):
-    """The stream Pipeline shards launch on (stream 1 of the device)."""
-    return capi.lib().mpdev_get_stream(device, 1)
-
-
-def run_batches(chain_ops_or_chain, shards, devices):
-    """One Pipeline.run() per device shard, all devices concurrently."""
-    chains = _chains_for(chain_ops_or_chain, devices)
-    for ch, imgs in zip(chains, shards):
-        ch.submit(imgs)
-    for ch in chains:
-        ch.wait()
-
-
-_CHAIN_CACHE = {}
-
-
-def _chains_for(chain, devices):
-    key = (id(chain), tuple(devices))
-    if key not in _CHAIN_CACHE:
-        if isinstance(chain, Chain) and len(devices) == 1:
-            capi.lib().mppipe_set_device(chain.ptr, devices[0])
-            _CHAIN_CACHE[key] = [chain]
-        else:
-            ops = chain._ops if isinstance(chain, Chain) else chain
-            _CHAIN_CACHE[key] = [Chain(ops, device=d) for d in devices]
-    return _CHAIN_CACHE[key]
-
-
-def e2e_gaussian(devices, n_images, shape, sigma, steps=2):
-    """Host buffers in, host buffers out: n_images pinned arrays are streamed
-    through upload -> gaussian -> download on every device; returns images/s of
-    the best step (wall clock around the public call, which returns when the
-    results are in host memory)."""
-    import time
-    h, w, c = shape
-    rng = np.random.default_rng(4000)
-    per_dev = max(1, n_images // len(devices))
-    chains, ins, outs = [], [], []
-    for d in devices:
-        chains.append(Chain([("gaussian", sigma)], device=d))
-        a = [pinned_empty(shape, np.float32) for _ in range(per_dev)]
-        seed = rng.random(shape, dtype=np.float32)
-        for x in a:
-            x[...] = seed
-        ins.append(a)
-        outs.append([pinned_empty(shape, np.float32) for _ in range(per_dev)])
-    import threading
-    best = None
-    for _ in range(steps + 1):
-        t0 = time.perf_counter()
-        ths = [threading.Thread(target=ch.run_host, args=(i, o)) for ch, i, o in zip(chains, ins, outs)]
-        for t in ths:
-            t.start()
-        for t in ths:
-            t.join()
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    total = per_dev * len(devices)
-    nbytes = h * w * c * 4 * total
-    for group in ins + outs:
-        for a in group:
-            pinned_free(a)
-    for ch in chains:
-        ch.close()
-    return {"images_per_s": total / best, "h2d_bytes": nbytes, "d2h_bytes": nbytes, "images": total}

@@ -335,3 +335,49 @@ def test_full_size_properties_4k(mp):
     # and a strip of it against the oracle (rows 0..95: full width, all strips, top border)
     want = so.gaussian(a[:128], 2.0)[:96]
     assert np.abs(ga[:96] - want).max() <= TOL32
+
+
+def test_full_frame_4k_single_image_against_oracle(mp):
+    """BASELINE config 2's shape, one image: the eager call splits it into ~8 row chunks
+    (mp_gauss_stream.cu launch_cr).  The WHOLE frame is compared with scipy -- every chunk boundary,
+    every strip, all four borders."""
+    a = synth.noise_f32(2160, 3840, 3, 2001)
+    got = mp.capi.DeviceImage(a).apply("gaussian", 2.0).numpy()
+    want = so.gaussian(a, 2.0)
+    assert np.abs(got - want).max() <= TOL32
+    assert np.abs(got[-16:] - want[-16:]).max() <= TOL32      # bottom border on its own
+
+
+def test_full_frame_4k_batch_of_64_against_oracle(mp):
+    """The benchmarked launch shape: >= 64 4K images in ONE launch through pointer tables (chunks = 1,
+    1,152 items over 148 persistent CTAs), sources untouched (views).  First, middle and last image
+    of the launch are compared with scipy over the whole frame, the rest with the image of the same
+    seed (bit-identical: same kernel, same data)."""
+    seeds = [synth.noise_f32(2160, 3840, 3, 2100 + k) for k in range(3)]
+    base = [mp.capi.DeviceImage(s) for s in seeds]
+    src = [base[k % 3].clone() for k in range(64)]
+    views = [d.view() for d in src]
+    ch = mp.engine.Chain([("gaussian", 2.0)], device=0)
+    ch.run_views(views)
+    assert ch.last_launches == 1
+    wants = [so.gaussian(s, 2.0) for s in seeds]
+    outs = {}
+    for k in (0, 31, 63):
+        outs[k] = views[k].numpy()
+        assert np.abs(outs[k] - wants[k % 3]).max() <= TOL32, k
+        assert np.abs(outs[k][-16:] - wants[k % 3][-16:]).max() <= TOL32, k
+    for k in range(1, 64, 7):
+        ref = {0: 0, 1: 31, 2: 63}[k % 3]
+        assert np.array_equal(views[k].numpy(), outs[ref]), k
+    # the sources were read, not written
+    assert np.array_equal(src[5].numpy(), seeds[5 % 3])
+    # a second pass over the same sources through re-armed views gives the same bits
+    for v, d in zip(views, src):
+        v.rebind(d)
+    ch.run_views(views)
+    assert np.array_equal(views[31].numpy(), outs[31])
+    for v in views:
+        v.rebind(None)
+        v.close()
+    for d in src + base:
+        d.close()
