@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--e2e-images", type=int, default=16, help="images per GPU per e2e step (the same at every N)")
     ap.add_argument("--in-process", action="store_true",
                     help="one process drives --gpus N devices: headline workload + multi-device checks, one JSON line")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (0 = min(steps, 5), at least 3)")
     ap.add_argument("--no-in-process", action="store_true", help="under torchrun: skip rank 0's one-process leg")
     ap.add_argument("--cpu-images", type=int, default=0, help="images in the CPU sample (0 = one per core)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -281,9 +282,14 @@ class Resident:
                 b.close()
         L.mpdev_set_target_device(capi.DEVICE_LOC_NO_AFFINITY)
         L.mpdev_synchronize_all()
+        import ctypes as C
+        ptr_array = lambda imgs: (C.POINTER(capi.MPObjData) * len(imgs))(*[im.ptr for im in imgs])
+        self.in_arr = [ptr_array(imgs) for imgs in self.inputs]
+        self.view_arr = [[], []]
         for s in range(2):
             for di, d in enumerate(devices):
                 self.views[s].append([im.view() for im in self.inputs[di]])
+                self.view_arr[s].append(ptr_array(self.views[s][di]))
                 self.pipes[s].append(engine.Chain([("gaussian", SIGMA)], device=d))
         self.ran = [False, False]        # the set's views own results (must be re-armed before reuse)
         self.in_flight = [False, False]
@@ -296,18 +302,18 @@ class Resident:
             self.in_flight[s] = False
 
     def run_steps(self, n):
-        """n steps, step k on view set k % 2; the host prepares step k+1 (re-arming 256 views, pool
-        allocations, pointer tables, the launch) while the device runs step k.  Returns when the
-        last step's work is complete."""
+        """n steps, step k on view set k % 2; the host prepares step k+1 (re-arming 256 views per
+        device, pool allocations, pointer tables, the launch) while the device runs step k.  Returns
+        when the last step's work is complete."""
+        L = self.capi.lib()
         for k in range(n):
             s = k % 2
-            self._wait(s)               # the set's previous pass is complete
-            if self.ran[s]:
-                for di in range(len(self.devices)):
-                    for v, src in zip(self.views[s][di], self.inputs[di]):
-                        v.rebind(src)   # previous result back to the pool, borrow the noise input again
-            for ch, vs in zip(self.pipes[s], self.views[s]):
-                ch.submit_views(vs)
+            for di, ch in enumerate(self.pipes[s]):
+                if self.in_flight[s]:
+                    ch.wait()           # the set's previous pass on this device is complete
+                if self.ran[s]:         # previous results back to the pool, borrow the noise inputs again
+                    L.mpobj_view_rebind_many(self.view_arr[s][di], self.in_arr[di], self.batch)
+                self.capi.check(L.mppipe_submit_views(ch.ptr, self.view_arr[s][di], self.batch), "mppipe_submit_views")
             self.in_flight[s] = True
             self.ran[s] = True
             self.last_set = s
@@ -396,7 +402,7 @@ def e2e_leg(capi, engine, devices, per_dev, steps, dist):
     mean_t = sum(times) / len(times)
     return {"value": images / mean_t, "unit": "images/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
             "images_per_step": int(images), "images_per_gpu_per_step": per_dev, "steps": steps,
-            "step_s": {"mean": mean_t, "min": min(times), "max": max(times)},
+            "step_s": {"mean": mean_t, "min": min(times), "max": max(times), "all": [round(t, 5) for t in times]},
             "host_result_max_abs_err": err,
             "note": "pinned host -> device -> blur -> pinned host, copies in the timed region; mean of steps, "
                     "slowest rank per step, one untimed pass first"}
@@ -564,7 +570,7 @@ def run_b200(args, dist):
     if args.no_e2e:
         e2e = {"value": 0.0, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     else:
-        e2e = e2e_leg(capi, engine, devices, args.e2e_images, max(3, min(args.steps, 5)), dist)
+        e2e = e2e_leg(capi, engine, devices, args.e2e_images, args.e2e_steps or max(3, min(args.steps, 5)), dist)
 
     line = {
         "metric": "augmented images/sec (4K RGB fp32 pipeline)", "value": value, "unit": "images/s",

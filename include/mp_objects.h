@@ -48,6 +48,8 @@ MPObjData *mpobj_view_data(MPObjData *obj);
  * none and may be destroyed).  Call it on a view that owns its buffer or holds none -- never on one
  * that still borrows.  A Generator epoch over fixed inputs is: rebind, submit, wait, read, repeat. */
 void mpobj_view_rebind(MPObjData *view, MPObjData *src);
+/* The same for n views at once (srcs == NULL: only return the buffers). */
+void mpobj_view_rebind_many(MPObjData **views, MPObjData **srcs, int n);
 
 /* ---- new entry points -------------------------------------------------- */
 

@@ -88,6 +88,8 @@ int mppipe_get_fusion(void);
  *   pw(op,...)            fused fp32 pointwise program      u8(op,...)   composed RGBA8 byte tables
  *   grey(pre|post)        rgb2grey with the pointwise ops it absorbed
  *   gather(flip,rotate,flip;pre|post)   fliplr / rotate / pointwise ops in one gather pass
+ *   gauss(pre|post)       a Gaussian with the pointwise ops before and after it applied inside the
+ *                         stencil kernel (on the landed rows / on the finished rows)
  *   op                    an operator run on its own (transpose, gaussian, foreign, ...)
  * Returns the number of segments, or -1 (bad arguments / buffer too small). */
 int mppipe_plan(const MPPipeline *p, int typenum, int channels, char *buf, int cap);

@@ -130,6 +130,7 @@ SYMBOLS = {
     "mpobj_clone_data": (_OBJ, [_OBJ, C.c_int, C.c_int]),
     "mpobj_view_data": (_OBJ, [_OBJ]),
     "mpobj_view_rebind": (None, [_OBJ, _OBJ]),
+    "mpobj_view_rebind_many": (None, [C.POINTER(_OBJ), C.POINTER(_OBJ), C.c_int]),
     "mpobj_copy_to_host_into": (C.c_int, [_OBJ, C.c_void_p, C.c_size_t]),
     "mpobj_upload_async": (C.c_int, [_OBJ, C.c_void_p, C.c_size_t]),
     "mpobj_download_async": (C.c_int, [_OBJ, C.c_void_p, C.c_size_t]),

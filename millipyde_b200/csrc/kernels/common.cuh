@@ -107,6 +107,23 @@ __device__ __forceinline__ void pw_apply_tile(const PwProgram &prog, float (&r)[
     }
 }
 
+// pw_apply_tile for a program that lives in device memory (per-image records of a batched launch):
+// every op is fetched through the read-only path, the same words for all lanes.
+template <int C, int N>
+__device__ __forceinline__ void pw_apply_tile_g(const PwProgram *__restrict__ prog, float (&r)[N], int ch0)
+{
+    const int n = __ldg(&prog->n);
+    for (int i = 0; i < n; ++i) {
+        PwProgram one;   // (ops sit at offset 4 + 16 i: scalar loads)
+        one.n = 1;
+        one.ops[0].kind = __ldg(&prog->ops[i].kind);
+        one.ops[0].a = __ldg(&prog->ops[i].a);
+        one.ops[0].b = __ldg(&prog->ops[i].b);
+        one.ops[0].c = __ldg(&prog->ops[i].c);
+        pw_apply_tile<C, N>(one, r, ch0);
+    }
+}
+
 // Luma of skimage.color.rgb2gray / src/millipyde_image.cpp:64, fp32 flavour.
 __device__ __forceinline__ float luma_f32(float r, float g, float b)
 {

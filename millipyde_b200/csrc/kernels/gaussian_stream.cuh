@@ -32,6 +32,12 @@ struct GaussStreamParams {
     int chunk_rows;              // rows per work item
     int n_chunks;
     int radius;                  // actual radius (<= R); w[d] = 0 beyond it
+    // Pointwise programs fused around the blur (device memory, null = none): image i applies
+    // pw_tab[2 i] to every input sample before the horizontal filter and pw_tab[2 i + 1] to every
+    // output sample (pw_stride = 2), or all images share pw_tab[0], pw_tab[1] (pw_stride = 0).
+    // Only the *_sets kernels look at it.
+    const PwProgram *pw_tab;
+    int pw_stride;
     float w[16];
     unsigned long long ww[16];   // (w[d], w[d]) packed for fma.rn.f32x2
 };

@@ -207,6 +207,11 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc[q][j][e] = 0.f;
 
+        const PwProgram *post = nullptr;   // this image's "after the blur" program (null or empty: none)
+        if (SETS && p.pw_tab) {
+            post = p.pw_tab + (size_t)img * p.pw_stride + 1;
+            if (__ldg(&post->n) == 0) post = nullptr;
+        }
         const uint32_t item_g0 = waited;   // == released: items are whole turns of the ring
         int ring_row = 0;                  // (c % 6) * 8
         // Output.  The block that completes with chunk c is rows ob .. ob+7, ob = 8 (c - NCH + 1).  Its
@@ -292,6 +297,16 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
                 for (int u = 0; u < kPair; ++u) {
                     const int q = q0 + u;
                     if (q >= kMmTiles) continue;
+                    if (SETS && post) {
+                        // (c0, c2) and (c1, c3) are the column pair (2g, 2g + 1) of tile q in two rows
+                        float r2[2] = {nxt[u][NCH - 1][0], nxt[u][NCH - 1][2]};
+                        float r3[2] = {nxt[u][NCH - 1][1], nxt[u][NCH - 1][3]};
+                        const int ch0 = (gx0 + 16 * q + 2 * g) % C;
+                        pw_apply_tile_g<C, 2>(post, r2, ch0);
+                        pw_apply_tile_g<C, 2>(post, r3, ch0);
+                        nxt[u][NCH - 1][0] = r2[0]; nxt[u][NCH - 1][2] = r2[1];
+                        nxt[u][NCH - 1][1] = r3[0]; nxt[u][NCH - 1][3] = r3[1];
+                    }
                     sts_f2(my_stage + 16 * q, nxt[u][NCH - 1][0], nxt[u][NCH - 1][2]);                        // block row 2t
                     sts_f2(my_stage + 4 * kMmStagePitch + 16 * q, nxt[u][NCH - 1][1], nxt[u][NCH - 1][3]);   // block row 2t + 1
                 }

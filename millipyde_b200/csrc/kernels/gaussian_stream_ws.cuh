@@ -180,6 +180,13 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
         const int lo = gx_start < 0 ? -gx_start : 0;
         const int hi = min(G::ROW, p.row_elems - gx_start);
         const uint32_t row_bytes = (uint32_t)(hi - lo) * 4u;
+        // this image's "before the blur" program (null or empty: none) and the channel of ring column 0
+        const PwProgram *pre = nullptr;
+        if (SETS && p.pw_tab) {
+            pre = p.pw_tab + (size_t)img * p.pw_stride;
+            if (__ldg(&pre->n) == 0) pre = nullptr;
+        }
+        const int ch_start = ((gx_start % C) + C) % C;
 
         // every load this warp issued has been consumed: its ring is quiescent
         if (lo > 0 || hi < G::ROW) {
@@ -228,6 +235,21 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
                 if (MMA) mbar_wait_sleep(&my_full[slot], (takes / K::in_slots) & 1u, kWsSleepNs);
                 else mbar_wait(&my_full[slot], (takes / K::in_slots) & 1u);
                 ++takes;
+                if (SETS && pre) {
+                    // fused pointwise ops in front of the blur: rewrite the landed row in place, each
+                    // sample once (the lanes' filter windows overlap 4.6x, so doing it on the window
+                    // registers would repeat the work).  Only the in-image part [lo, hi): what lies
+                    // outside is the blur's zero padding of the *transformed* image and stays zero.
+                    float *row = my_in + (size_t)slot * G::ROW;
+                    for (int i = lo + 4 * lane; i < hi; i += 128) {
+                        float4 v = *reinterpret_cast<float4 *>(row + i);
+                        float r4[4] = {v.x, v.y, v.z, v.w};
+                        pw_apply_tile_g<C, 4>(pre, r4, (ch_start + i) % C);
+                        *reinterpret_cast<float4 *>(row + i) = make_float4(r4[0], r4[1], r4[2], r4[3]);
+                    }
+                    fence_proxy_async();   // the slot's next writer is the TMA unit
+                    __syncwarp();
+                }
                 if (SETS) ws_row_pass<C, R>(my_in + (size_t)slot * G::ROW + lane * kGsPH, out, w_img);
                 else ws_row_pass<C, R>(my_in + (size_t)slot * G::ROW + lane * kGsPH, out, w_one);
             } else {
@@ -308,6 +330,11 @@ __device__ __forceinline__ void ws_body(const GaussStreamParams &p, const GaussW
             float *base = p.out_tab ? p.out_tab[img] : p.out + (size_t)img * p.image_stride;
             const int set = SETS ? img % kGsMaxSets : 0;
             auto w = [&](int d) -> uint64_t { return SETS ? ws.ww[set][d] : p.ww[d]; };
+            const PwProgram *post = nullptr;
+            if (SETS && p.pw_tab) {
+                post = p.pw_tab + (size_t)img * p.pw_stride + 1;
+                if (__ldg(&post->n) == 0) post = nullptr;
+            }
             float *optr = base + ((long)y0 - 2 * R) * p.row_elems + gx;  // only dereferenced when valid
             unsigned rel = (unsigned)(-2 * R);                            // output row - y0, wraps below 0
 
@@ -323,9 +350,10 @@ __device__ __forceinline__ void ws_body(const GaussStreamParams &p, const GaussW
                     for (int j = 1; j < 2 * R; ++j) A[j - 1] = ffma2(w(j < R ? R - j : j - R), v, A[j]);
                     A[2 * R - 1] = fmul2(w(R), v);
                     if (rel < n_valid) {
-                        float o_lo, o_hi;
-                        unpack2(o, o_lo, o_hi);
-                        __stcs(reinterpret_cast<float2 *>(optr), make_float2(o_lo, o_hi));
+                        float o2[2];
+                        unpack2(o, o2[0], o2[1]);
+                        if (SETS && post) pw_apply_tile_g<C, 2>(post, o2, gx % C);
+                        __stcs(reinterpret_cast<float2 *>(optr), make_float2(o2[0], o2[1]));
                     }
                     ++rel;
                     optr += p.row_elems;

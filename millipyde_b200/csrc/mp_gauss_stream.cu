@@ -160,12 +160,13 @@ int gauss_stream_bucket(int radius) { return bucket_for(radius); }
 // n_images <= kGsMaxSets images of one radius bucket, image i filtered with gps[i].
 MPStatus launch_gauss_stream_sets(int device, cudaStream_t s, int H, int W, int C, int n_images,
                                   const float *const *in_tab, float *const *out_tab,
-                                  const GaussParams<float> *gps)
+                                  const GaussParams<float> *gps, int gps_stride, const PwProgram *pw_tab,
+                                  int pw_stride)
 {
     if (n_images < 1 || n_images > kGsMaxSets) return MP_ERROR_INVALID_ARGUMENT;
     int bucket = 0;
     for (int i = 0; i < n_images; ++i) {
-        const int b = bucket_for(gps[i].radius);
+        const int b = bucket_for(gps[(size_t)i * gps_stride].radius);
         if (!b) return MP_ERROR_INVALID_ARGUMENT;
         if (b > bucket) bucket = b;
     }
@@ -177,10 +178,13 @@ MPStatus launch_gauss_stream_sets(int device, cudaStream_t s, int H, int W, int 
     p.row_elems = W * C;
     p.n_strips = (p.row_elems + kGsTW - 1) / kGsTW;
     p.radius = bucket;
+    p.pw_tab = pw_tab;
+    p.pw_stride = pw_stride;
     static thread_local GaussWeightSets sets;  // 7 KB: keep it off the worker's stack frames
     for (int i = 0; i < n_images; ++i)
         for (int d = 0; d < 14; ++d) {
-            const float w = d <= gps[i].radius ? gps[i].w[d] : 0.f;
+            const GaussParams<float> &gi = gps[(size_t)i * gps_stride];
+            const float w = d <= gi.radius ? gi.w[d] : 0.f;
             unsigned int bits;
             memcpy(&bits, &w, 4);
             sets.ww[i][d] = ((unsigned long long)bits << 32) | bits;

@@ -254,6 +254,11 @@ void mpobj_view_rebind(MPObjData *view, MPObjData *src)
     if (src->ndims <= 3) memcpy(dims, src->dims, sizeof(int) * 2 * (size_t)src->ndims);
 }
 
+void mpobj_view_rebind_many(MPObjData **views, MPObjData **srcs, int n)
+{
+    for (int i = 0; views && i < n; ++i) mpobj_view_rebind(views[i], srcs ? srcs[i] : NULL);
+}
+
 MPObjData *mpobj_create(const void *host, int ndims, const long *shape, int typenum)
 {
     if (mp::ensure_initialized() != MILLIPYDE_SUCCESS) return NULL;

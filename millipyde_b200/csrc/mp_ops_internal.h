@@ -68,9 +68,13 @@ void launch_gather_f32(cudaStream_t s, int channels, const mpk::GatherParams &g,
 // fp32 roofline path (kernels/gaussian_stream.cuh)
 bool gauss_stream_supported(int W, int C, int radius);
 int gauss_stream_bucket(int radius);  // smallest compiled radius >= radius, 0 if none
+// n_images <= 64; image i is filtered with gps[i * gps_stride] (stride 0: one sigma for all) and, when
+// pw_tab (DEVICE memory) is given, wrapped in the pointwise programs pw_tab[i * pw_stride] (before the
+// blur) and pw_tab[i * pw_stride + 1] (after it); pw_stride is 2 (per image) or 0 (one pair for all).
 MPStatus launch_gauss_stream_sets(int device, cudaStream_t s, int H, int W, int C, int n_images,
                                   const float *const *in_tab, float *const *out_tab,
-                                  const mpk::GaussParams<float> *gps);  // n_images <= 64, per-image weights
+                                  const mpk::GaussParams<float> *gps, int gps_stride = 1,
+                                  const mpk::PwProgram *pw_tab = nullptr, int pw_stride = 0);
 MPStatus launch_gauss_stream(int device, cudaStream_t s, const Img &d, const float *in, float *out,
                              const mpk::GaussParams<float> &gp);
 // n_images of one shape in one launch: either a contiguous batch (in/out +

@@ -127,9 +127,9 @@ void note_status(mp_pipeline *p, MPStatus st)
 
 // ------------------------------------------------------------------ fusion pass
 struct Segment {
-    enum Kind { SINGLE, PW_F32, GREY_F32, PW_RGBA8, GATHER_F32 } kind;
-    const Stage *single = nullptr;  // SINGLE
-    PwProgram pre = {}, post = {};  // PW_F32 uses `pre`; GREY_F32 and GATHER_F32 use both
+    enum Kind { SINGLE, PW_F32, GREY_F32, PW_RGBA8, GATHER_F32, GAUSS_F32 } kind;
+    const Stage *single = nullptr;  // SINGLE; GAUSS_F32: the gaussian stage (sigma = single->a[0])
+    PwProgram pre = {}, post = {};  // PW_F32 uses `pre`; GREY_F32, GATHER_F32 and GAUSS_F32 use both
     U8Program u8 = {};
     // GATHER_F32: flips before / after the (optional) rotate, and its angle
     bool flip_pre = false, flip_post = false, has_rotate = false;
@@ -196,6 +196,25 @@ std::vector<Segment> compile(const std::vector<const Stage *> &ops, mp::Family f
                 out.push_back(seg);
                 i = j;
                 continue;
+            }
+        }
+        // a Gaussian absorbs the pointwise ops next to it: the ones before it are applied to every
+        // sample as it lands in shared memory (once per sample, halo columns included; the zero
+        // padding stays zero), the ones after it to the finished output rows before they are stored
+        if (fuse && fam == mp::FAM_F32 && (is_pointwise(s->kind) || s->kind == OP_GAUSSIAN)) {
+            Segment seg;
+            seg.kind = Segment::GAUSS_F32;
+            size_t j = i;
+            while (j < ops.size() && is_pointwise(ops[j]->kind) && seg.pre.n < kMaxPw) seg.pre.ops[seg.pre.n++] = to_pw(*ops[j++]);
+            if (j < ops.size() && ops[j]->kind == OP_GAUSSIAN && ops[j]->a[0] > 1e-15) {
+                seg.single = ops[j++];
+                while (j < ops.size() && is_pointwise(ops[j]->kind) && seg.post.n < kMaxPw)
+                    seg.post.ops[seg.post.n++] = to_pw(*ops[j++]);
+                if (seg.pre.n + seg.post.n > 0) {   // a bare Gaussian keeps its own (SINGLE) path
+                    out.push_back(seg);
+                    i = j;
+                    continue;
+                }
             }
         }
         if (fuse && fam == mp::FAM_F32 && (is_pointwise(s->kind) || (s->kind == OP_GREY && channels >= 3))) {
@@ -329,6 +348,14 @@ std::string signature(const Segment &g)
         case Segment::GATHER_F32:
             snprintf(b, sizeof b, "T%d%d%d", (int)g.flip_pre, (int)g.flip_post, (int)g.has_rotate);
             break;
+        case Segment::GAUSS_F32: {
+            double w[kGaussMaxRadius + 1];
+            const int r = mp::oracle_weights(g.single->a[0], w, kGaussMaxRadius);
+            const int bucket = mp::gauss_stream_bucket(mp::effective_radius(w, r, ldexp(1.0, -24)));
+            if (bucket > 0) snprintf(b, sizeof b, "GP%d", bucket);
+            else snprintf(b, sizeof b, "GP:%.17g", g.single->a[0]);   // no streaming kernel: runs op by op
+            break;
+        }
         case Segment::PW_RGBA8: {
             // composed byte tables are built per program: same program, same launch shape
             std::string k = "U";
@@ -356,6 +383,12 @@ MPStatus run_segment_on(MPObjData *obj, const Segment &seg)
             std::vector<MPObjData *> one(1, obj);
             std::vector<const Segment *> one_seg(1, &seg);
             return run_gather(one, one_seg, d, obj->mem_loc, mp::stream_of(obj));
+        }
+        case Segment::GAUSS_F32: {   // no fused form for this layout / shape / radius: op by op
+            MPStatus st = seg.pre.n ? mp::op_pointwise_f32(obj, seg.pre) : MILLIPYDE_SUCCESS;
+            if (st == MILLIPYDE_SUCCESS) st = seg.single->func(obj, seg.single->args);
+            if (st == MILLIPYDE_SUCCESS && seg.post.n) st = mp::op_pointwise_f32(obj, seg.post);
+            return st;
         }
         default: return seg.single->func(obj, seg.single->args);
     }
@@ -457,12 +490,16 @@ constexpr int kMaxSets = 64;  // images per launch_gauss_stream_sets call (kerne
 // One launch for the Gaussian of a whole same-shape fp32 group (`sigmas` all equal), or one launch
 // per 64 images with per-image weight sets when the sigmas were drawn per image (same radius bucket:
 // realize() keyed the group on it).
+//
+// `progs` (optional): 2 n pointwise programs, image i's "before" and "after" the blur (GAUSS_F32
+// segments).  They travel as per-image records behind the pointer tables and the kernel applies them
+// on the fly -- the chain pointwise -> gaussian -> pointwise is one launch and one HBM round trip.
 MPStatus run_gaussian_batch(const std::vector<MPObjData *> &objs, const mp::Img &d, const std::vector<double> &sigmas,
-                            int device, cudaStream_t s, bool *handled)
+                            int device, cudaStream_t s, bool *handled, const std::vector<PwProgram> *progs = nullptr)
 {
     *handled = false;
     const size_t n = objs.size();
-    if (n < 2) return MILLIPYDE_SUCCESS;
+    if (n < 2 && !progs) return MILLIPYDE_SUCCESS;
     bool same = true;
     for (size_t i = 1; i < n; ++i) same = same && sigmas[i] == sigmas[0];
     std::vector<GaussParams<float>> gps(same ? 1 : n);
@@ -476,19 +513,29 @@ MPStatus run_gaussian_batch(const std::vector<MPObjData *> &objs, const mp::Img 
         gps[i].radius = eff;
         for (int k = 0; k <= eff; ++k) gps[i].w[k] = (float)w[k];
     }
-    return run_batched(objs, objs[0]->nbytes, device, s, handled,
-                       [&](const float *const *in_tab, float *const *out_tab, int m) {
-                           if (same)
-                               return mp::launch_gauss_stream_batch(device, s, d.H, d.W, d.C, m, nullptr, nullptr, 0,
-                                                                    in_tab, out_tab, gps[0]);
-                           for (int off = 0; off < m; off += kMaxSets) {
-                               const int cnt = m - off < kMaxSets ? m - off : kMaxSets;
-                               MPStatus st = mp::launch_gauss_stream_sets(device, s, d.H, d.W, d.C, cnt, in_tab + off,
-                                                                          out_tab + off, gps.data() + off);
-                               if (st != MILLIPYDE_SUCCESS) return st;
-                           }
-                           return (MPStatus)MILLIPYDE_SUCCESS;
-                       });
+    bool same_progs = true;
+    if (progs)
+        for (size_t i = 1; i < n && same_progs; ++i)
+            same_progs = !memcmp(&(*progs)[2 * i], &(*progs)[0], 2 * sizeof(PwProgram));
+    const size_t n_records = progs ? (same_progs ? 2 : 2 * n) : 0;
+    return run_batched(
+        objs, objs[0]->nbytes, device, s, handled,
+        [&](const float *const *in_tab, float *const *out_tab, int m) {
+            if (same && !progs)
+                return mp::launch_gauss_stream_batch(device, s, d.H, d.W, d.C, m, nullptr, nullptr, 0, in_tab, out_tab,
+                                                     gps[0]);
+            const PwProgram *tab = progs ? (const PwProgram *)g_records : nullptr;
+            const int pw_stride = (progs && !same_progs) ? 2 : 0;
+            for (int off = 0; off < m; off += kMaxSets) {
+                const int cnt = m - off < kMaxSets ? m - off : kMaxSets;
+                MPStatus st = mp::launch_gauss_stream_sets(device, s, d.H, d.W, d.C, cnt, in_tab + off, out_tab + off,
+                                                           same ? gps.data() : gps.data() + off, same ? 0 : 1,
+                                                           tab ? tab + (size_t)off * pw_stride : nullptr, pw_stride);
+                if (st != MILLIPYDE_SUCCESS) return st;
+            }
+            return (MPStatus)MILLIPYDE_SUCCESS;
+        },
+        progs ? progs->data() : nullptr, n_records * sizeof(PwProgram));
 }
 
 // The gather segment for one image (tables null) or a same-shape group.
@@ -580,6 +627,18 @@ void run_segment_group(mp_pipeline *p, const std::vector<MPObjData *> &objs, con
         for (size_t i = 0; i < n; ++i) sigmas[i] = segs[i]->single->a[0];
         bool handled = false;
         note_status(p, run_gaussian_batch(objs, cur, sigmas, device, s, &handled));
+        if (handled) return;
+    }
+    if (seg.kind == Segment::GAUSS_F32 && f32) {
+        std::vector<double> sigmas(n);
+        std::vector<PwProgram> progs(2 * n);
+        for (size_t i = 0; i < n; ++i) {
+            sigmas[i] = segs[i]->single->a[0];
+            progs[2 * i] = segs[i]->pre;
+            progs[2 * i + 1] = segs[i]->post;
+        }
+        bool handled = false;
+        note_status(p, run_gaussian_batch(objs, cur, sigmas, device, s, &handled, &progs));
         if (handled) return;
     }
     if ((seg.kind == Segment::PW_F32 || seg.kind == Segment::GREY_F32) && n >= 2 && f32 &&
@@ -1100,6 +1159,7 @@ int mppipe_plan(const MPPipeline *p, int typenum, int channels, char *buf, int c
                 out += "u8(" + t + ")";
                 break;
             }
+            case Segment::GAUSS_F32: out += "gauss(" + prog(g.pre) + "|" + prog(g.post) + ")"; break;
             case Segment::GATHER_F32:
                 out += std::string("gather(") + (g.flip_pre ? "fliplr" : "-") + "," + (g.has_rotate ? "rotate" : "-") + "," +
                        (g.flip_post ? "fliplr" : "-") + ";" + prog(g.pre) + "|" + prog(g.post) + ")";

@@ -51,6 +51,25 @@ def test_grey_absorbs_the_pointwise_ops_around_it():
     assert plan(ops, F32, 3) == (2, "grey(brightness|adjust_gamma);transpose")
 
 
+def test_gaussian_absorbs_the_pointwise_ops_around_it():
+    """north star (2): a chain of pointwise and stencil ops is ONE HBM round trip -- the ops before the
+    blur run on the rows as they land in shared memory, the ops after it on the finished rows
+    (the reference: one kernel + one stream sync per stage, src/gpupipeline.c:373-392)."""
+    ops = [("adjust_gamma", 1.5, 1.0), ("gaussian", 2.0), ("brightness", 0.1)]
+    for c in (1, 3, 4):
+        assert plan(ops, F32, c) == (1, "gauss(adjust_gamma|brightness)")
+    assert plan(ops[:2], F32, 3) == (1, "gauss(adjust_gamma|)")
+    assert plan(ops[1:], F32, 3) == (1, "gauss(|brightness)")
+    assert plan([("gaussian", 2.0)], F32, 3) == (1, "gaussian")          # a bare blur keeps its own launch path
+    # two blurs: each takes the pointwise ops in front of it, the last one also those behind it
+    two = [("brightness", 0.1), ("gaussian", 2.0), ("adjust_gamma", 2.0, 1.0), ("gaussian", 1.0), ("brightness", -0.1)]
+    assert plan(two, F32, 3) == (2, "gauss(brightness|adjust_gamma);gauss(|brightness)")
+    # the reference layouts (fp64 grey, RGBA8) have no fused stencil
+    assert plan(ops, F64, 1) == (3, "adjust_gamma;gaussian;brightness")
+    assert plan(ops, U8, 4) == (3, "adjust_gamma;gaussian;brightness")
+    assert plan(ops, F32, 3, fusion=False) == (3, "adjust_gamma;gaussian;brightness")
+
+
 def test_two_rotates_do_not_compose():
     """A second resample starts a new gather segment; pointwise ops between them ride on the first."""
     ops = [("rotate", 10.0), ("brightness", 0.1), ("rotate", 20.0)]
@@ -73,7 +92,7 @@ def test_random_stages_plan_like_their_operators():
     ops = [("random_brightness", -0.2, 0.2), ("random_gaussian", 0.5, 2.0), ("random_rotate", 0.0, 120.0)]
     capi.lib().mprand_seed(11)
     try:
-        assert plan(ops, F32, 3) == (3, "pw(brightness);gaussian;gather(-,rotate,-;|)")
+        assert plan(ops, F32, 3) == (2, "gauss(brightness|);gather(-,rotate,-;|)")
     finally:
         capi.lib().mprand_seed(0)
 

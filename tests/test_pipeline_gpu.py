@@ -350,8 +350,7 @@ def test_full_frame_4k_single_image_against_oracle(mp):
 
 def test_full_frame_4k_batch_of_64_against_oracle(mp):
     """The benchmarked launch shape: >= 64 4K images in ONE launch through pointer tables (chunks = 1,
-    1,152 items over 148 persistent CTAs), sources untouched (views).  First, middle and last image
-    of the launch are compared with scipy over the whole frame, the rest with the image of the same
+    1,152 items over 148 persistent CTAs), sources untouched (views).  Three images across the launch (one per seed) are compared with scipy over the whole frame, the rest with the image of the same
     seed (bit-identical: same kernel, same data)."""
     seeds = [synth.noise_f32(2160, 3840, 3, 2100 + k) for k in range(3)]
     base = [mp.capi.DeviceImage(s) for s in seeds]
@@ -362,12 +361,12 @@ def test_full_frame_4k_batch_of_64_against_oracle(mp):
     assert ch.last_launches == 1
     wants = [so.gaussian(s, 2.0) for s in seeds]
     outs = {}
-    for k in (0, 31, 63):
+    for k in (0, 31, 62):
         outs[k] = views[k].numpy()
         assert np.abs(outs[k] - wants[k % 3]).max() <= TOL32, k
         assert np.abs(outs[k][-16:] - wants[k % 3][-16:]).max() <= TOL32, k
     for k in range(1, 64, 7):
-        ref = {0: 0, 1: 31, 2: 63}[k % 3]
+        ref = {0: 0, 1: 31, 2: 62}[k % 3]
         assert np.array_equal(views[k].numpy(), outs[ref]), k
     # the sources were read, not written
     assert np.array_equal(src[5].numpy(), seeds[5 % 3])
@@ -381,3 +380,86 @@ def test_full_frame_4k_batch_of_64_against_oracle(mp):
         v.close()
     for d in src + base:
         d.close()
+
+
+@pytest.mark.parametrize("c", [1, 3, 4])
+def test_pointwise_ops_fuse_into_the_gaussian(mp, c):
+    """north star (2): pointwise -> gaussian -> pointwise is ONE launch and one HBM round trip.  The ops
+    before the blur are applied to the rows as they land in shared memory (the blur's zero padding is
+    padding of the *transformed* image: brightness must not leak into it), the ops after it to the
+    finished rows.  Compared with the oracle and with the unfused execution of the same chain."""
+    chains = [
+        [("adjust_gamma", 1.5, 1.0), ("gaussian", 2.0), ("brightness", 0.1)],
+        [("brightness", 0.25), ("gaussian", 2.0)],
+        [("gaussian", 0.7), ("colorize", 0.9, 1.2, 0.5), ("adjust_gamma", 0.8, 0.9)],
+        [("colorize", 1.3, 0.7, 1.1), ("adjust_gamma", 2.2, 1.0), ("gaussian", 1.3), ("brightness", -0.1),
+         ("adjust_gamma", 0.5, 1.0)],
+    ]
+    for chain in chains:
+        for h, w in [(75, 250 if c != 1 else 252), (140, 640), (33, 1284)]:
+            if (w * c) % 4:
+                continue
+            imgs = [synth.noise_f32(h, w, c, 7000 + k) for k in range(5)]
+            dev = [mp.capi.DeviceImage(a) for a in imgs]
+            ch = mp.engine.Chain(chain, device=0)
+            ch.run(dev)
+            assert ch.last_segments == 1 and ch.last_launches == 1, (chain, ch.last_segments, ch.last_launches)
+            single = mp.capi.DeviceImage(imgs[0])
+            ch1 = mp.engine.Chain(chain, device=0)
+            ch1.run([single])                                   # a batch of one takes the same kernel
+            assert ch1.last_launches == 1
+            mp.lib.mppipe_set_fusion(0)
+            try:
+                unf = [mp.capi.DeviceImage(a) for a in imgs[:2]]
+                mp.engine.Chain(chain, device=0).run(unf)
+            finally:
+                mp.lib.mppipe_set_fusion(1)
+            for k, (a, d) in enumerate(zip(imgs, dev)):
+                got = d.numpy()
+                assert np.abs(got - so.apply_chain(a, chain)).max() <= TOL32, (chain, h, w)
+                if k < 2:
+                    assert np.abs(got - unf[k].numpy()).max() <= 2e-6
+            assert np.array_equal(single.numpy(), dev[0].numpy())
+
+
+def test_fused_gaussian_falls_back_op_by_op_outside_the_streaming_envelope(mp):
+    """sigma = 3.3 has no streaming bucket and 250 x 3 floats per row is not a multiple of 4: the
+    GAUSS segment then runs its three parts one after the other (still correct, three launches)."""
+    chain = [("adjust_gamma", 1.5, 1.0), ("gaussian", 3.3), ("brightness", 0.1)]
+    imgs = [synth.noise_f32(60, 128, 3, 7100 + k) for k in range(3)]
+    dev = [mp.capi.DeviceImage(a) for a in imgs]
+    ch = mp.engine.Chain(chain, device=0)
+    ch.run(dev)
+    assert ch.last_segments == 1
+    for a, d in zip(imgs, dev):
+        assert np.abs(d.numpy() - so.apply_chain(a, chain)).max() <= TOL32
+    chain = [("brightness", 0.1), ("gaussian", 2.0)]
+    imgs = [synth.noise_f32(60, 250, 3, 7200 + k) for k in range(3)]
+    dev = [mp.capi.DeviceImage(a) for a in imgs]
+    mp.engine.Chain(chain, device=0).run(dev)
+    for a, d in zip(imgs, dev):
+        assert np.abs(d.numpy() - so.apply_chain(a, chain)).max() <= TOL32
+
+
+def test_fused_gaussian_with_per_image_programs_and_sigmas(mp):
+    """A Generator-style stream: every image has its own gamma, sigma and brightness.  One GAUSS
+    segment; the kernel reads image i's two programs and weight set from the per-image records."""
+    n = 70
+    imgs = [synth.noise_f32(40, 160, 3, 7300 + k) for k in range(n)]
+    chain = [("random_adjust_gamma", .5, 2., 1., 1.), ("random_gaussian", 1.0, 1.25), ("random_brightness", -.2, .2)]
+    mp.lib.mprand_seed(77)
+    draws = []
+    for _ in range(n):
+        gam = (_draw(mp, .5, 2.), _draw(mp, 1., 1.))
+        sg = _draw(mp, 1.0, 1.25)
+        b = _draw(mp, -.2, .2)
+        draws.append((gam, sg, b))
+    mp.lib.mprand_seed(77)
+    dev = [mp.capi.DeviceImage(a) for a in imgs]
+    ch = mp.engine.Chain(chain, device=0)
+    ch.run(dev)
+    mp.lib.mprand_seed(0)
+    assert ch.last_launches <= 2 * 2, ch.last_launches      # <= 2 radius buckets x 2 sets of 64
+    for a, d, (gam, sg, b) in zip(imgs, dev, draws):
+        want = so.apply_chain(a, [("adjust_gamma", *gam), ("gaussian", sg), ("brightness", b)])
+        assert np.abs(d.numpy() - want).max() <= TOL32
