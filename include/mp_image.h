@@ -100,6 +100,20 @@ int mpimg_gaussian_effective_radius(double sigma, int *full);
 void mpimg_set_gauss_column(int mode);
 int mpimg_get_gauss_column(void);
 
+/*
+ * Declared value range of fp32 images (new).  The fp32 layout is defined for image data in [0, 1]
+ * (the north star's contract, tolerances are stated on it), and under MP_RANGE_UNIT (default) the
+ * Gaussian may use the tensor-core column pass, whose fp16 correction operands OVERFLOW for
+ * |sample| >= 65504: such samples produce Inf/NaN.  A caller whose float images carry other data
+ * (uint16-range, HDR, arbitrary arrays) declares MP_RANGE_ANY: every fp32 Gaussian then runs on the
+ * fp32 FMA pipe (no range limit, same 1e-5 contract relative to the data's scale).  Also settable
+ * with the environment variable MILLIPYDE_VALUE_RANGE=unit|any, read on first use.
+ */
+#define MP_RANGE_UNIT 0
+#define MP_RANGE_ANY 1
+void mpimg_set_value_range(int mode);
+int mpimg_get_value_range(void);
+
 #ifdef __cplusplus
 }
 #endif

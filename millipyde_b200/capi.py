@@ -21,6 +21,8 @@ HOST_LOC = -1
 DEVICE_LOC_NO_AFFINITY = -2
 SEMANTICS_ORACLE = 0
 SEMANTICS_REFERENCE = 1
+RANGE_UNIT = 0     # fp32 images hold [0, 1] data (default): the Gaussian may use fp16 correction operands
+RANGE_ANY = 1      # arbitrary float data: |sample| >= 65504 is safe, the Gaussian stays on the FMA pipe
 
 NPY_UBYTE, NPY_FLOAT, NPY_DOUBLE = 2, 11, 12
 
@@ -121,6 +123,8 @@ SYMBOLS = {
     "mpimg_get_semantics": (C.c_int, []),
     "mpimg_set_gauss_column": (None, [C.c_int]),
     "mpimg_get_gauss_column": (C.c_int, []),
+    "mpimg_set_value_range": (None, [C.c_int]),
+    "mpimg_get_value_range": (C.c_int, []),
     "mpimg_gaussian_effective_radius": (C.c_int, [C.c_double, C.POINTER(C.c_int)]),
     # mp_objects.h
     "mpobj_copy_from_host": (None, [_OBJ, C.c_void_p, C.c_size_t]),

@@ -38,8 +38,21 @@ bool gauss_stream_supported(int W, int C, int radius)
 // MILLIPYDE_GAUSS_COLUMN=fma asks for the FMA-pipe kernel (A/B measurements and parity tests; the
 // two agree to ~1e-6, not bit for bit).
 static std::atomic<int> g_column{-1};
+static std::atomic<int> g_range{-1};
+static int value_range()
+{
+    int m = g_range.load(std::memory_order_relaxed);
+    if (m < 0) {
+        const char *e = getenv("MILLIPYDE_VALUE_RANGE");
+        m = (e && strcmp(e, "any") == 0) ? MP_RANGE_ANY : MP_RANGE_UNIT;
+        g_range.store(m);
+    }
+    return m;
+}
 static bool use_mma_column()
 {
+    // fp16 correction operands: only for data declared to lie in [0, 1] (include/mp_image.h)
+    if (value_range() == MP_RANGE_ANY) return false;
     int m = g_column.load(std::memory_order_relaxed);
     if (m < 0) {
         const char *e = getenv("MILLIPYDE_GAUSS_COLUMN");
@@ -209,4 +222,6 @@ void mpimg_set_gauss_column(int mode)
     mp::g_column.store(mode == MP_GAUSS_COLUMN_FMA ? MP_GAUSS_COLUMN_FMA : MP_GAUSS_COLUMN_MMA);
 }
 int mpimg_get_gauss_column(void) { return mp::use_mma_column() ? MP_GAUSS_COLUMN_MMA : MP_GAUSS_COLUMN_FMA; }
+void mpimg_set_value_range(int mode) { mp::g_range.store(mode == MP_RANGE_ANY ? MP_RANGE_ANY : MP_RANGE_UNIT); }
+int mpimg_get_value_range(void) { return mp::value_range(); }
 }

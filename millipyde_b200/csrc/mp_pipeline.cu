@@ -1059,7 +1059,7 @@ static MPStatus submit_impl(MPPipeline *p, MPObjData **objs, int n, bool views)
     }
     if (!mpdev_is_valid_device(device)) return GPUPIPELINE_ERROR_UNUSABLE_DEVICE;
     p->cycled = cycle;
-    p->soft_wait = !cycle;
+    p->soft_wait = true;   // every shard (and every receiver shard) is counted in `pending`: wait on that
     for (mp_pipeline *q = p->receiver; q; q = q->receiver)
         if (!mpdev_is_valid_device(q->device)) q->device = device;
 
@@ -1078,9 +1078,7 @@ static MPStatus submit_impl(MPPipeline *p, MPObjData **objs, int n, bool views)
 MPStatus mppipe_wait(MPPipeline *p)
 {
     if (!p) return MP_ERROR_INVALID_ARGUMENT;
-    if (p->cycled) {
-        mpdev_hard_synchronize_all();
-    } else if (p->soft_wait) {
+    if (p->soft_wait) {
         // every shard's worker returns only after its device work is complete, and a sender registers
         // its receiver's shards before it finishes: own shards first, then down the chain
         for (mp_pipeline *q = p; q; q = q->receiver) {
@@ -1293,6 +1291,7 @@ extern "C" MPStatus mppipe_run_host(MPPipeline *p, const void *const *host_in, v
 {
     if (!p || n < 0 || ndims < 2 || ndims > 3 || !shape || (n > 0 && (!host_in || !host_out || !results)))
         return MP_ERROR_INVALID_ARGUMENT;
+    if (p->receiver) return MP_ERROR_INVALID_ARGUMENT;   // the host stream has no hand-off: say so, do not drop it
     MPStatus st = mp::ensure_initialized();
     if (st != MILLIPYDE_SUCCESS) return st;
     reset_counters(p);

@@ -88,6 +88,20 @@ static PyObject *mod_set_semantics(PyObject *self, PyObject *arg)
     Py_RETURN_NONE;
 }
 
+/* fp32 images are defined on [0, 1]; declare 'any' for other float data (include/mp_image.h) */
+static PyObject *mod_set_value_range(PyObject *self, PyObject *arg)
+{
+    const char *s = PyUnicode_AsUTF8(arg);
+    if (!s) return NULL;
+    if (strcmp(s, "unit") == 0) mpimg_set_value_range(MP_RANGE_UNIT);
+    else if (strcmp(s, "any") == 0) mpimg_set_value_range(MP_RANGE_ANY);
+    else {
+        PyErr_SetString(PyExc_ValueError, "value range must be 'unit' or 'any'");
+        return NULL;
+    }
+    Py_RETURN_NONE;
+}
+
 static PyObject *mod_get_semantics(PyObject *self, PyObject *Py_UNUSED(a))
 {
     return PyUnicode_FromString(mpimg_get_semantics() == MP_SEMANTICS_REFERENCE ? "reference" : "oracle");
@@ -158,6 +172,9 @@ static PyMethodDef module_methods[] = {
     {"seed", mod_seed, METH_O, "seed the random source of random_* ops and probabilities (0: entropy)"},
     {"set_semantics", mod_set_semantics, METH_O, "'oracle' (scikit-image rules) or 'reference' (kernel-exact)"},
     {"get_semantics", mod_get_semantics, METH_NOARGS, "current semantics"},
+    {"set_value_range", mod_set_value_range, METH_O,
+     "'unit' (default): float32 images hold [0, 1] data -- gaussian() may use fp16 correction operands and returns "
+     "Inf/NaN for |sample| >= 65504; 'any': arbitrary float data, no range limit (FMA-pipe Gaussian)"},
     {"set_fusion", mod_set_fusion, METH_O, "enable/disable the chain fusion pass"},
     {"launch_count", mod_launch_count, METH_NOARGS, "kernels launched by the library so far"},
     {"pinned_empty", mod_pinned_empty, METH_VARARGS, "pinned_empty(shape, dtype=float32): page-locked ndarray"},

@@ -302,10 +302,15 @@ static int pipeline_init(MPPipelineObject *self, PyObject *args, PyObject *kwds)
             return -1;
         }
     }
+    if (self->pipe) {
+        /* a second __init__: another Pipeline may hold this one's executor as its receiver
+         * (connect_to), so it cannot be replaced underneath it */
+        PyErr_SetString(PyExc_RuntimeError, "Pipeline is already initialised; construct a new one");
+        return -1;
+    }
     int all;
     MPPipeline *pipe = build_pipe(operations, device_id, &all);
     if (!pipe) return -1;
-    if (self->pipe) mppipe_destroy(self->pipe);
     self->pipe = pipe;
     Py_INCREF(inputs);
     Py_INCREF(operations);

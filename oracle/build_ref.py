@@ -110,6 +110,68 @@ def build(verbose: bool = True, force: bool = False) -> str:
     return target
 
 
+# ---------------------------------------------------------------------------------------------
+# The boundary proven by construction: the reference's seven CPython type files, compiled unmodified
+# from /root/reference/src against the reference's own headers, linked against libmp_b200.so INSTEAD
+# of its four HIP translation units (setup.py:48-66 source list minus millipyde_image.cpp,
+# millipyde_objects.cpp, millipyde_devices.cpp, millipyde_workers.cpp; millipyde.c's mperr_str /
+# random_* come from the library too).  If a symbol the reference's host code calls were missing or
+# had another signature, this would not link or not run.
+HYBRID_SOURCES = ["device.c", "gpuarray.c", "gpugenerator.c", "gpuimage.c", "gpuoperation.c", "gpupipeline.c",
+                  "millipyde_module.c"]
+
+
+def hybrid_so_path() -> str:
+    return os.path.join(OUT, "hybrid", "millipyde" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def hybrid_available() -> bool:
+    return os.path.exists(hybrid_so_path())
+
+
+def build_hybrid(verbose: bool = True, force: bool = False) -> str:
+    src = os.path.join(REF, "src")
+    if not os.path.isdir(src):
+        raise FileNotFoundError(f"{src}: reference sources not present (expected on the GPU box)")
+    import numpy
+    root = os.path.dirname(HERE)
+    libdir = os.path.join(root, "millipyde_b200")
+    lib = os.path.join(libdir, "libmp_b200.so")
+    if not os.path.exists(lib):
+        raise FileNotFoundError(f"{lib}: build the product first (python -m millipyde_b200.build)")
+    target = hybrid_so_path()
+    os.makedirs(os.path.dirname(target), exist_ok=True)
+    if hybrid_available() and not force and os.path.getmtime(target) >= os.path.getmtime(lib):
+        return target
+    inc = ["-I", os.path.join(src, "include"), "-I", sysconfig.get_paths()["include"], "-I", numpy.get_include()]
+    objs = []
+    for name in HYBRID_SOURCES:
+        obj = os.path.join(OUT, "hybrid", name + ".o")
+        cmd = ["gcc", "-fPIC", "-O2", "-w", "-DNPY_NO_DEPRECATED_API=NPY_1_7_API_VERSION"] + inc + \
+              ["-c", os.path.join(src, name), "-o", obj]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+        objs.append(obj)
+    # --no-undefined would also flag the CPython symbols an extension leaves to the interpreter, so the
+    # check is explicit: every undefined non-Python symbol must be one libmp_b200.so (or libc) defines
+    cmd = ["gcc", "-shared", "-o", target] + objs + ["-L", libdir, "-lmp_b200",
+                                                     "-Wl,-rpath,$ORIGIN/../../../millipyde_b200", "-lpthread"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return target
+
+
+def load_hybrid():
+    """Import the reference's host code bound to libmp_b200.so (GPU required)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("millipyde", hybrid_so_path())
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def load():
     """Import the shim-built reference as module `millipyde_reference` (GPU required)."""
     import importlib.util
@@ -120,4 +182,7 @@ def load():
 
 
 if __name__ == "__main__":
-    print(build(verbose=True, force="--force" in sys.argv))
+    if "--hybrid" in sys.argv:
+        print(build_hybrid(verbose=True, force="--force" in sys.argv))
+    else:
+        print(build(verbose=True, force="--force" in sys.argv))

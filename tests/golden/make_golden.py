@@ -43,8 +43,10 @@ def case_key(prefix, case):
     return prefix + "/" + "_".join(str(c) for c in case)
 
 
-def main(out_path):
-    ref = build_ref.load()
+def main(out_path, hybrid=False):
+    # --hybrid: the reference's own CPython host code linked against libmp_b200.so (oracle/build_ref.py
+    # build_hybrid) instead of the reference's kernels; run with MILLIPYDE_SEMANTICS=reference
+    ref = build_ref.load_hybrid() if hybrid else build_ref.load()
     out = {}
     for name, img in inputs().items():
         out[f"{name}/input"] = img
@@ -70,4 +72,5 @@ def main(out_path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "reference_outputs.npz"))
+    argv = [a for a in sys.argv[1:] if a != "--hybrid"]
+    main(argv[0] if argv else os.path.join(ROOT, "gpurun_out", "reference_outputs.npz"), hybrid="--hybrid" in sys.argv)

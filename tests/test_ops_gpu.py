@@ -166,6 +166,36 @@ def test_f32_streaming_gaussian_column_forms_agree(capi):
     assert np.abs(outs[0].astype(np.float64) - so.gaussian(a, 2.0)).max() <= 2e-6
 
 
+def test_f32_gaussian_declared_value_range(capi):
+    """fp32 images are defined on [0, 1] (include/mp_image.h): under MP_RANGE_UNIT the tensor-core
+    column pass converts operands to fp16 and overflows for |sample| >= 65504.  A caller with other
+    float data declares MP_RANGE_ANY and gets the FMA-pipe kernel: uint16-range and 1e6-range data
+    then blur to the oracle within the contract relative to the data's scale, no Inf/NaN."""
+    L = capi.lib()
+    assert L.mpimg_get_value_range() == capi.RANGE_UNIT
+    base = synth.noise_f32(96, 640, 3, 7200)
+    try:
+        L.mpimg_set_value_range(capi.RANGE_ANY)
+        assert L.mpimg_get_gauss_column() == 1          # no fp16 operands for undeclared ranges
+        for scale in (65535.0, 1.0e6):
+            a = (base * np.float32(scale)).astype(np.float32)
+            a[10, 100, 1] = np.float32(scale)           # a sample at the top of the range
+            got = dev(capi, a).apply("gaussian", 2.0).numpy()
+            assert np.isfinite(got).all()
+            assert np.abs(got - so.gaussian(a, 2.0)).max() <= TOL32 * scale
+        # the chain executor follows the declaration too (batched launch)
+        from millipyde_b200 import engine
+        imgs = [(base * np.float32(70000.0)).astype(np.float32) for _ in range(3)]
+        devs = [dev(capi, x) for x in imgs]
+        engine.Chain([("gaussian", 2.0)], device=0).run(devs)
+        for x, d in zip(imgs, devs):
+            got = d.numpy()
+            assert np.isfinite(got).all() and np.abs(got - so.gaussian(x, 2.0)).max() <= TOL32 * 70000.0
+    finally:
+        L.mpimg_set_value_range(capi.RANGE_UNIT)
+    assert L.mpimg_get_gauss_column() == 0
+
+
 def test_f32_gaussian_edge_cases(capi):
     a = synth.noise_f32(5, 7, 3, 1)                 # smaller than the kernel support
     assert np.abs(dev(capi, a).apply("gaussian", 2.0).numpy() - so.gaussian(a, 2.0)).max() <= TOL32
