@@ -101,6 +101,26 @@ void mpimg_set_gauss_column(int mode);
 int mpimg_get_gauss_column(void);
 
 /*
+ * numpy-ufunc-exact elementwise operators on float32 images (new).  What the
+ * extension's __array_ufunc__ dispatches np.add / np.subtract / np.multiply / np.power / np.clip /
+ * np.maximum / np.minimum with scalar (or, for multiply, per-channel) operands to, instead of the
+ * reference's D2H + CPU path (its __array_ufunc__ is a printing stub, src/gpuarray.c:147-191).
+ * No clamp, no special case for alpha: exactly the ufunc.  MPFunc signature, so it chains in a
+ * Pipeline like the eight operators.  float32 layouts only (MP_ERROR_UNSUPPORTED_LAYOUT otherwise;
+ * MP_EW_MUL with per-channel factors needs <= 3 channels).
+ */
+#define MP_EW_ADD 4   /* v + a */
+#define MP_EW_MUL 5   /* v * a (all channels) or v * (a | b | c) by channel when per_channel != 0 */
+#define MP_EW_POW 6   /* powf(v, a) */
+#define MP_EW_CLIP 7  /* min(max(v, a), b) */
+typedef struct {
+    double kind;         /* one of MP_EW_* (a double so the block stays an all-double POD like the reference's *Args) */
+    double a, b, c;
+    double per_channel;
+} ElementwiseArgs;
+MPStatus mpimg_elementwise(MPObjData *obj, void *args);
+
+/*
  * Declared value range of fp32 images (new).  The fp32 layout is defined for image data in [0, 1]
  * (the north star's contract, tolerances are stated on it), and under MP_RANGE_UNIT (default) the
  * Gaussian may use the tensor-core column pass, whose fp16 correction operands OVERFLOW for

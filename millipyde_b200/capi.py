@@ -61,6 +61,12 @@ class GammaArgs(C.Structure):
     _fields_ = [("gamma", C.c_double), ("gain", C.c_double)]
 
 
+class ElementwiseArgs(C.Structure):
+    """include/mp_image.h: kind is one of MP_EW_ADD (4), MP_EW_MUL (5), MP_EW_POW (6), MP_EW_CLIP (7)."""
+    _fields_ = [("kind", C.c_double), ("a", C.c_double), ("b", C.c_double), ("c", C.c_double),
+                ("per_channel", C.c_double)]
+
+
 class RandomRangeArgs(C.Structure):
     _fields_ = [("min", C.c_double), ("max", C.c_double)]
 
@@ -118,6 +124,7 @@ SYMBOLS = {
     "mpimg_random_brightness": (C.c_int, [_OBJ, C.c_void_p]),
     "mpimg_random_adjust_gamma": (C.c_int, [_OBJ, C.c_void_p]),
     "mpimg_random_colorize": (C.c_int, [_OBJ, C.c_void_p]),
+    "mpimg_elementwise": (C.c_int, [_OBJ, C.c_void_p]),
     "mpimg_func_from_name": (C.c_void_p, [C.c_char_p, C.POINTER(C.c_size_t)]),
     "mpimg_set_semantics": (None, [C.c_int]),
     "mpimg_get_semantics": (C.c_int, []),

@@ -13,6 +13,13 @@ enum PwKind : int {
     PW_BRIGHTNESS = 1,  // a = delta                     src/millipyde_image.cpp:384-398
     PW_GAMMA = 2,       // a = gamma, b = gain           :438-454
     PW_COLORIZE = 3,    // a, b, c = r, g, b multipliers :494-524 (float analogue)
+    // numpy-ufunc-exact forms (no clamp, alpha treated like any channel): what __array_ufunc__
+    // dispatches np.add / np.multiply / np.power / np.clip on a float32 gpuimage to
+    // (reference: the printing stub src/gpuarray.c:147-191 -- there these run on the host)
+    PW_EW_ADD = 4,      // v + a
+    PW_EW_MUL = 5,      // v * (a | b | c by channel; a for single-channel images)
+    PW_EW_POW = 6,      // powf(v, a)
+    PW_EW_CLIP = 7,     // min(max(v, a), b)
 };
 
 struct PwOp {
@@ -67,11 +74,22 @@ __device__ __forceinline__ float pw_apply_one(const PwOp &op, float v, int ch)
         default: return v;
     }
 }
+// the ufunc-exact kinds, shared by the scalar and the tile form (every channel, alpha included)
+__device__ __forceinline__ float pw_ew_one(const PwOp &op, float v, int ch)
+{
+    switch (op.kind) {
+        case PW_EW_ADD: return v + op.a;
+        case PW_EW_MUL: return v * (ch == 0 ? op.a : (ch == 1 ? op.b : op.c));
+        case PW_EW_POW: return powf(v, op.a);
+        default: return fminf(fmaxf(v, op.a), op.b);
+    }
+}
 
 template <int C>
 __device__ __forceinline__ float pw_apply(const PwProgram &prog, float v, int ch)
 {
-    for (int i = 0; i < prog.n; ++i) v = pw_apply_one<C>(prog.ops[i], v, ch);
+    for (int i = 0; i < prog.n; ++i)
+        v = prog.ops[i].kind >= PW_EW_ADD ? pw_ew_one(prog.ops[i], v, C == 1 ? 0 : ch) : pw_apply_one<C>(prog.ops[i], v, ch);
     return v;
 }
 
@@ -100,6 +118,16 @@ __device__ __forceinline__ void pw_apply_tile(const PwProgram &prog, float (&r)[
                         const int ch = (C == 4) ? ((ch0 + k) & 3) : (ch0 + k) % 3;
                         if (ch < 3) r[k] = fminf(1.f, r[k] * (ch == 0 ? op.a : (ch == 1 ? op.b : op.c)));
                     }
+                }
+                break;
+            case PW_EW_ADD:
+            case PW_EW_MUL:
+            case PW_EW_POW:
+            case PW_EW_CLIP:
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    const int ch = C == 1 ? 0 : (C == 4 ? ((ch0 + k) & 3) : (ch0 + k) % 3);
+                    r[k] = pw_ew_one(op, r[k], ch);
                 }
                 break;
             default: break;

@@ -487,6 +487,20 @@ MPStatus mpimg_brightness(MPObjData *obj, void *args)
     return MP_ERROR_UNSUPPORTED_LAYOUT;
 }
 
+MPStatus mpimg_elementwise(MPObjData *obj, void *args)
+{
+    if (!args) return MP_ERROR_INVALID_ARGUMENT;
+    mp::Img d;
+    cudaStream_t s;
+    MPStatus st = begin(obj, &d, &s);
+    if (st != MILLIPYDE_SUCCESS) return st;
+    if (d.fam != mp::FAM_F32) return MP_ERROR_UNSUPPORTED_LAYOUT;
+    PwProgram p = {};
+    st = mp::op_elementwise_program((const ElementwiseArgs *)args, d.C, &p);
+    if (st != MILLIPYDE_SUCCESS) return st;
+    return pointwise_f32(obj, d, s, p);
+}
+
 MPStatus mpimg_adjust_gamma(MPObjData *obj, void *args)
 {
     if (!args) return MP_ERROR_INVALID_ARGUMENT;
@@ -817,6 +831,23 @@ MPStatus op_pointwise_f32(MPObjData *obj, const PwProgram &prog)
     if (st != MILLIPYDE_SUCCESS) return st;
     if (d.fam != FAM_F32) return MP_ERROR_UNSUPPORTED_LAYOUT;
     return pointwise_f32(obj, d, s, prog);
+}
+
+MPStatus op_elementwise_program(const ElementwiseArgs *a, int channels, PwProgram *prog)
+{
+    const int kind = (int)a->kind;
+    if (kind < MP_EW_ADD || kind > MP_EW_CLIP) return MP_ERROR_INVALID_ARGUMENT;
+    PwOp op = {kind, (float)a->a, (float)a->b, (float)a->c};
+    if (kind == MP_EW_MUL) {
+        if (a->per_channel != 0) {
+            if (channels != 3) return MP_ERROR_UNSUPPORTED_LAYOUT;
+        } else {
+            op.b = op.c = op.a;
+        }
+    }
+    prog->n = 1;
+    prog->ops[0] = op;
+    return MILLIPYDE_SUCCESS;
 }
 
 MPStatus op_pointwise_rgba8(MPObjData *obj, const U8Program &prog)

@@ -6,6 +6,7 @@
 #include "kernels/common.cuh"
 #include "kernels/gather_params.cuh"
 #include "mp_abi.h"
+#include "mp_image.h"
 
 namespace mp {
 
@@ -46,6 +47,8 @@ MPStatus launch_gaussian(int device, cudaStream_t s, const Img &d, const void *i
 MPStatus op_pointwise_f32(MPObjData *obj, const mpk::PwProgram &prog);
 MPStatus op_pointwise_rgba8(MPObjData *obj, const mpk::U8Program &prog);
 MPStatus op_grey_f32(MPObjData *obj, const mpk::PwProgram &pre, const mpk::PwProgram &post);
+// ElementwiseArgs (include/mp_image.h) -> a one-op pointwise program for an image with `channels` channels
+MPStatus op_elementwise_program(const ElementwiseArgs *a, int channels, mpk::PwProgram *prog);
 
 // The *_tab record tables (device memory, one entry per image) carry per-image parameters for
 // chains with random_* stages; null = the single program / angle passed by value.

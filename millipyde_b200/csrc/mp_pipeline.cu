@@ -28,6 +28,7 @@ namespace {
 
 enum OpKind {
     OP_GREY, OP_TRANSPOSE, OP_GAUSSIAN, OP_FLIPLR, OP_ROTATE, OP_BRIGHTNESS, OP_GAMMA, OP_COLORIZE,
+    OP_ELEMENTWISE,  // mpimg_elementwise: a ufunc-exact pointwise op (fuses like the other pointwise ops on fp32)
     OP_RANDOM,   // one of the mpimg_random_* operators: parameters are drawn per image at run time
     OP_FOREIGN,  // an MPFunc that is not one of ours: called as-is, one image at a time
     OP_NULL,     // func == NULL: skipped, as src/gpupipeline.c:393-396
@@ -37,11 +38,21 @@ struct Stage {
     OpKind kind;
     MPFunc func;
     void *args;          // owned copy for our operators, caller's pointer for foreign ones
-    double a[3];
+    double a[5];         // the leading doubles of the args block (ElementwiseArgs is the longest)
     double probability;  // <= 0: always (the reference tests `probability > 0`, :380)
 };
 
 std::atomic<int> g_fusion{1};
+
+bool is_pointwise(OpKind k);
+// Can this stage ride in a fused pointwise program of an image with `channels` channels?  (A per-channel
+// np.multiply needs exactly the three factors a PwOp carries.)
+bool is_pw(const Stage &s, int channels)
+{
+    if (!is_pointwise(s.kind)) return false;
+    if (s.kind == OP_ELEMENTWISE && (int)s.a[0] == MP_EW_MUL && s.a[4] != 0 && channels != 3) return false;
+    return true;
+}
 
 OpKind classify(MPFunc f, size_t *arg_bytes)
 {
@@ -55,6 +66,7 @@ OpKind classify(MPFunc f, size_t *arg_bytes)
     if (f == mpimg_brightness) { *arg_bytes = sizeof(BrightnessArgs); return OP_BRIGHTNESS; }
     if (f == mpimg_adjust_gamma) { *arg_bytes = sizeof(GammaArgs); return OP_GAMMA; }
     if (f == mpimg_colorize) { *arg_bytes = sizeof(ColorizeArgs); return OP_COLORIZE; }
+    if (f == mpimg_elementwise) { *arg_bytes = sizeof(ElementwiseArgs); return OP_ELEMENTWISE; }
     if (f == mpimg_random_rotate || f == mpimg_random_gaussian || f == mpimg_random_brightness) {
         *arg_bytes = sizeof(RandomRangeArgs);
         return OP_RANDOM;
@@ -64,7 +76,7 @@ OpKind classify(MPFunc f, size_t *arg_bytes)
     return OP_FOREIGN;
 }
 
-bool is_pointwise(OpKind k) { return k == OP_BRIGHTNESS || k == OP_GAMMA || k == OP_COLORIZE; }
+bool is_pointwise(OpKind k) { return k == OP_BRIGHTNESS || k == OP_GAMMA || k == OP_COLORIZE || k == OP_ELEMENTWISE; }
 
 // Per-device page-locked arenas for pointer tables.  A shard's worker owns one arena of the device's
 // ring while it enqueues (under the device's `enqueue` mutex, which also keeps the launches of two
@@ -141,6 +153,12 @@ PwOp to_pw(const Stage &s)
     switch (s.kind) {
         case OP_BRIGHTNESS: return PwOp{PW_BRIGHTNESS, (float)s.a[0], 0.f, 0.f};
         case OP_GAMMA: return PwOp{PW_GAMMA, (float)s.a[0], (float)s.a[1], 0.f};
+        case OP_ELEMENTWISE: {   // a = {kind, a, b, c, per_channel}; uniform factors are replicated
+            const bool per_channel = s.a[4] != 0;
+            const float m = (float)s.a[1];
+            if ((int)s.a[0] == MP_EW_MUL && !per_channel) return PwOp{PW_EW_MUL, m, m, m};
+            return PwOp{(int)s.a[0], m, (float)s.a[2], (float)s.a[3]};
+        }
         default: return PwOp{PW_COLORIZE, (float)s.a[0], (float)s.a[1], (float)s.a[2]};
     }
 }
@@ -169,7 +187,7 @@ std::vector<Segment> compile(const std::vector<const Stage *> &ops, mp::Family f
     while (i < ops.size()) {
         const Stage *s = ops[i];
         // fliplr / rotate (+ the pointwise ops around them) -> one gather pass
-        if (fuse && fam == mp::FAM_F32 && (s->kind == OP_FLIPLR || s->kind == OP_ROTATE || is_pointwise(s->kind))) {
+        if (fuse && fam == mp::FAM_F32 && (s->kind == OP_FLIPLR || s->kind == OP_ROTATE || is_pw(*s, channels))) {
             Segment seg;
             seg.kind = Segment::GATHER_F32;
             size_t j = i;
@@ -183,7 +201,7 @@ std::vector<Segment> compile(const std::vector<const Stage *> &ops, mp::Family f
                     seg.has_rotate = true;
                     seg.angle = t->a[0];
                     geometric = true;
-                } else if (is_pointwise(t->kind)) {
+                } else if (is_pw(*t, channels)) {
                     PwProgram &prog = seg.has_rotate ? seg.post : seg.pre;
                     if (prog.n == kMaxPw) break;
                     prog.ops[prog.n++] = to_pw(*t);
@@ -201,14 +219,14 @@ std::vector<Segment> compile(const std::vector<const Stage *> &ops, mp::Family f
         // a Gaussian absorbs the pointwise ops next to it: the ones before it are applied to every
         // sample as it lands in shared memory (once per sample, halo columns included; the zero
         // padding stays zero), the ones after it to the finished output rows before they are stored
-        if (fuse && fam == mp::FAM_F32 && (is_pointwise(s->kind) || s->kind == OP_GAUSSIAN)) {
+        if (fuse && fam == mp::FAM_F32 && (is_pw(*s, channels) || s->kind == OP_GAUSSIAN)) {
             Segment seg;
             seg.kind = Segment::GAUSS_F32;
             size_t j = i;
-            while (j < ops.size() && is_pointwise(ops[j]->kind) && seg.pre.n < kMaxPw) seg.pre.ops[seg.pre.n++] = to_pw(*ops[j++]);
+            while (j < ops.size() && is_pw(*ops[j], channels) && seg.pre.n < kMaxPw) seg.pre.ops[seg.pre.n++] = to_pw(*ops[j++]);
             if (j < ops.size() && ops[j]->kind == OP_GAUSSIAN && ops[j]->a[0] > 1e-15) {
                 seg.single = ops[j++];
-                while (j < ops.size() && is_pointwise(ops[j]->kind) && seg.post.n < kMaxPw)
+                while (j < ops.size() && is_pw(*ops[j], channels) && seg.post.n < kMaxPw)
                     seg.post.ops[seg.post.n++] = to_pw(*ops[j++]);
                 if (seg.pre.n + seg.post.n > 0) {   // a bare Gaussian keeps its own (SINGLE) path
                     out.push_back(seg);
@@ -217,14 +235,14 @@ std::vector<Segment> compile(const std::vector<const Stage *> &ops, mp::Family f
                 }
             }
         }
-        if (fuse && fam == mp::FAM_F32 && (is_pointwise(s->kind) || (s->kind == OP_GREY && channels >= 3))) {
+        if (fuse && fam == mp::FAM_F32 && (is_pw(*s, channels) || (s->kind == OP_GREY && channels >= 3))) {
             Segment seg;
             seg.kind = Segment::PW_F32;
             bool grey = false;
             size_t j = i;
             while (j < ops.size()) {
                 const Stage *t = ops[j];
-                if (is_pointwise(t->kind)) {
+                if (is_pw(*t, grey ? 1 : channels)) {
                     PwProgram &prog = grey ? seg.post : seg.pre;
                     if (prog.n == kMaxPw) break;
                     if (!(grey && t->kind == OP_COLORIZE))  // colorize is a no-op on grey (:647-651)
@@ -245,11 +263,12 @@ std::vector<Segment> compile(const std::vector<const Stage *> &ops, mp::Family f
                 continue;
             }
         }
-        if (fuse && fam == mp::FAM_RGBA8 && is_pointwise(s->kind)) {
+        if (fuse && fam == mp::FAM_RGBA8 && is_pw(*s, channels) && s->kind != OP_ELEMENTWISE) {
             Segment seg;
             seg.kind = Segment::PW_RGBA8;
             size_t j = i;
-            while (j < ops.size() && is_pointwise(ops[j]->kind) && seg.u8.n < kMaxPw) seg.u8.ops[seg.u8.n++] = to_u8(*ops[j++]);
+            while (j < ops.size() && is_pw(*ops[j], channels) && ops[j]->kind != OP_ELEMENTWISE && seg.u8.n < kMaxPw)
+                seg.u8.ops[seg.u8.n++] = to_u8(*ops[j++]);
             if (j - i >= 2) {
                 out.push_back(seg);
                 i = j;
@@ -323,7 +342,7 @@ void realize(const mp_pipeline *p, std::vector<Stage> *out)
 // one-op-at-a-time launches.
 std::string signature(const Segment &g)
 {
-    char b[96];
+    char b[192];
     switch (g.kind) {
         case Segment::SINGLE: {
             const Stage &st = *g.single;
@@ -341,7 +360,8 @@ std::string signature(const Segment &g)
             } else if (st.kind == OP_ROTATE && g_fusion.load()) {
                 snprintf(b, sizeof b, "S%d", (int)st.kind);
             } else {
-                snprintf(b, sizeof b, "S%d:%.17g,%.17g,%.17g", (int)st.kind, st.a[0], st.a[1], st.a[2]);
+                snprintf(b, sizeof b, "S%d:%.17g,%.17g,%.17g,%.17g,%.17g", (int)st.kind, st.a[0], st.a[1], st.a[2], st.a[3],
+                         st.a[4]);
             }
             break;
         }
@@ -965,7 +985,7 @@ MPPipeline *mppipe_create(const MPRunnable *stages, int num_stages, int device_i
             s.args = malloc(bytes);
             memcpy(s.args, stages[i].args, bytes);
             const double *a = (const double *)s.args;
-            for (size_t k = 0; k < bytes / sizeof(double) && k < 3; ++k) s.a[k] = a[k];
+            for (size_t k = 0; k < bytes / sizeof(double) && k < 5; ++k) s.a[k] = a[k];
         }
         p->stages.push_back(s);
     }
@@ -1137,11 +1157,11 @@ int mppipe_plan(const MPPipeline *p, int typenum, int channels, char *buf, int c
     for (const Stage &st : realized) ops.push_back(&st);
     const std::vector<Segment> segs = compile(ops, fam, channels);
     static const char *const kOp[] = {"rgb2grey", "transpose", "gaussian", "fliplr", "rotate", "brightness",
-                                      "adjust_gamma", "colorize", "random", "foreign", "null"};
-    static const char *const kPw[] = {"none", "brightness", "adjust_gamma", "colorize"};
+                                      "adjust_gamma", "colorize", "elementwise", "random", "foreign", "null"};
+    static const char *const kPw[] = {"none", "brightness", "adjust_gamma", "colorize", "add", "multiply", "power", "clip"};
     auto prog = [](const PwProgram &g) {
         std::string t;
-        for (int i = 0; i < g.n; ++i) t += (i ? "," : "") + std::string(kPw[g.ops[i].kind & 3]);
+        for (int i = 0; i < g.n; ++i) t += (i ? "," : "") + std::string(kPw[g.ops[i].kind & 7]);
         return t;
     };
     std::string out;

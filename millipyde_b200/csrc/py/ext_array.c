@@ -8,6 +8,8 @@
  * mutate in place and return None; unlike the reference, an MPStatus other than
  * success raises RuntimeError instead of being dropped.
  */
+#include <math.h>
+#include <strings.h>
 #include "ext_common.h"
 
 /* ------------------------------------------------------------------ lifecycle */
@@ -248,8 +250,123 @@ static PyObject *array_function(MPArrayObject *self, PyObject *args, PyObject *k
     return res;
 }
 
-/* __array_ufunc__(ufunc, method, *inputs, **kwargs) -- a working version of the
- * reference's printing stub (src/gpuarray.c:147-191): same host-copy rule. */
+/* A Python / numpy scalar as a double; 0 if `o` is not a real scalar (arrays, gpuarrays, complex). */
+static int scalar_as_double(PyObject *o, double *out)
+{
+    if (PyBool_Check(o)) return 0;   /* numpy would promote differently: leave it to the host path */
+    /* Python floats / ints are "weak" scalars (NEP 50): the float32 image keeps float32.  numpy scalars
+     * carry their type: only float32 / float16 leave the result float32 (np.float64(0.3) promotes). */
+    if ((PyFloat_Check(o) && !PyArray_IsScalar(o, Double)) || PyLong_Check(o) || PyArray_IsScalar(o, Float) ||
+        PyArray_IsScalar(o, Half)) {
+        double v = PyFloat_AsDouble(o);
+        if (v == -1.0 && PyErr_Occurred()) {
+            PyErr_Clear();
+            return 0;
+        }
+        *out = v;
+        return 1;
+    }
+    return 0;
+}
+
+/* A per-channel factor array: a 1-D float32 ndarray of three values (a list or a float64 array would
+ * promote the float32 image to float64 in numpy: host path). */
+static int triple_as_doubles(PyObject *o, double *out)
+{
+    if (MP_IS_GPU_OBJECT(o) || !PyArray_Check(o) || PyArray_TYPE((PyArrayObject *)o) != NPY_FLOAT) return 0;
+    PyArrayObject *a = (PyArrayObject *)PyArray_FROM_OTF(o, NPY_DOUBLE, NPY_ARRAY_IN_ARRAY);
+    if (!a) {
+        PyErr_Clear();
+        return 0;
+    }
+    int ok = PyArray_NDIM(a) == 1 && PyArray_DIM(a, 0) == 3;
+    for (int i = 0; ok && i < 3; ++i) out[i] = ((double *)PyArray_DATA(a))[i];
+    Py_DECREF(a);
+    return ok;
+}
+
+/* ufuncs that ARE a pointwise device kernel on a float32 image: np.add, np.subtract,
+ * np.multiply (scalar, or three per-channel factors on an RGB image), np.power (scalar exponent),
+ * np.clip, np.maximum, np.minimum with scalar bounds.  The result is a NEW object of the caller's
+ * type on the same device -- no D2H, no CPU arithmetic; the source is not modified.  Everything else
+ * (other ufuncs, methods other than __call__, out=, dtype=, where=, array operands, non-float32
+ * layouts) returns NULL with *handled = 0 and takes the host path like src/gpuarray.c:147-191. */
+static PyObject *device_ufunc(MPArrayObject *self, PyObject *ufunc, PyObject *method, PyObject *inputs, PyObject *kwds,
+                              int *handled)
+{
+    *handled = 0;
+    if (!self->obj || !self->obj->device_data || self->obj->type != NPY_FLOAT) return NULL;
+    if (kwds && PyDict_Size(kwds) > 0) return NULL;
+    if (!PyUnicode_Check(method) || strcmp(PyUnicode_AsUTF8(method), "__call__") != 0) return NULL;
+    PyObject *name = PyObject_GetAttrString(ufunc, "__name__");
+    if (!name) {
+        PyErr_Clear();
+        return NULL;
+    }
+    const char *fn = PyUnicode_Check(name) ? PyUnicode_AsUTF8(name) : "";
+    const Py_ssize_t n = PyTuple_GET_SIZE(inputs);
+    PyObject *x0 = n > 0 ? PyTuple_GET_ITEM(inputs, 0) : NULL, *x1 = n > 1 ? PyTuple_GET_ITEM(inputs, 1) : NULL;
+    ElementwiseArgs ew = {0, 0, 0, 0, 0};
+    double v = 0, t[3];
+    int ok = 0;
+    const int self_first = x0 == (PyObject *)self, self_second = x1 == (PyObject *)self;
+    const int channels = self->obj->ndims == 3 ? self->obj->dims[2] : 1;
+    if (n == 2 && (strcmp(fn, "add") == 0 || strcmp(fn, "multiply") == 0) && (self_first || self_second)) {
+        PyObject *other = self_first ? x1 : x0;          /* commutative */
+        const int mul = fn[0] == 'm';
+        if (scalar_as_double(other, &v)) {
+            ew.kind = mul ? MP_EW_MUL : MP_EW_ADD;
+            ew.a = v;
+            ok = 1;
+        } else if (mul && channels == 3 && triple_as_doubles(other, t)) {
+            ew.kind = MP_EW_MUL;
+            ew.a = t[0]; ew.b = t[1]; ew.c = t[2];
+            ew.per_channel = 1;
+            ok = 1;
+        }
+    } else if (n == 2 && strcmp(fn, "subtract") == 0 && self_first && scalar_as_double(x1, &v)) {
+        ew.kind = MP_EW_ADD;      /* x - s == x + (-s) exactly in IEEE arithmetic */
+        ew.a = -v;
+        ok = 1;
+    } else if (n == 2 && strcmp(fn, "power") == 0 && self_first && scalar_as_double(x1, &v)) {
+        ew.kind = MP_EW_POW;
+        ew.a = v;
+        ok = 1;
+    } else if (n == 3 && strcmp(fn, "clip") == 0 && self_first && scalar_as_double(x1, &v) &&
+               scalar_as_double(PyTuple_GET_ITEM(inputs, 2), &t[0])) {
+        ew.kind = MP_EW_CLIP;
+        ew.a = v; ew.b = t[0];
+        ok = 1;
+    } else if (n == 2 && (strcmp(fn, "maximum") == 0 || strcmp(fn, "minimum") == 0) && (self_first || self_second) &&
+               scalar_as_double(self_first ? x1 : x0, &v) && v == v) {
+        ew.kind = MP_EW_CLIP;     /* one-sided clip (NaN bounds propagate in numpy: host path) */
+        ew.a = fn[1] == 'a' ? v : -INFINITY;
+        ew.b = fn[1] == 'a' ? INFINITY : v;
+        ok = 1;
+    }
+    Py_DECREF(name);
+    /* the scalar must be exactly representable in the image's float32 arithmetic, as numpy's weak
+     * scalar promotion makes it (a Python float operand is cast to float32 before the loop runs) */
+    if (!ok) return NULL;
+    MPArrayObject *copy = (MPArrayObject *)mpext_clone(self, self->obj->mem_loc, 0);
+    if (!copy) {
+        PyErr_Clear();
+        return NULL;
+    }
+    MPStatus st;
+    Py_BEGIN_ALLOW_THREADS
+    st = mpimg_elementwise(copy->obj, &ew);
+    Py_END_ALLOW_THREADS
+    if (st != MILLIPYDE_SUCCESS) {
+        Py_DECREF(copy);
+        return NULL;
+    }
+    *handled = 1;
+    return (PyObject *)copy;
+}
+
+/* __array_ufunc__(ufunc, method, *inputs, **kwargs): the ufuncs above run on the device; the rest
+ * follows the reference's host-copy rule (its own version is a printing stub, src/gpuarray.c:147-191). */
 static PyObject *array_ufunc(MPArrayObject *self, PyObject *args, PyObject *kwds)
 {
     if (PyTuple_Size(args) < 2) {
@@ -258,6 +375,15 @@ static PyObject *array_ufunc(MPArrayObject *self, PyObject *args, PyObject *kwds
     }
     PyObject *ufunc = PyTuple_GetItem(args, 0), *method = PyTuple_GetItem(args, 1);
     PyObject *inputs = PyTuple_GetSlice(args, 2, PyTuple_Size(args));
+    {
+        int handled = 0;
+        PyObject *on_device = device_ufunc(self, ufunc, method, inputs, kwds, &handled);
+        if (handled) {
+            Py_DECREF(inputs);
+            return on_device;
+        }
+        if (PyErr_Occurred()) PyErr_Clear();
+    }
     PyObject *host_in = hostify_tuple(inputs);
     Py_DECREF(inputs);
     if (!host_in) return NULL;

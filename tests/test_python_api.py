@@ -209,6 +209,92 @@ def test_np_functions_that_are_device_operators_stay_on_the_device():
 
 
 @gpu
+def test_np_ufuncs_that_are_pointwise_kernels_stay_on_the_device():
+    """__array_ufunc__ (the reference's is a printing stub, src/gpuarray.c:147-191):
+    np.add / subtract / multiply / power / clip / maximum / minimum with scalar operands (multiply also
+    with three per-channel factors) on a float32 gpuimage run the pointwise kernel on a device-side copy
+    and return a gpuimage with numpy's exact semantics -- no clamp, float32 arithmetic with the scalar
+    cast to float32 (NEP 50), source untouched.  Anything else takes the host path."""
+    from tests import synth
+    a = synth.noise_f32(37, 52, 3, 44) * np.float32(1.7) - np.float32(0.2)        # leaves [0, 1] on both sides
+    g = mp.gpuimage(a)
+    n0 = mp.launch_count()
+    cases = [
+        (np.add(g, 0.3), a + np.float32(0.3)),
+        (np.add(0.3, g), np.float32(0.3) + a),
+        (g + 0.25, a + np.float32(0.25)) if hasattr(g, "__add__") else (np.add(g, 0.25), a + np.float32(0.25)),
+        (np.subtract(g, 0.1), a - np.float32(0.1)),
+        (np.multiply(g, 1.5), a * np.float32(1.5)),
+        (np.multiply(g, np.float32(0.5)), a * np.float32(0.5)),
+        (np.multiply(g, np.array([0.5, 1.5, 1.1], np.float32)), a * np.array([0.5, 1.5, 1.1], np.float32)),
+        (np.multiply(np.array([0.5, 1.5, 1.1], np.float32), g), np.array([0.5, 1.5, 1.1], np.float32) * a),
+        (np.clip(g, 0.0, 1.0), np.clip(a, 0.0, 1.0)),
+        (np.maximum(g, 0.5), np.maximum(a, np.float32(0.5))),
+        (np.minimum(0.5, g), np.minimum(np.float32(0.5), a)),
+    ]
+    assert mp.launch_count() - n0 >= len(cases)                  # kernels ran: nothing came from the host
+    for k, (got, want) in enumerate(cases):
+        assert type(got) is mp.gpuimage and got.shape == a.shape, k
+        h = np.array(got)
+        assert h.dtype == np.float32 and np.array_equal(h, want), k
+    p = np.array(np.power(mp.gpuimage(np.abs(a)), 1.5))
+    assert p.dtype == np.float32 and np.allclose(p, np.power(np.abs(a), np.float32(1.5)), rtol=2e-6, atol=1e-7)
+    assert np.array_equal(np.array(g), a)                         # ufuncs do not mutate
+    # composition stays on the device: brightness as numpy spells it
+    b = np.clip(np.add(g, 0.2), 0.0, 1.0)
+    assert type(b) is mp.gpuimage and np.array_equal(np.array(b), np.clip(a + np.float32(0.2), 0, 1))
+    # host path (numpy semantics preserved): float64 scalar types promote, array operands, other ufuncs,
+    # out=/dtype= arguments, non-float32 layouts
+    r = np.add(g, np.float64(0.3))
+    assert isinstance(r, np.ndarray) and r.dtype == np.float64 and np.array_equal(r, a + np.float64(0.3))
+    r = np.add(g, a)
+    assert isinstance(r, np.ndarray) and np.array_equal(r, a + a)
+    r = np.multiply(g, [0.5, 1.5, 1.1])                           # a list is a float64 array to numpy
+    assert isinstance(r, np.ndarray) and r.dtype == np.float64
+    assert isinstance(np.sqrt(mp.gpuimage(np.abs(a))), np.ndarray)
+    assert isinstance(np.add(g, 0.3, dtype=np.float64), np.ndarray)
+    rgba = np.random.default_rng(5).integers(0, 256, (16, 24, 4), dtype=np.uint8)
+    r = np.add(mp.gpuimage(rgba), 1)
+    assert isinstance(r, np.ndarray) and np.array_equal(r, rgba + 1)
+    grey = synth.noise_f32(20, 33, 1, 45)
+    r = np.multiply(mp.gpuimage(grey), 2.0)
+    assert type(r) is mp.gpuimage and np.array_equal(np.array(r), grey * np.float32(2.0))
+    r = np.multiply(mp.gpuimage(grey[:, :3].copy()), [1.0, 2.0, 3.0])          # broadcasting over a 2-D image: host
+    assert isinstance(r, np.ndarray)
+
+
+@gpu
+def test_elementwise_ops_chain_and_fuse_in_a_pipeline():
+    """mpimg_elementwise has the MPFunc signature: through the C ABI it is a pipeline stage like the
+    eight operators and fuses with them (here into the Gaussian's launch)."""
+    import ctypes as C
+    from millipyde_b200 import capi, engine
+    from oracle import skimage_oracle as so
+    from tests import synth
+    L = capi.lib()
+    imgs = [synth.noise_f32(64, 160, 3, 50 + k) for k in range(4)]
+    dev = [capi.DeviceImage(x) for x in imgs]
+    arr = (capi.MPRunnable * 3)()
+    ew1 = capi.ElementwiseArgs(5, 0.5, 0.0, 0.0, 0.0)          # multiply by 0.5
+    g = capi.GaussianArgs(2.0)
+    ew2 = capi.ElementwiseArgs(4, 0.25, 0.0, 0.0, 0.0)         # add 0.25
+    for k, (fn, a) in enumerate((("mpimg_elementwise", ew1), ("mpimg_gaussian", g), ("mpimg_elementwise", ew2))):
+        arr[k].func = C.cast(getattr(L, fn), C.c_void_p)
+        arr[k].args = C.cast(C.pointer(a), C.c_void_p)
+        arr[k].probability = -1.0
+    buf = C.create_string_buffer(256)
+    pipe = L.mppipe_create(arr, 3, 0)
+    assert L.mppipe_plan(pipe, 11, 3, buf, len(buf)) == 1 and buf.value == b"gauss(multiply|add)"
+    objs = (C.POINTER(capi.MPObjData) * len(dev))(*[d.ptr for d in dev])
+    assert L.mppipe_run(pipe, objs, len(dev)) == 0
+    assert L.mppipe_last_launches(pipe) == 1
+    for x, d in zip(imgs, dev):
+        want = so.gaussian(x * np.float32(0.5), 2.0) + 0.25
+        assert np.abs(d.numpy() - want).max() <= 1e-5
+    L.mppipe_destroy(pipe)
+
+
+@gpu
 def test_np_function_protocol():
     lst = [[1, 2, 3], [4, 5, 6], [7, 8, 9]]
     want = np.transpose(np.array(lst))
