@@ -48,7 +48,8 @@ void mppipe_connect(MPPipeline *from, MPPipeline *to);
  * involved are idle.  Objects are mutated in place like the eager ops do. */
 MPStatus mppipe_run(MPPipeline *p, MPObjData **objs, int n);
 
-/* mppipe_run for views made by mpobj_view_data (all on the pipeline's device): the first launch
+/* mppipe_run for views made by mpobj_view_data (each runs on the device its borrowed buffer lives on,
+ * one shard per device): the first launch
  * that touches an image reads the borrowed buffer and writes the view's own; a view no stage
  * touched is deep-copied.  On return every view owns its buffer (or holds none, on error). */
 MPStatus mppipe_run_views(MPPipeline *p, MPObjData **views, int n);

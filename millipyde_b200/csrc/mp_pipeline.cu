@@ -1071,11 +1071,12 @@ static MPStatus submit_impl(MPPipeline *p, MPObjData **objs, int n, bool views)
         }
     }
     if (views) {
-        // a view stays where the buffer it borrows lives: one shard, on that device
-        if (cycle && n > 0 && objs[0]) device = objs[0]->mem_loc;
+        // a view stays where the buffer it borrows lives: one shard per device that holds views (a
+        // Generator spreading its stream borrows from per-device replicas of its inputs)
         cycle = false;
         for (int i = 0; i < n; ++i)
-            if (!objs[i] || !objs[i]->device_data || objs[i]->mem_loc != device) return MP_ERROR_INVALID_ARGUMENT;
+            if (!objs[i] || !objs[i]->device_data || !mpdev_is_valid_device(objs[i]->mem_loc)) return MP_ERROR_INVALID_ARGUMENT;
+        if (n > 0) device = objs[0]->mem_loc;
     }
     if (!mpdev_is_valid_device(device)) return GPUPIPELINE_ERROR_UNUSABLE_DEVICE;
     p->cycled = cycle;
@@ -1088,7 +1089,7 @@ static MPStatus submit_impl(MPPipeline *p, MPObjData **objs, int n, bool views)
     std::map<int, std::vector<MPObjData *>> shards;
     int cur = device;
     for (int i = 0; i < n; ++i) {
-        if (objs[i]) shards[cur].push_back(objs[i]);
+        if (objs[i]) shards[views ? objs[i]->mem_loc : cur].push_back(objs[i]);
         if (cycle && ((i + 1) % THREADS_PER_DEVICE == 0)) cur = mpdev_get_next_device(cur);
     }
     for (auto &kv : shards) submit_shard(p, std::move(kv.second), kv.first, views);

@@ -649,16 +649,47 @@ static int produce_batch(MPGeneratorObject *g, long count)
         MPObjData *o = ((MPArrayObject *)PyList_GetItem(g->inputs, k))->obj;
         if (!o || !o->device_data || o->mem_loc != dev) use_views = 0;
     }
+    /* Spreading over several devices: every device gets ONE replica of each input it needs for this
+     * batch (a peer copy over NVLink, made now so a caller who mutated an input since the last batch
+     * is honoured) and its outputs are views of that replica -- not one cross-device clone per output,
+     * which would pull the whole stream through the home device's links. */
+    const int spread = !use_views && bound == DEVICE_LOC_NO_AFFINITY && ndev > 1;
+    PyObject **replica = spread ? (PyObject **)calloc((size_t)ndev * (size_t)n_in, sizeof(PyObject *)) : NULL;
+    int spread_ok = spread && replica != NULL;
+    for (Py_ssize_t k = 0; spread_ok && k < n_in; ++k) {
+        MPObjData *o = ((MPArrayObject *)PyList_GetItem(g->inputs, k))->obj;
+        if (!o || !o->device_data) spread_ok = 0;
+    }
     for (long k = 0; k < count; ++k) {
-        PyObject *input = PyList_GetItem(g->inputs, (g->produced + k) % n_in);
-        /* the executor assigns image k to device block k / THREADS_PER_DEVICE: clone it there */
-        PyObject *c = use_views ? mpext_wrap_obj(Py_TYPE(input), mpobj_view_data(((MPArrayObject *)input)->obj))
-                                : mpext_clone((MPArrayObject *)input, dev, 0);
+        const Py_ssize_t which = (g->produced + k) % n_in;
+        PyObject *input = PyList_GetItem(g->inputs, which);
+        PyObject *c;
+        if (use_views) {
+            c = mpext_wrap_obj(Py_TYPE(input), mpobj_view_data(((MPArrayObject *)input)->obj));
+        } else if (spread_ok) {
+            PyObject **slot = &replica[(size_t)dev * (size_t)n_in + (size_t)which];
+            if (!*slot) {
+                if (((MPArrayObject *)input)->obj->mem_loc == dev) {
+                    Py_INCREF(input);
+                    *slot = input;
+                } else {
+                    *slot = mpext_clone((MPArrayObject *)input, dev, 0);
+                }
+            }
+            c = *slot ? mpext_wrap_obj(Py_TYPE(input), mpobj_view_data(((MPArrayObject *)*slot)->obj)) : NULL;
+        } else {
+            /* the executor assigns image k to device block k / THREADS_PER_DEVICE: clone it there */
+            c = mpext_clone((MPArrayObject *)input, dev, 0);
+        }
         if (!c) {
-            if (use_views) /* the views made so far still borrow: they must not free the inputs' buffers */
+            if (use_views || spread_ok) /* the views made so far still borrow: they must not free what they borrow */
                 for (long j = 0; j < k; ++j) objs[j]->device_data = NULL;
             Py_DECREF(batch);
             free(objs);
+            if (replica) {
+                for (size_t r = 0; r < (size_t)ndev * (size_t)n_in; ++r) Py_XDECREF(replica[r]);
+                free(replica);
+            }
             return -1;
         }
         objs[k] = ((MPArrayObject *)c)->obj;
@@ -669,9 +700,13 @@ static int produce_batch(MPGeneratorObject *g, long count)
     }
     MPStatus st;
     Py_BEGIN_ALLOW_THREADS
-    st = use_views ? mppipe_run_views(g->pipe, objs, (int)count) : mppipe_run(g->pipe, objs, (int)count);
+    st = (use_views || spread_ok) ? mppipe_run_views(g->pipe, objs, (int)count) : mppipe_run(g->pipe, objs, (int)count);
     Py_END_ALLOW_THREADS
     free(objs);
+    if (replica) { /* every view owns its result now; the replicas retire in stream order */
+        for (size_t r = 0; r < (size_t)ndev * (size_t)n_in; ++r) Py_XDECREF(replica[r]);
+        free(replica);
+    }
     if (st != MILLIPYDE_SUCCESS) {
         Py_DECREF(batch);
         mpext_raise_status(st, "Generator");
