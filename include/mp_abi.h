@@ -199,6 +199,11 @@ const char *mperr_str(MPStatus status);
 MPStatus random_int_in_range(int min, int max, int *result);
 MPStatus random_double_in_range(double min, double max, double *result);
 void mprand_seed(uint64_t seed); /* new: 0 restores the entropy source */
+/* new: the draw a Pipeline / Generator run makes for parameter `slot` (0..5 in declaration order; 7 = the
+ * stage's probability coin, on [0, 1]) of stage `stage` of image `image` (its position in the stream) --
+ * Philox-4x32-10 keyed by the run (mppipe_last_run_key).  The same function is evaluated on the host and
+ * in the kernel that fills per-image parameter records, so a stream can be predicted and replayed. */
+double mprand_keyed_double(uint64_t run_key, uint64_t image, unsigned stage, unsigned slot, double min, double max);
 
 #ifdef __cplusplus
 }

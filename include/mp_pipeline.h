@@ -76,6 +76,21 @@ MPStatus mppipe_run_host(MPPipeline *p, const void *const *host_in, void *const 
                          size_t out_capacity, MPHostResult *results, int n, int ndims,
                          const long *shape, int typenum);
 
+/* Random source of a run (new).  Every coin flip and random_* parameter of a run is a pure function of
+ * (run key, stream index of the image, stage, slot) -- mprand_keyed_double -- independent of devices,
+ * shards and threads.  The stream index of objs[i] is first_index + i: a Generator sets first_index to
+ * the number of outputs produced so far, so its stream does not depend on the look-ahead.  The run key is
+ * drawn per mppipe_submit / mppipe_run_host (seeded: a function of the seed and the run number).
+ * Per-image parameter records are filled on the device when every image of a launch shares the chain's
+ * shape (mppipe_set_device_draws(0) evaluates the same draws on the host instead: an A/B switch). */
+void mppipe_set_index_base(MPPipeline *p, unsigned long long first_index);
+unsigned long long mppipe_last_run_key(const MPPipeline *p);
+/* Draw the key now and keep it for every later run of `p`: with mppipe_set_index_base, a Generator's
+ * output k is then the same whatever the batch (look-ahead) boundaries are. */
+void mppipe_hold_run_key(MPPipeline *p);
+void mppipe_set_device_draws(int enabled);
+int mppipe_get_device_draws(void);
+
 /* Fusion on (default) / off: off reproduces the reference's one-kernel-per-stage execution with the
  * same kernels, for A/B parity tests. */
 void mppipe_set_fusion(int enabled);

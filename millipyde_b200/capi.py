@@ -110,6 +110,7 @@ SYMBOLS = {
     "random_int_in_range": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "random_double_in_range": (C.c_int, [C.c_double, C.c_double, C.POINTER(C.c_double)]),
     "mprand_seed": (None, [C.c_uint64]),
+    "mprand_keyed_double": (C.c_double, [C.c_uint64, C.c_uint64, C.c_uint, C.c_uint, C.c_double, C.c_double]),
     # mp_image.h
     "mpimg_color_to_greyscale": (C.c_int, [_OBJ, C.c_void_p]),
     "mpimg_transpose": (C.c_int, [_OBJ, C.c_void_p]),
@@ -206,6 +207,11 @@ SYMBOLS = {
     "mppipe_run_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t,
                                   C.POINTER(MPHostResult), C.c_int, C.c_int, C.POINTER(C.c_long), C.c_int]),
     "mppipe_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int]),
+    "mppipe_set_index_base": (None, [C.c_void_p, C.c_ulonglong]),
+    "mppipe_last_run_key": (C.c_ulonglong, [C.c_void_p]),
+    "mppipe_hold_run_key": (None, [C.c_void_p]),
+    "mppipe_set_device_draws": (None, [C.c_int]),
+    "mppipe_get_device_draws": (C.c_int, []),
     "mppipe_set_fusion": (None, [C.c_int]),
     "mppipe_get_fusion": (C.c_int, []),
     "mppipe_last_launches": (C.c_ulonglong, [C.c_void_p]),

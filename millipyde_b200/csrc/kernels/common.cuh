@@ -96,10 +96,9 @@ __device__ __forceinline__ float pw_apply(const PwProgram &prog, float v, int ch
 // The same program applied to a register tile of N samples whose channels are ch0, ch0+1, ...
 // (mod C): the op switch is taken once per op, not once per sample.
 template <int C, int N>
-__device__ __forceinline__ void pw_apply_tile(const PwProgram &prog, float (&r)[N], int ch0)
+__device__ __forceinline__ void pw_apply_op_tile_impl(const PwOp &op, float (&r)[N], int ch0)
 {
-    for (int i = 0; i < prog.n; ++i) {
-        const PwOp op = prog.ops[i];
+    {
         switch (op.kind) {
             case PW_BRIGHTNESS:
 #pragma unroll
@@ -134,22 +133,36 @@ __device__ __forceinline__ void pw_apply_tile(const PwProgram &prog, float (&r)[
         }
     }
 }
-
-// pw_apply_tile for a program that lives in device memory (per-image records of a batched launch):
-// every op is fetched through the read-only path, the same words for all lanes.
 template <int C, int N>
-__device__ __forceinline__ void pw_apply_tile_g(const PwProgram *__restrict__ prog, float (&r)[N], int ch0)
+__device__ __forceinline__ void pw_apply_tile(const PwProgram &prog, float (&r)[N], int ch0)
 {
-    const int n = __ldg(&prog->n);
-    for (int i = 0; i < n; ++i) {
-        PwProgram one;   // (ops sit at offset 4 + 16 i: scalar loads)
-        one.n = 1;
-        one.ops[0].kind = __ldg(&prog->ops[i].kind);
-        one.ops[0].a = __ldg(&prog->ops[i].a);
-        one.ops[0].b = __ldg(&prog->ops[i].b);
-        one.ops[0].c = __ldg(&prog->ops[i].c);
-        pw_apply_tile<C, N>(one, r, ch0);
-    }
+    for (int i = 0; i < prog.n; ++i) pw_apply_op_tile_impl<C, N>(prog.ops[i], r, ch0);
+}
+
+// A program staged in shared memory for kernels that apply it many times (the streaming Gaussian's
+// fused pre/post ops): ops on 16-byte boundaries so that one op is one LDS.128 broadcast.
+struct alignas(16) PwSmem {
+    int n;
+    int pad[3];
+    int4 ops[kMaxPw];
+};
+// one warp copies `src` (device memory; null = empty program) into its own PwSmem
+__device__ __forceinline__ void pw_smem_load(PwSmem *dst, const PwProgram *__restrict__ src, int lane)
+{
+    if (lane == 0) dst->n = src ? __ldg(&src->n) : 0;
+    if (src) reinterpret_cast<int *>(dst->ops)[lane] = __ldg(reinterpret_cast<const int *>(src->ops) + lane);  // 8 ops x 4 words
+    __syncwarp();
+}
+__device__ __forceinline__ PwOp pw_smem_op(const PwSmem &p, int i)
+{
+    const int4 raw = p.ops[i];
+    return PwOp{raw.x, __int_as_float(raw.y), __int_as_float(raw.z), __int_as_float(raw.w)};
+}
+// one op on a register tile (the body of pw_apply_tile for a single op)
+template <int C, int N>
+__device__ __forceinline__ void pw_apply_op_tile(const PwOp &op, float (&r)[N], int ch0)
+{
+    pw_apply_op_tile_impl<C, N>(op, r, ch0);
 }
 
 // Luma of skimage.color.rgb2gray / src/millipyde_image.cpp:64, fp32 flavour.

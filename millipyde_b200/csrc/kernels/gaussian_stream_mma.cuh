@@ -58,7 +58,8 @@ struct MmGeom {
     static constexpr size_t H_BYTES = (size_t)kMmRing * kMmPitch * 4;
     static constexpr size_t STAGE_BYTES = (size_t)MmK::col_warps * 8 * kMmStagePitch * 4;
     static constexpr int N_BARS = MmK::row_warps * MmK::in_slots + 2 * MmK::groups;
-    static constexpr size_t SMEM = IN_BYTES + H_BYTES + STAGE_BYTES + 8 * N_BARS + 64;
+    static constexpr size_t PROG_BYTES = (size_t)(MmK::threads / 32) * sizeof(PwSmem);   // one fused program per warp
+    static constexpr size_t SMEM = IN_BYTES + H_BYTES + STAGE_BYTES + 8 * N_BARS + 64 + PROG_BYTES;
 };
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1,
@@ -126,6 +127,7 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
     uint64_t *in_full = bars;
     uint64_t *h_full = bars + MmK::row_warps * MmK::in_slots;
     uint64_t *h_empty = h_full + MmK::groups;
+    PwSmem *s_prog = reinterpret_cast<PwSmem *>(smem_raw + G::IN_BYTES + G::H_BYTES + G::STAGE_BYTES + 8 * G::N_BARS + 64);
 
     // the warp index is read from lane 0 so that the compiler knows it is warp-uniform: ring slots,
     // barrier and bulk-copy addresses then live in uniform registers (UBLKCP without R2UR loops)
@@ -142,7 +144,7 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
 
     if (warp < MmK::row_warps) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMmRowRegs));
-        ws_row_role<C, R, SETS, kMmPitch, true>(p, ws, s_in, s_h, in_full, h_full, h_empty, warp, lane);
+        ws_row_role<C, R, SETS, kMmPitch, true>(p, ws, s_in, s_h, in_full, h_full, h_empty, warp, lane, s_prog);
         return;
     }
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kMmColRegs));
@@ -207,10 +209,11 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc[q][j][e] = 0.f;
 
-        const PwProgram *post = nullptr;   // this image's "after the blur" program (null or empty: none)
+        PwSmem *my_prog = s_prog + warp;   // this warp's copy of the image's "after the blur" program
+        int n_post = 0;
         if (SETS && p.pw_tab) {
-            post = p.pw_tab + (size_t)img * p.pw_stride + 1;
-            if (__ldg(&post->n) == 0) post = nullptr;
+            pw_smem_load(my_prog, p.pw_tab + (size_t)img * p.pw_stride + 1, lane);
+            n_post = my_prog->n;
         }
         const uint32_t item_g0 = waited;   // == released: items are whole turns of the ring
         int ring_row = 0;                  // (c % 6) * 8
@@ -297,13 +300,16 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
                 for (int u = 0; u < kPair; ++u) {
                     const int q = q0 + u;
                     if (q >= kMmTiles) continue;
-                    if (SETS && post) {
+                    if (SETS && n_post) {
                         // (c0, c2) and (c1, c3) are the column pair (2g, 2g + 1) of tile q in two rows
                         float r2[2] = {nxt[u][NCH - 1][0], nxt[u][NCH - 1][2]};
                         float r3[2] = {nxt[u][NCH - 1][1], nxt[u][NCH - 1][3]};
                         const int ch0 = (gx0 + 16 * q + 2 * g) % C;
-                        pw_apply_tile_g<C, 2>(post, r2, ch0);
-                        pw_apply_tile_g<C, 2>(post, r3, ch0);
+                        for (int k = 0; k < n_post; ++k) {
+                            const PwOp op = pw_smem_op(*my_prog, k);
+                            pw_apply_op_tile<C, 2>(op, r2, ch0);
+                            pw_apply_op_tile<C, 2>(op, r3, ch0);
+                        }
                         nxt[u][NCH - 1][0] = r2[0]; nxt[u][NCH - 1][2] = r2[1];
                         nxt[u][NCH - 1][1] = r3[0]; nxt[u][NCH - 1][3] = r3[1];
                     }

@@ -58,7 +58,8 @@ struct WsGeom {
     static constexpr size_t IN_BYTES = (size_t)kWsRowWarps * kWsInSlots * ROW * 4;
     static constexpr size_t H_BYTES = (size_t)kWsGroups * kWsRows * kGsTW * 4;
     static constexpr int N_BARS = kWsRowWarps * kWsInSlots + 2 * kWsGroups;
-    static constexpr size_t SMEM = IN_BYTES + H_BYTES + 8 * N_BARS + 64;
+    static constexpr size_t PROG_BYTES = (size_t)(kWsThreads / 32) * sizeof(PwSmem);   // one fused program per warp
+    static constexpr size_t SMEM = IN_BYTES + H_BYTES + 8 * N_BARS + 64 + PROG_BYTES;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
@@ -147,8 +148,9 @@ __device__ __forceinline__ int ws_steps(int n_rows)
 template <int C, int R, bool SETS, int PITCH, bool MMA>
 __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const GaussWeightSets &ws, float *s_in,
                                             float *s_h, uint64_t *in_full, uint64_t *h_full, uint64_t *h_empty,
-                                            int warp, int lane)
+                                            int warp, int lane, PwSmem *s_prog)
 {
+    PwSmem *my_prog = s_prog + warp;   // this warp's copy of the current image's "before the blur" program
     using G = WsGeom<C, R>;
     using K = WsK<MMA>;
     const int items_per_image = p.n_strips * p.n_chunks;
@@ -181,10 +183,10 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
         const int hi = min(G::ROW, p.row_elems - gx_start);
         const uint32_t row_bytes = (uint32_t)(hi - lo) * 4u;
         // this image's "before the blur" program (null or empty: none) and the channel of ring column 0
-        const PwProgram *pre = nullptr;
-        if (SETS && p.pw_tab) {
-            pre = p.pw_tab + (size_t)img * p.pw_stride;
-            if (__ldg(&pre->n) == 0) pre = nullptr;
+        int n_pre = 0;
+        if (SETS && p.pw_tab) {   // staged in this warp's shared-memory slot: it is applied to every row of the item
+            pw_smem_load(my_prog, p.pw_tab + (size_t)img * p.pw_stride, lane);
+            n_pre = my_prog->n;
         }
         const int ch_start = ((gx_start % C) + C) % C;
 
@@ -235,17 +237,21 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
                 if (MMA) mbar_wait_sleep(&my_full[slot], (takes / K::in_slots) & 1u, kWsSleepNs);
                 else mbar_wait(&my_full[slot], (takes / K::in_slots) & 1u);
                 ++takes;
-                if (SETS && pre) {
+                if (SETS && n_pre) {
                     // fused pointwise ops in front of the blur: rewrite the landed row in place, each
                     // sample once (the lanes' filter windows overlap 4.6x, so doing it on the window
                     // registers would repeat the work).  Only the in-image part [lo, hi): what lies
                     // outside is the blur's zero padding of the *transformed* image and stays zero.
+                    // One pass over the row per op: the op lives in registers, the row in shared memory.
                     float *row = my_in + (size_t)slot * G::ROW;
-                    for (int i = lo + 4 * lane; i < hi; i += 128) {
-                        float4 v = *reinterpret_cast<float4 *>(row + i);
-                        float r4[4] = {v.x, v.y, v.z, v.w};
-                        pw_apply_tile_g<C, 4>(pre, r4, (ch_start + i) % C);
-                        *reinterpret_cast<float4 *>(row + i) = make_float4(r4[0], r4[1], r4[2], r4[3]);
+                    for (int k = 0; k < n_pre; ++k) {
+                        const PwOp op = pw_smem_op(*my_prog, k);
+                        for (int i = lo + 4 * lane; i < hi; i += 128) {
+                            float4 v = *reinterpret_cast<float4 *>(row + i);
+                            float r4[4] = {v.x, v.y, v.z, v.w};
+                            pw_apply_op_tile<C, 4>(op, r4, (ch_start + i) % C);
+                            *reinterpret_cast<float4 *>(row + i) = make_float4(r4[0], r4[1], r4[2], r4[3]);
+                        }
                     }
                     fence_proxy_async();   // the slot's next writer is the TMA unit
                     __syncwarp();
@@ -283,6 +289,7 @@ __device__ __forceinline__ void ws_body(const GaussStreamParams &p, const GaussW
     uint64_t *in_full = bars;                                        // [10][3]
     uint64_t *h_full = bars + kWsRowWarps * kWsInSlots;               // [3]
     uint64_t *h_empty = h_full + kWsGroups;                           // [3]
+    PwSmem *s_prog = reinterpret_cast<PwSmem *>(smem_raw + G::IN_BYTES + G::H_BYTES + 8 * G::N_BARS + 64);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -299,7 +306,7 @@ __device__ __forceinline__ void ws_body(const GaussStreamParams &p, const GaussW
     const long n_items = (long)p.n_images * items_per_image;
 
     if (warp < kWsRowWarps) {
-        ws_row_role<C, R, SETS, kGsTW, false>(p, ws, s_in, s_h, in_full, h_full, h_empty, warp, lane);
+        ws_row_role<C, R, SETS, kGsTW, false>(p, ws, s_in, s_h, in_full, h_full, h_empty, warp, lane, s_prog);
     } else {
         // ============================================================ COLUMN warp
         // A[j] is the partial sum of output row (r - R + j) when filtered row r arrives.  Row r
@@ -330,10 +337,11 @@ __device__ __forceinline__ void ws_body(const GaussStreamParams &p, const GaussW
             float *base = p.out_tab ? p.out_tab[img] : p.out + (size_t)img * p.image_stride;
             const int set = SETS ? img % kGsMaxSets : 0;
             auto w = [&](int d) -> uint64_t { return SETS ? ws.ww[set][d] : p.ww[d]; };
-            const PwProgram *post = nullptr;
+            PwSmem *my_prog = s_prog + warp;
+            int n_post = 0;
             if (SETS && p.pw_tab) {
-                post = p.pw_tab + (size_t)img * p.pw_stride + 1;
-                if (__ldg(&post->n) == 0) post = nullptr;
+                pw_smem_load(my_prog, p.pw_tab + (size_t)img * p.pw_stride + 1, lane);
+                n_post = my_prog->n;
             }
             float *optr = base + ((long)y0 - 2 * R) * p.row_elems + gx;  // only dereferenced when valid
             unsigned rel = (unsigned)(-2 * R);                            // output row - y0, wraps below 0
@@ -352,7 +360,8 @@ __device__ __forceinline__ void ws_body(const GaussStreamParams &p, const GaussW
                     if (rel < n_valid) {
                         float o2[2];
                         unpack2(o, o2[0], o2[1]);
-                        if (SETS && post) pw_apply_tile_g<C, 2>(post, o2, gx % C);
+                        if (SETS)
+                            for (int k = 0; k < n_post; ++k) pw_apply_op_tile<C, 2>(pw_smem_op(*my_prog, k), o2, gx % C);
                         __stcs(reinterpret_cast<float2 *>(optr), make_float2(o2[0], o2[1]));
                     }
                     ++rel;

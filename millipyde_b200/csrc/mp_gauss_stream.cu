@@ -176,9 +176,11 @@ MPStatus launch_gauss_stream_sets(int device, cudaStream_t s, int H, int W, int 
                                   const GaussParams<float> *gps, int gps_stride, const PwProgram *pw_tab,
                                   int pw_stride)
 {
-    if (n_images < 1 || n_images > kGsMaxSets) return MP_ERROR_INVALID_ARGUMENT;
+    // per-image weights: at most kGsMaxSets images (image i uses set i % kGsMaxSets); one sigma for all
+    // (gps_stride 0): every set is the same, any number of images
+    if (n_images < 1 || (gps_stride != 0 && n_images > kGsMaxSets)) return MP_ERROR_INVALID_ARGUMENT;
     int bucket = 0;
-    for (int i = 0; i < n_images; ++i) {
+    for (int i = 0; i < (gps_stride ? n_images : 1); ++i) {
         const int b = bucket_for(gps[(size_t)i * gps_stride].radius);
         if (!b) return MP_ERROR_INVALID_ARGUMENT;
         if (b > bucket) bucket = b;
@@ -194,7 +196,7 @@ MPStatus launch_gauss_stream_sets(int device, cudaStream_t s, int H, int W, int 
     p.pw_tab = pw_tab;
     p.pw_stride = pw_stride;
     static thread_local GaussWeightSets sets;  // 7 KB: keep it off the worker's stack frames
-    for (int i = 0; i < n_images; ++i)
+    for (int i = 0; i < (gps_stride ? n_images : kGsMaxSets); ++i)
         for (int d = 0; d < 14; ++d) {
             const GaussParams<float> &gi = gps[(size_t)i * gps_stride];
             const float w = d <= gi.radius ? gi.w[d] : 0.f;

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -21,6 +22,9 @@
 #include "mp_objects.h"
 #include "mp_ops_internal.h"
 #include "mp_pipeline.h"
+#include "mp_internal_rng.h"
+#include "mp_rng.h"
+#include "kernels/records.cuh"
 
 using namespace mpk;
 
@@ -40,7 +44,13 @@ struct Stage {
     void *args;          // owned copy for our operators, caller's pointer for foreign ones
     double a[5];         // the leading doubles of the args block (ElementwiseArgs is the longest)
     double probability;  // <= 0: always (the reference tests `probability > 0`, :380)
+    // a realised random_* stage remembers where its parameters came from: a[i] is the draw
+    // keyed_range(run, image, rstage, slot i, lo[i], hi[i]) (mp_rng.h); kFixedStage = not drawn
+    uint32_t rstage = kFixedStage;
+    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
 };
+
+std::atomic<int> g_device_draws{1};   // fill per-image records on the device when a launch's images share the template
 
 std::atomic<int> g_fusion{1};
 
@@ -114,6 +124,11 @@ struct mp_pipeline {
     mp_pipeline *receiver = nullptr;
     std::atomic<unsigned long long> launches{0};
     std::atomic<int> segments{0};
+    // random source of the run in flight: every draw is keyed_*(run_key, index_base + position of the
+    // image in the submitted array, stage, slot) -- independent of devices, shards and threads
+    uint64_t run_key = 0;
+    uint64_t index_base = 0;
+    bool key_held = false;   // mppipe_hold_run_key: one key for every run (a Generator's whole stream)
     std::atomic<int> status{MILLIPYDE_SUCCESS};
     // devices touched by the run in flight (for mppipe_wait)
     std::mutex mux;
@@ -146,6 +161,11 @@ struct Segment {
     // GATHER_F32: flips before / after the (optional) rotate, and its angle
     bool flip_pre = false, flip_post = false, has_rotate = false;
     double angle = 0;
+    // where the values above came from (fixed arguments or keyed draws): what the device-side record
+    // fill evaluates when every image of a launch shares it
+    PwTemplate pre_t = {}, post_t = {};
+    uint32_t angle_stage = kFixedStage;
+    double angle_lo = 0, angle_hi = 0;
 };
 
 PwOp to_pw(const Stage &s)
@@ -161,6 +181,33 @@ PwOp to_pw(const Stage &s)
         }
         default: return PwOp{PW_COLORIZE, (float)s.a[0], (float)s.a[1], (float)s.a[2]};
     }
+}
+
+PwTemplateOp to_pw_t(const Stage &s)
+{
+    const PwOp v = to_pw(s);
+    PwTemplateOp t = {};
+    t.kind = v.kind;
+    t.stage = s.rstage;
+    if (s.rstage == kFixedStage) {
+        t.lo[0] = t.hi[0] = v.a;
+        t.lo[1] = t.hi[1] = v.b;
+        t.lo[2] = t.hi[2] = v.c;
+    } else {   // brightness: (delta); gamma: (gamma, gain); colorize: (r, g, b) -- the PwOp's a, b, c in order
+        const int np = s.kind == OP_BRIGHTNESS ? 1 : (s.kind == OP_GAMMA ? 2 : 3);
+        for (int i = 0; i < np; ++i) {
+            t.lo[i] = s.lo[i];
+            t.hi[i] = s.hi[i];
+        }
+    }
+    return t;
+}
+
+// append a pointwise stage to a segment's program (value form and template form stay in step)
+void push_pw(PwProgram &prog, PwTemplate &tmpl, const Stage &s)
+{
+    tmpl.ops[tmpl.n++] = to_pw_t(s);
+    prog.ops[prog.n++] = to_pw(s);
 }
 
 U8Op to_u8(const Stage &s)
@@ -200,11 +247,14 @@ std::vector<Segment> compile(const std::vector<const Stage *> &ops, mp::Family f
                 } else if (t->kind == OP_ROTATE && !seg.has_rotate) {
                     seg.has_rotate = true;
                     seg.angle = t->a[0];
+                    seg.angle_stage = t->rstage;
+                    seg.angle_lo = t->rstage == kFixedStage ? t->a[0] : t->lo[0];
+                    seg.angle_hi = t->rstage == kFixedStage ? t->a[0] : t->hi[0];
                     geometric = true;
                 } else if (is_pw(*t, channels)) {
                     PwProgram &prog = seg.has_rotate ? seg.post : seg.pre;
                     if (prog.n == kMaxPw) break;
-                    prog.ops[prog.n++] = to_pw(*t);
+                    push_pw(prog, seg.has_rotate ? seg.post_t : seg.pre_t, *t);
                 } else {
                     break;
                 }
@@ -223,11 +273,11 @@ std::vector<Segment> compile(const std::vector<const Stage *> &ops, mp::Family f
             Segment seg;
             seg.kind = Segment::GAUSS_F32;
             size_t j = i;
-            while (j < ops.size() && is_pw(*ops[j], channels) && seg.pre.n < kMaxPw) seg.pre.ops[seg.pre.n++] = to_pw(*ops[j++]);
+            while (j < ops.size() && is_pw(*ops[j], channels) && seg.pre.n < kMaxPw) push_pw(seg.pre, seg.pre_t, *ops[j++]);
             if (j < ops.size() && ops[j]->kind == OP_GAUSSIAN && ops[j]->a[0] > 1e-15) {
                 seg.single = ops[j++];
                 while (j < ops.size() && is_pw(*ops[j], channels) && seg.post.n < kMaxPw)
-                    seg.post.ops[seg.post.n++] = to_pw(*ops[j++]);
+                    push_pw(seg.post, seg.post_t, *ops[j++]);
                 if (seg.pre.n + seg.post.n > 0) {   // a bare Gaussian keeps its own (SINGLE) path
                     out.push_back(seg);
                     i = j;
@@ -246,7 +296,7 @@ std::vector<Segment> compile(const std::vector<const Stage *> &ops, mp::Family f
                     PwProgram &prog = grey ? seg.post : seg.pre;
                     if (prog.n == kMaxPw) break;
                     if (!(grey && t->kind == OP_COLORIZE))  // colorize is a no-op on grey (:647-651)
-                        prog.ops[prog.n++] = to_pw(*t);
+                        push_pw(prog, grey ? seg.post_t : seg.pre_t, *t);
                     ++j;
                 } else if (t->kind == OP_GREY && !grey && channels >= 3) {
                     grey = true;
@@ -291,18 +341,21 @@ std::vector<Segment> compile(const std::vector<const Stage *> &ops, mp::Family f
 // Per-image realisation of the chain: coin flips (src/gpupipeline.c:380-387) and, for random_*
 // stages, the parameter draws the reference makes inside the gpuimage method.  The result is a
 // list of concrete stages (args point at the stage's own doubles).
-void realize(const mp_pipeline *p, std::vector<Stage> *out)
+//
+// Every draw is a pure function of (p->run_key, image, stage index, slot) -- mp_rng.h -- so the
+// stream an image sees does not depend on which device, shard or worker thread handles it, costs no
+// syscall, and can be re-evaluated on the device (kernels/records.cuh).
+void realize(const mp_pipeline *p, uint64_t image, std::vector<Stage> *out)
 {
     const size_t ns = p->stages.size();
+    const uint64_t key = p->run_key;
     out->clear();
     out->reserve(ns);  // args pointers below rely on no reallocation
     for (size_t k = 0; k < ns; ++k) {
         const Stage &st = p->stages[k];
         bool run = st.kind != OP_NULL;
-        if (run && st.probability > 0) {
-            double u = 0;
-            if (random_double_in_range(0.0, 1.0, &u) == MILLIPYDE_SUCCESS && u > st.probability) run = false;
-        }
+        if (run && st.probability > 0 && mprng::keyed_u01(key, image, (uint32_t)k, mprng::kCoinSlot) > st.probability)
+            run = false;   // runs iff rand <= p, src/gpuoperation.c:204
         if (!run) continue;
         if (st.kind != OP_RANDOM) {
             out->push_back(st);
@@ -310,24 +363,18 @@ void realize(const mp_pipeline *p, std::vector<Stage> *out)
         }
         Stage c = st;
         c.probability = -1;
-        const double *r = (const double *)st.args;
-        auto draw = [](double lo, double hi) {
-            double v = lo;
-            random_double_in_range(lo, hi, &v);
-            return v;
-        };
-        if (st.func == mpimg_random_rotate) { c.kind = OP_ROTATE; c.func = mpimg_rotate; c.a[0] = draw(r[0], r[1]); }
-        else if (st.func == mpimg_random_gaussian) { c.kind = OP_GAUSSIAN; c.func = mpimg_gaussian; c.a[0] = draw(r[0], r[1]); }
-        else if (st.func == mpimg_random_brightness) { c.kind = OP_BRIGHTNESS; c.func = mpimg_brightness; c.a[0] = draw(r[0], r[1]); }
-        else if (st.func == mpimg_random_adjust_gamma) {
-            c.kind = OP_GAMMA; c.func = mpimg_adjust_gamma;
-            c.a[0] = draw(r[0], r[1]);
-            c.a[1] = draw(r[2], r[3]);
-        } else {
-            c.kind = OP_COLORIZE; c.func = mpimg_colorize;
-            c.a[0] = draw(r[0], r[1]);
-            c.a[1] = draw(r[2], r[3]);
-            c.a[2] = draw(r[4], r[5]);
+        c.rstage = (uint32_t)k;
+        const double *r = (const double *)st.args;   // (min, max) pairs in parameter order
+        int np = 1;
+        if (st.func == mpimg_random_rotate) { c.kind = OP_ROTATE; c.func = mpimg_rotate; }
+        else if (st.func == mpimg_random_gaussian) { c.kind = OP_GAUSSIAN; c.func = mpimg_gaussian; }
+        else if (st.func == mpimg_random_brightness) { c.kind = OP_BRIGHTNESS; c.func = mpimg_brightness; }
+        else if (st.func == mpimg_random_adjust_gamma) { c.kind = OP_GAMMA; c.func = mpimg_adjust_gamma; np = 2; }
+        else { c.kind = OP_COLORIZE; c.func = mpimg_colorize; np = 3; }
+        for (int i = 0; i < np; ++i) {
+            c.lo[i] = r[2 * i];
+            c.hi[i] = r[2 * i + 1];
+            c.a[i] = mprng::keyed_range(key, image, (uint32_t)k, (uint32_t)i, c.lo[i], c.hi[i]);
         }
         out->push_back(c);
     }
@@ -422,6 +469,10 @@ MPStatus run_segment_on(MPObjData *obj, const Segment &seg)
 // `records` (optional): per-image parameter records, uploaded behind the tables in the same copy;
 // `launch` finds them at g_records (device address), valid for the duration of the call.
 thread_local const void *g_records = nullptr;
+// stream indices of the images of the group being launched (aligned with its objs) and the run's key:
+// what the device-side record fill keys its draws with
+thread_local const std::vector<uint64_t> *g_index = nullptr;
+thread_local uint64_t g_run_key = 0;
 
 // Views (mpobj_view_data) whose buffer still belongs to someone else, for the shard this worker
 // thread is running.  The launch that first rewrites such an image must not free its input.
@@ -458,9 +509,20 @@ MPStatus materialize(int device, cudaStream_t s, MPObjData *o)
     return MILLIPYDE_SUCCESS;
 }
 
+// Device-side record fill (kernels/records.cuh): `records` then holds the launch's template(s) followed
+// by the images' stream indices (8 bytes each, at offset index_offset); `fill` is called with the
+// device addresses of both and of a fresh buffer of out_bytes, writes the per-image records there, and
+// `launch` finds THAT buffer at g_records.
+struct FillSpec {
+    size_t index_offset = 0;
+    size_t out_bytes = 0;
+    std::function<void(const void *d_templates, const unsigned long long *d_index, void *d_out)> fill;
+};
+
 template <typename Launch>
 MPStatus run_batched(const std::vector<MPObjData *> &objs, size_t out_bytes, int device, cudaStream_t s,
-                     bool *handled, Launch launch, const void *records = nullptr, size_t record_bytes = 0)
+                     bool *handled, Launch launch, const void *records = nullptr, size_t record_bytes = 0,
+                     const FillSpec *fill = nullptr)
 {
     *handled = false;
     const size_t n = objs.size();
@@ -469,6 +531,14 @@ MPStatus run_batched(const std::vector<MPObjData *> &objs, size_t out_bytes, int
     if (!h_tab) return MILLIPYDE_SUCCESS;
     void *d_tab = mp::pool_alloc(device, s, tab_bytes + record_bytes);
     if (!d_tab) return MP_ERROR_DEVICE_ALLOC;
+    void *d_filled = nullptr;
+    if (fill) {
+        d_filled = mp::pool_alloc(device, s, fill->out_bytes);
+        if (!d_filled) {
+            mp::pool_free(device, s, d_tab);
+            return MP_ERROR_DEVICE_ALLOC;
+        }
+    }
     if (record_bytes) memcpy((char *)h_tab + tab_bytes, records, record_bytes);
     g_records = record_bytes ? (const char *)d_tab + tab_bytes : nullptr;
     const int out_device = g_out_device >= 0 ? g_out_device : device;
@@ -478,12 +548,19 @@ MPStatus run_batched(const std::vector<MPObjData *> &objs, size_t out_bytes, int
         if (!fresh[i]) {
             for (size_t k = 0; k < i; ++k) mp::pool_free(device, s, fresh[k]);
             mp::pool_free(device, s, d_tab);
+            if (d_filled) mp::pool_free(device, s, d_filled);
             return MP_ERROR_DEVICE_ALLOC;
         }
         h_tab[i] = objs[i]->device_data;
         h_tab[n + i] = fresh[i];
     }
     MP_CUDA_TRY(cudaMemcpyAsync(d_tab, h_tab, tab_bytes + record_bytes, cudaMemcpyHostToDevice, s));
+    if (fill) {
+        const char *base = (const char *)d_tab + tab_bytes;
+        fill->fill(base, (const unsigned long long *)(base + fill->index_offset), d_filled);
+        mp::count_launch();
+        g_records = d_filled;
+    }
     MPStatus st = launch((const float *const *)d_tab, (float *const *)((void **)d_tab + n), (int)n);
     cudaError_t e = cudaGetLastError();
     if (st == MILLIPYDE_SUCCESS && e != cudaSuccess) {
@@ -501,8 +578,47 @@ MPStatus run_batched(const std::vector<MPObjData *> &objs, size_t out_bytes, int
         }
     }
     mp::pool_free(device, s, d_tab);
+    if (d_filled) mp::pool_free(device, s, d_filled);
     *handled = st == MILLIPYDE_SUCCESS;
     return st;
+}
+
+// The per-image programs of a launch, either host-evaluated (`progs`, per_image programs per image) or
+// -- when every image shares the template and something in it is drawn -- as a template + the images'
+// stream indices for the device-side fill.  Returns true when the device path applies and sets up
+// `blob` (what to upload) and `fill`.
+bool plan_pw_fill(const std::vector<const Segment *> &segs, const std::vector<uint64_t> &index, int per_image, bool use_pre,
+                  uint64_t run_key, cudaStream_t s, std::vector<char> *blob, FillSpec *fill)
+{
+    if (!g_device_draws.load() || segs.size() < 2 || index.size() != segs.size()) return false;
+    const Segment &s0 = *segs[0];
+    bool drawn = false;
+    for (int i = 0; i < s0.pre_t.n; ++i) drawn = drawn || s0.pre_t.ops[i].stage != kFixedStage;
+    for (int i = 0; i < s0.post_t.n; ++i) drawn = drawn || s0.post_t.ops[i].stage != kFixedStage;
+    if (!drawn) return false;
+    for (size_t i = 1; i < segs.size(); ++i)
+        if (memcmp(&segs[i]->pre_t, &s0.pre_t, sizeof(PwTemplate)) || memcmp(&segs[i]->post_t, &s0.post_t, sizeof(PwTemplate)))
+            return false;
+    const size_t n = segs.size();
+    const size_t t_bytes = (size_t)per_image * sizeof(PwTemplate);
+    blob->resize(t_bytes + n * sizeof(unsigned long long));
+    PwTemplate *t = (PwTemplate *)blob->data();
+    if (per_image == 2) {
+        t[0] = s0.pre_t;
+        t[1] = s0.post_t;
+    } else {
+        t[0] = use_pre ? s0.pre_t : s0.post_t;
+    }
+    unsigned long long *idx = (unsigned long long *)(blob->data() + t_bytes);
+    for (size_t i = 0; i < n; ++i) idx[i] = index[i];
+    fill->index_offset = t_bytes;
+    fill->out_bytes = n * per_image * sizeof(PwProgram);
+    const int total = (int)n * per_image * kMaxPw;
+    fill->fill = [=](const void *d_t, const unsigned long long *d_idx, void *d_out) {
+        records_fill_pw_kernel<<<(total + 127) / 128, 128, 0, s>>>((PwProgram *)d_out, (const PwTemplate *)d_t, per_image,
+                                                                   d_idx, (int)n, run_key);
+    };
+    return true;
 }
 
 constexpr int kMaxSets = 64;  // images per launch_gauss_stream_sets call (kernels/gaussian_stream.cuh: kGsMaxSets)
@@ -515,7 +631,8 @@ constexpr int kMaxSets = 64;  // images per launch_gauss_stream_sets call (kerne
 // segments).  They travel as per-image records behind the pointer tables and the kernel applies them
 // on the fly -- the chain pointwise -> gaussian -> pointwise is one launch and one HBM round trip.
 MPStatus run_gaussian_batch(const std::vector<MPObjData *> &objs, const mp::Img &d, const std::vector<double> &sigmas,
-                            int device, cudaStream_t s, bool *handled, const std::vector<PwProgram> *progs = nullptr)
+                            int device, cudaStream_t s, bool *handled, const std::vector<PwProgram> *progs = nullptr,
+                            const std::vector<const Segment *> *segs = nullptr)
 {
     *handled = false;
     const size_t n = objs.size();
@@ -538,6 +655,11 @@ MPStatus run_gaussian_batch(const std::vector<MPObjData *> &objs, const mp::Img 
         for (size_t i = 1; i < n && same_progs; ++i)
             same_progs = !memcmp(&(*progs)[2 * i], &(*progs)[0], 2 * sizeof(PwProgram));
     const size_t n_records = progs ? (same_progs ? 2 : 2 * n) : 0;
+    // programs that differ only by their draws: template + indices up, records filled on the device
+    std::vector<char> blob;
+    FillSpec fill;
+    const bool on_device = progs && !same_progs && segs && g_index &&
+                           plan_pw_fill(*segs, *g_index, 2, true, g_run_key, s, &blob, &fill);
     return run_batched(
         objs, objs[0]->nbytes, device, s, handled,
         [&](const float *const *in_tab, float *const *out_tab, int m) {
@@ -546,8 +668,9 @@ MPStatus run_gaussian_batch(const std::vector<MPObjData *> &objs, const mp::Img 
                                                      gps[0]);
             const PwProgram *tab = progs ? (const PwProgram *)g_records : nullptr;
             const int pw_stride = (progs && !same_progs) ? 2 : 0;
-            for (int off = 0; off < m; off += kMaxSets) {
-                const int cnt = m - off < kMaxSets ? m - off : kMaxSets;
+            const int per_launch = same ? m : kMaxSets;   // one sigma: the weight sets are all alike, no limit
+            for (int off = 0; off < m; off += per_launch) {
+                const int cnt = m - off < per_launch ? m - off : per_launch;
                 MPStatus st = mp::launch_gauss_stream_sets(device, s, d.H, d.W, d.C, cnt, in_tab + off, out_tab + off,
                                                            same ? gps.data() : gps.data() + off, same ? 0 : 1,
                                                            tab ? tab + (size_t)off * pw_stride : nullptr, pw_stride);
@@ -555,7 +678,8 @@ MPStatus run_gaussian_batch(const std::vector<MPObjData *> &objs, const mp::Img 
             }
             return (MPStatus)MILLIPYDE_SUCCESS;
         },
-        progs ? progs->data() : nullptr, n_records * sizeof(PwProgram));
+        on_device ? (const void *)blob.data() : (progs ? (const void *)progs->data() : nullptr),
+        on_device ? blob.size() : n_records * sizeof(PwProgram), on_device ? &fill : nullptr);
 }
 
 // The gather segment for one image (tables null) or a same-shape group.
@@ -604,9 +728,44 @@ MPStatus run_gather(const std::vector<MPObjData *> &objs, const std::vector<cons
         return MILLIPYDE_SUCCESS;
     };
     if (n >= 2) {
+        // images that share the segment's template and differ only by their draws (angle, program
+        // parameters): one template + the stream indices go up, the records are filled on the device
+        std::vector<char> blob;
+        FillSpec fill;
+        bool on_device = false;
+        if (!vars.empty() && g_device_draws.load() && g_index && g_index->size() == n) {
+            const Segment &s0 = *segs[0];
+            on_device = true;
+            for (size_t i = 1; i < n && on_device; ++i)
+                on_device = segs[i]->angle_stage == s0.angle_stage && segs[i]->angle_lo == s0.angle_lo &&
+                            segs[i]->angle_hi == s0.angle_hi && !memcmp(&segs[i]->pre_t, &s0.pre_t, sizeof(PwTemplate)) &&
+                            !memcmp(&segs[i]->post_t, &s0.post_t, sizeof(PwTemplate));
+            if (on_device) {
+                blob.resize(sizeof(GatherTemplate) + n * sizeof(unsigned long long));
+                GatherTemplate *t = (GatherTemplate *)blob.data();
+                t->angle_lo = s0.angle_lo;
+                t->angle_hi = s0.angle_hi;
+                t->angle_stage = s0.angle_stage;
+                t->width = d.W;
+                t->height = d.H;
+                t->pre = s0.pre_t;
+                t->post = s0.post_t;
+                unsigned long long *idx = (unsigned long long *)(blob.data() + sizeof(GatherTemplate));
+                for (size_t i = 0; i < n; ++i) idx[i] = (*g_index)[i];
+                fill.index_offset = sizeof(GatherTemplate);
+                fill.out_bytes = n * sizeof(GatherVar);
+                const int total = (int)n * (1 + 2 * kMaxPw);
+                const uint64_t key = g_run_key;
+                fill.fill = [=](const void *d_t, const unsigned long long *d_idx, void *d_out) {
+                    records_fill_gather_kernel<<<(total + 127) / 128, 128, 0, s>>>((GatherVar *)d_out, (const GatherTemplate *)d_t,
+                                                                                   d_idx, (int)n, key);
+                };
+            }
+        }
         bool handled = false;
-        MPStatus st = run_batched(objs, objs[0]->nbytes, device, s, &handled, launch, vars.data(),
-                                  vars.size() * sizeof(GatherVar));
+        MPStatus st = run_batched(objs, objs[0]->nbytes, device, s, &handled, launch,
+                                  on_device ? (const void *)blob.data() : (const void *)vars.data(),
+                                  on_device ? blob.size() : vars.size() * sizeof(GatherVar), on_device ? &fill : nullptr);
         if (st != MILLIPYDE_SUCCESS || handled) return st;
     }
     for (size_t i = 0; i < n; ++i) {  // one image, or the arena was exhausted
@@ -658,7 +817,7 @@ void run_segment_group(mp_pipeline *p, const std::vector<MPObjData *> &objs, con
             progs[2 * i + 1] = segs[i]->post;
         }
         bool handled = false;
-        note_status(p, run_gaussian_batch(objs, cur, sigmas, device, s, &handled, &progs));
+        note_status(p, run_gaussian_batch(objs, cur, sigmas, device, s, &handled, &progs, &segs));
         if (handled) return;
     }
     if ((seg.kind == Segment::PW_F32 || seg.kind == Segment::GREY_F32) && n >= 2 && f32 &&
@@ -676,6 +835,9 @@ void run_segment_group(mp_pipeline *p, const std::vector<MPObjData *> &objs, con
                 if (grey) progs.push_back(segs[i]->post);
             }
         bool handled = false;
+        std::vector<char> blob;
+        FillSpec fill;
+        const bool on_device = !same && g_index && plan_pw_fill(segs, *g_index, grey ? 2 : 1, true, g_run_key, s, &blob, &fill);
         MPStatus st = run_batched(
             objs, out_bytes, device, s, &handled,
             [&](const float *const *in_tab, float *const *out_tab, int m) {
@@ -684,7 +846,8 @@ void run_segment_group(mp_pipeline *p, const std::vector<MPObjData *> &objs, con
                 else mp::launch_pw_f32_batch(s, cur, seg.pre, in_tab, out_tab, m, tab);
                 return MILLIPYDE_SUCCESS;
             },
-            progs.data(), progs.size() * sizeof(PwProgram));
+            on_device ? (const void *)blob.data() : (const void *)progs.data(),
+            on_device ? blob.size() : progs.size() * sizeof(PwProgram), on_device ? &fill : nullptr);
         note_status(p, st);
         if (handled) {
             if (grey)
@@ -761,12 +924,13 @@ constexpr size_t kHandoffChunk = 32;  // images per hand-off chunk of a cross-de
 struct ShardTask {
     mp_pipeline *pipe;
     std::vector<MPObjData *> objs;
+    std::vector<uint64_t> index;  // stream index of every object (position in the submitted array + the pipeline's base)
     int device;
     bool views;  // objs borrow their buffers (mppipe_run_views)
     cudaEvent_t after = nullptr;  // work of the sending shard that wrote into this device's memory
 };
 
-void submit_shard(mp_pipeline *p, std::vector<MPObjData *> objs, int device, bool views = false,
+void submit_shard(mp_pipeline *p, std::vector<MPObjData *> objs, std::vector<uint64_t> index, int device, bool views = false,
                   cudaEvent_t after = nullptr);
 
 void shard_worker(void *arg)
@@ -835,7 +999,7 @@ void shard_worker(void *arg)
         std::vector<std::vector<Segment>> segs(n);
         size_t rounds = 0;
         for (size_t i = c0; i < c1; ++i) {
-            realize(p, &realized[i]);
+            realize(p, t->index[i], &realized[i]);
             std::vector<const Stage *> ops;
             for (const Stage &st : realized[i]) ops.push_back(&st);
             mp::Img d;
@@ -857,13 +1021,18 @@ void shard_worker(void *arg)
             for (auto &g : groups) {
                 std::vector<MPObjData *> objs;
                 std::vector<const Segment *> sp;
+                std::vector<uint64_t> idx;
                 for (size_t i : g.second) {
                     objs.push_back(t->objs[i]);
                     sp.push_back(&segs[i][r]);
+                    idx.push_back(t->index[i]);
                 }
                 const bool last = remote >= 0 && r + 1 == segs[g.second[0]].size();
                 g_out_device = last ? remote : -1;
+                g_index = &idx;
+                g_run_key = p->run_key;
                 run_segment_group(p, objs, sp, device, batch_stream);
+                g_index = nullptr;
                 g_out_device = -1;
             }
             p->segments.fetch_add((int)groups.size());
@@ -899,7 +1068,8 @@ void shard_worker(void *arg)
                 }
             }
             submit_shard(p->receiver, std::vector<MPObjData *>(t->objs.begin() + c0, t->objs.begin() + c1),
-                         p->receiver->device, false, after);
+                         std::vector<uint64_t>(t->index.begin() + c0, t->index.begin() + c1), p->receiver->device, false,
+                         after);
         }
     }
     if (t->views) g_borrowed = nullptr;
@@ -939,7 +1109,8 @@ void shard_worker(void *arg)
     p->cv.notify_all();
 }
 
-void submit_shard(mp_pipeline *p, std::vector<MPObjData *> objs, int device, bool views, cudaEvent_t after)
+void submit_shard(mp_pipeline *p, std::vector<MPObjData *> objs, std::vector<uint64_t> index, int device, bool views,
+                  cudaEvent_t after)
 {
     if (objs.empty()) return;
     {
@@ -947,7 +1118,7 @@ void submit_shard(mp_pipeline *p, std::vector<MPObjData *> objs, int device, boo
         p->in_flight.push_back(device);
         ++p->pending;
     }
-    ShardTask *t = new ShardTask{p, std::move(objs), device, views, after};
+    ShardTask *t = new ShardTask{p, std::move(objs), std::move(index), device, views, after};
     mpdev_submit_work(device, shard_worker, t);
 }
 
@@ -1086,13 +1257,28 @@ static MPStatus submit_impl(MPPipeline *p, MPObjData **objs, int n, bool views)
 
     // Image i -> device: blocks of THREADS_PER_DEVICE images, round-robin over the valid
     // devices starting at the recommended one (src/gpupipeline.c:267-283).
+    // one random-source key per run, shared down the receiver chain (stages are numbered per pipeline,
+    // so a receiver offsets its stage numbers through its own key)
+    {
+        const uint64_t key = p->key_held ? p->run_key : mp::next_run_key();
+        uint64_t salt = 0;
+        for (mp_pipeline *q = p; q; q = q->receiver) {
+            q->run_key = key + 0x9E3779B97F4A7C15ull * salt++;
+            q->index_base = p->index_base;
+        }
+    }
     std::map<int, std::vector<MPObjData *>> shards;
+    std::map<int, std::vector<uint64_t>> shard_index;
     int cur = device;
     for (int i = 0; i < n; ++i) {
-        if (objs[i]) shards[views ? objs[i]->mem_loc : cur].push_back(objs[i]);
+        if (objs[i]) {
+            const int dev = views ? objs[i]->mem_loc : cur;
+            shards[dev].push_back(objs[i]);
+            shard_index[dev].push_back(p->index_base + (uint64_t)i);
+        }
         if (cycle && ((i + 1) % THREADS_PER_DEVICE == 0)) cur = mpdev_get_next_device(cur);
     }
-    for (auto &kv : shards) submit_shard(p, std::move(kv.second), kv.first, views);
+    for (auto &kv : shards) submit_shard(p, std::move(kv.second), std::move(shard_index[kv.first]), kv.first, views);
     return MILLIPYDE_SUCCESS;
 }
 
@@ -1153,7 +1339,8 @@ int mppipe_plan(const MPPipeline *p, int typenum, int channels, char *buf, int c
     all.stages = p->stages;
     for (Stage &st : all.stages) st.probability = -1;
     std::vector<Stage> realized;
-    realize(&all, &realized);
+    all.run_key = mp::peek_run_key();
+    realize(&all, 0, &realized);
     std::vector<const Stage *> ops;
     for (const Stage &st : realized) ops.push_back(&st);
     const std::vector<Segment> segs = compile(ops, fam, channels);
@@ -1189,6 +1376,20 @@ int mppipe_plan(const MPPipeline *p, int typenum, int channels, char *buf, int c
     memcpy(buf, out.c_str(), out.size() + 1);
     return (int)segs.size();
 }
+
+void mppipe_set_index_base(MPPipeline *p, unsigned long long first_index)
+{
+    if (p) p->index_base = first_index;
+}
+unsigned long long mppipe_last_run_key(const MPPipeline *p) { return p ? p->run_key : 0; }
+void mppipe_hold_run_key(MPPipeline *p)
+{
+    if (!p || p->key_held) return;
+    p->run_key = mp::next_run_key();
+    p->key_held = true;
+}
+void mppipe_set_device_draws(int enabled) { g_device_draws.store(enabled ? 1 : 0); }
+int mppipe_get_device_draws(void) { return g_device_draws.load(); }
 
 void mppipe_set_fusion(int enabled) { g_fusion.store(enabled ? 1 : 0); }
 int mppipe_get_fusion(void) { return g_fusion.load(); }
@@ -1263,7 +1464,7 @@ void host_worker(void *arg)
         if (st == MILLIPYDE_SUCCESS) st = mpobj_upload_async(o, t->host_in[i], t->in_bytes);
 
         std::vector<Stage> mine;
-        realize(p, &mine);
+        realize(p, p->index_base + (uint64_t)i, &mine);
         std::vector<const Stage *> ops;
         for (const Stage &sg : mine) ops.push_back(&sg);
         if (st == MILLIPYDE_SUCCESS) {
@@ -1316,6 +1517,7 @@ extern "C" MPStatus mppipe_run_host(MPPipeline *p, const void *const *host_in, v
     MPStatus st = mp::ensure_initialized();
     if (st != MILLIPYDE_SUCCESS) return st;
     reset_counters(p);
+    if (!p->key_held) p->run_key = mp::next_run_key();
     size_t es;
     switch (typenum) {
         case MP_NPY_UBYTE: es = 1; break;

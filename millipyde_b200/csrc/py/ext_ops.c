@@ -699,6 +699,10 @@ static int produce_batch(MPGeneratorObject *g, long count)
             dev = mpdev_get_next_device(dev);
     }
     MPStatus st;
+    /* one random-source key for the Generator's whole stream, images numbered by output index: output k
+     * is the same draw whatever the look-ahead and however the batch is spread over the devices */
+    mppipe_hold_run_key(g->pipe);
+    mppipe_set_index_base(g->pipe, (unsigned long long)g->produced);
     Py_BEGIN_ALLOW_THREADS
     st = (use_views || spread_ok) ? mppipe_run_views(g->pipe, objs, (int)count) : mppipe_run(g->pipe, objs, (int)count);
     Py_END_ALLOW_THREADS

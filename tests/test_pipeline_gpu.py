@@ -138,35 +138,33 @@ def test_probability_is_per_image(mp):
     assert 16 <= n_flip <= 48
 
 
-def _draw(mp, lo, hi):
-    import ctypes
-    v = ctypes.c_double()
-    assert mp.lib.random_double_in_range(lo, hi, ctypes.byref(v)) == 0
-    return v.value
+def _keyed(mp, chain, image, stage, slot, lo, hi):
+    """The draw the executor (host or device) made for parameter `slot` of stage `stage` of image
+    `image` in the chain's last run: mprand_keyed_double (include/mp_abi.h), Philox-4x32-10."""
+    return mp.lib.mprand_keyed_double(mp.lib.mppipe_last_run_key(chain.ptr), image, stage, slot, lo, hi)
 
 
 def test_random_chain_is_one_launch_per_segment_and_matches_oracle(mp):
     """Per-image parameter records: 70 images with their own brightness delta, sigma and colour
     multipliers run as a handful of launches (the Gaussians split by radius bucket and into sets of
     64), and every image equals the oracle evaluated with ITS draws.  The draws are predicted by
-    replaying the seeded generator in the executor's order (image by image, stage by stage)."""
+    evaluating the keyed generator (run key, image index, stage, slot) the executor uses."""
     n = 70
     imgs = [synth.noise_f32(40, 160, 3, 3000 + k) for k in range(n)]
     chain = [("random_brightness", -.2, .2), ("random_gaussian", .5, 2.),
              ("random_colorize", .5, 1.5, .5, 1.5, .5, 1.5), ("rgb2grey",), ("random_adjust_gamma", .5, 2., 1., 1.)]
     mp.lib.mprand_seed(1234)
-    draws = []
-    for _ in range(n):
-        b = _draw(mp, -.2, .2)
-        sg = _draw(mp, .5, 2.)
-        col = (_draw(mp, .5, 1.5), _draw(mp, .5, 1.5), _draw(mp, .5, 1.5))
-        gam = (_draw(mp, .5, 2.), _draw(mp, 1., 1.))
-        draws.append((b, sg, col, gam))
-    mp.lib.mprand_seed(1234)
     dev = [mp.capi.DeviceImage(a) for a in imgs]
     ch = mp.engine.Chain(chain, device=0)
     ch.run(dev)
     mp.lib.mprand_seed(0)
+    draws = []      # stage k of the chain, parameter slots in declaration order
+    for i in range(n):
+        b = _keyed(mp, ch, i, 0, 0, -.2, .2)
+        sg = _keyed(mp, ch, i, 1, 0, .5, 2.)
+        col = tuple(_keyed(mp, ch, i, 2, s, .5, 1.5) for s in range(3))
+        gam = (_keyed(mp, ch, i, 4, 0, .5, 2.), _keyed(mp, ch, i, 4, 1, 1., 1.))
+        draws.append((b, sg, col, gam))
     # brightness: 1 launch; Gaussian: <= 5 buckets x 2 sets; colorize+grey+gamma: 1 per bucket group
     assert ch.last_launches <= 5 * (1 + 2 + 1), ch.last_launches
     assert ch.last_launches < n
@@ -186,18 +184,18 @@ def test_random_rotate_records_match_eager_rotates(mp, c):
     n = 9
     imgs = [synth.noise_f32(48, 64, c, 3100 + k) for k in range(n)]
     for chain, replay in (
-        ([("random_rotate", 0., 120.)], lambda: [("rotate", _draw(mp, 0., 120.))]),
+        ([("random_rotate", 0., 120.)], lambda ch, i: [("rotate", _keyed(mp, ch, i, 0, 0, 0., 120.))]),
         ([("fliplr",), ("random_rotate", 0., 120.), ("random_brightness", -.2, .2)],
-         lambda: [("fliplr",), ("rotate", _draw(mp, 0., 120.)), ("brightness", _draw(mp, -.2, .2))]),
+         lambda ch, i: [("fliplr",), ("rotate", _keyed(mp, ch, i, 1, 0, 0., 120.)),
+                        ("brightness", _keyed(mp, ch, i, 2, 0, -.2, .2))]),
     ):
-        mp.lib.mprand_seed(4321)
-        eager_chains = [replay() for _ in range(n)]
         mp.lib.mprand_seed(4321)
         dev = [mp.capi.DeviceImage(a) for a in imgs]
         ch = mp.engine.Chain(chain, device=0)
         ch.run(dev)
         mp.lib.mprand_seed(0)
-        assert ch.last_launches == 1
+        eager_chains = [replay(ch, i) for i in range(n)]
+        assert ch.last_launches == 2        # the record fill + the gather
         for a, d, ec in zip(imgs, dev, eager_chains):
             want = so.apply_chain(a, ec)
             assert np.abs(d.numpy() - want).max() <= TOL32
@@ -417,7 +415,10 @@ def test_pointwise_ops_fuse_into_the_gaussian(mp, c):
                 mp.lib.mppipe_set_fusion(1)
             for k, (a, d) in enumerate(zip(imgs, dev)):
                 got = d.numpy()
-                assert np.abs(got - so.apply_chain(a, chain)).max() <= TOL32, (chain, h, w)
+                want = so.apply_chain(a, chain)
+                if c == 4:      # alpha is untouched by pointwise ops (as in the reference's RGBA kernels); the blur takes it
+                    want[..., 3] = so.apply_chain(a, [op for op in chain if op[0] == "gaussian"])[..., 3]
+                assert np.abs(got - want).max() <= TOL32, (chain, h, w)
                 if k < 2:
                     assert np.abs(got - unf[k].numpy()).max() <= 2e-6
             assert np.array_equal(single.numpy(), dev[0].numpy())
@@ -449,18 +450,66 @@ def test_fused_gaussian_with_per_image_programs_and_sigmas(mp):
     imgs = [synth.noise_f32(40, 160, 3, 7300 + k) for k in range(n)]
     chain = [("random_adjust_gamma", .5, 2., 1., 1.), ("random_gaussian", 1.0, 1.25), ("random_brightness", -.2, .2)]
     mp.lib.mprand_seed(77)
-    draws = []
-    for _ in range(n):
-        gam = (_draw(mp, .5, 2.), _draw(mp, 1., 1.))
-        sg = _draw(mp, 1.0, 1.25)
-        b = _draw(mp, -.2, .2)
-        draws.append((gam, sg, b))
-    mp.lib.mprand_seed(77)
     dev = [mp.capi.DeviceImage(a) for a in imgs]
     ch = mp.engine.Chain(chain, device=0)
     ch.run(dev)
     mp.lib.mprand_seed(0)
-    assert ch.last_launches <= 2 * 2, ch.last_launches      # <= 2 radius buckets x 2 sets of 64
+    draws = [((_keyed(mp, ch, i, 0, 0, .5, 2.), _keyed(mp, ch, i, 0, 1, 1., 1.)), _keyed(mp, ch, i, 1, 0, 1.0, 1.25),
+              _keyed(mp, ch, i, 2, 0, -.2, .2)) for i in range(n)]
+    assert ch.last_launches <= 2 * 3, ch.last_launches      # <= 2 radius buckets x (record fill + 2 sets of 64)
     for a, d, (gam, sg, b) in zip(imgs, dev, draws):
         want = so.apply_chain(a, [("adjust_gamma", *gam), ("gaussian", sg), ("brightness", b)])
         assert np.abs(d.numpy() - want).max() <= TOL32
+
+
+def test_device_side_draws_equal_host_draws(mp):
+    """when the images of a launch share the chain's shape, the host uploads one
+    template + the stream indices and a kernel evaluates the counter-based generator and fills the
+    per-image records (kernels/records.cuh).  mppipe_set_device_draws(0) evaluates the same keyed
+    function on the host and uploads the records: pointwise / grey / fused-Gaussian results must be
+    bit-identical (the gather's device-side cos/sin may differ from libm in the last place)."""
+    n = 40
+    imgs = [synth.noise_f32(48, 160, 3, 8000 + k) for k in range(n)]
+    chains = {
+        "pw": [("random_brightness", -.2, .2), ("random_adjust_gamma", .5, 2., .9, 1.)],
+        "grey": [("random_colorize", .5, 1.5, .5, 1.5, .5, 1.5), ("rgb2grey",), ("random_brightness", -.1, .1)],
+        "gauss": [("random_adjust_gamma", .8, 1.6, 1., 1.), ("gaussian", 2.0), ("random_brightness", -.2, .2)],
+        "gather": [("random_brightness", -.1, .1), ("random_rotate", 0., 90.), ("fliplr",)],
+    }
+    assert mp.lib.mppipe_get_device_draws() == 1
+    for name, chain in chains.items():
+        outs = {}
+        for on_device in (1, 0):
+            mp.lib.mppipe_set_device_draws(on_device)
+            mp.lib.mprand_seed(99)
+            dev = [mp.capi.DeviceImage(a) for a in imgs]
+            ch = mp.engine.Chain(chain, device=0)
+            ch.run(dev)
+            outs[on_device] = ([d.numpy() for d in dev], ch.last_launches)
+        mp.lib.mppipe_set_device_draws(1)
+        mp.lib.mprand_seed(0)
+        assert outs[1][1] == outs[0][1] + 1, name            # the record-fill kernel is the only extra launch
+        for x, y in zip(outs[1][0], outs[0][0]):
+            if name == "gather":
+                assert np.abs(x - y).max() <= 1e-6
+            else:
+                assert np.array_equal(x, y), name
+
+
+def test_random_stream_does_not_depend_on_batching(mp):
+    """Draws are keyed by (run, image index, stage, slot): image k of a stream gets the same parameters
+    whether it runs in one batch of 24 or in three batches of 8 with the index base moved along."""
+    imgs = [synth.noise_f32(32, 96, 3, 8100 + k) for k in range(24)]
+    chain = [("random_brightness", -.2, .2, {"probability": 0.7}), ("random_gaussian", .5, 2.)]
+    mp.lib.mprand_seed(5)
+    whole = [mp.capi.DeviceImage(a) for a in imgs]
+    ch = mp.engine.Chain(chain, device=0)
+    mp.lib.mppipe_hold_run_key(ch.ptr)
+    ch.run(whole)
+    parts = [mp.capi.DeviceImage(a) for a in imgs]
+    for b in range(3):
+        mp.lib.mppipe_set_index_base(ch.ptr, 8 * b)
+        ch.run(parts[8 * b: 8 * b + 8])
+    mp.lib.mprand_seed(0)
+    for w, p in zip(whole, parts):
+        assert np.array_equal(w.numpy(), p.numpy())
