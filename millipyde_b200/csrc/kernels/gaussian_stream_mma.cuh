@@ -300,19 +300,6 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
                 for (int u = 0; u < kPair; ++u) {
                     const int q = q0 + u;
                     if (q >= kMmTiles) continue;
-                    if (SETS && n_post) {
-                        // (c0, c2) and (c1, c3) are the column pair (2g, 2g + 1) of tile q in two rows
-                        float r2[2] = {nxt[u][NCH - 1][0], nxt[u][NCH - 1][2]};
-                        float r3[2] = {nxt[u][NCH - 1][1], nxt[u][NCH - 1][3]};
-                        const int ch0 = (gx0 + 16 * q + 2 * g) % C;
-                        for (int k = 0; k < n_post; ++k) {
-                            const PwOp op = pw_smem_op(*my_prog, k);
-                            pw_apply_op_tile<C, 2>(op, r2, ch0);
-                            pw_apply_op_tile<C, 2>(op, r3, ch0);
-                        }
-                        nxt[u][NCH - 1][0] = r2[0]; nxt[u][NCH - 1][2] = r2[1];
-                        nxt[u][NCH - 1][1] = r3[0]; nxt[u][NCH - 1][3] = r3[1];
-                    }
                     sts_f2(my_stage + 16 * q, nxt[u][NCH - 1][0], nxt[u][NCH - 1][2]);                        // block row 2t
                     sts_f2(my_stage + 4 * kMmStagePitch + 16 * q, nxt[u][NCH - 1][1], nxt[u][NCH - 1][3]);   // block row 2t + 1
                 }
@@ -320,6 +307,23 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
             // hand back every group whose 12 rows are now consumed (the MMAs above used every sample)
             ring_row = ring_row == kMmRing - 8 ? 0 : ring_row + 8;
             const uint32_t done = item_g0 + (uint32_t)(8 * (c + 1)) / MmK::rows;
+            if (SETS && n_post) {
+                // fused pointwise ops behind the blur: a separate pass over the staged block (8 rows x 80
+                // floats, this warp's own), one vector at a time so that it costs the role no registers.  Doing it on
+                // the accumulator fragments instead puts a data-dependent loop between the MMAs and the
+                // staging stores and serialises the tiles (measured: 0.41x of the bare blur; this: see DESIGN.md).
+                __syncwarp();   // every lane's part of the block is staged
+#pragma unroll 1
+                for (int f = lane; f < 160; f += 32) {      // float4 index in the 8 x 20 block
+                    const int row = f / 20, col = 4 * (f - 20 * row);
+                    float *sp = stage + row * kMmStagePitch + col;
+                    const float4 t4 = *reinterpret_cast<const float4 *>(sp);
+                    float v[4] = {t4.x, t4.y, t4.z, t4.w};
+                    const int ch = (gx0 + col) % C;
+                    for (int k = 0; k < n_post; ++k) pw_apply_op_tile<C, 4>(pw_smem_op(*my_prog, k), v, ch);
+                    *reinterpret_cast<float4 *>(sp) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
             fence_proxy_async();   // the staged rows are read by the async proxy
             __syncwarp();          // every lane has read the chunk and staged its part of the block
             if (lane == 0) {

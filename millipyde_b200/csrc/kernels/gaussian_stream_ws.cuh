@@ -242,16 +242,15 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
                     // sample once (the lanes' filter windows overlap 4.6x, so doing it on the window
                     // registers would repeat the work).  Only the in-image part [lo, hi): what lies
                     // outside is the blur's zero padding of the *transformed* image and stays zero.
-                    // One pass over the row per op: the op lives in registers, the row in shared memory.
+                    // One vector at a time: the pass must not cost the role registers (it has 80).
                     float *row = my_in + (size_t)slot * G::ROW;
-                    for (int k = 0; k < n_pre; ++k) {
-                        const PwOp op = pw_smem_op(*my_prog, k);
-                        for (int i = lo + 4 * lane; i < hi; i += 128) {
-                            float4 v = *reinterpret_cast<float4 *>(row + i);
-                            float r4[4] = {v.x, v.y, v.z, v.w};
-                            pw_apply_op_tile<C, 4>(op, r4, (ch_start + i) % C);
-                            *reinterpret_cast<float4 *>(row + i) = make_float4(r4[0], r4[1], r4[2], r4[3]);
-                        }
+#pragma unroll 1
+                    for (int i = lo + 4 * lane; i < hi; i += 128) {
+                        const float4 t4 = *reinterpret_cast<const float4 *>(row + i);
+                        float v[4] = {t4.x, t4.y, t4.z, t4.w};
+                        const int ch = (ch_start + i) % C;
+                        for (int k = 0; k < n_pre; ++k) pw_apply_op_tile<C, 4>(pw_smem_op(*my_prog, k), v, ch);
+                        *reinterpret_cast<float4 *>(row + i) = make_float4(v[0], v[1], v[2], v[3]);
                     }
                     fence_proxy_async();   // the slot's next writer is the TMA unit
                     __syncwarp();

@@ -173,6 +173,8 @@ static PyObject *hostify_tuple(PyObject *seq)
     return out;
 }
 
+static int scalar_as_double(PyObject *o, double *out);
+
 /* numpy functions that ARE one of the device operators: np.fliplr(img) and
  * np.transpose(img) [2-D, or HWC with axes=(1, 0, 2)] run the CUDA kernel on a device-side copy and
  * return a new object of the caller's type -- no D2H, no CPU work; the source is not modified (numpy
@@ -215,6 +217,20 @@ static PyObject *device_function(MPArrayObject *self, PyObject *func, PyObject *
             if (same) op = mpimg_transpose;
         }
     }
+    /* np.clip(img, lo, hi) with scalar bounds on a float32 image: numpy routes the *function* np.clip
+     * here (not the clip ufunc), so it is recognised at this level and run as the elementwise kernel */
+    ElementwiseArgs ew = {0, 0, 0, 0, 0};
+    void *op_args = NULL;
+    if (!op && fn && strcmp(fn, "clip") == 0 && nargs == 3 && !has_kw && self->obj->type == NPY_FLOAT) {
+        double lo, hi;
+        if (scalar_as_double(PyTuple_GET_ITEM(fargs, 1), &lo) && scalar_as_double(PyTuple_GET_ITEM(fargs, 2), &hi)) {
+            ew.kind = MP_EW_CLIP;
+            ew.a = lo;
+            ew.b = hi;
+            op = mpimg_elementwise;
+            op_args = &ew;
+        }
+    }
     Py_DECREF(name);
     if (!op) return NULL;
     MPArrayObject *copy = (MPArrayObject *)mpext_clone(self, self->obj->mem_loc, 0);
@@ -224,7 +240,7 @@ static PyObject *device_function(MPArrayObject *self, PyObject *func, PyObject *
     }
     MPStatus st;
     Py_BEGIN_ALLOW_THREADS
-    st = op(copy->obj, NULL);
+    st = op(copy->obj, op_args);
     Py_END_ALLOW_THREADS
     if (st != MILLIPYDE_SUCCESS) { /* e.g. an integer gpuarray: the host path below handles it */
         Py_DECREF(copy);
@@ -296,7 +312,13 @@ static PyObject *device_ufunc(MPArrayObject *self, PyObject *ufunc, PyObject *me
 {
     *handled = 0;
     if (!self->obj || !self->obj->device_data || self->obj->type != NPY_FLOAT) return NULL;
-    if (kwds && PyDict_Size(kwds) > 0) return NULL;
+    if (kwds && PyDict_Size(kwds) > 0) {
+        /* np.clip(...) always passes out=None along; any real keyword (out array, dtype, where, casting) is the host's */
+        PyObject *out = PyDict_GetItemString(kwds, "out");
+        if (PyDict_Size(kwds) != 1 || !out) return NULL;
+        if (out != Py_None && !(PyTuple_Check(out) && PyTuple_GET_SIZE(out) == 1 && PyTuple_GET_ITEM(out, 0) == Py_None))
+            return NULL;
+    }
     if (!PyUnicode_Check(method) || strcmp(PyUnicode_AsUTF8(method), "__call__") != 0) return NULL;
     PyObject *name = PyObject_GetAttrString(ufunc, "__name__");
     if (!name) {

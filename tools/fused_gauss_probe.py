@@ -16,6 +16,7 @@ from millipyde_b200 import capi, engine
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+    only = os.environ.get("PROBE_ONLY")
     h, w = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (2160, 3840)
     capi.initialize()
     L = capi.lib()
@@ -25,11 +26,16 @@ def main():
     views = [d.view() for d in src]
     out = {"images": n, "shape": [h, w, 3]}
     chains = {"gaussian": [("gaussian", 2.0)],
+              # per-image weight sets, no pointwise program: what the *_sets kernel costs by itself
+              "gaussian_per_image_sigma": [("random_gaussian", 2.0, 2.000001)],
+              "gaussian_add0": [("gaussian", 2.0), ("brightness", 0.0)],
               "gamma_gaussian_brightness": [("adjust_gamma", 1.5, 1.0), ("gaussian", 2.0), ("brightness", 0.1)],
               "brightness_gaussian": [("brightness", 0.1), ("gaussian", 2.0)],
               "gaussian_colorize": [("gaussian", 2.0), ("colorize", 0.9, 1.1, 1.0)]}
     first = True
     for name, ops in chains.items():
+        if only and name != only:
+            continue
         ch = engine.Chain(ops, device=0)
         times = []
         for rep in range(6):
@@ -46,7 +52,7 @@ def main():
         out[name] = {"images/s": round(n / best, 1), "launches": int(ch.last_launches), "segments": int(ch.last_segments),
                      "GB/s_algorithmic": round(n * 2 * h * w * 12 / best / 1e9, 1)}
         ch.close()
-    for k in list(chains)[1:]:
+    for k in [c for c in list(chains)[1:] if c in out and "gaussian" in out]:
         out[k]["vs_bare_gaussian"] = round(out[k]["images/s"] / out["gaussian"]["images/s"], 3)
     print(json.dumps(out))
 
