@@ -99,6 +99,16 @@ __device__ __forceinline__ float pw_apply(const PwProgram &prog, float v, int ch
 
 // The same program applied to a register tile of N samples whose channels are ch0, ch0+1, ...
 // (mod C): the op switch is taken once per op, not once per sample.
+// channel of element k of a run that starts at channel ch0 (0 <= ch0 < C): no integer division
+template <int C>
+__device__ __forceinline__ int pw_channel(int ch0, int k)
+{
+    if (C == 1) return 0;
+    if (C == 4) return (ch0 + k) & 3;
+    const int t = ch0 + (k % 3);
+    return t >= 3 ? t - 3 : t;
+}
+
 template <int C, int N>
 __device__ __forceinline__ void pw_apply_op_tile_impl(const PwOp &op, float (&r)[N], int ch0)
 {
@@ -118,7 +128,7 @@ __device__ __forceinline__ void pw_apply_op_tile_impl(const PwOp &op, float (&r)
                 if (C >= 3) {
 #pragma unroll
                     for (int k = 0; k < N; ++k) {
-                        const int ch = (C == 4) ? ((ch0 + k) & 3) : (ch0 + k) % 3;
+                        const int ch = pw_channel<C>(ch0, k);
                         if (ch < 3) r[k] = fminf(1.f, r[k] * (ch == 0 ? op.a : (ch == 1 ? op.b : op.c)));
                     }
                 }
@@ -129,8 +139,7 @@ __device__ __forceinline__ void pw_apply_op_tile_impl(const PwOp &op, float (&r)
             case PW_EW_CLIP:
 #pragma unroll
                 for (int k = 0; k < N; ++k) {
-                    const int ch = C == 1 ? 0 : (C == 4 ? ((ch0 + k) & 3) : (ch0 + k) % 3);
-                    r[k] = pw_ew_one(op, r[k], ch);
+                    r[k] = pw_ew_one(op, r[k], pw_channel<C>(ch0, k));
                 }
                 break;
             default: break;

@@ -225,6 +225,7 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
         int ob = -8 * (NCH - 1);
         const int gx0 = strip * kGsTW + wc * (16 * kMmTiles);     // first column of the warp's slice
         const int cols = min(16 * kMmTiles, p.row_elems - gx0);    // <= 0: the slice is outside the image
+        const int post_ch0 = (gx0 + 4 * (lane < 20 ? lane : 0)) % C;   // channel of this lane's vector column (post pass)
         float *gdst = base + ((long)y0 + ob) * p.row_elems + gx0;  // block row 0; only used when valid
 
         for (int c = 0; c < n_chunks8; ++c) {
@@ -309,19 +310,33 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
             const uint32_t done = item_g0 + (uint32_t)(8 * (c + 1)) / MmK::rows;
             if (SETS && n_post) {
                 // fused pointwise ops behind the blur: a separate pass over the staged block (8 rows x 80
-                // floats, this warp's own), one vector at a time so that it costs the role no registers.  Doing it on
+                // floats, this warp's own).  Doing it on
                 // the accumulator fragments instead puts a data-dependent loop between the MMAs and the
                 // staging stores and serialises the tiles (measured: 0.41x of the bare blur; this: see DESIGN.md).
                 __syncwarp();   // every lane's part of the block is staged
-#pragma unroll 1
-                for (int f = lane; f < 160; f += 32) {      // float4 index in the 8 x 20 block
-                    const int row = f / 20, col = 4 * (f - 20 * row);
-                    float *sp = stage + row * kMmStagePitch + col;
-                    const float4 t4 = *reinterpret_cast<const float4 *>(sp);
-                    float v[4] = {t4.x, t4.y, t4.z, t4.w};
-                    const int ch = (gx0 + col) % C;
-                    for (int k = 0; k < n_post; ++k) pw_apply_op_tile<C, 4>(pw_smem_op(*my_prog, k), v, ch);
-                    *reinterpret_cast<float4 *>(sp) = make_float4(v[0], v[1], v[2], v[3]);
+                // lane l < 20 owns vector column l of the 8 x 80 block: its channel phase is an item
+                // constant, the eight rows go through four at a time (16 registers), the op is decoded
+                // once per four vectors
+                if (lane < 20) {
+                    float *sp = stage + 4 * lane;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        float v[4][4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const float4 t4 = *reinterpret_cast<const float4 *>(sp + (4 * half + r) * kMmStagePitch);
+                            v[r][0] = t4.x; v[r][1] = t4.y; v[r][2] = t4.z; v[r][3] = t4.w;
+                        }
+                        for (int k = 0; k < n_post; ++k) {
+                            const PwOp op = pw_smem_op(*my_prog, k);
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) pw_apply_op_tile<C, 4>(op, v[r], post_ch0);
+                        }
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+                            *reinterpret_cast<float4 *>(sp + (4 * half + r) * kMmStagePitch) =
+                                make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+                    }
                 }
             }
             fence_proxy_async();   // the staged rows are read by the async proxy

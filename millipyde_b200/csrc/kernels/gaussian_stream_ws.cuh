@@ -189,6 +189,7 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
             n_pre = my_prog->n;
         }
         const int ch_start = ((gx_start % C) + C) % C;
+        const int pre_ch0 = (ch_start + lo + 4 * lane) % C;   // channel of the first sample of this lane's first vector
 
         // every load this warp issued has been consumed: its ring is quiescent
         if (lo > 0 || hi < G::ROW) {
@@ -242,15 +243,30 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
                     // sample once (the lanes' filter windows overlap 4.6x, so doing it on the window
                     // registers would repeat the work).  Only the in-image part [lo, hi): what lies
                     // outside is the blur's zero padding of the *transformed* image and stays zero.
-                    // One vector at a time: the pass must not cost the role registers (it has 80).
                     float *row = my_in + (size_t)slot * G::ROW;
-#pragma unroll 1
-                    for (int i = lo + 4 * lane; i < hi; i += 128) {
-                        const float4 t4 = *reinterpret_cast<const float4 *>(row + i);
-                        float v[4] = {t4.x, t4.y, t4.z, t4.w};
-                        const int ch = (ch_start + i) % C;
-                        for (int k = 0; k < n_pre; ++k) pw_apply_op_tile<C, 4>(pw_smem_op(*my_prog, k), v, ch);
-                        *reinterpret_cast<float4 *>(row + i) = make_float4(v[0], v[1], v[2], v[3]);
+                    constexpr int NQ = (G::ROW / 4 + 31) / 32;   // vectors per lane (6 for a 712-float row)
+#pragma unroll
+                    for (int j0 = 0; j0 < NQ; j0 += 3) {         // three vectors at a time: 12 registers
+                        float v[3][4];
+#pragma unroll
+                        for (int u = 0; u < 3; ++u) {
+                            const int i = lo + 4 * (lane + 32 * (j0 + u));
+                            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (j0 + u < NQ && i < hi) t4 = *reinterpret_cast<const float4 *>(row + i);
+                            v[u][0] = t4.x; v[u][1] = t4.y; v[u][2] = t4.z; v[u][3] = t4.w;
+                        }
+                        for (int k = 0; k < n_pre; ++k) {
+                            const PwOp op = pw_smem_op(*my_prog, k);
+#pragma unroll
+                            for (int u = 0; u < 3; ++u)   // vector j starts 128 j floats after vector 0: 128 = 2 (mod 3), 0 (mod 4)
+                                pw_apply_op_tile<C, 4>(op, v[u], pw_channel<C>(pre_ch0, C == 3 ? (2 * (j0 + u)) % 3 : 0));
+                        }
+#pragma unroll
+                        for (int u = 0; u < 3; ++u) {
+                            const int i = lo + 4 * (lane + 32 * (j0 + u));
+                            if (j0 + u < NQ && i < hi)
+                                *reinterpret_cast<float4 *>(row + i) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+                        }
                     }
                     fence_proxy_async();   // the slot's next writer is the TMA unit
                     __syncwarp();
