@@ -32,10 +32,10 @@ struct GaussStreamParams {
     int chunk_rows;              // rows per work item
     int n_chunks;
     int radius;                  // actual radius (<= R); w[d] = 0 beyond it
-    // Pointwise programs fused around the blur (device memory, null = none): image i applies
-    // pw_tab[2 i] to every input sample before the horizontal filter and pw_tab[2 i + 1] to every
-    // output sample (pw_stride = 2), or all images share pw_tab[0], pw_tab[1] (pw_stride = 0).
-    // Only the *_sets kernels look at it.
+    // Pointwise work fused around the blur (device memory, null = none): image i applies the program
+    // pw_tab[2 i] to every input sample before the horizontal filter, and pw_tab[2 i + 1] -- n = 0, or
+    // ONE op read as out = min(max(v + a, b), c) -- to every output sample (pw_stride = 2); or all
+    // images share pw_tab[0], pw_tab[1] (pw_stride = 0).  Only the *_sets kernels look at it.
     const PwProgram *pw_tab;
     int pw_stride;
     float w[16];

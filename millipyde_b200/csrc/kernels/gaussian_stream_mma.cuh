@@ -209,11 +209,21 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc[q][j][e] = 0.f;
 
-        PwSmem *my_prog = s_prog + warp;   // this warp's copy of the image's "after the blur" program
-        int n_post = 0;
+        // "After the blur": one add-and-clamp, out = min(max(v + pb, plo), phi) -- what brightness, clip and
+        // the clamps of colorize / multiply compose to (their per-channel factors run BEFORE the blur: it
+        // is linear).  Three straight-line instructions per accumulator, so they interleave with the
+        // MMAs; a general program here (a loop over ops between the MMAs and the staging stores) put
+        // the role's chunk latency over its budget and halved the kernel.
+        float pb = 0.f, plo = 0.f, phi = 0.f;
+        bool has_post = false;
         if (SETS && p.pw_tab) {
-            pw_smem_load(my_prog, p.pw_tab + (size_t)img * p.pw_stride + 1, lane);
-            n_post = my_prog->n;
+            const PwProgram *pp = p.pw_tab + (size_t)img * p.pw_stride + 1;
+            if (__ldg(&pp->n) != 0) {
+                has_post = true;
+                pb = __ldg(&pp->ops[0].a);
+                plo = __ldg(&pp->ops[0].b);
+                phi = __ldg(&pp->ops[0].c);
+            }
         }
         const uint32_t item_g0 = waited;   // == released: items are whole turns of the ring
         int ring_row = 0;                  // (c % 6) * 8
@@ -225,7 +235,6 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
         int ob = -8 * (NCH - 1);
         const int gx0 = strip * kGsTW + wc * (16 * kMmTiles);     // first column of the warp's slice
         const int cols = min(16 * kMmTiles, p.row_elems - gx0);    // <= 0: the slice is outside the image
-        const int post_ch0 = (gx0 + 4 * (lane < 20 ? lane : 0)) % C;   // channel of this lane's vector column (post pass)
         float *gdst = base + ((long)y0 + ob) * p.row_elems + gx0;  // block row 0; only used when valid
 
         for (int c = 0; c < n_chunks8; ++c) {
@@ -301,6 +310,10 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
                 for (int u = 0; u < kPair; ++u) {
                     const int q = q0 + u;
                     if (q >= kMmTiles) continue;
+                    if (SETS && has_post) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) nxt[u][NCH - 1][e] = fminf(fmaxf(nxt[u][NCH - 1][e] + pb, plo), phi);
+                    }
                     sts_f2(my_stage + 16 * q, nxt[u][NCH - 1][0], nxt[u][NCH - 1][2]);                        // block row 2t
                     sts_f2(my_stage + 4 * kMmStagePitch + 16 * q, nxt[u][NCH - 1][1], nxt[u][NCH - 1][3]);   // block row 2t + 1
                 }
@@ -308,37 +321,6 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
             // hand back every group whose 12 rows are now consumed (the MMAs above used every sample)
             ring_row = ring_row == kMmRing - 8 ? 0 : ring_row + 8;
             const uint32_t done = item_g0 + (uint32_t)(8 * (c + 1)) / MmK::rows;
-            if (SETS && n_post) {
-                // fused pointwise ops behind the blur: a separate pass over the staged block (8 rows x 80
-                // floats, this warp's own).  Doing it on
-                // the accumulator fragments instead puts a data-dependent loop between the MMAs and the
-                // staging stores and serialises the tiles (measured: 0.41x of the bare blur; this: see DESIGN.md).
-                __syncwarp();   // every lane's part of the block is staged
-                // lane l < 20 owns vector column l of the 8 x 80 block: its channel phase is an item
-                // constant, the eight rows go through four at a time (16 registers), the op is decoded
-                // once per four vectors
-                if (lane < 20) {
-                    float *sp = stage + 4 * lane;
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        float v[4][4];
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            const float4 t4 = *reinterpret_cast<const float4 *>(sp + (4 * half + r) * kMmStagePitch);
-                            v[r][0] = t4.x; v[r][1] = t4.y; v[r][2] = t4.z; v[r][3] = t4.w;
-                        }
-                        for (int k = 0; k < n_post; ++k) {
-                            const PwOp op = pw_smem_op(*my_prog, k);
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) pw_apply_op_tile<C, 4>(op, v[r], post_ch0);
-                        }
-#pragma unroll
-                        for (int r = 0; r < 4; ++r)
-                            *reinterpret_cast<float4 *>(sp + (4 * half + r) * kMmStagePitch) =
-                                make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
-                    }
-                }
-            }
             fence_proxy_async();   // the staged rows are read by the async proxy
             __syncwarp();          // every lane has read the chunk and staged its part of the block
             if (lane == 0) {

@@ -352,11 +352,16 @@ __device__ __forceinline__ void ws_body(const GaussStreamParams &p, const GaussW
             float *base = p.out_tab ? p.out_tab[img] : p.out + (size_t)img * p.image_stride;
             const int set = SETS ? img % kGsMaxSets : 0;
             auto w = [&](int d) -> uint64_t { return SETS ? ws.ww[set][d] : p.ww[d]; };
-            PwSmem *my_prog = s_prog + warp;
-            int n_post = 0;
+            float pb = 0.f, plo = 0.f, phi = 0.f;   // "after the blur": out = min(max(v + pb, plo), phi)
+            bool has_post = false;
             if (SETS && p.pw_tab) {
-                pw_smem_load(my_prog, p.pw_tab + (size_t)img * p.pw_stride + 1, lane);
-                n_post = my_prog->n;
+                const PwProgram *pp = p.pw_tab + (size_t)img * p.pw_stride + 1;
+                if (__ldg(&pp->n) != 0) {
+                    has_post = true;
+                    pb = __ldg(&pp->ops[0].a);
+                    plo = __ldg(&pp->ops[0].b);
+                    phi = __ldg(&pp->ops[0].c);
+                }
             }
             float *optr = base + ((long)y0 - 2 * R) * p.row_elems + gx;  // only dereferenced when valid
             unsigned rel = (unsigned)(-2 * R);                            // output row - y0, wraps below 0
@@ -375,8 +380,10 @@ __device__ __forceinline__ void ws_body(const GaussStreamParams &p, const GaussW
                     if (rel < n_valid) {
                         float o2[2];
                         unpack2(o, o2[0], o2[1]);
-                        if (SETS)
-                            for (int k = 0; k < n_post; ++k) pw_apply_op_tile<C, 2>(pw_smem_op(*my_prog, k), o2, gx % C);
+                        if (SETS && has_post) {
+                            o2[0] = fminf(fmaxf(o2[0] + pb, plo), phi);
+                            o2[1] = fminf(fmaxf(o2[1] + pb, plo), phi);
+                        }
                         __stcs(reinterpret_cast<float2 *>(optr), make_float2(o2[0], o2[1]));
                     }
                     ++rel;

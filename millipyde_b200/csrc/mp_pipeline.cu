@@ -5,6 +5,7 @@
 // (src/gpupipeline.c:234-403) and the serial Generator loop
 // (src/gpugenerator.c:203-281).  See include/mp_pipeline.h for the contract.
 #include <chrono>
+#include <cmath>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -164,6 +165,12 @@ struct Segment {
     // where the values above came from (fixed arguments or keyed draws): what the device-side record
     // fill evaluates when every image of a launch shares it
     PwTemplate pre_t = {}, post_t = {};
+    // GAUSS_F32: what the streaming kernel is handed.  k_pre = pre + the per-channel factors of the
+    // ops behind the blur (the blur is linear, so they run in front of it); k_post = empty or ONE op
+    // read as out = min(max(v + a, b), c), what the add / clamp parts of those ops compose to.
+    PwProgram k_pre = {}, k_post = {};
+    PwTemplate k_pre_t = {}, k_post_t = {};
+    bool tmpl_ok = true;   // the templates reproduce the values (false: a drawn parameter went through arithmetic)
     uint32_t angle_stage = kFixedStage;
     double angle_lo = 0, angle_hi = 0;
 };
@@ -217,6 +224,70 @@ U8Op to_u8(const Stage &s)
         case OP_GAMMA: return U8Op{PW_GAMMA, 0, s.a[0], s.a[1], 0};
         default: return U8Op{PW_COLORIZE, 0, s.a[0], s.a[1], s.a[2]};
     }
+}
+
+// ---- pointwise ops behind a Gaussian, folded -------------------------------------------------
+// Every op the fold accepts is g(y) = clamp(a_ch y + b, l, h) with a_ch >= 0; compositions of such maps
+// are again of that form, f(v) = clamp(A_ch v + B, L, H).  The kernel applies v + B and the clamp to the
+// finished rows (three instructions on the accumulator fragments) and A_ch -- by linearity of the blur --
+// to the samples in front of it.  An op that would make B, L or H differ between channels, or that is
+// not affine (gamma, power), ends the fold: it and what follows run as a segment of their own.
+struct PostFold {
+    double A[3] = {1, 1, 1};
+    double B = 0, L = -HUGE_VAL, H = HUGE_VAL;
+    int n = 0;              // ops absorbed
+    bool drawn_other = false;   // a drawn parameter other than "one brightness" took part
+    const Stage *only_brightness = nullptr;
+};
+
+bool fold_post(PostFold &f, const Stage &t, int channels)
+{
+    double a[3] = {1, 1, 1}, b = 0, l = -HUGE_VAL, h = HUGE_VAL;
+    bool per_channel = false;
+    switch (t.kind) {
+        case OP_BRIGHTNESS:
+            if (channels == 4) return false;   // skips alpha: not the same map on every channel
+            b = t.a[0]; l = 0; h = 1;
+            break;
+        case OP_COLORIZE:
+            if (channels == 1) { ++f.n; return true; }   // no-op on grey (:647-651)
+            if (channels != 3) return false;
+            a[0] = t.a[0]; a[1] = t.a[1]; a[2] = t.a[2]; h = 1;
+            per_channel = true;
+            break;
+        case OP_ELEMENTWISE: {
+            const int kind = (int)t.a[0];
+            if (kind == MP_EW_ADD) b = t.a[1];
+            else if (kind == MP_EW_CLIP) { l = t.a[2]; h = t.a[3]; if (!(l <= h)) return false; }
+            else if (kind == MP_EW_MUL) {
+                if (t.a[4] != 0) { a[0] = t.a[1]; a[1] = t.a[2]; a[2] = t.a[3]; per_channel = true; }
+                else a[0] = a[1] = a[2] = t.a[1];
+            } else return false;
+            break;
+        }
+        default: return false;
+    }
+    for (int c = 0; c < 3; ++c)
+        if (!(a[c] > 0) || !std::isfinite(a[c])) return false;   // clamp bounds would swap (or collapse)
+    if (per_channel && (a[0] != a[1] || a[1] != a[2])) {
+        // channel-dependent slope: B, L, H stay common to the channels only from this state
+        if (f.B != 0 || !(f.L == -HUGE_VAL || f.L == 0) || f.H != HUGE_VAL) return false;
+        if (channels != 3) return false;
+    }
+    auto clampd = [](double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); };
+    const double u = a[0];   // the slope applied to B, L, H (uniform, or they are 0 / infinite)
+    for (int c = 0; c < 3; ++c) f.A[c] *= a[c];
+    f.B = u * f.B + b;
+    f.L = clampd(f.L == -HUGE_VAL ? -HUGE_VAL : u * f.L + b, l, h);
+    f.H = clampd(f.H == HUGE_VAL ? HUGE_VAL : u * f.H + b, l, h);
+    if (t.rstage != kFixedStage) {
+        if (t.kind == OP_BRIGHTNESS && f.n == 0) f.only_brightness = &t;
+        else f.drawn_other = true;
+    } else if (f.only_brightness) {
+        f.drawn_other = true;   // a drawn delta followed by more ops: its bounds went through arithmetic
+    }
+    ++f.n;
+    return true;
 }
 
 // Compile the surviving stages of one group into segments.  `fam`/`channels`
@@ -276,9 +347,43 @@ std::vector<Segment> compile(const std::vector<const Stage *> &ops, mp::Family f
             while (j < ops.size() && is_pw(*ops[j], channels) && seg.pre.n < kMaxPw) push_pw(seg.pre, seg.pre_t, *ops[j++]);
             if (j < ops.size() && ops[j]->kind == OP_GAUSSIAN && ops[j]->a[0] > 1e-15) {
                 seg.single = ops[j++];
-                while (j < ops.size() && is_pw(*ops[j], channels) && seg.post.n < kMaxPw)
+                PostFold fold;
+                while (j < ops.size() && is_pw(*ops[j], channels) && seg.post.n < kMaxPw && seg.pre.n + 1 < kMaxPw &&
+                       fold_post(fold, *ops[j], channels))
                     push_pw(seg.post, seg.post_t, *ops[j++]);
                 if (seg.pre.n + seg.post.n > 0) {   // a bare Gaussian keeps its own (SINGLE) path
+                    seg.k_pre = seg.pre;
+                    seg.k_pre_t = seg.pre_t;
+                    if (fold.A[0] != 1 || fold.A[1] != 1 || fold.A[2] != 1) {
+                        const PwOp mul = {PW_EW_MUL, (float)fold.A[0], (float)fold.A[1], (float)fold.A[2]};
+                        PwTemplateOp mt = {};
+                        mt.kind = PW_EW_MUL;
+                        mt.stage = kFixedStage;
+                        for (int c = 0; c < 3; ++c) mt.lo[c] = mt.hi[c] = (&mul.a)[c];
+                        seg.k_pre.ops[seg.k_pre.n++] = mul;
+                        seg.k_pre_t.ops[seg.k_pre_t.n++] = mt;
+                        for (int q = 0; q < seg.post.n; ++q)   // a drawn colorize / multiply: the product is not a plain draw
+                            if (seg.post_t.ops[q].stage != kFixedStage && seg.post.ops[q].kind != PW_BRIGHTNESS) seg.tmpl_ok = false;
+                    }
+                    if (seg.post.n > 0 && (fold.B != 0 || fold.L != -HUGE_VAL || fold.H != HUGE_VAL)) {
+                        seg.k_post.n = 1;
+                        seg.k_post.ops[0] = PwOp{PW_EW_ADD, (float)fold.B, (float)fold.L, (float)fold.H};
+                        PwTemplateOp pt = {};
+                        pt.kind = PW_EW_ADD;
+                        pt.stage = kFixedStage;
+                        pt.lo[0] = pt.hi[0] = (float)fold.B;
+                        pt.lo[1] = pt.hi[1] = (float)fold.L;
+                        pt.lo[2] = pt.hi[2] = (float)fold.H;
+                        if (fold.only_brightness && !fold.drawn_other) {   // out = clamp(v + delta, 0, 1), delta drawn: slot 0
+                            pt.stage = fold.only_brightness->rstage;
+                            pt.lo[0] = fold.only_brightness->lo[0];
+                            pt.hi[0] = fold.only_brightness->hi[0];
+                        } else if (fold.drawn_other) {
+                            seg.tmpl_ok = false;
+                        }
+                        seg.k_post_t.n = 1;
+                        seg.k_post_t.ops[0] = pt;
+                    }
                     out.push_back(seg);
                     i = j;
                     continue;
@@ -592,22 +697,27 @@ bool plan_pw_fill(const std::vector<const Segment *> &segs, const std::vector<ui
 {
     if (!g_device_draws.load() || segs.size() < 2 || index.size() != segs.size()) return false;
     const Segment &s0 = *segs[0];
+    // a fused Gaussian hands the kernel its folded programs (k_pre, k_post), everything else pre / post
+    const bool gauss = s0.kind == Segment::GAUSS_F32;
+    auto pre_of = [gauss](const Segment &g) -> const PwTemplate & { return gauss ? g.k_pre_t : g.pre_t; };
+    auto post_of = [gauss](const Segment &g) -> const PwTemplate & { return gauss ? g.k_post_t : g.post_t; };
     bool drawn = false;
-    for (int i = 0; i < s0.pre_t.n; ++i) drawn = drawn || s0.pre_t.ops[i].stage != kFixedStage;
-    for (int i = 0; i < s0.post_t.n; ++i) drawn = drawn || s0.post_t.ops[i].stage != kFixedStage;
+    for (int i = 0; i < pre_of(s0).n; ++i) drawn = drawn || pre_of(s0).ops[i].stage != kFixedStage;
+    for (int i = 0; i < post_of(s0).n; ++i) drawn = drawn || post_of(s0).ops[i].stage != kFixedStage;
     if (!drawn) return false;
-    for (size_t i = 1; i < segs.size(); ++i)
-        if (memcmp(&segs[i]->pre_t, &s0.pre_t, sizeof(PwTemplate)) || memcmp(&segs[i]->post_t, &s0.post_t, sizeof(PwTemplate)))
+    for (size_t i = 0; i < segs.size(); ++i)
+        if (!segs[i]->tmpl_ok || memcmp(&pre_of(*segs[i]), &pre_of(s0), sizeof(PwTemplate)) ||
+            memcmp(&post_of(*segs[i]), &post_of(s0), sizeof(PwTemplate)))
             return false;
     const size_t n = segs.size();
     const size_t t_bytes = (size_t)per_image * sizeof(PwTemplate);
     blob->resize(t_bytes + n * sizeof(unsigned long long));
     PwTemplate *t = (PwTemplate *)blob->data();
     if (per_image == 2) {
-        t[0] = s0.pre_t;
-        t[1] = s0.post_t;
+        t[0] = pre_of(s0);
+        t[1] = post_of(s0);
     } else {
-        t[0] = use_pre ? s0.pre_t : s0.post_t;
+        t[0] = use_pre ? pre_of(s0) : post_of(s0);
     }
     unsigned long long *idx = (unsigned long long *)(blob->data() + t_bytes);
     for (size_t i = 0; i < n; ++i) idx[i] = index[i];
@@ -813,8 +923,8 @@ void run_segment_group(mp_pipeline *p, const std::vector<MPObjData *> &objs, con
         std::vector<PwProgram> progs(2 * n);
         for (size_t i = 0; i < n; ++i) {
             sigmas[i] = segs[i]->single->a[0];
-            progs[2 * i] = segs[i]->pre;
-            progs[2 * i + 1] = segs[i]->post;
+            progs[2 * i] = segs[i]->k_pre;
+            progs[2 * i + 1] = segs[i]->k_post;
         }
         bool handled = false;
         note_status(p, run_gaussian_batch(objs, cur, sigmas, device, s, &handled, &progs, &segs));

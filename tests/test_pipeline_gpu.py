@@ -389,6 +389,7 @@ def test_pointwise_ops_fuse_into_the_gaussian(mp, c):
     chains = [
         [("adjust_gamma", 1.5, 1.0), ("gaussian", 2.0), ("brightness", 0.1)],
         [("brightness", 0.25), ("gaussian", 2.0)],
+        [("gaussian", 1.5), ("colorize", 0.9, 1.2, 0.5), ("brightness", -0.05)],
         [("gaussian", 0.7), ("colorize", 0.9, 1.2, 0.5), ("adjust_gamma", 0.8, 0.9)],
         # (no gamma < 1 behind the blur: x^0.5 near 0 amplifies the blur's ~3e-7 error past the contract)
         [("colorize", 1.3, 0.7, 1.1), ("adjust_gamma", 2.2, 1.0), ("gaussian", 1.3), ("brightness", -0.1),
@@ -402,11 +403,20 @@ def test_pointwise_ops_fuse_into_the_gaussian(mp, c):
             dev = [mp.capi.DeviceImage(a) for a in imgs]
             ch = mp.engine.Chain(chain, device=0)
             ch.run(dev)
-            assert ch.last_segments == 1 and ch.last_launches == 1, (chain, ch.last_segments, ch.last_launches)
+            # what the fusion pass promises for this chain and layout (tests/test_fusion_plan.py pins the
+            # rules: everything in front of the blur and every scale / add / clamp behind it is absorbed;
+            # a gamma behind it, or an alpha-skipping op on RGBA, is one more pointwise launch)
+            import ctypes as C
+            buf = C.create_string_buffer(256)
+            nseg = mp.lib.mppipe_plan(ch.ptr, 11, c, buf, len(buf))
+            assert buf.value.decode().startswith("gauss(") and nseg <= 2, buf.value
+            if c == 3 and chain[-1][0] != "adjust_gamma":
+                assert nseg == 1, buf.value
+            assert ch.last_segments == nseg and ch.last_launches == nseg, (chain, buf.value, ch.last_launches)
             single = mp.capi.DeviceImage(imgs[0])
             ch1 = mp.engine.Chain(chain, device=0)
-            ch1.run([single])                                   # a batch of one takes the same kernel
-            assert ch1.last_launches == 1
+            ch1.run([single])                                   # a batch of one takes the same kernels
+            assert ch1.last_launches == nseg
             mp.lib.mppipe_set_fusion(0)
             try:
                 unf = [mp.capi.DeviceImage(a) for a in imgs[:2]]
