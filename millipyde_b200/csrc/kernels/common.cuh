@@ -134,13 +134,23 @@ __device__ __forceinline__ void pw_apply_op_tile_impl(const PwOp &op, float (&r)
                 }
                 break;
             case PW_EW_ADD:
+#pragma unroll
+                for (int k = 0; k < N; ++k) r[k] = r[k] + op.a;
+                break;
             case PW_EW_MUL:
-            case PW_EW_POW:
-            case PW_EW_CLIP:
 #pragma unroll
                 for (int k = 0; k < N; ++k) {
-                    r[k] = pw_ew_one(op, r[k], pw_channel<C>(ch0, k));
+                    const int ch = pw_channel<C>(ch0, k);
+                    r[k] = r[k] * (ch == 0 ? op.a : (ch == 1 ? op.b : op.c));
                 }
+                break;
+            case PW_EW_CLIP:
+#pragma unroll
+                for (int k = 0; k < N; ++k) r[k] = fminf(fmaxf(r[k], op.a), op.b);
+                break;
+            case PW_EW_POW:   // out of line (see pw_powf): the only case with a call in it
+#pragma unroll
+                for (int k = 0; k < N; ++k) r[k] = pw_powf(r[k], op.a);
                 break;
             default: break;
         }
