@@ -9,10 +9,12 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 #include <map>
 #include <mutex>
 #include <string>
 
+#include "kernels/gaussian_global.cuh"
 #include "kernels/gaussian_tile.cuh"
 #include "kernels/geometry.cuh"
 #include "kernels/pointwise.cuh"
@@ -131,8 +133,9 @@ int oracle_weights(double sigma, double *w, int max_radius)
 {
     int r = (int)(8.0 * sigma + 0.5);
     if (r > max_radius) {
-        // taps this far out are < exp(-0.5 * 64) relative: renormalising over the
-        // capped support changes nothing representable
+        // Callers with a fixed-size table (the fusion pass's radius-bucket query): the taps beyond are
+        // < exp(-32) of the centre.  launch_gaussian itself never truncates: larger radii take the
+        // global-memory kernel with the full support (oracle_weights_full).
         r = max_radius;
     }
     double total = 0;
@@ -142,6 +145,20 @@ int oracle_weights(double sigma, double *w, int max_radius)
     }
     for (int d = 0; d <= r; ++d) w[d] /= total;
     return r;
+}
+
+// The same kernel over its whole nominal support, whatever the radius.
+std::vector<double> oracle_weights_full(double sigma)
+{
+    const int r = (int)(8.0 * sigma + 0.5);
+    std::vector<double> w((size_t)r + 1);
+    double total = 0;
+    for (int d = 0; d <= r; ++d) {
+        w[d] = exp(-0.5 / (sigma * sigma) * (double)d * d);
+        total += d ? 2 * w[d] : w[d];
+    }
+    for (double &v : w) v /= total;
+    return w;
 }
 
 // Smallest radius whose dropped tail mass is <= eps (weights already normalised).
@@ -714,6 +731,31 @@ static void launch_f64_fixed(int device, cudaStream_t s, const Img &d, const voi
     count_launch();
 }
 
+// Any radius, any float type: rows then columns through a pool-allocated intermediate
+// (kernels/gaussian_global.cuh).  `w` holds radius + 1 weights on the host.
+template <typename T>
+static MPStatus launch_global(int device, cudaStream_t s, const Img &d, const void *in, void *out, const double *w,
+                              int radius)
+{
+    const size_t total = d.npix * (size_t)d.C;
+    T *tmp = (T *)pool_alloc(device, s, total * sizeof(T));
+    double *dw = (double *)pool_alloc(device, s, ((size_t)radius + 1) * sizeof(double));
+    if (!tmp || !dw) {
+        if (tmp) pool_free(device, s, tmp);
+        if (dw) pool_free(device, s, dw);
+        return MP_ERROR_DEVICE_ALLOC;
+    }
+    // pageable source: the runtime stages it before the call returns, `w` may die afterwards
+    MP_CUDA_TRY(cudaMemcpyAsync(dw, w, ((size_t)radius + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
+    const int grid = grid_for(device, total, 256);
+    gauss_global_pass_kernel<T, true><<<grid, 256, 0, s>>>((const T *)in, tmp, total, d.W * d.C, d.C, d.W, dw, radius);
+    gauss_global_pass_kernel<T, false><<<grid, 256, 0, s>>>(tmp, (T *)out, total, d.W * d.C, d.C, d.H, dw, radius);
+    count_launch(2);
+    pool_free(device, s, tmp);
+    pool_free(device, s, dw);
+    return MILLIPYDE_SUCCESS;
+}
+
 MPStatus launch_gaussian(int device, cudaStream_t s, const Img &d, const void *in, void *out, double sigma,
                          bool ref_rule)
 {
@@ -795,6 +837,11 @@ MPStatus launch_gaussian(int device, cudaStream_t s, const Img &d, const void *i
             launch_f64_fixed<8, true>(device, s, d, in, out, gp);
             return MILLIPYDE_SUCCESS;
         }
+        const int nominal = (int)(8.0 * sigma + 0.5);
+        if (nominal > kGaussMaxRadius) {   // sigma > ~15.9: the full support, no truncation (matches scipy to 1e-12)
+            const std::vector<double> wf = oracle_weights_full(sigma);
+            return launch_global<double>(device, s, d, in, out, wf.data(), nominal);
+        }
         gp.radius = oracle_weights(sigma, gp.w, kGaussMaxRadius);
         if (gp.radius == 16) {  // sigma = 2 under the oracle rule (truncate = 8)
             launch_f64_fixed<16, false>(device, s, d, in, out, gp);
@@ -804,9 +851,18 @@ MPStatus launch_gaussian(int device, cudaStream_t s, const Img &d, const void *i
             launch_f64_fixed<8, false>(device, s, d, in, out, gp);
             return MILLIPYDE_SUCCESS;
         }
-        return launch_tile<double, 1, false>(s, d, in, out, gp);
+        {
+            const MPStatus st = launch_tile<double, 1, false>(s, d, in, out, gp);
+            if (st != MP_ERROR_INVALID_ARGUMENT) return st;
+            return launch_global<double>(device, s, d, in, out, gp.w, gp.radius);   // the tile + halo exceeds shared memory
+        }
     }
     // fp32: scipy weights, evaluated over the effective support only
+    if ((int)(8.0 * sigma + 0.5) > kGaussMaxRadius) {
+        const std::vector<double> wf = oracle_weights_full(sigma);
+        const int eff_full = effective_radius(wf.data(), (int)wf.size() - 1, ldexp(1.0, -24));
+        return launch_global<float>(device, s, d, in, out, wf.data(), eff_full);
+    }
     int r = oracle_weights(sigma, w, kGaussMaxRadius);
     int eff = effective_radius(w, r, ldexp(1.0, -24));
     GaussParams<float> gp = {};
@@ -814,9 +870,12 @@ MPStatus launch_gaussian(int device, cudaStream_t s, const Img &d, const void *i
     for (int k = 0; k <= eff; ++k) gp.w[k] = (float)w[k];
     if (gauss_stream_supported(d.W, d.C, eff))
         return launch_gauss_stream(device, s, d, (const float *)in, (float *)out, gp);
-    if (d.C == 1) return launch_tile<float, 1, false>(s, d, in, out, gp);
-    if (d.C == 3) return launch_tile<float, 3, false>(s, d, in, out, gp);
-    return launch_tile<float, 4, false>(s, d, in, out, gp);
+    MPStatus st;
+    if (d.C == 1) st = launch_tile<float, 1, false>(s, d, in, out, gp);
+    else if (d.C == 3) st = launch_tile<float, 3, false>(s, d, in, out, gp);
+    else st = launch_tile<float, 4, false>(s, d, in, out, gp);
+    if (st != MP_ERROR_INVALID_ARGUMENT) return st;
+    return launch_global<float>(device, s, d, in, out, w, eff);   // the tile + halo exceeds shared memory
 }
 
 }  // namespace mp

@@ -196,6 +196,28 @@ def test_f32_gaussian_declared_value_range(capi):
     assert L.mpimg_get_gauss_column() == 0
 
 
+def test_gaussian_accepts_every_sigma(capi):
+    """The reference takes any sigma (src/millipyde_image.cpp:660-675).  Beyond the streaming buckets
+    the shared-memory tile kernel serves until a tile plus its halo no longer fits (sigma ~ 9 for fp64,
+    ~ 11 for fp32 RGB); beyond that, and beyond the 127-tap weight table (sigma > 15.9), the
+    global-memory two-pass kernel runs the FULL support int(8 sigma + 0.5) like scipy does."""
+    for sigma in (4.0, 9.5, 12.0, 20.0):
+        for c in (1, 3):
+            a = synth.noise_f32(70, 90, c, 7300 + c)
+            got = dev(capi, a).apply("gaussian", sigma).numpy()
+            assert np.abs(got - so.gaussian(a, sigma)).max() <= TOL32, (sigma, c)
+        g = synth.noise_f32(61, 83, 1, 7310).astype(np.float64)
+        got = dev(capi, g).apply("gaussian", sigma).numpy()
+        assert np.abs(got - so.gaussian(g, sigma)).max() <= 1e-12, sigma
+    # a batch through the executor takes the same route image by image
+    from millipyde_b200 import engine
+    imgs = [synth.noise_f32(40, 64, 3, 7320 + k) for k in range(3)]
+    devs = [dev(capi, x) for x in imgs]
+    engine.Chain([("brightness", 0.1), ("gaussian", 18.0)], device=0).run(devs)
+    for x, d in zip(imgs, devs):
+        assert np.abs(d.numpy() - so.apply_chain(x, [("brightness", 0.1), ("gaussian", 18.0)])).max() <= TOL32
+
+
 def test_f32_gaussian_edge_cases(capi):
     a = synth.noise_f32(5, 7, 3, 1)                 # smaller than the kernel support
     assert np.abs(dev(capi, a).apply("gaussian", 2.0).numpy() - so.gaussian(a, 2.0)).max() <= TOL32

@@ -42,25 +42,12 @@ timeout 600 python tools/bench_configs.py config4 --spread --ref-params --prefet
 timeout 600 python tools/bench_configs.py config4 --spread --ref-params --prefetch 512 --images 8192 --to-host >> $O/${T}_configs.jsonl 2>> $O/${T}_configs.err
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 tools/bench_configs.py config4 --ref-params --prefetch 256 >> $O/${T}_configs.jsonl 2>> $O/${T}_configs.err
 echo "== config 5: $((N/2)) pair(s)"
-nvidia-smi nvlink -gt d -i 0 > $O/${T}_nvlink_before.txt 2>&1
 timeout 600 python tools/bench_configs.py config5 --pairs $((N/2)) --threads >> $O/${T}_configs.jsonl 2>> $O/${T}_configs.err
-nvidia-smi nvlink -gt d -i 0 > $O/${T}_nvlink_after.txt 2>&1
 timeout 600 python tools/bench_configs.py config5 --pairs $((N/2)) >> $O/${T}_configs.jsonl 2>> $O/${T}_configs.err
 timeout 600 python tools/bench_configs.py config5 --pairs 1 >> $O/${T}_configs.jsonl 2>> $O/${T}_configs.err
 cat $O/${T}_configs.jsonl; tail -c 600 $O/${T}_configs.err
-python - <<PY
-import re
-def total(path):
-    tx = rx = 0
-    for ln in open(path):
-        m = re.search(r"Data (Tx|Rx): (\d+) KiB", ln)
-        if m:
-            if m.group(1) == "Tx": tx += int(m.group(2))
-            else: rx += int(m.group(2))
-    return tx, rx
-try:
-    b, a = total("$O/${T}_nvlink_before.txt"), total("$O/${T}_nvlink_after.txt")
-    print("nvlink GPU0 delta during config 5 (threads run): tx %.1f MiB rx %.1f MiB" % ((a[0]-b[0])/1024, (a[1]-b[1])/1024))
-except Exception as e:
-    print("nvlink counters unreadable", e)
-PY
+# NVLink bytes of the hand-off as the hardware counts them (nvidia-smi nvlink counters read N/A in this VM):
+# the sender's last kernel (the transpose) writes its outputs into the receiver's memory
+timeout 300 ncu --metrics nvltx__bytes.sum,nvlrx__bytes.sum,gpu__time_duration.sum --clock-control none -k regex:transpose -c 4 --csv \
+  --log-file $O/${T}_nvlink_ncu.csv python tools/bench_configs.py config5 --pairs 1 --images 16 --reps 0 > /dev/null 2>> $O/${T}_configs.err
+tail -6 $O/${T}_nvlink_ncu.csv
