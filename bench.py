@@ -102,7 +102,8 @@ class ClockSampler:
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, pci_bus_id: str | None = None):
+        self.pci = pci_bus_id   # the CUDA device's PCI bus id: NVML's enumeration order need not be CUDA's
         self.rows = []          # (arrival time, sm MHz, max MHz, watts, set of reasons)
         self.window = None      # (t0, t1) of the timed region
         self.proc = None
@@ -116,7 +117,8 @@ class ClockSampler:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.h = (pynvml.nvmlDeviceGetHandleByPciBusId(self.pci.encode()) if self.pci
+                      else pynvml.nvmlDeviceGetHandleByIndex(self.gpu))
             self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
             self.how = "NVML every 5 ms"
             self.thread = threading.Thread(target=self._pump_nvml, daemon=True)
@@ -453,7 +455,8 @@ def timed_resident(capi, engine, args, dist, devices, batch, seeds, physical_gpu
     """Warm up, then time exactly args.steps steps with CUDA events on the launching streams."""
     L = capi.lib()
     res = Resident(capi, engine, devices, batch, seeds)
-    sampler = ClockSampler(physical_gpu)
+    pci = ctypes.create_string_buffer(32)
+    sampler = ClockSampler(physical_gpu, pci.value.decode() if L.mpdev_pci_bus_id(devices[0], pci, 32) == 0 else None)
     sampler.start()
     try:
         t_warm = time.time()

@@ -70,6 +70,8 @@ void mpdev_event_record(MPEvent *ev, void *stream);
 float mpdev_event_elapsed_ms(MPEvent *start, MPEvent *stop); /* syncs on stop */
 MPStatus mpdev_mem_info(int device_id, size_t *free_bytes, size_t *total_bytes);
 int mpdev_sm_count(int device_id);
+/* PCI bus id of a device ("0000:1b:00.0"): how a monitoring tool (NVML) finds the same GPU */
+MPStatus mpdev_pci_bus_id(int device_id, char *buf, int len);
 /* write > L2-size bytes so the next timed launch starts cold */
 void mpdev_flush_l2(int device_id, void *stream);
 /* Hand the unused part of every device pool back to the driver (the pools otherwise keep every

@@ -190,6 +190,7 @@ SYMBOLS = {
     "mpdev_event_elapsed_ms": (C.c_float, [C.c_void_p, C.c_void_p]),
     "mpdev_mem_info": (C.c_int, [C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "mpdev_sm_count": (C.c_int, [C.c_int]),
+    "mpdev_pci_bus_id": (C.c_int, [C.c_int, C.c_char_p, C.c_int]),
     "mpdev_flush_l2": (None, [C.c_int, C.c_void_p]),
     "mpdev_trim_pools": (None, []),
     "mpdev_launch_count": (C.c_ulonglong, []),

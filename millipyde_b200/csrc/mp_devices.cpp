@@ -564,6 +564,13 @@ MPStatus mpdev_mem_info(int device_id, size_t *free_bytes, size_t *total_bytes)
 
 int mpdev_sm_count(int device_id) { return mp::sm_count(device_id); }
 
+MPStatus mpdev_pci_bus_id(int device_id, char *buf, int len)
+{
+    if (!buf || len < 13 || !in_range(device_id)) return MP_ERROR_INVALID_ARGUMENT;
+    MP_CUDA_TRY(cudaDeviceGetPCIBusId(buf, len, device_id));
+    return MILLIPYDE_SUCCESS;
+}
+
 void mpdev_flush_l2(int device_id, void *stream)
 {
     if (!mpdev_is_valid_device(device_id)) return;

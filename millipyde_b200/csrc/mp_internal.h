@@ -40,6 +40,10 @@ void *pool_alloc_on(int pool_device, cudaStream_t stream, size_t nbytes);
 // when a foreign caller left it NULL.
 cudaStream_t stream_of(const MPObjData *obj);
 
+// Make `waiter` wait for everything enqueued so far on `signaller` (a stream of device signal_dev):
+// one event, no host sync.
+void order_after(int signal_dev, cudaStream_t signaller, cudaStream_t waiter);
+
 extern std::atomic<unsigned long long> g_launch_count;
 inline void count_launch(unsigned n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
 

@@ -54,6 +54,10 @@ void chain_streams(int signal_dev, cudaStream_t signaller, cudaStream_t waiter)
 
 }  // namespace
 
+namespace mp {
+void order_after(int signal_dev, cudaStream_t signaller, cudaStream_t waiter) { chain_streams(signal_dev, signaller, waiter); }
+}  // namespace mp
+
 extern "C" {
 
 void mpobj_copy_from_host(MPObjData *obj, void *data, size_t nbytes)
