@@ -10,6 +10,7 @@ O=gpurun_out
 mkdir -p $O
 T=r2_${N}gpu
 { nvidia-smi topo -m; echo; lscpu | grep -E "Model name|Socket|NUMA|^CPU\(s\)"; echo; free -g | head -2; } > $O/${T}_topology.txt 2>&1
+if [ -z "${ONLY_CONFIGS:-}" ]; then
 echo "== pcie ceiling, 1..$N ranks"
 : > $O/${T}_pcie_ranks.jsonl
 for R in 1 2 4 8; do
@@ -36,9 +37,11 @@ for f in ("$O/${T}_bench_n1.json", "$O/${T}_bench.json"):
 PY
 echo "== pytest multigpu"
 timeout 600 python -m pytest tests/test_multigpu.py tests/test_reference_hybrid.py -m gpu -x -q 2>&1 | tail -8
+fi
 echo "== config 4: one Generator spreading 65536 outputs over $N devices"
 : > $O/${T}_configs.jsonl
 timeout 600 python tools/bench_configs.py config4 --spread --ref-params --prefetch 2048 >> $O/${T}_configs.jsonl 2>> $O/${T}_configs.err
+timeout 600 python tools/bench_configs.py config4 --spread --ref-params --prefetch 8192 >> $O/${T}_configs.jsonl 2>> $O/${T}_configs.err
 timeout 600 python tools/bench_configs.py config4 --spread --ref-params --prefetch 512 --images 8192 --to-host >> $O/${T}_configs.jsonl 2>> $O/${T}_configs.err
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 tools/bench_configs.py config4 --ref-params --prefetch 256 >> $O/${T}_configs.jsonl 2>> $O/${T}_configs.err
 echo "== config 5: $((N/2)) pair(s)"
