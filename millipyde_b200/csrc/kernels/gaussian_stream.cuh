@@ -17,6 +17,9 @@ template <int C, int R>
 struct GsGeom {
     static constexpr int HALO = (R * C + 3) / 4 * 4;          // halo rounded up to 16 bytes
     static constexpr int ROW = kGsTW + 2 * HALO;              // floats per staged row
+    // slot pitch: one more vector, where the landing of a row that is not 16-byte aligned in global
+    // memory (W * C % 4 != 0) spills before it is shifted into place
+    static constexpr int SLOT = ROW + 4;
 };
 
 struct GaussStreamParams {

@@ -54,7 +54,7 @@ constexpr int kMmColRegs = 120;
 template <int C, int R>
 struct MmGeom {
     static constexpr int NCH = (7 + 2 * R) / 8 + 1;   // chunks an output block spans
-    static constexpr size_t IN_BYTES = (size_t)MmK::row_warps * MmK::in_slots * GsGeom<C, R>::ROW * 4;
+    static constexpr size_t IN_BYTES = (size_t)MmK::row_warps * MmK::in_slots * GsGeom<C, R>::SLOT * 4;
     static constexpr size_t H_BYTES = (size_t)kMmRing * kMmPitch * 4;
     static constexpr size_t STAGE_BYTES = (size_t)MmK::col_warps * 8 * kMmStagePitch * 4;
     static constexpr int N_BARS = MmK::row_warps * MmK::in_slots + 2 * MmK::groups;
@@ -323,7 +323,22 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
             const uint32_t done = item_g0 + (uint32_t)(8 * (c + 1)) / MmK::rows;
             fence_proxy_async();   // the staged rows are read by the async proxy
             __syncwarp();          // every lane has read the chunk and staged its part of the block
-            if (lane == 0) {
+            if (SETS && (p.row_elems & 3)) {
+                // rows that are not whole vectors: their starts are not 16-byte aligned, so no bulk
+                // stores -- the staged block leaves as scalar stores, a row per 80 lanes' worth
+                if (lane == 0)
+                    while (released < done) mbar_arrive(&h_empty[released++ % MmK::groups]);
+                if (cols > 0) {
+#pragma unroll 1
+                    for (int r = 0; r < 8; ++r) {
+                        if ((unsigned)(ob + r) >= n_valid) continue;
+                        const float *srow = stage + ((r >> 1) + 4 * (r & 1)) * kMmStagePitch;
+                        float *drow = gdst + (long)r * p.row_elems;
+                        for (int cc = lane; cc < cols; cc += 32) __stcs(drow + cc, srow[cc]);
+                    }
+                }
+                __syncwarp();   // the staging rows are free again
+            } else if (lane == 0) {
                 while (released < done) mbar_arrive(&h_empty[released++ % MmK::groups]);
                 if (cols > 0) {
                     const uint32_t bytes = (uint32_t)cols * 4u;

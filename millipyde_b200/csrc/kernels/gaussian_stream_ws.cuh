@@ -55,7 +55,8 @@ template <int C, int R>
 struct WsGeom {
     static constexpr int HALO = GsGeom<C, R>::HALO;
     static constexpr int ROW = GsGeom<C, R>::ROW;
-    static constexpr size_t IN_BYTES = (size_t)kWsRowWarps * kWsInSlots * ROW * 4;
+    static constexpr int SLOT = GsGeom<C, R>::SLOT;
+    static constexpr size_t IN_BYTES = (size_t)kWsRowWarps * kWsInSlots * SLOT * 4;
     static constexpr size_t H_BYTES = (size_t)kWsGroups * kWsRows * kGsTW * 4;
     static constexpr int N_BARS = kWsRowWarps * kWsInSlots + 2 * kWsGroups;
     static constexpr size_t PROG_BYTES = (size_t)(kWsThreads / 32) * sizeof(PwSmem);   // one fused program per warp
@@ -156,7 +157,7 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
     const int items_per_image = p.n_strips * p.n_chunks;
     const long n_items = (long)p.n_images * items_per_image;
     // =============================================================== ROW warp
-    float *my_in = s_in + (size_t)warp * K::in_slots * G::ROW;
+    float *my_in = s_in + (size_t)warp * K::in_slots * G::SLOT;
     uint64_t *my_full = in_full + warp * K::in_slots;
     uint32_t loads = 0;   // rows issued so far by this warp (slot = loads % 3, parity from the count)
     uint32_t takes = 0;   // rows consumed so far
@@ -193,8 +194,8 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
 
         // every load this warp issued has been consumed: its ring is quiescent
         if (lo > 0 || hi < G::ROW) {
-            for (int i = lane; i < K::in_slots * G::ROW; i += 32) {
-                const int col = i % G::ROW;
+            for (int i = lane; i < K::in_slots * G::SLOT; i += 32) {
+                const int col = i % G::SLOT;
                 if (col < lo || col >= hi) my_in[i] = 0.f;
             }
             fence_proxy_async();
@@ -214,13 +215,28 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
         const long gstep = (long)K::rows * p.row_elems;
         int next_issue = live_lo;  // next live step to issue
 
+        // Rows that are not whole vectors (W * C % 4 != 0; *_sets kernels only): a row starts `sh` floats
+        // past a 16-byte boundary, sh = (row * (W * C % 4)) % 4.  The copy then starts at that boundary
+        // and covers the enclosing aligned span (it stays inside the allocation: the pool rounds sizes
+        // up to 16 bytes); the row is shifted into place after it has landed.
+        const int mis = SETS ? (p.row_elems & 3) : 0;
+        int row_issue = r_first + live_lo * K::rows;   // image row of the next copy / of the next row consumed
+        int row_take = row_issue;
         auto issue_next = [&]() {  // all lanes keep the counters; lane 0 talks to the TMA unit
             const uint32_t slot = loads % K::in_slots;
             if (lane == 0) {
-                mbar_expect_tx(&my_full[slot], row_bytes);
-                bulk_g2s(my_in + (size_t)slot * G::ROW + lo, gptr, row_bytes, &my_full[slot]);
+                if (SETS && mis) {
+                    const int sh = (row_issue * mis) & 3;
+                    const uint32_t bytes = ((uint32_t)(hi - lo + sh) * 4u + 15u) & ~15u;
+                    mbar_expect_tx(&my_full[slot], bytes);
+                    bulk_g2s(my_in + (size_t)slot * G::SLOT + lo, gptr - sh, bytes, &my_full[slot]);
+                } else {
+                    mbar_expect_tx(&my_full[slot], row_bytes);
+                    bulk_g2s(my_in + (size_t)slot * G::SLOT + lo, gptr, row_bytes, &my_full[slot]);
+                }
             }
             gptr += gstep;
+            row_issue += K::rows;
             ++loads;
             ++next_issue;
         };
@@ -238,12 +254,41 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
                 if (MMA) mbar_wait_sleep(&my_full[slot], (takes / K::in_slots) & 1u, kWsSleepNs);
                 else mbar_wait(&my_full[slot], (takes / K::in_slots) & 1u);
                 ++takes;
+                if (SETS && mis) {
+                    // shift the landed row sh floats down into place: block b of the destination is the
+                    // tail of landed block b and the head of block b + 1.  All lanes load, then all store
+                    // (lane l + 1 rewrites what lane l reads); what lies beyond `hi` becomes zero padding.
+                    const int sh = (row_take * mis) & 3;
+                    float *row = my_in + (size_t)slot * G::SLOT;
+                    constexpr int NQ = (G::SLOT / 4 + 31) / 32;
+#pragma unroll 1
+                    for (int j = 0; j < NQ; ++j) {
+                        const int i = lo + 4 * (lane + 32 * j);
+                        float o[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (i < hi) {
+                            const float4 v0 = *reinterpret_cast<const float4 *>(row + i);
+                            const float4 v1 = *reinterpret_cast<const float4 *>(row + i + 4);   // within SLOT: i + 7 < hi + 7 <= ROW + 4 + 3
+                            const float w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float pick = sh == 0 ? w[e] : (sh == 1 ? w[e + 1] : (sh == 2 ? w[e + 2] : w[e + 3]));
+                                o[e] = i + e < hi ? pick : 0.f;
+                            }
+                        }
+                        __syncwarp();
+                        if (i < G::SLOT) *reinterpret_cast<float4 *>(row + i) = make_float4(o[0], o[1], o[2], o[3]);
+                        __syncwarp();
+                    }
+                    fence_proxy_async();   // the slot's next writer is the TMA unit
+                    __syncwarp();
+                }
+                row_take += K::rows;
                 if (SETS && n_pre) {
                     // fused pointwise ops in front of the blur: rewrite the landed row in place, each
                     // sample once (the lanes' filter windows overlap 4.6x, so doing it on the window
                     // registers would repeat the work).  Only the in-image part [lo, hi): what lies
                     // outside is the blur's zero padding of the *transformed* image and stays zero.
-                    float *row = my_in + (size_t)slot * G::ROW;
+                    float *row = my_in + (size_t)slot * G::SLOT;
                     constexpr int NQ = (G::ROW / 4 + 31) / 32;   // vectors per lane (6 for a 712-float row)
 #pragma unroll
                     for (int j0 = 0; j0 < NQ; j0 += 3) {         // three vectors at a time: 12 registers
@@ -271,8 +316,8 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
                     fence_proxy_async();   // the slot's next writer is the TMA unit
                     __syncwarp();
                 }
-                if (SETS) ws_row_pass<C, R>(my_in + (size_t)slot * G::ROW + lane * kGsPH, out, w_img);
-                else ws_row_pass<C, R>(my_in + (size_t)slot * G::ROW + lane * kGsPH, out, w_one);
+                if (SETS) ws_row_pass<C, R>(my_in + (size_t)slot * G::SLOT + lane * kGsPH, out, w_img);
+                else ws_row_pass<C, R>(my_in + (size_t)slot * G::SLOT + lane * kGsPH, out, w_one);
             } else {
 #pragma unroll
                 for (int i = 0; i < kGsPH; ++i) out[i] = 0.f;
@@ -384,7 +429,12 @@ __device__ __forceinline__ void ws_body(const GaussStreamParams &p, const GaussW
                             o2[0] = fminf(fmaxf(o2[0] + pb, plo), phi);
                             o2[1] = fminf(fmaxf(o2[1] + pb, plo), phi);
                         }
-                        __stcs(reinterpret_cast<float2 *>(optr), make_float2(o2[0], o2[1]));
+                        if (SETS && (p.row_elems & 1)) {   // odd rows: the pair may be misaligned or straddle the row end
+                            __stcs(optr, o2[0]);
+                            if (gx + 1 < p.row_elems) __stcs(optr + 1, o2[1]);
+                        } else {
+                            __stcs(reinterpret_cast<float2 *>(optr), make_float2(o2[0], o2[1]));
+                        }
                     }
                     ++rel;
                     optr += p.row_elems;

@@ -240,7 +240,9 @@ cudaStream_t stream_of(const MPObjData *obj)
 static void *alloc_from(int pool_device, cudaStream_t stream, size_t nbytes, const char *what, int line)
 {
     void *p = nullptr;
-    if (nbytes == 0) nbytes = 16;
+    // whole 16-byte vectors: a kernel may read the aligned span that encloses a row (TMA bulk copies of
+    // images whose rows are not whole vectors end up to 12 bytes past the last sample)
+    nbytes = nbytes ? (nbytes + 15) & ~(size_t)15 : 16;
     if (!make_ready(pool_device) || !g_devices[pool_device].mempool) {
         record_cuda_error(cudaErrorInvalidDevice, what, __FILE__, line);
         return nullptr;

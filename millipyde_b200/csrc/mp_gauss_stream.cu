@@ -30,7 +30,9 @@ static int bucket_for(int radius)
 
 bool gauss_stream_supported(int W, int C, int radius)
 {
-    return ((size_t)W * C) % 4 == 0 && (size_t)W * C >= 64 && bucket_for(radius) != 0;
+    // any width: rows that are not whole vectors (W * C % 4 != 0) go through the *_sets kernels, which
+    // land the enclosing aligned span and shift it into place
+    return (size_t)W * C >= 64 && bucket_for(radius) != 0;
 }
 
 // Which column pass a launch uses: the tensor-core one (gaussian_stream_mma.cuh) wherever it is
@@ -161,6 +163,16 @@ MPStatus launch_gauss_stream_batch(int device, cudaStream_t s, int H, int W, int
         unsigned int bits;
         memcpy(&bits, &p.w[d], 4);
         p.ww[d] = ((unsigned long long)bits << 32) | bits;
+    }
+    if (p.row_elems & 3) {   // only the *_sets kernels shift misaligned rows into place: every set = these weights
+        static thread_local GaussWeightSets same_sets;
+        for (int i = 0; i < kGsMaxSets; ++i)
+            for (int d = 0; d < 14; ++d) same_sets.ww[i][d] = p.ww[d];
+        p.radius = bucket;
+        if (C == 1) return launch_c<1>(device, s, p, bucket, &same_sets);
+        if (C == 3) return launch_c<3>(device, s, p, bucket, &same_sets);
+        if (C == 4) return launch_c<4>(device, s, p, bucket, &same_sets);
+        return MP_ERROR_UNSUPPORTED_LAYOUT;
     }
     if (C == 1) return launch_c<1>(device, s, p, bucket);
     if (C == 3) return launch_c<3>(device, s, p, bucket);

@@ -151,6 +151,43 @@ def test_f32_streaming_gaussian_shapes(capi, c, column):
         L.mpimg_set_gauss_column(0)
 
 
+@pytest.mark.parametrize("column", ["mma", "fma"])
+def test_f32_streaming_gaussian_any_width(capi, column):
+    """Rows that are not whole 16-byte vectors (W * C % 4 = 1, 2, 3 -- e.g. every 1125-wide RGB fixture of
+    the reference as fp32): the streaming kernels land the enclosing aligned span of each row and shift
+    it into place, outputs leave as scalar stores.  Single images (row chunks), batches, several strips,
+    a last strip that ends mid-vector, fused pointwise ops."""
+    from millipyde_b200 import engine
+    L = capi.lib()
+    L.mpimg_set_gauss_column(1 if column == "fma" else 0)
+    try:
+        for c, widths in ((1, (65, 250, 251, 253, 1279)), (3, (22, 85, 250, 427)), (4, ())):
+            for w in widths:
+                assert (w * c) % 4 != 0
+                for h in (1, 9, 50, 131):
+                    a = synth.noise_f32(h, w, c, 7400 + w + h)
+                    for sigma in (2.0, 0.7):
+                        got = dev(capi, a).apply("gaussian", sigma).numpy()
+                        assert np.abs(got - so.gaussian(a, sigma)).max() <= TOL32, (h, w, c, sigma, column)
+        a = synth.noise_f32(700, 1125, 3, 7450)                        # the reference's fixture width; 3 row chunks
+        got = dev(capi, a).apply("gaussian", 2.0).numpy()
+        assert np.abs(got - so.gaussian(a, 2.0)).max() <= TOL32
+        imgs = [synth.noise_f32(90, 1125, 3, 7460 + k) for k in range(5)]
+        for chain in ([("gaussian", 2.0)], [("adjust_gamma", 1.5, 1.0), ("gaussian", 1.3), ("brightness", 0.1)],
+                      [("random_gaussian", 1.0, 2.0)]):
+            L.mprand_seed(3)
+            devs = [dev(capi, x) for x in imgs]
+            ch = engine.Chain(chain, device=0)
+            ch.run(devs)
+            key = L.mppipe_last_run_key(ch.ptr)
+            L.mprand_seed(0)
+            for i, (x, d) in enumerate(zip(imgs, devs)):
+                ops = [("gaussian", L.mprand_keyed_double(key, i, 0, 0, 1.0, 2.0))] if chain[0][0].startswith("random") else chain
+                assert np.abs(d.numpy() - so.apply_chain(x, ops)).max() <= TOL32, chain
+    finally:
+        L.mpimg_set_gauss_column(0)
+
+
 def test_f32_streaming_gaussian_column_forms_agree(capi):
     """Tensor-core and FMA-pipe column passes on the same input: the split-precision products cost
     well under 1e-6, and out-of-range rows/columns are exact zeros' worth in both."""
