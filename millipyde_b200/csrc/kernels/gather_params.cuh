@@ -28,6 +28,7 @@ struct GatherParams {
     RotateParams rp;
     PwProgram pw_pre, pw_post;
     const GatherVar *var_tab;  // per-image records (kernel template TAB = true), else null
+    int pitch;                 // row pitch of the staged box in floats (0: the geometry's default); chosen per angle
 };
 
 

@@ -309,8 +309,14 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
 #pragma unroll
                         for (int u = 0; u < 3; ++u) {
                             const int i = lo + 4 * (lane + 32 * (j0 + u));
-                            if (j0 + u < NQ && i < hi)
+                            if (j0 + u < NQ && i < hi) {
+                                if (SETS && mis) {   // a row may end inside a vector: what lies beyond stays zero padding
+#pragma unroll
+                                    for (int e = 1; e < 4; ++e)
+                                        if (i + e >= hi) v[u][e] = 0.f;
+                                }
                                 *reinterpret_cast<float4 *>(row + i) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+                            }
                         }
                     }
                     fence_proxy_async();   // the slot's next writer is the TMA unit

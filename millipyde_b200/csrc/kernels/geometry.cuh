@@ -381,14 +381,18 @@ struct GatherGeom {
     static constexpr int PITCH = TH == kGatherTile ? (C == 1 ? 68 : (C == 3 ? 164 : 212)) : (C == 1 ? 84 : ROW_MAX + 4);
     static_assert(PITCH >= ROW_MAX && PITCH % 4 == 0, "pitch");
     static_assert(TH == kGatherTile || TH == kGatherTileTall, "tile heights");
-    static constexpr size_t SMEM = (size_t)BOX * PITCH * sizeof(float);
+    // The launcher may pick any pitch in [PITCH, PITCH_MAX] (a multiple of 4): which bank a corner read
+    // of a rotated line hits is 3 * ix + pitch * iy, so the pitch with the fewest conflicts depends on
+    // the angle (mp_image_ops.cu: gather_pitch_for)
+    static constexpr int PITCH_MAX = PITCH + 16;
+    static constexpr size_t SMEM = (size_t)BOX * PITCH_MAX * sizeof(float);
 };
 
 template <int C, bool TAB = false, int TH = kGatherTile>
 __global__ void __launch_bounds__(256, 6)
 gather_f32_kernel(const __grid_constant__ GatherParams g)
 {
-    constexpr int PITCH = GatherGeom<C, TH>::PITCH;
+    const int PITCH = g.pitch ? g.pitch : GatherGeom<C, TH>::PITCH;
     constexpr int BOX = GatherGeom<C, TH>::BOX;
     constexpr int NPX = TH / 8;  // output pixels per thread
     extern __shared__ __align__(16) float box[];  // [bh][PITCH]

@@ -928,8 +928,70 @@ MPStatus op_grey_f32(MPObjData *obj, const PwProgram &pre, const PwProgram &post
 
 namespace mp {
 
-void launch_gather_f32(cudaStream_t s, int channels, const GatherParams &g, int n_images)
+// Row pitch of the gather's staged box for one rotation.  A warp reads the corners of 32 consecutive
+// output pixels, i.e. a line in the source at the rotation's angle: the word address of lane l is
+// C * ix(l) + pitch * iy(l) (+ channel, + corner), so how many lanes collide on a bank depends on the
+// angle and on pitch mod 32.  The launcher evaluates the few legal pitches (multiples of 4: the staged
+// rows are TMA destinations) on a handful of sub-pixel offsets and takes the best; at 30 degrees and
+// C = 3 the default pitch serialises 3 ways, the best 2 (the floor for mid angles).
+template <int C, int TH>
+static int gather_pitch_for(const RotateParams &rp)
 {
+    using G = GatherGeom<C, TH>;
+    int best_pitch = G::PITCH;
+    long best = -1;
+    for (int pitch = G::PITCH; pitch <= G::PITCH_MAX; pitch += 4) {
+        long cost = 0;
+        for (int sample = 0; sample < 12; ++sample) {
+            const double x0 = 40.0 + 0.37 * sample + 0.11 * (sample % 5), y0 = 40.0 + 0.53 * sample + 0.07 * (sample % 3);
+            for (int corner = 0; corner < 4; ++corner)
+                for (int c = 0; c < C; ++c) {
+                    // distinct addresses per bank, maximum over the banks = wavefronts of this load
+                    long addr[32];
+                    for (int l = 0; l < 32; ++l) {
+                        const int ix = (int)floor(x0 + rp.c * l) + (corner & 1), iy = (int)floor(y0 + rp.s * l) + (corner >> 1);
+                        addr[l] = (long)iy * pitch + (long)ix * C + c;
+                    }
+                    int worst = 0;
+                    for (int b = 0; b < 32; ++b) {
+                        int distinct = 0;
+                        long seen[32];
+                        for (int l = 0; l < 32; ++l) {
+                            if (((addr[l] % 32) + 32) % 32 != b) continue;
+                            bool dup = false;
+                            for (int k = 0; k < distinct; ++k) dup = dup || seen[k] == addr[l];
+                            if (!dup) seen[distinct++] = addr[l];
+                        }
+                        worst = distinct > worst ? distinct : worst;
+                    }
+                    cost += worst;
+                }
+        }
+        if (best < 0 || cost < best) {
+            best = cost;
+            best_pitch = pitch;
+        }
+    }
+    return best_pitch;
+}
+
+void launch_gather_f32(cudaStream_t s, int channels, const GatherParams &g_in, int n_images)
+{
+    GatherParams g = g_in;
+    g.pitch = 0;
+    if (g.has_rotate && !g.var_tab) {   // one angle for the whole launch: lay the box out for it
+        static thread_local double memo_c[3] = {2, 2, 2}, memo_s[3] = {2, 2, 2};
+        static thread_local int memo_pitch[3] = {0, 0, 0};
+        const int slot = channels == 1 ? 0 : (channels == 3 ? 1 : 2);
+        if (memo_c[slot] != g.rp.c || memo_s[slot] != g.rp.s) {
+            memo_pitch[slot] = channels == 1 ? gather_pitch_for<1, kGatherTileTall>(g.rp)
+                                             : (channels == 3 ? gather_pitch_for<3, kGatherTile>(g.rp)
+                                                              : gather_pitch_for<4, kGatherTile>(g.rp));
+            memo_c[slot] = g.rp.c;
+            memo_s[slot] = g.rp.s;
+        }
+        g.pitch = memo_pitch[slot];
+    }
     // single-channel images use 32 x 64 tiles: a 32 x 32 tile of 4-byte pixels is too little work per CTA
     const int th = channels == 1 ? kGatherTileTall : kGatherTile;
     dim3 grid((g.out_w + kGatherTile - 1) / kGatherTile, (g.out_h + th - 1) / th, n_images);
