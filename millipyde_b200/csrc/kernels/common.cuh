@@ -125,7 +125,12 @@ __device__ __forceinline__ void pw_apply_op_tile_impl(const PwOp &op, float (&r)
                     if (!(C == 4 && ((ch0 + k) & 3) == 3)) r[k] = clamp01(op.b * pow01(r[k], op.a));
                 break;
             case PW_COLORIZE:
-                if (C >= 3) {
+                if (C == 3) {   // the three factors in the run's channel order, selected once
+                    const float m[3] = {ch0 == 0 ? op.a : (ch0 == 1 ? op.b : op.c), ch0 == 0 ? op.b : (ch0 == 1 ? op.c : op.a),
+                                        ch0 == 0 ? op.c : (ch0 == 1 ? op.a : op.b)};
+#pragma unroll
+                    for (int k = 0; k < N; ++k) r[k] = fminf(1.f, r[k] * m[k % 3]);
+                } else if (C == 4) {
 #pragma unroll
                     for (int k = 0; k < N; ++k) {
                         const int ch = pw_channel<C>(ch0, k);
@@ -138,10 +143,14 @@ __device__ __forceinline__ void pw_apply_op_tile_impl(const PwOp &op, float (&r)
                 for (int k = 0; k < N; ++k) r[k] = r[k] + op.a;
                 break;
             case PW_EW_MUL:
+                if (C == 3) {
+                    const float m[3] = {ch0 == 0 ? op.a : (ch0 == 1 ? op.b : op.c), ch0 == 0 ? op.b : (ch0 == 1 ? op.c : op.a),
+                                        ch0 == 0 ? op.c : (ch0 == 1 ? op.a : op.b)};
 #pragma unroll
-                for (int k = 0; k < N; ++k) {
-                    const int ch = pw_channel<C>(ch0, k);
-                    r[k] = r[k] * (ch == 0 ? op.a : (ch == 1 ? op.b : op.c));
+                    for (int k = 0; k < N; ++k) r[k] = r[k] * m[k % 3];
+                } else {   // one factor for every channel (per-channel factors need exactly three channels)
+#pragma unroll
+                    for (int k = 0; k < N; ++k) r[k] = r[k] * op.a;
                 }
                 break;
             case PW_EW_CLIP:

@@ -41,6 +41,7 @@ struct GaussStreamParams {
     // images share pw_tab[0], pw_tab[1] (pw_stride = 0).  Only the *_sets kernels look at it.
     const PwProgram *pw_tab;
     int pw_stride;
+    int col_wait;                // COLUMN role's hand-off wait: 0 = probe + nanosleep, 1 = suspended try_wait (A/B switch)
     float w[16];
     unsigned long long ww[16];   // (w[d], w[d]) packed for fma.rn.f32x2
 };

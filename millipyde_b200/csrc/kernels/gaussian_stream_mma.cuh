@@ -240,7 +240,8 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
         for (int c = 0; c < n_chunks8; ++c) {
             const uint32_t need = item_g0 + (uint32_t)(8 * c + 7) / MmK::rows + 1u;
             while (waited < need) {
-                mbar_wait_sleep(&h_full[waited % MmK::groups], (waited / MmK::groups) & 1u, kWsSleepNs);
+                if (p.col_wait) mbar_wait_suspend(&h_full[waited % MmK::groups], (waited / MmK::groups) & 1u, 1000);
+                else mbar_wait_sleep(&h_full[waited % MmK::groups], (waited / MmK::groups) & 1u, kWsSleepNs);
                 ++waited;
             }
             const float *rp = ring + ring_row * kMmPitch;

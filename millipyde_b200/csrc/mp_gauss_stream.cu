@@ -67,6 +67,8 @@ static bool use_mma_column()
 template <int C, int R>
 static MPStatus launch_cr(int device, cudaStream_t s, GaussStreamParams &p, const GaussWeightSets *sets)
 {
+    static const int col_wait = [] { const char *e = getenv("MILLIPYDE_GAUSS_COLWAIT"); return e && *e == '1' ? 1 : 0; }();
+    p.col_wait = col_wait;
     const int sms = sm_count(device) ? sm_count(device) : 148;
     constexpr bool kHasMma = MmGeom<C, R>::NCH <= 4;
     const bool mma = kHasMma && use_mma_column();
