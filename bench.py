@@ -652,7 +652,8 @@ def run_in_process(args):
     out = {"launcher": "one process", "n_devices": len(devices), "images_per_step": images,
            "value": images / (dev_ms / args.steps / 1000.0), "unit": "images/s", "ms_per_step": dev_ms / args.steps,
            "wall_ms_per_step": wall_ms / args.steps, "steps": args.steps, "gpu_launches": launches,
-           "multi_device_check": multi_device_check(capi, engine, len(devices)) if len(devices) >= 2 else None}
+           # Pipeline.run() without a device cycles over every VISIBLE device (ndev), not only the N timed ones
+           "multi_device_check": multi_device_check(capi, engine, ndev) if ndev >= 2 else None}
     print(json.dumps(out), flush=True)
 
 
