@@ -613,7 +613,7 @@ def run_b200(args, dist):
             for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
                 env.pop(k, None)
             cmd = [sys.executable, os.path.abspath(__file__), "--in-process", "--gpus", str(args.gpus),
-                   "--steps", str(min(args.steps, 10)), "--warmup", str(args.warmup), "--batch", str(batch)]
+                   "--steps", str(args.steps), "--warmup", str(args.warmup), "--batch", str(batch)]
             try:
                 r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
                 rows = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]

@@ -60,6 +60,11 @@ typedef struct {
     long i;
     int return_to_host;
     int prefetch;
+    /* asynchronous look-ahead (explicit prefetch >= MP_ASYNC_PREFETCH): the batch the devices are working
+     * on while the consumer drains `ready`, and what must stay alive until it is done */
+    PyObject *inflight;       /* list of the batch's gpuimages, or NULL */
+    PyObject *inflight_keep;  /* list of per-batch input replicas the batch's views borrow from */
+    Py_ssize_t ready_pos;     /* next item of `ready` to hand out (popping the front of a list is O(n)) */
 } MPGeneratorObject;
 
 typedef struct {

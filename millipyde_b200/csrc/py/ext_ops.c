@@ -396,6 +396,13 @@ PyTypeObject MPPipeline_Type = {
 
 static void generator_dealloc(MPGeneratorObject *self)
 {
+    if (self->inflight && self->pipe) { /* the devices may still be reading what the batch borrows */
+        Py_BEGIN_ALLOW_THREADS
+        mppipe_wait(self->pipe);
+        Py_END_ALLOW_THREADS
+    }
+    Py_XDECREF(self->inflight);
+    Py_XDECREF(self->inflight_keep);
     Py_XDECREF(self->inputs);
     Py_XDECREF(self->operations);
     Py_XDECREF(self->ready);
@@ -414,6 +421,8 @@ static PyObject *generator_new(PyTypeObject *type, PyObject *args, PyObject *kwd
         self->produced = self->i = 0;
         self->return_to_host = 0;
         self->prefetch = 0;
+        self->inflight = self->inflight_keep = NULL;
+        self->ready_pos = 0;
     }
     return (PyObject *)self;
 }
@@ -633,48 +642,61 @@ static PyObject *pinned_result_array(const MPObjData *o)
     return arr;
 }
 
-static int produce_batch(MPGeneratorObject *g, long count)
+/* A look-ahead this long or longer (explicit prefetch=) runs asynchronously: batch k + 1 is on the
+ * devices while the consumer drains batch k.  Its views then borrow from per-batch REPLICAS of the
+ * inputs (one device-side copy of each input per device per batch: 6 / prefetch of the stream's
+ * traffic), so nothing the caller does to an input while iterating can reach a batch in flight. */
+#define MP_ASYNC_PREFETCH 32
+
+/* Build the next `count` outputs as views / clones and hand them to the executor.  sync != 0: wait and
+ * leave the finished batch in g->inflight; else return with the batch running. */
+static int submit_batch(MPGeneratorObject *g, long count, int async_mode)
 {
     const Py_ssize_t n_in = PyList_Size(g->inputs);
     const int bound = generator_device(g);
     const int ndev = mpdev_get_device_count();
     PyObject *batch = PyList_New(0);
+    PyObject *keep = PyList_New(0);
     MPObjData **objs = (MPObjData **)calloc((size_t)count, sizeof(MPObjData *));
     int dev = bound != DEVICE_LOC_NO_AFFINITY ? bound : mpdev_get_recommended_device();
     /* One device and every input already there: hand the executor VIEWS of the inputs instead of
      * clones.  The chain's first launch then reads the input itself and writes the output's own
      * buffer, which saves the clone's pass over every image (mppipe_run_views). */
-    int use_views = bound != DEVICE_LOC_NO_AFFINITY || ndev == 1;
+    int use_views = !async_mode && (bound != DEVICE_LOC_NO_AFFINITY || ndev == 1);
     for (Py_ssize_t k = 0; use_views && k < n_in; ++k) {
         MPObjData *o = ((MPArrayObject *)PyList_GetItem(g->inputs, k))->obj;
         if (!o || !o->device_data || o->mem_loc != dev) use_views = 0;
     }
-    /* Spreading over several devices: every device gets ONE replica of each input it needs for this
-     * batch (a peer copy over NVLink, made now so a caller who mutated an input since the last batch
-     * is honoured) and its outputs are views of that replica -- not one cross-device clone per output,
-     * which would pull the whole stream through the home device's links. */
-    const int spread = !use_views && bound == DEVICE_LOC_NO_AFFINITY && ndev > 1;
-    PyObject **replica = spread ? (PyObject **)calloc((size_t)ndev * (size_t)n_in, sizeof(PyObject *)) : NULL;
-    int spread_ok = spread && replica != NULL;
-    for (Py_ssize_t k = 0; spread_ok && k < n_in; ++k) {
+    /* Spreading over several devices, or running ahead of the consumer: every device gets ONE replica of
+     * each input it needs for this batch (a device-side / peer copy made now, so a caller who mutated an
+     * input since the last batch is honoured and one who mutates it during this one cannot hurt) and its
+     * outputs are views of that replica -- not one clone per output. */
+    const int spread = bound == DEVICE_LOC_NO_AFFINITY && ndev > 1;
+    const int replicate = !use_views && (spread || async_mode);
+    PyObject **replica = replicate ? (PyObject **)calloc((size_t)ndev * (size_t)n_in, sizeof(PyObject *)) : NULL;
+    int rep_ok = replicate && replica != NULL && batch && keep && objs;
+    for (Py_ssize_t k = 0; rep_ok && k < n_in; ++k) {
         MPObjData *o = ((MPArrayObject *)PyList_GetItem(g->inputs, k))->obj;
-        if (!o || !o->device_data) spread_ok = 0;
+        if (!o || !o->device_data) rep_ok = 0;
     }
-    for (long k = 0; k < count; ++k) {
+    int failed = !batch || !keep || !objs;
+    long made = 0;
+    for (long k = 0; !failed && k < count; ++k) {
         const Py_ssize_t which = (g->produced + k) % n_in;
         PyObject *input = PyList_GetItem(g->inputs, which);
         PyObject *c;
         if (use_views) {
             c = mpext_wrap_obj(Py_TYPE(input), mpobj_view_data(((MPArrayObject *)input)->obj));
-        } else if (spread_ok) {
+        } else if (rep_ok) {
             PyObject **slot = &replica[(size_t)dev * (size_t)n_in + (size_t)which];
             if (!*slot) {
-                if (((MPArrayObject *)input)->obj->mem_loc == dev) {
+                if (!async_mode && ((MPArrayObject *)input)->obj->mem_loc == dev) {
                     Py_INCREF(input);
                     *slot = input;
                 } else {
                     *slot = mpext_clone((MPArrayObject *)input, dev, 0);
                 }
+                if (*slot) PyList_Append(keep, *slot);
             }
             c = *slot ? mpext_wrap_obj(Py_TYPE(input), mpobj_view_data(((MPArrayObject *)*slot)->obj)) : NULL;
         } else {
@@ -682,39 +704,70 @@ static int produce_batch(MPGeneratorObject *g, long count)
             c = mpext_clone((MPArrayObject *)input, dev, 0);
         }
         if (!c) {
-            if (use_views || spread_ok) /* the views made so far still borrow: they must not free what they borrow */
-                for (long j = 0; j < k; ++j) objs[j]->device_data = NULL;
-            Py_DECREF(batch);
-            free(objs);
-            if (replica) {
-                for (size_t r = 0; r < (size_t)ndev * (size_t)n_in; ++r) Py_XDECREF(replica[r]);
-                free(replica);
-            }
-            return -1;
+            failed = 1;
+            break;
         }
         objs[k] = ((MPArrayObject *)c)->obj;
         PyList_Append(batch, c);
         Py_DECREF(c);
-        if (bound == DEVICE_LOC_NO_AFFINITY && ndev > 1 && (k + 1) % THREADS_PER_DEVICE == 0)
-            dev = mpdev_get_next_device(dev);
+        ++made;
+        if (spread && (k + 1) % THREADS_PER_DEVICE == 0) dev = mpdev_get_next_device(dev);
     }
-    MPStatus st;
-    /* one random-source key for the Generator's whole stream, images numbered by output index: output k
-     * is the same draw whatever the look-ahead and however the batch is spread over the devices */
-    mppipe_hold_run_key(g->pipe);
-    mppipe_set_index_base(g->pipe, (unsigned long long)g->produced);
-    Py_BEGIN_ALLOW_THREADS
-    st = (use_views || spread_ok) ? mppipe_run_views(g->pipe, objs, (int)count) : mppipe_run(g->pipe, objs, (int)count);
-    Py_END_ALLOW_THREADS
-    free(objs);
-    if (replica) { /* every view owns its result now; the replicas retire in stream order */
-        for (size_t r = 0; r < (size_t)ndev * (size_t)n_in; ++r) Py_XDECREF(replica[r]);
+    if (replica) {
+        for (size_t r = 0; r < (size_t)ndev * (size_t)n_in; ++r) Py_XDECREF(replica[r]); /* `keep` holds them */
         free(replica);
     }
+    const int borrowing = use_views || rep_ok;
+    MPStatus st = MILLIPYDE_SUCCESS;
+    if (!failed) {
+        /* one random-source key for the Generator's whole stream, images numbered by output index: output k
+         * is the same draw whatever the look-ahead and however the batch is spread over the devices */
+        mppipe_hold_run_key(g->pipe);
+        mppipe_set_index_base(g->pipe, (unsigned long long)g->produced);
+        Py_BEGIN_ALLOW_THREADS
+        if (borrowing) st = async_mode ? mppipe_submit_views(g->pipe, objs, (int)count) : mppipe_run_views(g->pipe, objs, (int)count);
+        else st = async_mode ? mppipe_submit(g->pipe, objs, (int)count) : mppipe_run(g->pipe, objs, (int)count);
+        Py_END_ALLOW_THREADS
+    } else if (borrowing) { /* the views made so far still borrow: they must not free what they borrow */
+        for (long j = 0; j < made; ++j) objs[j]->device_data = NULL;
+    }
+    free(objs);
+    if (failed || st != MILLIPYDE_SUCCESS) {
+        Py_XDECREF(batch);
+        Py_XDECREF(keep);
+        if (!failed) mpext_raise_status(st, "Generator");
+        else if (!PyErr_Occurred()) PyErr_NoMemory();
+        return -1;
+    }
+    Py_XSETREF(g->inflight, batch);
+    Py_XSETREF(g->inflight_keep, keep);
+    g->produced += count;
+    return 0;
+}
+
+/* Wait for the batch in flight (if it was submitted asynchronously), download it if the Generator
+ * returns host arrays, and append it to the ready list. */
+static int collect_batch(MPGeneratorObject *g, int was_async)
+{
+    PyObject *batch = g->inflight;
+    if (!batch) return 0;
+    g->inflight = NULL;
+    const long count = (long)PyList_Size(batch);
+    MPStatus st = MILLIPYDE_SUCCESS;
+    if (was_async) {
+        Py_BEGIN_ALLOW_THREADS
+        st = mppipe_wait(g->pipe);
+        Py_END_ALLOW_THREADS
+    }
+    Py_CLEAR(g->inflight_keep); /* every view owns its result now; the replicas retire in stream order */
     if (st != MILLIPYDE_SUCCESS) {
         Py_DECREF(batch);
         mpext_raise_status(st, "Generator");
         return -1;
+    }
+    if (g->ready_pos > 0) { /* drop what has been handed out */
+        PyList_SetSlice(g->ready, 0, g->ready_pos, NULL);
+        g->ready_pos = 0;
     }
     if (g->return_to_host) {
         /* all downloads of the batch in flight at once, into page-locked arrays, one wait each */
@@ -760,7 +813,6 @@ static int produce_batch(MPGeneratorObject *g, long count)
         for (long k = 0; k < count; ++k) PyList_Append(g->ready, PyList_GetItem(batch, k));
     }
     Py_DECREF(batch);
-    g->produced += count;
     return 0;
 }
 
@@ -789,22 +841,36 @@ static PyObject *generator_next(MPGeneratorObject *g)
         if (r) g->i++;
         return r;
     }
-    if (PyList_Size(g->ready) == 0) {
+    if (g->ready_pos >= PyList_Size(g->ready)) {
         /* default look-ahead: one block of THREADS_PER_DEVICE items per device when spreading, two
          * blocks on a single device -- enough for the executor to batch and overlap, small enough
-         * that a consumer that stops early has paid for at most a few items it never sees */
+         * that a consumer that stops early has paid for at most a few items it never sees.  An explicit
+         * look-ahead of MP_ASYNC_PREFETCH or more runs one batch ahead of the consumer. */
         long want = g->prefetch;
         if (want <= 0)
             want = (generator_device(g) == DEVICE_LOC_NO_AFFINITY && mpdev_get_device_count() > 1)
                        ? (long)THREADS_PER_DEVICE * mpdev_get_device_count()
                        : 2L * THREADS_PER_DEVICE;
-        if (g->max != NO_OUTPUT_MAX && g->produced + want > g->max) want = g->max - g->produced;
-        if (want < 1) want = 1;
-        if (produce_batch(g, want) < 0) return NULL;
+        const int async_mode = g->prefetch >= MP_ASYNC_PREFETCH;
+        long next = want;
+        if (g->max != NO_OUTPUT_MAX && g->produced + next > g->max) next = g->max - g->produced;
+        if (!g->inflight) { /* nothing running yet (first call, or the synchronous mode) */
+            if (next < 1) next = 1;
+            if (submit_batch(g, next, async_mode) < 0) return NULL;
+        }
+        if (collect_batch(g, async_mode) < 0) return NULL;
+        if (async_mode) { /* start the batch after this one: it runs while the consumer iterates */
+            next = want;
+            if (g->max != NO_OUTPUT_MAX && g->produced + next > g->max) next = g->max - g->produced;
+            if (next >= 1 && submit_batch(g, next, 1) < 0) return NULL;
+        }
     }
-    PyObject *item = PyList_GetItem(g->ready, 0);
+    PyObject *item = PyList_GetItem(g->ready, g->ready_pos);
+    if (!item) return NULL;
     Py_INCREF(item);
-    PySequence_DelItem(g->ready, 0);
+    Py_INCREF(Py_None);
+    PyList_SetItem(g->ready, g->ready_pos, Py_None); /* hand the reference over: the list keeps no output alive */
+    g->ready_pos++;
     g->i++;
     return item;
 }

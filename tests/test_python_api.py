@@ -452,6 +452,51 @@ def test_generator_random_augmentation_stream(so):
 
 
 @gpu
+def test_generator_async_lookahead_matches_the_synchronous_stream(so):
+    """prefetch >= 32 runs one batch ahead of the consumer (batch k + 1 is on the device while batch k is
+    being handed out); draws are keyed by output index, so the stream is the same as with the small
+    synchronous look-ahead -- and a caller who mutates an input while iterating cannot disturb a batch
+    in flight (its views borrow per-batch replicas), only later batches see the new input."""
+    from tests import synth
+    base_np = [synth.noise_f32(48, 64, 3, 4100 + k) for k in range(3)]
+    ops = lambda: [mp.Operation("fliplr", probability=.5), mp.Operation("random_brightness", -.2, .2),
+                   mp.Operation("random_gaussian", .5, 2.), mp.Operation("random_rotate", 0., 90., probability=.5)]
+    outs = {}
+    for pre in (8, 64):
+        base = [mp.gpuimage(a) for a in base_np]
+        mp.seed(123)
+        g = mp.Generator(base, ops(), outputs=150, prefetch=pre, device=0)
+        outs[pre] = [np.array(o) for o in g]
+        mp.seed(0)
+    assert len(outs[8]) == len(outs[64]) == 150
+    for a, b in zip(outs[8], outs[64]):
+        assert a.shape == b.shape and np.abs(a - b).max() <= 1e-6      # gather records: device vs device, same draws
+    # host outputs through the asynchronous path
+    base = [mp.gpuimage(a) for a in base_np]
+    g = mp.Generator(base, [mp.Operation("adjust_gamma", 1.5, 1.0)], outputs=100, prefetch=32, return_to_host=True)
+    for i, o in enumerate(g):
+        assert isinstance(o, np.ndarray)
+        assert np.abs(o - np.clip(so.adjust_gamma(base_np[i % 3], 1.5, 1.0), 0, 1)).max() <= 1e-5
+    # mutation while a batch is in flight
+    base = [mp.gpuimage(a) for a in base_np]
+    g = mp.Generator(base, [mp.Operation("fliplr")], outputs=160, prefetch=40, device=0)
+    seen = []
+    for i, o in enumerate(g):
+        if i == 5:
+            base[0].brightness(0.5)            # batches 0 (being drained) and 1 (in flight) were cut from the old input
+        seen.append(np.array(o))
+    flipped_old, flipped_new = base_np[0][:, ::-1], np.clip(base_np[0] + np.float32(0.5), 0, 1)[:, ::-1]
+    for i in range(0, 160, 3):
+        want = flipped_old if i < 80 else flipped_new
+        assert np.abs(seen[i] - want).max() <= 1e-6, i
+    # an abandoned generator with a batch in flight cleans up
+    g = mp.Generator(base, [mp.Operation("fliplr")], prefetch=64, device=0)
+    next(g)
+    del g
+    mp.synchronize()
+
+
+@gpu
 def test_generator_host_outputs_are_page_locked_recycled_and_never_aliased(so):
     """return_to_host=True downloads a batch's outputs together into recycled page-locked ndarrays:
     every output a consumer still holds must keep its own contents while later batches reuse the
