@@ -647,17 +647,27 @@ MPStatus run_batched(const std::vector<MPObjData *> &objs, size_t out_bytes, int
     if (record_bytes) memcpy((char *)h_tab + tab_bytes, records, record_bytes);
     g_records = record_bytes ? (const char *)d_tab + tab_bytes : nullptr;
     const int out_device = g_out_device >= 0 ? g_out_device : device;
+    // Outputs that will live on ANOTHER device (hand-off: this launch writes them over NVLink) are
+    // allocated in the order of that device's own work stream -- the stream the receiver will use them
+    // on -- and this stream waits for the allocation point through one event.  Allocating a peer pool's
+    // memory in the order of a foreign device's stream takes the allocator's slow path on every call
+    // (no reuse across devices' streams), which made connected pipelines host-bound.
+    cudaStream_t alloc_stream = out_device == device ? s : mp::device_stream(out_device, 1);
     std::vector<void *> fresh(n);
     for (size_t i = 0; i < n; ++i) {
-        fresh[i] = out_device == device ? mp::pool_alloc(device, s, out_bytes) : mp::pool_alloc_on(out_device, s, out_bytes);
+        fresh[i] = mp::pool_alloc(out_device, alloc_stream, out_bytes);
         if (!fresh[i]) {
-            for (size_t k = 0; k < i; ++k) mp::pool_free(device, s, fresh[k]);
+            for (size_t k = 0; k < i; ++k) mp::pool_free(out_device, alloc_stream, fresh[k]);
             mp::pool_free(device, s, d_tab);
             if (d_filled) mp::pool_free(device, s, d_filled);
             return MP_ERROR_DEVICE_ALLOC;
         }
         h_tab[i] = objs[i]->device_data;
         h_tab[n + i] = fresh[i];
+    }
+    if (out_device != device) {
+        mp::order_after(out_device, alloc_stream, s);
+        cudaSetDevice(device);
     }
     MP_CUDA_TRY(cudaMemcpyAsync(d_tab, h_tab, tab_bytes + record_bytes, cudaMemcpyHostToDevice, s));
     if (fill) {
@@ -679,7 +689,7 @@ MPStatus run_batched(const std::vector<MPObjData *> &objs, size_t out_bytes, int
             objs[i]->nbytes = out_bytes;
             objs[i]->mem_loc = out_device;
         } else {
-            mp::pool_free(device, s, fresh[i]);
+            mp::pool_free(out_device, alloc_stream, fresh[i]);
         }
     }
     mp::pool_free(device, s, d_tab);
