@@ -269,10 +269,21 @@ rotate_nearest_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
     int x = threadIdx.x + blockIdx.x * blockDim.x;
     int y = threadIdx.y + blockIdx.y * blockDim.y;
 
-    int x_rot = ((double)x - ((double)width / 2)) * cos(angle) -
-                ((double)y - ((double)height / 2)) * sin(angle) + ((double)width / 2);
-    int y_rot = ((double)x - ((double)width / 2)) * sin(angle) +
-                ((double)y - ((double)height / 2)) * cos(angle) + ((double)height / 2);
+    // cos / sin of the launch's one angle: evaluated by the device's own fp64 routines (the values the
+    // reference's kernel sees), but once per block instead of per pixel -- two ~50-instruction fp64
+    // routines per thread were most of this kernel's time
+    __shared__ double s_cs[2];
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        s_cs[0] = cos(angle);
+        s_cs[1] = sin(angle);
+    }
+    __syncthreads();
+    const double ca = s_cs[0], sa = s_cs[1];
+
+    int x_rot = ((double)x - ((double)width / 2)) * ca -
+                ((double)y - ((double)height / 2)) * sa + ((double)width / 2);
+    int y_rot = ((double)x - ((double)width / 2)) * sa +
+                ((double)y - ((double)height / 2)) * ca + ((double)height / 2);
 
     if (x < width && y < height) {
         size_t o = ((size_t)y * width + x) * K;
