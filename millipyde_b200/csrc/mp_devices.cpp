@@ -13,6 +13,7 @@
 #include <deque>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "mp_internal.h"
@@ -278,10 +279,95 @@ void *pool_alloc_on(int pool_device, cudaStream_t stream, size_t nbytes)
     return alloc_from(pool_device, stream, nbytes, "cudaMallocFromPoolAsync(peer)", __LINE__);
 }
 
+// ---- slabs: the output buffers of one batched launch in ONE pool allocation -------------------
+// A batched launch gives every image a fresh output buffer.  One cudaMallocFromPoolAsync and one
+// cudaFreeAsync per image and segment is what a chain of small images costs the host, and those
+// driver calls serialise inside a process -- the shards of 8 devices driven by one process ran at a
+// third of their single-device rate.  A slab is one allocation cut into equal sub-blocks; a sub-block
+// is an ordinary `device_data` pointer and goes back through pool_free like any other, which only
+// counts it down; the slab returns to the pool when its last sub-block does -- in the order of that
+// free's stream, made to wait (one event each) for the other streams that retired sub-blocks.
+namespace {
+struct Slab {
+    void *base;
+    int device;
+    int live;                      // sub-blocks not yet retired (under g_slab_mux)
+    struct Retired { cudaStream_t stream; int device; } streams[6];
+    int n_streams;
+};
+std::mutex g_slab_mux;
+std::unordered_map<void *, Slab *> g_slab_of;   // sub-block -> slab
+const bool g_slabs_on = [] { const char *e = getenv("MILLIPYDE_SLABS"); return !(e && *e == '0'); }();
+}  // namespace
+
+bool pool_alloc_many(int device_id, cudaStream_t stream, size_t n, size_t nbytes, void **out)
+{
+    // small images only: for large ones the driver calls are noise and a slab would pin gigabytes
+    // for as long as any one of its images lives
+    constexpr size_t kMaxSub = (size_t)32 << 20, kMaxSlab = (size_t)256 << 20;
+    if (!g_slabs_on || n < 4 || nbytes == 0 || nbytes > kMaxSub) return false;
+    const size_t stride = (nbytes + 255) & ~(size_t)255;
+    size_t per = kMaxSlab / stride;
+    if (per < 4) return false;
+    size_t done = 0;
+    while (done < n) {
+        const size_t cnt = n - done < per ? n - done : per;
+        char *base = (char *)alloc_from(device_id, stream, cnt * stride, "cudaMallocFromPoolAsync(slab)", __LINE__);
+        if (!base) {   // hand back what this call made; the caller falls back to (and reports from) single blocks
+            for (size_t i = 0; i < done; ++i) pool_free(device_id, stream, out[i]);
+            return false;
+        }
+        Slab *sl = new Slab{base, device_id, (int)cnt, {}, 0};
+        std::lock_guard<std::mutex> lk(g_slab_mux);
+        for (size_t i = 0; i < cnt; ++i) {
+            out[done + i] = base + i * stride;
+            g_slab_of[out[done + i]] = sl;
+        }
+        done += cnt;
+    }
+    return true;
+}
+
 void pool_free(int device_id, cudaStream_t stream, void *ptr)
 {
-    (void)device_id;
     if (!ptr) return;
+    Slab *sl = nullptr;
+    bool last = false;
+    Slab::Retired others[6];
+    int n_others = 0;
+    if (g_slabs_on) {
+        std::lock_guard<std::mutex> lk(g_slab_mux);
+        auto it = g_slab_of.find(ptr);
+        if (it != g_slab_of.end()) {
+            sl = it->second;
+            g_slab_of.erase(it);
+            bool known = false;
+            for (int k = 0; k < sl->n_streams; ++k) known = known || sl->streams[k].stream == stream;
+            if (!known && sl->n_streams < 6) sl->streams[sl->n_streams++] = Slab::Retired{stream, device_id};
+            else if (!known) sl->n_streams = 7;   // too many to list: drain the device before the release
+            last = --sl->live == 0;
+            if (last) {
+                n_others = sl->n_streams > 6 ? -1 : 0;
+                for (int k = 0; n_others >= 0 && k < sl->n_streams; ++k)
+                    if (sl->streams[k].stream != stream) others[n_others++] = sl->streams[k];
+            }
+        }
+    }
+    if (sl && !last) return;
+    if (sl) {
+        int prev = -1;
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (n_others < 0) {
+            cudaSetDevice(sl->device);
+            cudaDeviceSynchronize();
+        } else {
+            for (int k = 0; k < n_others; ++k) order_after(others[k].device, others[k].stream, stream);
+        }
+        if (prev >= 0) cudaSetDevice(prev);
+        ptr = sl->base;
+        delete sl;
+    }
+    (void)device_id;
     cudaError_t e = cudaFreeAsync(ptr, stream);
     if (e != cudaSuccess) record_cuda_error(e, "cudaFreeAsync", __FILE__, __LINE__);
 }

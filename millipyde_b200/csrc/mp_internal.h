@@ -31,6 +31,10 @@ bool ensure_peer(int a, int b);
 // with the release threshold lifted, so steady state never calls the OS).
 void *pool_alloc(int device_id, cudaStream_t stream, size_t nbytes);
 void pool_free(int device_id, cudaStream_t stream, void *ptr);
+// n equal blocks for the outputs of one batched launch, cut from one pool allocation (a "slab":
+// mp_devices.cpp).  Each out[i] is an ordinary buffer pointer and is released with pool_free.  false
+// (and nothing allocated) when the request is not worth a slab or cannot be served: allocate singly.
+bool pool_alloc_many(int device_id, cudaStream_t stream, size_t n, size_t nbytes, void **out);
 // Block from `pool_device`'s pool, allocated in the order of `stream`, which may belong to ANOTHER
 // device that has been granted access to the pool (mp::ensure_peer(stream's device, pool_device)):
 // a producer kernel can then write its result straight into the consumer device's memory over NVLink.

@@ -654,8 +654,9 @@ MPStatus run_batched(const std::vector<MPObjData *> &objs, size_t out_bytes, int
     // (no reuse across devices' streams), which made connected pipelines host-bound.
     cudaStream_t alloc_stream = out_device == device ? s : mp::device_stream(out_device, 1);
     std::vector<void *> fresh(n);
+    const bool slab = mp::pool_alloc_many(out_device, alloc_stream, n, out_bytes, fresh.data());
     for (size_t i = 0; i < n; ++i) {
-        fresh[i] = mp::pool_alloc(out_device, alloc_stream, out_bytes);
+        if (!slab) fresh[i] = mp::pool_alloc(out_device, alloc_stream, out_bytes);
         if (!fresh[i]) {
             for (size_t k = 0; k < i; ++k) mp::pool_free(out_device, alloc_stream, fresh[k]);
             mp::pool_free(device, s, d_tab);
