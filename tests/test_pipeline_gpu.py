@@ -525,3 +525,45 @@ def test_random_stream_does_not_depend_on_batching(mp):
     mp.lib.mprand_seed(0)
     for w, p in zip(whole, parts):
         assert np.array_equal(w.numpy(), p.numpy())
+
+
+def test_slab_outputs_are_ordinary_buffers(mp):
+    """The outputs of a batched launch of small images are sub-blocks of one pool allocation
+    (mp_devices.cpp: slabs).  They must behave like any buffer: outlive their siblings, be freed in
+    any order and on any stream, be handed to eager ops (which replace them), and survive more
+    batches allocating and retiring slabs around them."""
+    imgs = [synth.noise_f32(64, 96, 3, 9000 + k) for k in range(40)]
+    chain = [("brightness", 0.1), ("fliplr",)]
+    want = [so.apply_chain(a, chain) for a in imgs]
+    keep = []
+    for rnd in range(4):
+        dev = [mp.capi.DeviceImage(a) for a in imgs]
+        mp.engine.Chain(chain, device=0).run(dev)
+        # retire most of the batch out of order, keep a few from every round
+        for k in list(range(39, -1, -3)) + list(range(1, 40, 3)):
+            if k % 10 == rnd:
+                continue
+            dev[k].close()
+        survivors = [(k, dev[k]) for k in range(40) if dev[k].ptr]
+        keep.append(survivors)
+        # an eager op on a survivor replaces its sub-block with a fresh buffer and retires the sub-block
+        k0, d0 = survivors[0]
+        d0.apply("adjust_gamma", 2.0, 1.0)
+        assert np.abs(d0.numpy() - np.clip(so.adjust_gamma(want[k0], 2.0, 1.0), 0, 1)).max() <= TOL32
+    for rnd, survivors in enumerate(keep):
+        for k, d in survivors[1:]:
+            assert np.abs(d.numpy() - want[k]).max() <= TOL32, (rnd, k)
+            d.close()
+    # views (the Generator's path) take their results from slabs too
+    src = [mp.capi.DeviceImage(a) for a in imgs]
+    views = [d.view() for d in src]
+    ch = mp.engine.Chain(chain, device=0)
+    ch.run_views(views)
+    for rep in range(3):
+        for v, d in zip(views, src):
+            v.rebind(d)
+        ch.run_views(views)
+    for a, w, v in zip(imgs, want, views):
+        assert np.abs(v.numpy() - w).max() <= TOL32
+        v.rebind(None)
+        v.close()
