@@ -307,11 +307,26 @@ bool pool_alloc_many(int device_id, cudaStream_t stream, size_t n, size_t nbytes
     constexpr size_t kMaxSub = (size_t)32 << 20, kMaxSlab = (size_t)256 << 20;
     if (!g_slabs_on || n < 4 || nbytes == 0 || nbytes > kMaxSub) return false;
     const size_t stride = (nbytes + 255) & ~(size_t)255;
-    size_t per = kMaxSlab / stride;
-    if (per < 4) return false;
+    // Slabs come in three sizes per image size -- 16, 8 or 4 sub-blocks -- and what is left over is
+    // allocated singly: the pool caches freed blocks by size (release threshold = never), and slabs
+    // of every odd length (group sizes follow the coin flips) fragmented it until allocations failed.
+    size_t per = 16;
+    while (per > 4 && per * stride > kMaxSlab) per /= 2;
+    if (per * stride > kMaxSlab) return false;
     size_t done = 0;
     while (done < n) {
-        const size_t cnt = n - done < per ? n - done : per;
+        size_t cnt = per;
+        while (cnt > n - done && cnt > 4) cnt /= 2;
+        if (cnt > n - done) {   // fewer than 4 left: ordinary blocks
+            for (; done < n; ++done) {
+                out[done] = alloc_from(device_id, stream, nbytes, "cudaMallocFromPoolAsync", __LINE__);
+                if (!out[done]) {
+                    for (size_t i = 0; i < done; ++i) pool_free(device_id, stream, out[i]);
+                    return false;
+                }
+            }
+            break;
+        }
         char *base = (char *)alloc_from(device_id, stream, cnt * stride, "cudaMallocFromPoolAsync(slab)", __LINE__);
         if (!base) {   // hand back what this call made; the caller falls back to (and reports from) single blocks
             for (size_t i = 0; i < done; ++i) pool_free(device_id, stream, out[i]);
