@@ -238,6 +238,8 @@ cudaStream_t stream_of(const MPObjData *obj)
 // Stream-ordered block from `pool_device`'s pool.  On out-of-memory the pool's cached blocks may
 // be what is in the way (the release threshold is "never"): drain the device, hand the unused part
 // of the pool back to the driver and try once more before reporting the failure.
+void slab_cache_drop(int only_device);
+
 static void *alloc_from(int pool_device, cudaStream_t stream, size_t nbytes, const char *what, int line)
 {
     void *p = nullptr;
@@ -252,6 +254,7 @@ static void *alloc_from(int pool_device, cudaStream_t stream, size_t nbytes, con
     cudaError_t e = cudaMallocFromPoolAsync(&p, nbytes, pool, stream);
     if (e == cudaErrorMemoryAllocation) {
         (void)cudaGetLastError();
+        slab_cache_drop(pool_device);
         int prev = -1;
         if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
         cudaSetDevice(pool_device);
@@ -290,6 +293,7 @@ void *pool_alloc_on(int pool_device, cudaStream_t stream, size_t nbytes)
 namespace {
 struct Slab {
     void *base;
+    size_t bytes;
     int device;
     int live;                      // sub-blocks not yet retired (under g_slab_mux)
     struct Retired { cudaStream_t stream; int device; } streams[6];
@@ -297,6 +301,20 @@ struct Slab {
 };
 std::mutex g_slab_mux;
 std::unordered_map<void *, Slab *> g_slab_of;   // sub-block -> slab
+// Retired slabs are kept here, by device and size, instead of going back to the CUDA pool: the pool
+// splits a cached 200 MB block to serve the next 12 MB request, so slabs and single blocks in one
+// pool meant a fresh physical allocation (a millisecond) for most slabs and growth until allocations
+// failed.  A cached slab carries the event of its release; whoever takes it makes its stream wait.
+struct FreeSlab {
+    void *base;
+    cudaEvent_t released;
+};
+struct SlabCache {
+    std::unordered_map<size_t, std::vector<FreeSlab>> by_bytes;
+    size_t bytes = 0;
+};
+SlabCache g_slab_cache[64];                       // per device, under g_slab_mux
+constexpr size_t kSlabCacheBytes = (size_t)12 << 30;
 const bool g_slabs_on = [] { const char *e = getenv("MILLIPYDE_SLABS"); return !(e && *e == '0'); }();
 }  // namespace
 
@@ -327,12 +345,31 @@ bool pool_alloc_many(int device_id, cudaStream_t stream, size_t n, size_t nbytes
             }
             break;
         }
-        char *base = (char *)alloc_from(device_id, stream, cnt * stride, "cudaMallocFromPoolAsync(slab)", __LINE__);
+        char *base = nullptr;
+        cudaEvent_t released = nullptr;
+        if (device_id >= 0 && device_id < 64) {
+            std::lock_guard<std::mutex> lk(g_slab_mux);
+            auto it = g_slab_cache[device_id].by_bytes.find(cnt * stride);
+            if (it != g_slab_cache[device_id].by_bytes.end() && !it->second.empty()) {
+                base = (char *)it->second.back().base;
+                released = it->second.back().released;
+                it->second.pop_back();
+                g_slab_cache[device_id].bytes -= cnt * stride;
+            }
+        }
+        if (base) {   // ordered after whatever last used it
+            if (released) {
+                cudaStreamWaitEvent(stream, released, 0);
+                cudaEventDestroy(released);
+            }
+        } else {
+            base = (char *)alloc_from(device_id, stream, cnt * stride, "cudaMallocFromPoolAsync(slab)", __LINE__);
+        }
         if (!base) {   // hand back what this call made; the caller falls back to (and reports from) single blocks
             for (size_t i = 0; i < done; ++i) pool_free(device_id, stream, out[i]);
             return false;
         }
-        Slab *sl = new Slab{base, device_id, (int)cnt, {}, 0};
+        Slab *sl = new Slab{base, cnt * stride, device_id, (int)cnt, {}, 0};
         std::lock_guard<std::mutex> lk(g_slab_mux);
         for (size_t i = 0; i < cnt; ++i) {
             out[done + i] = base + i * stride;
@@ -378,13 +415,62 @@ void pool_free(int device_id, cudaStream_t stream, void *ptr)
         } else {
             for (int k = 0; k < n_others; ++k) order_after(others[k].device, others[k].stream, stream);
         }
-        if (prev >= 0) cudaSetDevice(prev);
         ptr = sl->base;
+        const size_t bytes = sl->bytes;
+        const int dev = sl->device;
         delete sl;
+        // keep it for the next launch of this size (up to a budget), stamped with its release point
+        bool cached = false;
+        if (dev >= 0 && dev < 64 && g_initialized.load()) {
+            cudaEvent_t ev = nullptr;
+            cudaSetDevice(device_id);   // the event belongs to the releasing stream's device
+            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventRecord(ev, stream) == cudaSuccess) {
+                std::lock_guard<std::mutex> lk(g_slab_mux);
+                if (g_slab_cache[dev].bytes + bytes <= kSlabCacheBytes) {
+                    g_slab_cache[dev].by_bytes[bytes].push_back(FreeSlab{ptr, ev});
+                    g_slab_cache[dev].bytes += bytes;
+                    cached = true;
+                }
+            }
+            if (!cached && ev) cudaEventDestroy(ev);
+            (void)cudaGetLastError();
+        }
+        if (prev >= 0) cudaSetDevice(prev);
+        if (cached) return;
     }
     (void)device_id;
     cudaError_t e = cudaFreeAsync(ptr, stream);
     if (e != cudaSuccess) record_cuda_error(e, "cudaFreeAsync", __FILE__, __LINE__);
+}
+
+// Give the cached slabs of every device back to their pools (mpdev_trim_pools, teardown, out of memory).
+void slab_cache_drop(int only_device)
+{
+    std::vector<std::pair<int, FreeSlab>> all;
+    {
+        std::lock_guard<std::mutex> lk(g_slab_mux);
+        for (int d = 0; d < 64; ++d) {
+            if (only_device >= 0 && d != only_device) continue;
+            for (auto &kv : g_slab_cache[d].by_bytes)
+                for (FreeSlab &f : kv.second) all.push_back({d, f});
+            g_slab_cache[d].by_bytes.clear();
+            g_slab_cache[d].bytes = 0;
+        }
+    }
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    for (auto &df : all) {
+        if (cudaSetDevice(df.first) != cudaSuccess) continue;
+        cudaStream_t s0 = device_stream(df.first, 0);
+        if (df.second.released) {
+            cudaStreamWaitEvent(s0, df.second.released, 0);
+            cudaEventDestroy(df.second.released);
+        }
+        cudaFreeAsync(df.second.base, s0);
+    }
+    (void)cudaGetLastError();
+    if (prev >= 0) cudaSetDevice(prev);
 }
 
 int sm_count(int device_id) { return in_range(device_id) ? g_devices[device_id].sm_count : 0; }
@@ -691,6 +777,7 @@ void mpdev_flush_l2(int device_id, void *stream)
 
 void mpdev_trim_pools(void)
 {
+    mp::slab_cache_drop(-1);
     int prev = -1;
     if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
     for (int i = 0; i < g_count; ++i) {
