@@ -314,7 +314,7 @@ struct SlabCache {
     size_t bytes = 0;
 };
 SlabCache g_slab_cache[64];                       // per device, under g_slab_mux
-constexpr size_t kSlabCacheBytes = (size_t)12 << 30;
+constexpr size_t kSlabCacheBytes = (size_t)64 << 30;   // soft: an allocation that fails drops the cache and retries
 const bool g_slabs_on = [] { const char *e = getenv("MILLIPYDE_SLABS"); return !(e && *e == '0'); }();
 }  // namespace
 
