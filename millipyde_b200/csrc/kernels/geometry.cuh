@@ -298,6 +298,85 @@ rotate_nearest_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
     }
 }
 
+// The same rule through a shared-memory box (the reference layouts' rotate: RGBA8 words, and fp64
+// greyscale under reference semantics as two words).  A block produces a 32 x 32 output tile; the
+// bounding box of the tile's source footprint (<= 52 x 52 pixels) is staged with coalesced row loads,
+// so the scattered reads of a rotated line hit shared memory instead of ~18 cache lines per warp load.
+// The source coordinates are the reference's expression, evaluated per pixel exactly as above
+// (bit-exact against the golden vectors); a coordinate the box does not hold -- it cannot happen with
+// the margins below, but exactness must not depend on that -- is read from global memory.
+constexpr int kNrTile = 32;
+constexpr int kNrBox = 52;
+
+template <int K>
+__global__ void __launch_bounds__(256)
+rotate_nearest_box_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int width, int height,
+                          double angle)
+{
+    __shared__ double s_cs[2];
+    __shared__ uint32_t box[kNrBox][kNrBox * K + 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        s_cs[0] = cos(angle);
+        s_cs[1] = sin(angle);
+    }
+    __syncthreads();
+    const double ca = s_cs[0], sa = s_cs[1];
+    const int ox0 = blockIdx.x * kNrTile, oy0 = blockIdx.y * kNrTile;
+    const int ox1 = min(ox0 + kNrTile, width) - 1, oy1 = min(oy0 + kNrTile, height) - 1;
+
+    // footprint of the tile: the map is affine, so its extremes are at the tile's corners
+    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const double fx = (double)((q & 1) ? ox1 : ox0) - ((double)width / 2);
+        const double fy = (double)((q & 2) ? oy1 : oy0) - ((double)height / 2);
+        const double xr = fx * ca - fy * sa + ((double)width / 2), yr = fx * sa + fy * ca + ((double)height / 2);
+        xmin = fmin(xmin, xr); xmax = fmax(xmax, xr);
+        ymin = fmin(ymin, yr); ymax = fmax(ymax, yr);
+    }
+    const int bx0 = __double2int_rd(xmin) - 2, by0 = __double2int_rd(ymin) - 2;
+    const int bw = min(__double2int_ru(xmax) + 3 - bx0, kNrBox), bh = min(__double2int_ru(ymax) + 3 - by0, kNrBox);
+    for (int r = w; r < bh; r += 8) {
+        const int sy = by0 + r;
+        const bool row_in = sy >= 0 && sy < height;
+        for (int c = lane; c < bw * K; c += 32) {
+            const int sx = bx0 + c / K;
+            uint32_t v = 0u;
+            if (row_in && sx >= 0 && sx < width) v = __ldg(in + ((size_t)sy * width + bx0) * K + c);
+            box[r][c] = v;
+        }
+    }
+    __syncthreads();
+
+    const int x = ox0 + lane;
+    if (x >= width) return;
+#pragma unroll
+    for (int k = 0; k < kNrTile / 8; ++k) {
+        const int y = oy0 + w + 8 * k;
+        if (y >= height) break;
+        int x_rot = ((double)x - ((double)width / 2)) * ca -
+                    ((double)y - ((double)height / 2)) * sa + ((double)width / 2);
+        int y_rot = ((double)x - ((double)width / 2)) * sa +
+                    ((double)y - ((double)height / 2)) * ca + ((double)height / 2);
+        const size_t o = ((size_t)y * width + x) * K;
+        if (x_rot >= 0 && x_rot < width && y_rot >= 0 && y_rot < height) {
+            const int cx = x_rot - bx0, cy = y_rot - by0;
+            if (cx >= 0 && cx < bw && cy >= 0 && cy < bh) {
+#pragma unroll
+                for (int c = 0; c < K; ++c) out[o + c] = box[cy][cx * K + c];
+            } else {
+                const size_t s = ((size_t)y_rot * width + x_rot) * K;
+#pragma unroll
+                for (int c = 0; c < K; ++c) out[o + c] = __ldg(in + s + c);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < K; ++c) out[o + c] = 0u;
+        }
+    }
+}
+
 // ----------------------------------------------------------- rotate, bilinear
 // skimage.transform.rotate defaults (order=1, mode='constant', cval=0, centre
 // (W/2-0.5, H/2-0.5)).  Source coordinates in fp64 (fp32 would carry ~2.4e-4 px
