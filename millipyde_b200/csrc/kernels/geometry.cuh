@@ -298,85 +298,6 @@ rotate_nearest_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
     }
 }
 
-// The same rule through a shared-memory box (the reference layouts' rotate: RGBA8 words, and fp64
-// greyscale under reference semantics as two words).  A block produces a 32 x 32 output tile; the
-// bounding box of the tile's source footprint (<= 52 x 52 pixels) is staged with coalesced row loads,
-// so the scattered reads of a rotated line hit shared memory instead of ~18 cache lines per warp load.
-// The source coordinates are the reference's expression, evaluated per pixel exactly as above
-// (bit-exact against the golden vectors); a coordinate the box does not hold -- it cannot happen with
-// the margins below, but exactness must not depend on that -- is read from global memory.
-constexpr int kNrTile = 32;
-constexpr int kNrBox = 52;
-
-template <int K>
-__global__ void __launch_bounds__(256)
-rotate_nearest_box_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int width, int height,
-                          double angle)
-{
-    __shared__ double s_cs[2];
-    __shared__ uint32_t box[kNrBox][kNrBox * K + 1];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        s_cs[0] = cos(angle);
-        s_cs[1] = sin(angle);
-    }
-    __syncthreads();
-    const double ca = s_cs[0], sa = s_cs[1];
-    const int ox0 = blockIdx.x * kNrTile, oy0 = blockIdx.y * kNrTile;
-    const int ox1 = min(ox0 + kNrTile, width) - 1, oy1 = min(oy0 + kNrTile, height) - 1;
-
-    // footprint of the tile: the map is affine, so its extremes are at the tile's corners
-    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const double fx = (double)((q & 1) ? ox1 : ox0) - ((double)width / 2);
-        const double fy = (double)((q & 2) ? oy1 : oy0) - ((double)height / 2);
-        const double xr = fx * ca - fy * sa + ((double)width / 2), yr = fx * sa + fy * ca + ((double)height / 2);
-        xmin = fmin(xmin, xr); xmax = fmax(xmax, xr);
-        ymin = fmin(ymin, yr); ymax = fmax(ymax, yr);
-    }
-    const int bx0 = __double2int_rd(xmin) - 2, by0 = __double2int_rd(ymin) - 2;
-    const int bw = min(__double2int_ru(xmax) + 3 - bx0, kNrBox), bh = min(__double2int_ru(ymax) + 3 - by0, kNrBox);
-    for (int r = w; r < bh; r += 8) {
-        const int sy = by0 + r;
-        const bool row_in = sy >= 0 && sy < height;
-        for (int c = lane; c < bw * K; c += 32) {
-            const int sx = bx0 + c / K;
-            uint32_t v = 0u;
-            if (row_in && sx >= 0 && sx < width) v = __ldg(in + ((size_t)sy * width + bx0) * K + c);
-            box[r][c] = v;
-        }
-    }
-    __syncthreads();
-
-    const int x = ox0 + lane;
-    if (x >= width) return;
-#pragma unroll
-    for (int k = 0; k < kNrTile / 8; ++k) {
-        const int y = oy0 + w + 8 * k;
-        if (y >= height) break;
-        int x_rot = ((double)x - ((double)width / 2)) * ca -
-                    ((double)y - ((double)height / 2)) * sa + ((double)width / 2);
-        int y_rot = ((double)x - ((double)width / 2)) * sa +
-                    ((double)y - ((double)height / 2)) * ca + ((double)height / 2);
-        const size_t o = ((size_t)y * width + x) * K;
-        if (x_rot >= 0 && x_rot < width && y_rot >= 0 && y_rot < height) {
-            const int cx = x_rot - bx0, cy = y_rot - by0;
-            if (cx >= 0 && cx < bw && cy >= 0 && cy < bh) {
-#pragma unroll
-                for (int c = 0; c < K; ++c) out[o + c] = box[cy][cx * K + c];
-            } else {
-                const size_t s = ((size_t)y_rot * width + x_rot) * K;
-#pragma unroll
-                for (int c = 0; c < K; ++c) out[o + c] = __ldg(in + s + c);
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < K; ++c) out[o + c] = 0u;
-        }
-    }
-}
-
 // ----------------------------------------------------------- rotate, bilinear
 // skimage.transform.rotate defaults (order=1, mode='constant', cval=0, centre
 // (W/2-0.5, H/2-0.5)).  Source coordinates in fp64 (fp32 would carry ~2.4e-4 px
@@ -550,20 +471,77 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
         const int r_lo = by0 < 0 ? -by0 : 0;
         const int r_hi = bh < g.rot_h - by0 ? bh : g.rot_h - by0;
         const bool any = c_hi > c_lo && r_hi > r_lo;
+        // Which part of box row r the tile really reads.  The tile's footprint is a rotated rectangle,
+        // its bounding box 1.9-2.2x its area: staging whole box rows made this kernel L2-bandwidth-bound
+        // (3.4 bytes moved per byte of output at 30 degrees).  Row Y of the source is touched by samples
+        // with ys in [Y - 1, Y + 1); the x-extent of the rectangle over that strip, widened by the
+        // bilinear corner and a margin, is all a row needs -- the rest of the box row is never read.
+        float vx[4], vy[4];
+        if (g.has_rotate) {
+            const float ux = (float)(rp.c * qhx), uy = (float)(rp.s * qhx), wx = (float)(-rp.s * qhy), wy = (float)(rp.c * qhy);
+            const float fxc = (float)(xc - bx0), fyc = (float)(yc - by0);   // box-relative: small numbers, fp32 is plenty
+            vx[0] = fxc + ux + wx; vy[0] = fyc + uy + wy;
+            vx[1] = fxc - ux + wx; vy[1] = fyc - uy + wy;
+            vx[2] = fxc - ux - wx; vy[2] = fyc - uy - wy;
+            vx[3] = fxc + ux - wx; vy[3] = fyc + uy - wy;
+        }
+        auto row_span = [&](int r, int *lo_out, int *hi_out) {
+            *lo_out = c_lo;
+            *hi_out = c_hi;
+            if (!g.has_rotate) return;
+            const float yl = (float)r - 1.05f, yh = (float)r + 1.05f;
+            float xa = 1e30f, xb = -1e30f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = (i + 1) & 3;
+                if (vy[i] >= yl && vy[i] <= yh) {
+                    xa = fminf(xa, vx[i]);
+                    xb = fmaxf(xb, vx[i]);
+                }
+                const float dy = vy[j] - vy[i];
+                if (dy != 0.f) {
+                    const float inv = 1.f / dy;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float t = ((e ? yh : yl) - vy[i]) * inv;
+                        if (t >= 0.f && t <= 1.f) {
+                            const float xe = vx[i] + t * (vx[j] - vx[i]);
+                            xa = fminf(xa, xe);
+                            xb = fmaxf(xb, xe);
+                        }
+                    }
+                }
+            }
+            if (xa > xb) {   // no sample reaches this row
+                *hi_out = *lo_out;
+                return;
+            }
+            // pixels floor(xa) - 1 .. floor(xb) + 2 (the second corner, plus a pixel of margin each side)
+            const int pa = (int)floorf(xa) - 1, pb = (int)floorf(xb) + 3;
+            int fl = (pa * C + shift) & ~3, fh = (pb * C + shift + 3) & ~3;
+            *lo_out = fl > c_lo ? fl : c_lo;
+            *hi_out = fh < c_hi ? fh : c_hi;
+            if (*hi_out < *lo_out) *hi_out = *lo_out;
+        };
         if (w == 0) {
             uint32_t bytes = 0;
+            int seg_lo[(BOX + 31) / 32], seg_hi[(BOX + 31) / 32];
 #pragma unroll
             for (int u = 0; u < (BOX + 31) / 32; ++u) {
                 const int r = lane + 32 * u;
-                if (any && r >= r_lo && r < r_hi) bytes += (uint32_t)(c_hi - c_lo) * 4u;
+                seg_lo[u] = seg_hi[u] = 0;
+                if (any && r >= r_lo && r < r_hi) {
+                    row_span(r, &seg_lo[u], &seg_hi[u]);
+                    bytes += (uint32_t)(seg_hi[u] - seg_lo[u]) * 4u;
+                }
             }
             mbar_expect_tx(&s_bar, bytes);  // arrive + expect: the barrier counts the 32 lanes
 #pragma unroll
             for (int u = 0; u < (BOX + 31) / 32; ++u) {
                 const int r = lane + 32 * u;
-                if (any && r >= r_lo && r < r_hi)
-                    bulk_g2s(box + r * PITCH + c_lo, src + ((long)(by0 + r) * row_len + col0 + c_lo),
-                             (uint32_t)(c_hi - c_lo) * 4u, &s_bar);
+                if (seg_hi[u] > seg_lo[u])
+                    bulk_g2s(box + r * PITCH + seg_lo[u], src + ((long)(by0 + r) * row_len + col0 + seg_lo[u]),
+                             (uint32_t)(seg_hi[u] - seg_lo[u]) * 4u, &s_bar);
             }
         }
         // tiles whose box leaves the image zero what the copies do not cover

@@ -365,11 +365,13 @@ MPStatus mpimg_rotate(MPObjData *obj, void *args)
     const bool nearest = d.fam == mp::FAM_RGBA8 || (d.fam == mp::FAM_F64 && semantics() == MP_SEMANTICS_REFERENCE);
     if (nearest) {
         const double rad = angle * 0.01745329252;  // src/millipyde_image.cpp:702
-        dim3 grid((d.W + kNrTile - 1) / kNrTile, (d.H + kNrTile - 1) / kNrTile);
+        // (a shared-memory box like the fp32 gather's was measured here too: 61 us per 4K RGBA8 image
+        // against 41 us for the direct form -- one word per pixel does not pay for the staging)
+        dim3 block(32, 8), grid((d.W + 31) / 32, (d.H + 7) / 8);
         if (d.fam == mp::FAM_RGBA8)
-            rotate_nearest_box_kernel<1><<<grid, 256, 0, s>>>((const uint32_t *)obj->device_data, (uint32_t *)out, d.W, d.H, rad);
+            rotate_nearest_kernel<1><<<grid, block, 0, s>>>((const uint32_t *)obj->device_data, (uint32_t *)out, d.W, d.H, rad);
         else
-            rotate_nearest_box_kernel<2><<<grid, 256, 0, s>>>((const uint32_t *)obj->device_data, (uint32_t *)out, d.W, d.H, rad);
+            rotate_nearest_kernel<2><<<grid, block, 0, s>>>((const uint32_t *)obj->device_data, (uint32_t *)out, d.W, d.H, rad);
     } else {
         RotateParams rp = mp::rotate_params(d.W, d.H, angle);
         if (d.fam == mp::FAM_F64) {
