@@ -100,6 +100,13 @@ int mpimg_gaussian_effective_radius(double sigma, int *full);
 void mpimg_set_gauss_column(int mode);
 int mpimg_get_gauss_column(void);
 
+/* Work-item plan of one streaming-Gaussian launch (diagnostic, needs no GPU; tests/test_kernel_models.py).
+ * `columns` = images x 640-float strips, `radius` = the radius bucket, `sms` = CTAs of the persistent
+ * grid.  out = { main_items, tail_cols, chunk_rows, n_chunks }: the first main_items columns are one
+ * item each (whole waves of the grid), each of the tail_cols columns behind them is cut into n_chunks
+ * row chunks of chunk_rows rows so that the last, partial wave is short. */
+void mpimg_gauss_stream_plan(long columns, int height, int radius, int sms, int mma, int out[4]);
+
 /*
  * numpy-ufunc-exact elementwise operators on float32 images (new).  What the
  * extension's __array_ufunc__ dispatches np.add / np.subtract / np.multiply / np.power / np.clip /

@@ -131,6 +131,7 @@ SYMBOLS = {
     "mpimg_get_semantics": (C.c_int, []),
     "mpimg_set_gauss_column": (None, [C.c_int]),
     "mpimg_get_gauss_column": (C.c_int, []),
+    "mpimg_gauss_stream_plan": (None, [C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "mpimg_set_value_range": (None, [C.c_int]),
     "mpimg_get_value_range": (C.c_int, []),
     "mpimg_gaussian_effective_radius": (C.c_int, [C.c_double, C.POINTER(C.c_int)]),

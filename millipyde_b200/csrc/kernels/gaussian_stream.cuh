@@ -32,7 +32,14 @@ struct GaussStreamParams {
     int height;
     int row_elems;               // W * C
     int n_strips;                // ceil(row_elems / TW)
-    int chunk_rows;              // rows per work item
+    // Work items.  A column is (image, strip); columns are numbered image-major.  The first
+    // main_items columns are one item each (all rows); each of the tail_cols columns behind them is
+    // cut into n_chunks row chunks of chunk_rows rows, numbered chunk-major (gs_item below).  The
+    // launcher makes the main part whole waves of the persistent grid and cuts the remainder so that
+    // it fills one more, short, wave (mp_gauss_stream.cu: gs_plan_items).
+    int main_items;
+    int tail_cols;
+    int chunk_rows;              // rows per tail item
     int n_chunks;
     int radius;                  // actual radius (<= R); w[d] = 0 beyond it
     // Pointwise work fused around the blur (device memory, null = none): image i applies the program
@@ -45,6 +52,35 @@ struct GaussStreamParams {
     float w[16];
     unsigned long long ww[16];   // (w[d], w[d]) packed for fma.rn.f32x2
 };
+
+// Work item -> (image, strip, rows [y0, y1)).  Evaluated once per item by every warp of both roles
+// (two integer divisions per ~2000 rows of work).
+struct GsItem {
+    int img, strip, y0, y1;
+};
+__device__ __forceinline__ long gs_item_count(const GaussStreamParams &p)
+{
+    return (long)p.main_items + (long)p.tail_cols * p.n_chunks;
+}
+__device__ __forceinline__ GsItem gs_item(const GaussStreamParams &p, long item)
+{
+    GsItem it;
+    int col;
+    if (item < p.main_items) {
+        col = (int)item;
+        it.y0 = 0;
+        it.y1 = p.height;
+    } else {
+        const int t = (int)(item - p.main_items);
+        const int chunk = t / p.tail_cols;
+        col = p.main_items + (t - chunk * p.tail_cols);
+        it.y0 = chunk * p.chunk_rows;
+        it.y1 = min(p.height, it.y0 + p.chunk_rows);
+    }
+    it.img = col / p.n_strips;
+    it.strip = col - it.img * p.n_strips;
+    return it;
+}
 
 // Per-image weight sets of a batched launch whose images share the radius bucket but not sigma
 // (Generator streams with random_gaussian).  The table travels in the kernel parameter block, i.e.

@@ -150,8 +150,7 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kMmColRegs));
 
     // ================================================================ COLUMN warp
-    const int items_per_image = p.n_strips * p.n_chunks;
-    const long n_items = (long)p.n_images * items_per_image;
+    const long n_items = gs_item_count(p);
     const int wc = warp - MmK::row_warps;   // 0..7: columns [80 wc, 80 wc + 80) of the strip
     const int g = lane >> 2, t = lane & 3;
     const float *ring = s_h + t * kMmPitch + wc * (16 * kMmTiles) + 2 * g;
@@ -161,15 +160,10 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
     uint32_t waited = 0;     // groups of the hand-off ring waited for so far (all items)
     uint32_t released = 0;   // groups handed back so far
 
-    int img = 0, rem = (int)blockIdx.x;
-    for (long item = blockIdx.x; item < n_items; item += gridDim.x, rem += (int)gridDim.x) {
-        while (rem >= items_per_image) {
-            rem -= items_per_image;
-            ++img;
-        }
-        const int chunk = rem / p.n_strips, strip = rem - chunk * p.n_strips;
-        const int y0 = chunk * p.chunk_rows;
-        const int y1 = min(p.height, y0 + p.chunk_rows);
+    for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const GsItem it = gs_item(p, item);
+        const int img = it.img, strip = it.strip;
+        const int y0 = it.y0, y1 = it.y1;
         const int n_rows = (y1 - y0) + 2 * R;
         const int n_chunks8 = ws_steps<true>(n_rows) / 4 * (kMmRing / 8);
         const unsigned n_valid = (unsigned)(y1 - y0);

@@ -154,8 +154,7 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
     PwSmem *my_prog = s_prog + warp;   // this warp's copy of the current image's "before the blur" program
     using G = WsGeom<C, R>;
     using K = WsK<MMA>;
-    const int items_per_image = p.n_strips * p.n_chunks;
-    const long n_items = (long)p.n_images * items_per_image;
+    const long n_items = gs_item_count(p);
     // =============================================================== ROW warp
     float *my_in = s_in + (size_t)warp * K::in_slots * G::SLOT;
     uint64_t *my_full = in_full + warp * K::in_slots;
@@ -163,19 +162,14 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
     uint32_t takes = 0;   // rows consumed so far
     uint32_t group = 0;   // groups produced so far (ring slot and parity)
 
-    int img = 0, rem = (int)blockIdx.x;  // item = img * items_per_image + rem, kept by add/compare only
-    for (long item = blockIdx.x; item < n_items; item += gridDim.x, rem += (int)gridDim.x) {
-        while (rem >= items_per_image) {
-            rem -= items_per_image;
-            ++img;
-        }
-        const int chunk = rem / p.n_strips, strip = rem - chunk * p.n_strips;
+    for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const GsItem it = gs_item(p, item);
+        const int img = it.img, strip = it.strip;
         const float *__restrict__ src = p.in_tab ? p.in_tab[img] : p.in + (size_t)img * p.image_stride;
         const WsSetOf w_img{ws, img % kGsMaxSets};
         const WsOneSet w_one{p};
         const int x0 = strip * kGsTW;
-        const int y0 = chunk * p.chunk_rows;
-        const int y1 = min(p.height, y0 + p.chunk_rows);
+        const int y0 = it.y0, y1 = it.y1;
         const int r_begin = y0 - R;
         const int n_rows = (y1 - y0) + 2 * R;
         const int n_steps = ws_steps<MMA>(n_rows);
@@ -368,8 +362,7 @@ __device__ __forceinline__ void ws_body(const GaussStreamParams &p, const GaussW
     }
     __syncthreads();  // the only CTA-wide barrier
 
-    const int items_per_image = p.n_strips * p.n_chunks;
-    const long n_items = (long)p.n_images * items_per_image;
+    const long n_items = gs_item_count(p);
 
     if (warp < kWsRowWarps) {
         ws_row_role<C, R, SETS, kGsTW, false>(p, ws, s_in, s_h, in_full, h_full, h_empty, warp, lane, s_prog);
@@ -386,16 +379,11 @@ __device__ __forceinline__ void ws_body(const GaussStreamParams &p, const GaussW
         for (int i = 0; i < 2 * R; ++i) A[i] = 0ull;
         uint32_t group = 0;
 
-        int img = 0, rem = (int)blockIdx.x;
-        for (long item = blockIdx.x; item < n_items; item += gridDim.x, rem += (int)gridDim.x) {
-            while (rem >= items_per_image) {
-                rem -= items_per_image;
-                ++img;
-            }
-            const int chunk = rem / p.n_strips, strip = rem - chunk * p.n_strips;
+        for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const GsItem it = gs_item(p, item);
+            const int img = it.img, strip = it.strip;
             const int gx = strip * kGsTW + 2 * vt;
-            const int y0 = chunk * p.chunk_rows;
-            const int y1 = min(p.height, y0 + p.chunk_rows);
+            const int y0 = it.y0, y1 = it.y1;
             const int n_rows = (y1 - y0) + 2 * R;
             const int n_steps = (n_rows + kWsRows - 1) / kWsRows;
             // rows [y0, y1) of columns gx, gx+1; the first filtered row completes output row y0 - 2R

@@ -471,77 +471,20 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
         const int r_lo = by0 < 0 ? -by0 : 0;
         const int r_hi = bh < g.rot_h - by0 ? bh : g.rot_h - by0;
         const bool any = c_hi > c_lo && r_hi > r_lo;
-        // Which part of box row r the tile really reads.  The tile's footprint is a rotated rectangle,
-        // its bounding box 1.9-2.2x its area: staging whole box rows made this kernel L2-bandwidth-bound
-        // (3.4 bytes moved per byte of output at 30 degrees).  Row Y of the source is touched by samples
-        // with ys in [Y - 1, Y + 1); the x-extent of the rectangle over that strip, widened by the
-        // bilinear corner and a margin, is all a row needs -- the rest of the box row is never read.
-        float vx[4], vy[4];
-        if (g.has_rotate) {
-            const float ux = (float)(rp.c * qhx), uy = (float)(rp.s * qhx), wx = (float)(-rp.s * qhy), wy = (float)(rp.c * qhy);
-            const float fxc = (float)(xc - bx0), fyc = (float)(yc - by0);   // box-relative: small numbers, fp32 is plenty
-            vx[0] = fxc + ux + wx; vy[0] = fyc + uy + wy;
-            vx[1] = fxc - ux + wx; vy[1] = fyc - uy + wy;
-            vx[2] = fxc - ux - wx; vy[2] = fyc - uy - wy;
-            vx[3] = fxc + ux - wx; vy[3] = fyc + uy - wy;
-        }
-        auto row_span = [&](int r, int *lo_out, int *hi_out) {
-            *lo_out = c_lo;
-            *hi_out = c_hi;
-            if (!g.has_rotate) return;
-            const float yl = (float)r - 1.05f, yh = (float)r + 1.05f;
-            float xa = 1e30f, xb = -1e30f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int j = (i + 1) & 3;
-                if (vy[i] >= yl && vy[i] <= yh) {
-                    xa = fminf(xa, vx[i]);
-                    xb = fmaxf(xb, vx[i]);
-                }
-                const float dy = vy[j] - vy[i];
-                if (dy != 0.f) {
-                    const float inv = 1.f / dy;
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const float t = ((e ? yh : yl) - vy[i]) * inv;
-                        if (t >= 0.f && t <= 1.f) {
-                            const float xe = vx[i] + t * (vx[j] - vx[i]);
-                            xa = fminf(xa, xe);
-                            xb = fmaxf(xb, xe);
-                        }
-                    }
-                }
-            }
-            if (xa > xb) {   // no sample reaches this row
-                *hi_out = *lo_out;
-                return;
-            }
-            // pixels floor(xa) - 1 .. floor(xb) + 2 (the second corner, plus a pixel of margin each side)
-            const int pa = (int)floorf(xa) - 1, pb = (int)floorf(xb) + 3;
-            int fl = (pa * C + shift) & ~3, fh = (pb * C + shift + 3) & ~3;
-            *lo_out = fl > c_lo ? fl : c_lo;
-            *hi_out = fh < c_hi ? fh : c_hi;
-            if (*hi_out < *lo_out) *hi_out = *lo_out;
-        };
         if (w == 0) {
             uint32_t bytes = 0;
-            int seg_lo[(BOX + 31) / 32], seg_hi[(BOX + 31) / 32];
 #pragma unroll
             for (int u = 0; u < (BOX + 31) / 32; ++u) {
                 const int r = lane + 32 * u;
-                seg_lo[u] = seg_hi[u] = 0;
-                if (any && r >= r_lo && r < r_hi) {
-                    row_span(r, &seg_lo[u], &seg_hi[u]);
-                    bytes += (uint32_t)(seg_hi[u] - seg_lo[u]) * 4u;
-                }
+                if (any && r >= r_lo && r < r_hi) bytes += (uint32_t)(c_hi - c_lo) * 4u;
             }
             mbar_expect_tx(&s_bar, bytes);  // arrive + expect: the barrier counts the 32 lanes
 #pragma unroll
             for (int u = 0; u < (BOX + 31) / 32; ++u) {
                 const int r = lane + 32 * u;
-                if (seg_hi[u] > seg_lo[u])
-                    bulk_g2s(box + r * PITCH + seg_lo[u], src + ((long)(by0 + r) * row_len + col0 + seg_lo[u]),
-                             (uint32_t)(seg_hi[u] - seg_lo[u]) * 4u, &s_bar);
+                if (any && r >= r_lo && r < r_hi)
+                    bulk_g2s(box + r * PITCH + c_lo, src + ((long)(by0 + r) * row_len + col0 + c_lo),
+                             (uint32_t)(c_hi - c_lo) * 4u, &s_bar);
             }
         }
         // tiles whose box leaves the image zero what the copies do not cover

@@ -64,6 +64,57 @@ static bool use_mma_column()
     return m == MP_GAUSS_COLUMN_MMA;
 }
 
+// Row steps a work item of n_out output rows costs its CTA: the rows it filters (n_out + 2R halo
+// rows) rounded the way the kernels round them (kernels/gaussian_stream_ws.cuh: ws_steps).
+static long item_row_steps(int n_out, int R, bool mma)
+{
+    const int n_rows = n_out + 2 * R;
+    if (!mma) return (long)((n_rows + 9) / 10) * 10;
+    return (long)((((n_rows + 7 + 11) / 12) + 3) & ~3) * 12;
+}
+
+// Work items of one launch.  A column is (image, strip), `columns` of them, `height` rows each; the
+// grid is one persistent CTA per SM and CTA b takes items b, b + sms, ...
+//   main part: the first floor(columns / sms) * sms columns, one item each -- whole waves, no halo
+//       rows re-filtered;
+//   tail: the remaining columns (< sms) cut into c row chunks each.  Every chunk re-filters 2R halo
+//       rows and pads its row count to the hand-off ring, but the tail's makespan is what the whole
+//       grid waits for: c minimises waves(c) * steps(rows / c).  (256 4K RGB images on 148 SMs: 4608
+//       columns = 31 waves + 20 columns; as 20 more whole columns they cost a 32nd wave with 128 SMs
+//       idle, as 140 chunks of 309 rows a sixth of one.)
+// A launch with fewer columns than SMs is all tail (a single 4K image: 18 columns x 8 chunks).
+void gs_plan_items(long columns, int height, int R, int sms, bool mma, int *main_items, int *tail_cols,
+                   int *chunk_rows, int *n_chunks)
+{
+    if (sms < 1) sms = 1;
+    // MILLIPYDE_GAUSS_TAIL=0: every column is cut the same way (the round-1 schedule; A/B measurements)
+    static const bool split_tail = [] { const char *e = getenv("MILLIPYDE_GAUSS_TAIL"); return !(e && *e == '0'); }();
+    const long whole = split_tail ? columns / sms * sms : 0;
+    const int tail = (int)(columns - whole);
+    *main_items = (int)whole;
+    *tail_cols = tail > 0 ? tail : 1;
+    *chunk_rows = height;
+    *n_chunks = 0;
+    if (tail == 0) return;
+    const int c_max = height / (4 * R) > 1 ? height / (4 * R) : 1;
+    long best = 0;
+    int chunks = 1;
+    for (int c = 1; c <= c_max && c <= 64; ++c) {
+        const int rows = (height + c - 1) / c;
+        const int c_eff = (height + rows - 1) / rows;   // chunks that start inside the image
+        const long waves = ((long)tail * c_eff + sms - 1) / sms;
+        const long cost = waves * item_row_steps(rows, R, mma);
+        if (best == 0 || cost * 100 < best * 98) {  // prefer fewer chunks unless the gain is real
+            best = cost;
+            chunks = c;
+        }
+    }
+    *chunk_rows = (height + chunks - 1) / chunks;
+    // rounding the chunk height up can leave the last chunks empty (770 rows in 64 chunks of 13 end
+    // at chunk 59): count the chunks that start inside the image, every item must own at least one row
+    *n_chunks = (height + *chunk_rows - 1) / *chunk_rows;
+}
+
 template <int C, int R>
 static MPStatus launch_cr(int device, cudaStream_t s, GaussStreamParams &p, const GaussWeightSets *sets)
 {
@@ -88,30 +139,10 @@ static MPStatus launch_cr(int device, cudaStream_t s, GaussStreamParams &p, cons
         }
         configured[device].store(true, std::memory_order_release);
     }
-    // One persistent CTA per SM.  An item is (image, strip, row chunk); the number of row chunks is
-    // the one that wastes least: more chunks fill the last wave of CTAs better, but every chunk
-    // re-filters 2R halo rows.  useful(c) = rows / (rows + 2R c)  x  items c / (waves(c) sms).
-    long items = (long)p.n_images * p.n_strips;
-    int chunks = 1;
-    {
-        double best = 0;
-        const int c_max = p.height / (4 * R) > 1 ? p.height / (4 * R) : 1;
-        for (int c = 1; c <= c_max && c <= 64; ++c) {
-            const long it = items * c;
-            const long waves = (it + sms - 1) / sms;
-            const double useful = (double)p.height / (p.height + 2.0 * R * c) * (double)it / (double)(waves * sms);
-            if (useful > best * 1.02) {  // prefer fewer chunks unless the gain is real
-                best = useful;
-                chunks = c;
-            }
-        }
-    }
-    p.chunk_rows = (p.height + chunks - 1) / chunks;
-    // rounding the chunk height up can leave the last chunks empty (770 rows in 64 chunks of 13 end
-    // at chunk 59): count the chunks that start inside the image, every item must own at least one row
-    chunks = (p.height + p.chunk_rows - 1) / p.chunk_rows;
-    p.n_chunks = chunks;
-    items *= chunks;
+    // One persistent CTA per SM, items dealt round-robin (gs_plan_items below)
+    gs_plan_items((long)p.n_images * p.n_strips, p.height, R, sms, mma, &p.main_items, &p.tail_cols, &p.chunk_rows,
+                  &p.n_chunks);
+    const long items = (long)p.main_items + (long)p.tail_cols * p.n_chunks;
     const int grid = (int)(items < sms ? items : sms);
     if constexpr (kHasMma) {
         if (mma) {
@@ -240,4 +271,8 @@ void mpimg_set_gauss_column(int mode)
 int mpimg_get_gauss_column(void) { return mp::use_mma_column() ? MP_GAUSS_COLUMN_MMA : MP_GAUSS_COLUMN_FMA; }
 void mpimg_set_value_range(int mode) { mp::g_range.store(mode == MP_RANGE_ANY ? MP_RANGE_ANY : MP_RANGE_UNIT); }
 int mpimg_get_value_range(void) { return mp::value_range(); }
+void mpimg_gauss_stream_plan(long columns, int height, int radius, int sms, int mma, int out[4])
+{
+    mp::gs_plan_items(columns, height, radius, sms, mma != 0, &out[0], &out[1], &out[2], &out[3]);
+}
 }

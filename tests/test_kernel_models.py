@@ -229,3 +229,68 @@ def test_skewed_transpose_layout_is_conflict_free_and_tma_aligned():
                             banks = [b for a, _, _ in half for b in ((a + e * pitch) % 32, (a + e * pitch + 1) % 32)]
                             assert len(set(banks)) == len(banks), (K, tw, i0, e)
                             assert all(a % 2 == 0 for a, _, _ in half)
+
+
+# ------------------------------------------------------------------ work items of a streaming-Gaussian launch
+def _plan(columns, height, radius, sms, mma=1):
+    import ctypes
+
+    from millipyde_b200 import capi
+    out = (ctypes.c_int * 4)()
+    capi.lib().mpimg_gauss_stream_plan(columns, height, radius, sms, mma, out)
+    return tuple(out)
+
+
+def _gs_item(plan, n_strips, height, item):
+    """kernels/gaussian_stream.cuh: gs_item."""
+    main_items, tail_cols, chunk_rows, _ = plan
+    if item < main_items:
+        col, y0, y1 = item, 0, height
+    else:
+        chunk, j = divmod(item - main_items, tail_cols)
+        col, y0 = main_items + j, chunk * chunk_rows
+        y1 = min(height, y0 + chunk_rows)
+    return col // n_strips, col % n_strips, y0, y1
+
+
+def _row_steps(n_out, radius, mma=1):
+    n_rows = n_out + 2 * radius
+    return steps(n_rows) * ROWS_PER_GROUP if mma else (n_rows + 9) // 10 * 10
+
+
+@pytest.mark.parametrize("n_images,height,n_strips,radius,sms", [
+    (256, 2160, 18, 11, 148),     # the headline launch: 31 whole waves + 20 columns
+    (1, 2160, 18, 11, 148),       # one 4K image: all tail
+    (64, 2160, 18, 11, 148), (16, 1080, 9, 11, 148), (1024, 1080, 9, 11, 148), (3, 770, 1, 3, 148),
+    (37, 45, 2, 11, 148), (148, 300, 1, 7, 148), (149, 300, 1, 7, 148), (5, 7, 3, 11, 4), (1, 1, 1, 3, 148),
+])
+def test_stream_items_cover_every_row_of_every_column_once(n_images, height, n_strips, radius, sms):
+    columns = n_images * n_strips
+    plan = _plan(columns, height, radius, sms)
+    main_items, tail_cols, chunk_rows, n_chunks = plan
+    n_items = main_items + tail_cols * n_chunks
+    assert main_items % sms == 0 and main_items <= columns
+    assert n_items == main_items or main_items + tail_cols == columns
+    covered = np.zeros((columns, height), np.int32)
+    for item in range(n_items):
+        img, strip, y0, y1 = _gs_item(plan, n_strips, height, item)
+        assert 0 <= img < n_images and 0 <= strip < n_strips and 0 <= y0 < y1 <= height   # every item owns a row
+        covered[img * n_strips + strip, y0:y1] += 1
+    assert (covered == 1).all()
+
+
+def test_stream_items_tail_is_a_short_wave():
+    """256 x 4K RGB on 148 SMs (bench.py's launch): the 20 columns behind the 31 whole waves go
+    through as one wave of short items, and the launch's makespan drops below 32 whole waves."""
+    plan = _plan(256 * 18, 2160, 11, 148)
+    main_items, tail_cols, chunk_rows, n_chunks = plan
+    assert (main_items, tail_cols) == (31 * 148, 20)
+    assert tail_cols * n_chunks <= 148
+    per_cta = np.zeros(148, np.int64)
+    for item in range(main_items + tail_cols * n_chunks):
+        _, _, y0, y1 = _gs_item(plan, 18, 2160, item)
+        per_cta[item % 148] += _row_steps(y1 - y0, 11)
+    whole_waves = 32 * _row_steps(2160, 11)
+    assert per_cta.max() < 0.98 * whole_waves
+    # a single image is cut as before: 18 columns x 8 chunks = 144 items in one wave
+    assert _plan(18, 2160, 11, 148) == (0, 18, 270, 8)
