@@ -322,15 +322,25 @@ gauss_rgba8_int_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ o
 // above runs).  Packed as fma.rm.f32x2 over the (r, g) and (b, -) halves of a pixel, a tap costs two
 // issue slots per pixel instead of twelve.
 //
-// Tile: 32 x 48 output pixels per CTA.  Staging converts the 48 x 64 input pixels to float4 once
-// (alpha dropped).  Pass 1: thread = (input row, run of 8 pixels), lanes on consecutive rows -- the
-// row pitch of 49 float4 spreads them over the banks.  Pass 2: thread = (column, run of 6 rows),
-// lanes on consecutive columns, so shared loads and the 4-byte global stores are contiguous.
+// Effective radius.  A tap with 255 * w < 1 contributes (int)(byte * w) = 0 for every byte, in both
+// passes (the vertical pass reads bytes again), so it need not be evaluated: at sigma = 2 the
+// reference's 17 taps are 11 (w[6] = 0.0022 -> 255 w = 0.57).  The launcher picks the smallest
+// instantiated radius R that holds every tap with floor(255 * w) >= 1 (bit-exact by construction).
+//
+// Tile: 32 x 48 output pixels per CTA.  Staging converts the (32 + 2R) x (48 + 2R) input pixels to
+// float4 once (alpha dropped).  Pass 1: thread = (input row, run of 8 pixels), lanes on consecutive
+// rows -- the row pitch of 33 + 2R float4 (odd) spreads them over the banks.  Pass 2: thread =
+// (column, run of 6 rows), lanes on consecutive columns, so shared loads and the 4-byte global
+// stores are contiguous.
 constexpr int kU8R = 8;               // the reference's radius (17 taps), src/millipyde_image.cpp:744
 constexpr int kU8TW = 32, kU8TH = 48;
-constexpr int kU8InW = kU8TW + 2 * kU8R, kU8InH = kU8TH + 2 * kU8R;  // 48 x 64
-constexpr int kU8PitchIn = kU8InW + 1, kU8PitchH = kU8TW + 1;        // in float4 units
-constexpr size_t kU8Smem = ((size_t)kU8InH * kU8PitchIn + (size_t)kU8InH * kU8PitchH) * 16;
+template <int R>
+struct U8Geom {
+    static constexpr int InW = kU8TW + 2 * R, InH = kU8TH + 2 * R;    // 48 x 64 at R = 8
+    static constexpr int PitchIn = InW + 1, PitchH = kU8TW + 1;        // in float4 units
+    static constexpr size_t Smem = ((size_t)InH * PitchIn + (size_t)InH * PitchH) * 16;
+    static_assert(InH <= 64, "pass 1 has 64 thread rows");
+};
 
 struct GaussU8ChainParams {
     unsigned long long ww[kU8R + 1];  // ((float)w[d], (float)w[d]) packed
@@ -343,38 +353,40 @@ __device__ __forceinline__ uint64_t ffma2_rm(uint64_t a, uint64_t b, uint64_t c)
     return d;
 }
 
+template <int R>
 __global__ void __launch_bounds__(256, 2)
 gauss_rgba8_chain_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int width, int height,
                          const __grid_constant__ GaussU8ChainParams gp)
 {
+    using G = U8Geom<R>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *s_in = reinterpret_cast<float4 *>(smem_raw);                 // [64][49]
-    float4 *s_h = s_in + kU8InH * kU8PitchIn;                            // [64][33]
+    float4 *s_in = reinterpret_cast<float4 *>(smem_raw);                 // [InH][InW + 1]
+    float4 *s_h = s_in + G::InH * G::PitchIn;                            // [InH][33]
     const int x0 = blockIdx.x * kU8TW, y0 = blockIdx.y * kU8TH;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr float kM = 8388608.f;  // 2^23
     const uint64_t m2 = ((uint64_t)__float_as_uint(kM) << 32) | __float_as_uint(kM);
 
-    // ---- staging: 64 rows x 48 pixels = 12 per thread, row-major over the threads (a row is 192
-    // contiguous bytes).  All twelve loads are issued before the first conversion.
+    // ---- staging: InH rows x InW pixels, row-major over the threads (a row is contiguous bytes).
+    // All loads are issued before the first conversion.
     {
-        constexpr int PER = kU8InH * kU8InW / 256;
-        static_assert(PER * 256 == kU8InH * kU8InW, "whole pixels per thread");
+        constexpr int N = G::InH * G::InW, PER = (N + 255) / 256;
         uint32_t v[PER];
 #pragma unroll
         for (int u = 0; u < PER; ++u) {
             const int idx = tid + 256 * u;
-            const int r = idx / kU8InW, j = idx - r * kU8InW;
-            const int gy = y0 - kU8R + r, gx = x0 - kU8R + j;
+            const int r = idx / G::InW, j = idx - r * G::InW;
+            const int gy = y0 - R + r, gx = x0 - R + j;
             v[u] = 0;
-            if (gy >= 0 && gy < height && gx >= 0 && gx < width) v[u] = __ldg(in + (size_t)gy * width + gx);
+            if (idx < N && gy >= 0 && gy < height && gx >= 0 && gx < width) v[u] = __ldg(in + (size_t)gy * width + gx);
         }
 #pragma unroll
         for (int u = 0; u < PER; ++u) {
             const int idx = tid + 256 * u;
-            const int r = idx / kU8InW, j = idx - r * kU8InW;
-            s_in[r * kU8PitchIn + j] = make_float4((float)(v[u] & 0xff), (float)((v[u] >> 8) & 0xff),
-                                                   (float)((v[u] >> 16) & 0xff), 0.f);
+            const int r = idx / G::InW, j = idx - r * G::InW;
+            if (idx < N)
+                s_in[r * G::PitchIn + j] = make_float4((float)(v[u] & 0xff), (float)((v[u] >> 8) & 0xff),
+                                                       (float)((v[u] >> 16) & 0xff), 0.f);
         }
     }
     __syncthreads();
@@ -382,29 +394,31 @@ gauss_rgba8_chain_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__
     // ---- pass 1 (rows): thread = (row, run of 8 output pixels)
     {
         const int row = (warp & 1) * 32 + lane, run = warp >> 1;
-        const float4 *src = s_in + row * kU8PitchIn + 8 * run;
-        uint64_t a_lo[8], a_hi[8];
+        if (row < G::InH) {
+            const float4 *src = s_in + row * G::PitchIn + 8 * run;
+            uint64_t a_lo[8], a_hi[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a_lo[i] = a_hi[i] = m2;
+            for (int i = 0; i < 8; ++i) a_lo[i] = a_hi[i] = m2;
 #pragma unroll
-        for (int j = 0; j < 8 + 2 * kU8R; ++j) {
-            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(src + j);
+            for (int j = 0; j < 8 + 2 * R; ++j) {
+                const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(src + j);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int k = j - i - kU8R;  // tap index of input j for output i
-                if (k >= -kU8R && k <= kU8R) {
-                    const uint64_t w = gp.ww[k < 0 ? -k : k];
-                    a_lo[i] = ffma2_rm(v.x, w, a_lo[i]);
-                    a_hi[i] = ffma2_rm(v.y, w, a_hi[i]);
+                for (int i = 0; i < 8; ++i) {
+                    const int k = j - i - R;  // tap index of input j for output i
+                    if (k >= -R && k <= R) {
+                        const uint64_t w = gp.ww[k < 0 ? -k : k];
+                        a_lo[i] = ffma2_rm(v.x, w, a_lo[i]);
+                        a_hi[i] = ffma2_rm(v.y, w, a_hi[i]);
+                    }
                 }
             }
-        }
-        float4 *dst = s_h + row * kU8PitchH + 8 * run;
+            float4 *dst = s_h + row * G::PitchH + 8 * run;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float r = __uint_as_float((uint32_t)a_lo[i]), g = __uint_as_float((uint32_t)(a_lo[i] >> 32));
-            const float b = __uint_as_float((uint32_t)a_hi[i]);
-            dst[i] = make_float4(r - kM, g - kM, b - kM, 0.f);  // exact: integers below 256
+            for (int i = 0; i < 8; ++i) {
+                const float r = __uint_as_float((uint32_t)a_lo[i]), g = __uint_as_float((uint32_t)(a_lo[i] >> 32));
+                const float b = __uint_as_float((uint32_t)a_hi[i]);
+                dst[i] = make_float4(r - kM, g - kM, b - kM, 0.f);  // exact: integers below 256
+            }
         }
     }
     __syncthreads();
@@ -412,17 +426,17 @@ gauss_rgba8_chain_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__
     // ---- pass 2 (columns): thread = (column, run of 6 output rows)
     {
         const int col = lane, run = warp;
-        const float4 *src = s_h + (6 * run) * kU8PitchH + col;
+        const float4 *src = s_h + (6 * run) * G::PitchH + col;
         uint64_t a_lo[6], a_hi[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) a_lo[i] = a_hi[i] = m2;
 #pragma unroll
-        for (int j = 0; j < 6 + 2 * kU8R; ++j) {
-            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(src + j * kU8PitchH);
+        for (int j = 0; j < 6 + 2 * R; ++j) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(src + j * G::PitchH);
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
-                const int k = j - i - kU8R;
-                if (k >= -kU8R && k <= kU8R) {
+                const int k = j - i - R;
+                if (k >= -R && k <= R) {
                     const uint64_t w = gp.ww[k < 0 ? -k : k];
                     a_lo[i] = ffma2_rm(v.x, w, a_lo[i]);
                     a_hi[i] = ffma2_rm(v.y, w, a_hi[i]);
@@ -442,5 +456,11 @@ gauss_rgba8_chain_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__
         }
     }
 }
+
+// (Measured and not kept: the same chain with the three live channels of two pixels packed into
+// three register pairs -- no alpha lane, 1.5 instead of 2 FFMA2 per pixel and tap -- on 64 x 48 tiles,
+// also as a persistent kernel prefetching the next tile: 52-55 us per 4K image against 54 us for the
+// kernel above.  ncu: FMA pipe 44 %, issue 53 %, LSU 52 % -- neither form is bound by the FMA count
+// any more; the tile phases (stage, barrier, rows, barrier, columns) at 16-24 warps per SM are.)
 
 }  // namespace mpk

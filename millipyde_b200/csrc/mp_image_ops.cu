@@ -8,7 +8,9 @@
 // header where the shape or dtype changes, and returns a real MPStatus.
 #include <cmath>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 #include <map>
 #include <mutex>
@@ -812,13 +814,27 @@ MPStatus launch_gaussian(int device, cudaStream_t s, const Img &d, const void *i
             chain_ok = found;
         }
         if (chain_ok) {
-            static bool configured[64] = {};  // the attribute is per device
-            if (device >= 0 && device < 64 && !configured[device]) {
-                cudaFuncSetAttribute(gauss_rgba8_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kU8Smem);
-                configured[device] = true;
-            }
+            // taps with 255 * w < 1 add (int)(byte * w) = 0 for every byte: not evaluated (gaussian_tile.cuh)
+            int r_eff = 1;
+            for (int k = 1; k <= R; ++k)
+                if ((int)(255 * gp.w[k]) >= 1) r_eff = k;
             dim3 cgrid((d.W + kU8TW - 1) / kU8TW, (d.H + kU8TH - 1) / kU8TH);
-            gauss_rgba8_chain_kernel<<<cgrid, 256, kU8Smem, s>>>((const uint32_t *)in, (uint32_t *)out, d.W, d.H, cp);
+            auto go = [&](auto rc) {
+                constexpr int RR = decltype(rc)::value;
+                static std::atomic<bool> configured[64] = {};  // the attribute is per device (and instantiation)
+                if (device >= 0 && device < 64 && !configured[device].load(std::memory_order_acquire)) {
+                    cudaFuncSetAttribute(gauss_rgba8_chain_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)U8Geom<RR>::Smem);
+                    configured[device].store(true, std::memory_order_release);
+                }
+                gauss_rgba8_chain_kernel<RR><<<cgrid, 256, U8Geom<RR>::Smem, s>>>((const uint32_t *)in, (uint32_t *)out,
+                                                                                 d.W, d.H, cp);
+            };
+            if (r_eff <= 3) go(std::integral_constant<int, 3>{});
+            else if (r_eff <= 4) go(std::integral_constant<int, 4>{});
+            else if (r_eff <= 5) go(std::integral_constant<int, 5>{});
+            else if (r_eff <= 6) go(std::integral_constant<int, 6>{});
+            else go(std::integral_constant<int, 8>{});
             count_launch();
             return MILLIPYDE_SUCCESS;
         }

@@ -320,9 +320,11 @@ def test_rgba8_pointwise_bit_exact(capi, charlie_small):
 
 
 def test_rgba8_gaussian_bit_exact(capi, charlie_small):
+    # the sigmas walk through every effective-radius instantiation of the chain kernel (taps whose
+    # (int)(255 * w) is 0 are not evaluated: radius 3 at sigma 1, 5 at sigma 2, all 8 from sigma ~3)
     for a in rgba_inputs(charlie_small):
-        for sigma in [2.0, 1.0]:
-            assert np.array_equal(dev(capi, a).apply("gaussian", sigma).numpy(), rx.gaussian(a, sigma))
+        for sigma in [2.0, 1.0, 0.4, 1.3, 1.6, 2.4, 2.8, 3.5, 9.0]:
+            assert np.array_equal(dev(capi, a).apply("gaussian", sigma).numpy(), rx.gaussian(a, sigma)), sigma
 
 
 def test_rgba8_rotate_nearest(capi, charlie_small):
