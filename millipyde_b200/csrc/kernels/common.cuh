@@ -302,6 +302,12 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, 
         "r"(parity), "r"(sleep_ns)
         : "memory");
 }
+// Either of the two, chosen by a launch parameter (bit 30: suspended try_wait with the hint in the low bits)
+__device__ __forceinline__ void mbar_wait_cfg(uint64_t *bar, uint32_t parity, uint32_t cfg)
+{
+    if (cfg & 0x40000000u) mbar_wait_suspend(bar, parity, cfg & 0x3fffffffu);
+    else mbar_wait_sleep(bar, parity, cfg);
+}
 // global -> shared 1-D bulk copy through the TMA unit; bytes % 16 == 0, both sides 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {

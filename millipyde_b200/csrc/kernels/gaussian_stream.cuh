@@ -49,6 +49,10 @@ struct GaussStreamParams {
     const PwProgram *pw_tab;
     int pw_stride;
     int col_wait;                // COLUMN role's hand-off wait: 0 = probe + nanosleep, 1 = suspended try_wait (A/B switch)
+    // nanoseconds a blocked wait sleeps between probes (tensor-core flavour): [0] a ROW warp waiting for
+    // its TMA row, [1] a ROW warp waiting for the COLUMN warps to hand a ring group back, [2] a COLUMN
+    // warp waiting for a filtered group.  Bit 30 set: a suspended try_wait with that time hint instead.
+    unsigned wait_ns[3];
     float w[16];
     unsigned long long ww[16];   // (w[d], w[d]) packed for fma.rn.f32x2
 };

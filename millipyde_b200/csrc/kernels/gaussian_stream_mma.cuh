@@ -235,7 +235,7 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
             const uint32_t need = item_g0 + (uint32_t)(8 * c + 7) / MmK::rows + 1u;
             while (waited < need) {
                 if (p.col_wait) mbar_wait_suspend(&h_full[waited % MmK::groups], (waited / MmK::groups) & 1u, 1000);
-                else mbar_wait_sleep(&h_full[waited % MmK::groups], (waited / MmK::groups) & 1u, kWsSleepNs);
+                else mbar_wait_cfg(&h_full[waited % MmK::groups], (waited / MmK::groups) & 1u, p.wait_ns[2]);
                 ++waited;
             }
             const float *rp = ring + ring_row * kMmPitch;

@@ -245,7 +245,7 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
                 // the slot consumed in the previous live step is free again: keep the ring full
                 if (next_issue < live_hi) issue_next();
                 const uint32_t slot = takes % K::in_slots;
-                if (MMA) mbar_wait_sleep(&my_full[slot], (takes / K::in_slots) & 1u, kWsSleepNs);
+                if (MMA) mbar_wait_cfg(&my_full[slot], (takes / K::in_slots) & 1u, p.wait_ns[0]);
                 else mbar_wait(&my_full[slot], (takes / K::in_slots) & 1u);
                 ++takes;
                 if (SETS && mis) {
@@ -324,7 +324,7 @@ __device__ __forceinline__ void ws_row_role(const GaussStreamParams &p, const Ga
             }
             // hand-off ring: wait until the COLUMN warps have drained this group slot
             const uint32_t gs = group % K::groups;
-            if (MMA) mbar_wait_sleep(&h_empty[gs], ((group / K::groups) & 1u) ^ 1u, kWsSleepNs);
+            if (MMA) mbar_wait_cfg(&h_empty[gs], ((group / K::groups) & 1u) ^ 1u, p.wait_ns[1]);
             else mbar_wait(&h_empty[gs], ((group / K::groups) & 1u) ^ 1u);
             float *hrow = hbase + (size_t)gs * (K::rows * PITCH);
 #pragma unroll

@@ -198,6 +198,27 @@ grey_f64_kernel(const double *__restrict__ in, double *__restrict__ out, size_t 
 
 // ---------------------------------------------------------------- fp64, H x W
 
+// v ** g in double for the oracle rule (numpy's float64 power; the tests allow 1e-12).  The library
+// pow is ~150 fp64 instructions per sample and B200's fp64 pipe is narrow (a 4K image took 79 us, a
+// quarter of the HBM rate), so the exponents that are a few multiplications or a square root are
+// evaluated as such (correctly rounded steps: within 2 ulp of pow), and any other exponent as
+// exp(g * log v) for v > 0 (relative error <= |g log v| * 2^-52: 1e-14 on image data); only samples
+// that are not positive and finite take the library call, which knows every special case.
+__device__ __forceinline__ double pow64(double v, double g)
+{
+    if (g == 2.0) return v * v;
+    if (g == 1.0) return v;
+    if (g == 0.5 && v >= 0.0) return sqrt(v);
+    if (g == 1.5 && v >= 0.0) return v * sqrt(v);
+    if (g == 3.0) return v * v * v;
+    if (g == 4.0) {
+        const double q = v * v;
+        return q * q;
+    }
+    if (v > 0.0 && v < 1.7e308) return exp(g * log(v));
+    return pow(v, g);
+}
+
 // `float_pow`: reference semantics -- powf on float-converted operands
 // (src/millipyde_image.cpp:447); otherwise pow in double (the test oracle).
 __device__ __forceinline__ double pw64(const PwOp64 &op, double v, bool float_pow)
@@ -205,7 +226,7 @@ __device__ __forceinline__ double pw64(const PwOp64 &op, double v, bool float_po
     if (op.kind == PW_BRIGHTNESS) {
         v = v + op.a;
     } else if (op.kind == PW_GAMMA) {
-        v = float_pow ? op.b * powf(v, op.a) : op.b * pow(v, op.a);
+        v = float_pow ? op.b * powf(v, op.a) : op.b * pow64(v, op.a);
     } else {
         return v;
     }

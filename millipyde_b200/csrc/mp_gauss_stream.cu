@@ -120,6 +120,26 @@ static MPStatus launch_cr(int device, cudaStream_t s, GaussStreamParams &p, cons
 {
     static const int col_wait = [] { const char *e = getenv("MILLIPYDE_GAUSS_COLWAIT"); return e && *e == '1' ? 1 : 0; }();
     p.col_wait = col_wait;
+    // MILLIPYDE_GAUSS_WAIT="a,b,c": sleep between probes of the three blocked waits (kernels/gaussian_stream.cuh:
+    // wait_ns); a value with a leading 's' asks for a suspended try_wait with that hint (A/B measurements)
+    static const struct WaitCfg {
+        unsigned v[3];
+        WaitCfg()
+        {
+            v[0] = v[1] = v[2] = kWsSleepNs;
+            const char *e = getenv("MILLIPYDE_GAUSS_WAIT");
+            for (int i = 0; e && *e && i < 3; ++i) {
+                unsigned flag = 0;
+                if (*e == 's') { flag = 0x40000000u; ++e; }
+                char *end = nullptr;
+                const unsigned long n = strtoul(e, &end, 10);
+                if (end == e) break;
+                v[i] = (unsigned)(n & 0x3fffffffu) | flag;
+                e = *end == ',' ? end + 1 : end;
+            }
+        }
+    } wait_cfg;
+    for (int i = 0; i < 3; ++i) p.wait_ns[i] = wait_cfg.v[i];
     const int sms = sm_count(device) ? sm_count(device) : 148;
     constexpr bool kHasMma = MmGeom<C, R>::NCH <= 4;
     const bool mma = kHasMma && use_mma_column();

@@ -351,6 +351,21 @@ def test_f64_ops_oracle_semantics(capi, charlie_small):
     assert np.array_equal(dev(capi, g).apply("colorize", 2.0, 2.0, 2.0).numpy(), g)   # no-op on grey
 
 
+def test_f64_gamma_every_exponent_form(capi):
+    """pow64 (kernels/pointwise.cuh): multiplication / square-root forms, exp(g log v), and the
+    library pow for zeros -- all against numpy's float64 power (clamped to [0, 1] like the kernel)."""
+    rng = np.random.default_rng(77)
+    g = rng.random((61, 83))
+    g[::7, ::5] = 0.0
+    g[3, 4] = 1.0
+    g[5, 6] = 1e-300
+    for gamma, gain in [(2.0, 1.0), (1.0, 0.9), (0.5, 1.0), (1.5, 1.0), (3.0, 1.0), (4.0, 1.0), (2.2, 1.0),
+                        (0.45, 1.0), (7.3, 1.0), (1.5, 2.5), (0.1, 0.7)]:
+        got = dev(capi, g).apply("adjust_gamma", gamma, gain).numpy()
+        want = np.clip(so.adjust_gamma(g, gamma, gain), 0, 1)
+        assert np.abs(got - want).max() < TOL64, (gamma, gain)
+
+
 def test_f64_ops_reference_semantics(capi, charlie_small):
     g = so.rgb2grey(charlie_small)
     L = capi.lib()
