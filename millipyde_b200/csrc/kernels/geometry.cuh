@@ -411,12 +411,13 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
     // memory, copied to shared memory once per block); everything else is common to the launch
     __shared__ GatherVar s_var;
     __shared__ uint64_t s_bar;
+    __shared__ int s_geo[4];  // the tile's source box (bx0, by0, bw, bh): computed by warp 0 for the block
     if (TAB) {
         for (int i = threadIdx.x; i < (int)(sizeof(GatherVar) / 4); i += blockDim.x)
             reinterpret_cast<int *>(&s_var)[i] = reinterpret_cast<const int *>(g.var_tab + blockIdx.z)[i];
     }
     if (threadIdx.x == 0) {
-        mbar_init(&s_bar, 32);
+        mbar_init(&s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -426,80 +427,110 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
     const float *__restrict__ src = g.in_tab ? g.in_tab[blockIdx.z] : g.in;
     float *__restrict__ dst = g.out_tab ? g.out_tab[blockIdx.z] : g.out;
     const int ox0 = blockIdx.x * kGatherTile, oy0 = blockIdx.y * TH;
-    const int ox1 = min(ox0 + kGatherTile, g.out_w) - 1, oy1 = min(oy0 + TH, g.out_h) - 1;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-
-    // footprint of the tile in the rotate's space (after the post map): both maps are affine, so the
-    // image of the tile is a parallelogram around the image of its centre, and its bounding box has
-    // half-extents |M| * (half-extents of the tile) -- a dozen fp64 operations instead of mapping
-    // the four corners and reducing them
-    const double hx = 0.5 * (ox1 - ox0), hy = 0.5 * (oy1 - oy0);
-    const double pcx = ox0 + hx, pcy = oy0 + hy;
-    const double qcy = g.post.ay * pcy + g.post.by * pcx + g.post.cy;
-    const double qcx = g.post.ax * pcy + g.post.bx * pcx + g.post.cx;
-    const double qhy = abs(g.post.ay) * hy + abs(g.post.by) * hx;
-    const double qhx = abs(g.post.ax) * hy + abs(g.post.bx) * hx;
-    double xc = qcx, yc = qcy, ex = qhx, ey = qhy;
-    if (g.has_rotate) {
-        const double fx = qcx - rp.cx, fy = qcy - rp.cy;
-        xc = rp.c * fx - rp.s * fy + rp.cx;
-        yc = rp.s * fx + rp.c * fy + rp.cy;
-        ex = fabs(rp.c) * qhx + fabs(rp.s) * qhy;
-        ey = fabs(rp.s) * qhx + fabs(rp.c) * qhy;
-    }
-    const double xmin = xc - ex, xmax = xc + ex, ymin = yc - ey, ymax = yc + ey;
-    const int bx0 = __double2int_rd(xmin) - 1, by0 = __double2int_rd(ymin) - 1;
-    const int bw = min(__double2int_ru(xmax) + 2 - bx0, BOX);
-    const int bh = min(__double2int_ru(ymax) + 2 - by0, BOX);
-    const int row_floats = bw * C;
+    // the warp index through a shuffle: the compiler then knows it is warp-uniform
+    const int lane = threadIdx.x & 31, w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
 
     const bool identity_pre = g.pre.ay == 1 && g.pre.by == 0 && g.pre.cy == 0 && g.pre.ax == 0 &&
                               g.pre.bx == 1 && g.pre.cx == 0 && pw_pre.n == 0;
     const bool rows_aligned = ((g.src_w * C) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
-    int shift = 0;  // floats between a staged row's start and box column 0 (same for every row)
     const bool tma = identity_pre && rows_aligned;
-    if (tma) {
-        // ---- TMA staging.  Column arithmetic is per row and in floats, so 32 bits do.
-        const int row_len = g.src_w * C;
+    const int row_len = g.src_w * C;
+
+    // What follows from the box, in integers (every warp evaluates this once it knows the box):
+    //   shift      floats between a staged row's start and box column 0 (same for every row)
+    //   want       staged floats of a row: [0, want)
+    //   col0       image-row float held by box-row float 0
+    //   [c_lo, c_hi)  the part of every box row that exists in the image (multiples of 4)
+    //   [r_lo, r_hi)  the box rows that lie inside the image
+    int bx0, by0, bw, bh, shift = 0, want = 0, col0 = 0, c_lo = 0, c_hi = 0, r_lo = 0, r_hi = 0;
+    bool any = true;
+    auto derive = [&]() {
+        if (!tma) return;
         shift = (bx0 * C) & 3;  // two's complement: right for bx0 < 0 too; row_len % 4 == 0
-        const int want = (shift + row_floats + 3) & ~3;  // staged floats of a row: [0, want)
-        const int col0 = bx0 * C - shift;                // image-row float held by box-row float 0
-        // the part [c_lo, c_hi) of every box row that exists in the image (multiples of 4)
-        const int c_lo = col0 < 0 ? -col0 : 0;
-        const int c_hi = want < row_len - col0 ? want : row_len - col0;
-        // box rows [r_lo, r_hi) lie inside the image
-        const int r_lo = by0 < 0 ? -by0 : 0;
-        const int r_hi = bh < g.rot_h - by0 ? bh : g.rot_h - by0;
-        const bool any = c_hi > c_lo && r_hi > r_lo;
-        if (w == 0) {
-            uint32_t bytes = 0;
-#pragma unroll
-            for (int u = 0; u < (BOX + 31) / 32; ++u) {
-                const int r = lane + 32 * u;
-                if (any && r >= r_lo && r < r_hi) bytes += (uint32_t)(c_hi - c_lo) * 4u;
-            }
-            mbar_expect_tx(&s_bar, bytes);  // arrive + expect: the barrier counts the 32 lanes
-#pragma unroll
-            for (int u = 0; u < (BOX + 31) / 32; ++u) {
-                const int r = lane + 32 * u;
-                if (any && r >= r_lo && r < r_hi)
-                    bulk_g2s(box + r * PITCH + c_lo, src + ((long)(by0 + r) * row_len + col0 + c_lo),
-                             (uint32_t)(c_hi - c_lo) * 4u, &s_bar);
-            }
+        want = (shift + bw * C + 3) & ~3;
+        col0 = bx0 * C - shift;
+        c_lo = col0 < 0 ? -col0 : 0;
+        c_hi = want < row_len - col0 ? want : row_len - col0;
+        r_lo = by0 < 0 ? -by0 : 0;
+        r_hi = bh < g.rot_h - by0 ? bh : g.rot_h - by0;
+        any = c_hi > c_lo && r_hi > r_lo;
+    };
+
+    if (w == 0) {
+        // Footprint of the tile in the rotate's space (after the post map): both maps are affine, so
+        // the image of the tile is a parallelogram around the image of its centre, and its bounding box
+        // has half-extents |M| * (half-extents of the tile) -- a dozen fp64 operations instead of
+        // mapping the four corners and reducing them.  One warp does it for the block (the kernel is
+        // issue-bound: eight warps repeating it were an eighth of its instructions).
+        const int ox1 = min(ox0 + kGatherTile, g.out_w) - 1, oy1 = min(oy0 + TH, g.out_h) - 1;
+        const double hx = 0.5 * (ox1 - ox0), hy = 0.5 * (oy1 - oy0);
+        const double pcx = ox0 + hx, pcy = oy0 + hy;
+        const double qcy = g.post.ay * pcy + g.post.by * pcx + g.post.cy;
+        const double qcx = g.post.ax * pcy + g.post.bx * pcx + g.post.cx;
+        const double qhy = abs(g.post.ay) * hy + abs(g.post.by) * hx;
+        const double qhx = abs(g.post.ax) * hy + abs(g.post.bx) * hx;
+        double xc = qcx, yc = qcy, ex = qhx, ey = qhy;
+        if (g.has_rotate) {
+            const double fx = qcx - rp.cx, fy = qcy - rp.cy;
+            xc = rp.c * fx - rp.s * fy + rp.cx;
+            yc = rp.s * fx + rp.c * fy + rp.cy;
+            ex = fabs(rp.c) * qhx + fabs(rp.s) * qhy;
+            ey = fabs(rp.s) * qhx + fabs(rp.c) * qhy;
         }
-        // tiles whose box leaves the image zero what the copies do not cover
-        if (!any || c_lo > 0 || c_hi < want || r_lo > 0 || r_hi < bh) {
+        const double xmin = xc - ex, xmax = xc + ex, ymin = yc - ey, ymax = yc + ey;
+        bx0 = __double2int_rd(xmin) - 1;
+        by0 = __double2int_rd(ymin) - 1;
+        bw = min(__double2int_ru(xmax) + 2 - bx0, BOX);
+        bh = min(__double2int_ru(ymax) + 2 - by0, BOX);
+        if (lane == 0) {
+            s_geo[0] = bx0;
+            s_geo[1] = by0;
+            s_geo[2] = bw;
+            s_geo[3] = bh;
+        }
+        derive();
+        if (tma && any && lane == 0) {
+            // ---- TMA staging: one 1-D bulk copy per box row that lies in the image, all on one
+            // mbarrier; one lane issues them from uniform registers (per-lane addresses cost an
+            // election loop per copy)
+            const uint32_t row_bytes = (uint32_t)(c_hi - c_lo) * 4u;
+            mbar_expect_tx(&s_bar, row_bytes * (uint32_t)(r_hi - r_lo));
+            const float *gsrc = src + ((long)(by0 + r_lo) * row_len + col0 + c_lo);
+            float *bdst = box + r_lo * PITCH + c_lo;
+            for (int r = r_lo; r < r_hi; ++r, gsrc += row_len, bdst += PITCH) bulk_g2s(bdst, gsrc, row_bytes, &s_bar);
+        }
+    }
+    __syncthreads();  // the box is known to every warp
+    if (w != 0) {
+        bx0 = s_geo[0];
+        by0 = s_geo[1];
+        bw = s_geo[2];
+        bh = s_geo[3];
+        derive();
+    }
+    // a tile whose box misses the image: every corner of every sample is the rotate's cval
+    const bool all_zero = tma && !any;
+
+    if (tma) {
+        // tiles whose box leaves the image zero what the copies do not cover: whole rows outside
+        // [r_lo, r_hi), and the ends [0, c_lo) and [c_hi, want) of the rows inside
+        if (any && (c_lo > 0 || c_hi < want || r_lo > 0 || r_hi < bh)) {
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int r = w; r < bh; r += 8) {
-                float *brow = box + r * PITCH;
-                const bool row_in = any && r >= r_lo && r < r_hi;
-                for (int c = lane; c < want; c += 32)
-                    if (!row_in || c < c_lo || c >= c_hi) brow[c] = 0.f;
+                float4 *brow = reinterpret_cast<float4 *>(box + r * PITCH);
+                if (r < r_lo || r >= r_hi) {
+                    for (int v = lane; v < (want >> 2); v += 32) brow[v] = zero4;
+                } else {
+                    for (int v = lane; v < (c_lo >> 2); v += 32) brow[v] = zero4;
+                    for (int v = (c_hi >> 2) + lane; v < (want >> 2); v += 32) brow[v] = zero4;
+                }
             }
         }
     } else {
         // ---- scalar staging through the pre map (and the pre-rotate pointwise ops)
         constexpr int PER_LANE = (BOX * C + 31) / 32;
         const bool has_pre = pw_pre.n > 0;
+        const int row_floats = bw * C;
         for (int r = w; r < bh; r += 8) {
             const int cy = by0 + r;
             const bool row_in = cy >= 0 && cy < g.rot_h;
@@ -525,11 +556,17 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
             }
         }
     }
-    // (the TMA path waits for its copies after the coordinate set-up below)
-    if (!tma) __syncthreads();
 
+    if (!all_zero) {
+        // only the issuing warp polls the mbarrier; the others park at the CTA barrier, which costs no
+        // issue slots (all 8 warps polling was 24 % of the kernel's instructions: 244 M probes per launch)
+        if (tma && w == 0) mbar_wait_suspend(&s_bar, 0, 2000);
+        __syncthreads();  // the copies have landed (warp 0 saw them) and so has every warp's staging / zero fill
+    }
     const int x = ox0 + lane;
-    // output pixel (x, y): q = post(x, y); stepping y by 8 moves q by 8 * (post.ay, post.ax)
+    if (x >= g.out_w) return;
+    // output pixel (x, y): q = post(x, y); stepping y by 8 moves q by 8 * (post.ay, post.ax).  (Set up
+    // after the barrier: held across it, the four fp64 values cost the 40-register budget spills.)
     const int y_first = oy0 + w;
     const int qy = g.post.ay * y_first + g.post.by * x + g.post.cy;
     const int qx = g.post.ax * y_first + g.post.bx * x + g.post.cx;
@@ -542,44 +579,47 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
         dxs = rp.c * dqx - rp.s * dqy;
         dys = rp.s * dqx + rp.c * dqy;
     }
-    if (tma) {
-        // only the issuing warp polls the mbarrier; the others park at the CTA barrier, which costs no
-        // issue slots (all 8 warps polling was 24 % of the kernel's instructions: 244 M probes per launch)
-        if (w == 0) mbar_wait_suspend(&s_bar, 0, 2000);
-        __syncthreads();  // the copies have landed (warp 0 saw them) and so has the zero fill of edge tiles
-    }
-    if (x >= g.out_w) return;
+    // pixels of this thread that exist: rows y_first + 8 k below the bottom edge
+    const int n_live = y_first < g.out_h ? min(NPX, (g.out_h - y_first + 7) >> 3) : 0;
     const float *origin = box + shift - by0 * PITCH - bx0 * C;  // box address of source pixel (0, 0)
     float acc[NPX * C];
 #pragma unroll
-    for (int k = 0; k < NPX; ++k) {
-        if (y_first + 8 * k >= g.out_h) {  // past the bottom edge: its footprint is not in the box
+    for (int i = 0; i < NPX * C; ++i) acc[i] = 0.f;
+    if (all_zero) {
+        // nothing staged, nothing to read
+    } else if (g.has_rotate) {
 #pragma unroll
-            for (int c = 0; c < C; ++c) acc[k * C + c] = 0.f;
-        } else if (g.has_rotate) {
-            // recomputing from k keeps every row one rounding away from the direct formula
-            const double xk = xs + k * dxs, yk = ys + k * dys;
-            const int ix = __double2int_rd(xk), iy = __double2int_rd(yk);
-            const float dx = (float)(xk - (double)ix), dy = (float)(yk - (double)iy);
-            const float *c00 = origin + iy * PITCH + ix * C;
+        for (int k = 0; k < NPX; ++k) {
+            if (k < n_live) {
+                // recomputing from k keeps every row one rounding away from the direct formula
+                const double xk = xs + k * dxs, yk = ys + k * dys;
+                const int ix = __double2int_rd(xk), iy = __double2int_rd(yk);
+                const float dx = (float)(xk - (double)ix), dy = (float)(yk - (double)iy);
+                const float *c00 = origin + iy * PITCH + ix * C;
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float top = (1.f - dx) * c00[c] + dx * c00[C + c];
-                const float bot = (1.f - dx) * c00[PITCH + c] + dx * c00[PITCH + C + c];
-                acc[k * C + c] = (1.f - dy) * top + dy * bot;
+                for (int c = 0; c < C; ++c) {
+                    const float top = (1.f - dx) * c00[c] + dx * c00[C + c];
+                    const float bot = (1.f - dx) * c00[PITCH + c] + dx * c00[PITCH + C + c];
+                    acc[k * C + c] = (1.f - dy) * top + dy * bot;
+                }
             }
-        } else {
-            const float *c00 = origin + (qy + k * dqy) * PITCH + (qx + k * dqx) * C;
+        }
+    } else {
 #pragma unroll
-            for (int c = 0; c < C; ++c) acc[k * C + c] = c00[c];
+        for (int k = 0; k < NPX; ++k) {
+            if (k < n_live) {
+                const float *c00 = origin + (qy + k * dqy) * PITCH + (qx + k * dqx) * C;
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[k * C + c] = c00[c];
+            }
         }
     }
     pw_apply_tile<C, NPX * C>(pw_post, acc, 0);
+    float *o = dst + ((size_t)y_first * g.out_w + x) * C;
+    const size_t ostep = (size_t)8 * g.out_w * C;
 #pragma unroll
-    for (int k = 0; k < NPX; ++k) {
-        const int y = y_first + 8 * k;
-        if (y < g.out_h) {
-            float *o = dst + ((size_t)y * g.out_w + x) * C;
+    for (int k = 0; k < NPX; ++k, o += ostep) {
+        if (k < n_live) {
 #pragma unroll
             for (int c = 0; c < C; ++c) o[c] = acc[k * C + c];
         }
