@@ -316,6 +316,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
+// the same with both shared-memory operands already 32-bit shared addresses (issue loops step them)
+__device__ __forceinline__ void bulk_g2s_raw(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar_smem)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar_smem)
+                 : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -488,17 +488,6 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
             s_geo[2] = bw;
             s_geo[3] = bh;
         }
-        derive();
-        if (tma && any && lane == 0) {
-            // ---- TMA staging: one 1-D bulk copy per box row that lies in the image, all on one
-            // mbarrier; one lane issues them from uniform registers (per-lane addresses cost an
-            // election loop per copy)
-            const uint32_t row_bytes = (uint32_t)(c_hi - c_lo) * 4u;
-            mbar_expect_tx(&s_bar, row_bytes * (uint32_t)(r_hi - r_lo));
-            const float *gsrc = src + ((long)(by0 + r_lo) * row_len + col0 + c_lo);
-            float *bdst = box + r_lo * PITCH + c_lo;
-            for (int r = r_lo; r < r_hi; ++r, gsrc += row_len, bdst += PITCH) bulk_g2s(bdst, gsrc, row_bytes, &s_bar);
-        }
     }
     __syncthreads();  // the box is known to every warp
     if (w != 0) {
@@ -506,7 +495,22 @@ gather_f32_kernel(const __grid_constant__ GatherParams g)
         by0 = s_geo[1];
         bw = s_geo[2];
         bh = s_geo[3];
-        derive();
+    }
+    derive();
+    if (tma && any && lane == 0) {
+        // ---- TMA staging: one 1-D bulk copy per box row that lies in the image, all on one mbarrier.
+        // Lane 0 of warp w issues rows r_lo + w, + 8, ... from uniform registers: eight warps issue
+        // side by side (one warp issuing ~50 copies one after the other took longer than the copies
+        // themselves), and per-lane addresses would cost an election loop per copy.  Warp 0 posts the
+        // byte count; a copy that completes before that only drives the count negative meanwhile.
+        const uint32_t row_bytes = (uint32_t)(c_hi - c_lo) * 4u;
+        if (w == 0) mbar_expect_tx(&s_bar, row_bytes * (uint32_t)(r_hi - r_lo));
+        const uint32_t bar32 = smem_addr(&s_bar);
+        uint32_t sdst = smem_addr(box) + (uint32_t)((r_lo + w) * PITCH + c_lo) * 4u;
+        const float *gsrc = src + ((long)(by0 + r_lo + w) * row_len + col0 + c_lo);
+        const long gstep = 8l * row_len;
+        const uint32_t sstep = 8u * (uint32_t)PITCH * 4u;
+        for (int r = r_lo + w; r < r_hi; r += 8, gsrc += gstep, sdst += sstep) bulk_g2s_raw(sdst, gsrc, row_bytes, bar32);
     }
     // a tile whose box misses the image: every corner of every sample is the rotate's cval
     const bool all_zero = tma && !any;
