@@ -72,13 +72,22 @@ transpose_tma_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid < 32) {
-        const uint32_t row_bytes = (uint32_t)tw * K * 4u;
-        if (tid == 0) mbar_expect_tx(&bar, row_bytes * (uint32_t)th);
-        __syncwarp();
-        for (int y = tid; y < th; y += 32)
-            bulk_g2s(tile + y * P, in + ((size_t)(y0 + y) * width + x0) * K, row_bytes, &bar);
-        if (tid == 0) mbar_wait(&bar, 0);   // one poller; the other warps park at the barrier below
+    {
+        // Lane 0 of warp w issues rows w, w + 8, ... from uniform registers: the eight warps issue side by
+        // side (one warp issuing all the copies of a tile serially took longer than the copies), and
+        // per-lane addresses would cost an election loop per copy.  Thread 0 posts the byte count; a
+        // copy that completes before that only drives the count negative meanwhile.
+        const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);
+        if ((tid & 31) == 0) {
+            const uint32_t row_bytes = (uint32_t)tw * K * 4u;
+            if (w == 0) mbar_expect_tx(&bar, row_bytes * (uint32_t)th);
+            const uint32_t bar32 = smem_addr(&bar);
+            uint32_t sdst = smem_addr(tile) + (uint32_t)(w * P) * 4u;
+            const uint32_t *gsrc = in + ((size_t)(y0 + w) * width + x0) * K;
+            const size_t gstep = (size_t)8 * width * K;
+            for (int y = w; y < th; y += 8, gsrc += gstep, sdst += 8u * P * 4u) bulk_g2s_raw(sdst, gsrc, row_bytes, bar32);
+            if (w == 0) mbar_wait(&bar, 0);   // one poller; the other warps park at the barrier below
+        }
     }
     __syncthreads();
     // output row (x0 + r) holds pixels y0 .. y0+th-1: th*K words, written as th*K/4 vectors
@@ -131,14 +140,19 @@ transpose_tma64_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ o
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid < 32) {
-        const uint32_t row_bytes = (uint32_t)tw * K * 4u;
-        if (tid == 0) mbar_expect_tx(&bar, row_bytes * (uint32_t)th);
-        __syncwarp();
-        for (int y = tid; y < th; y += 32)
-            bulk_g2s(tile + y * kT64Pitch + 4 * ((y >> S) & 7), in + ((size_t)(y0 + y) * width + x0) * K, row_bytes,
-                     &bar);
-        if (tid == 0) mbar_wait(&bar, 0);   // one poller; the other warps park at the barrier below
+    {
+        // lane 0 of warp w issues rows w, w + 8, ... (see transpose_tma_kernel)
+        const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);
+        if ((tid & 31) == 0) {
+            const uint32_t row_bytes = (uint32_t)tw * K * 4u;
+            if (w == 0) mbar_expect_tx(&bar, row_bytes * (uint32_t)th);
+            const uint32_t bar32 = smem_addr(&bar), tile32 = smem_addr(tile);
+            const uint32_t *gsrc = in + ((size_t)(y0 + w) * width + x0) * K;
+            const size_t gstep = (size_t)8 * width * K;
+            for (int y = w; y < th; y += 8, gsrc += gstep)
+                bulk_g2s_raw(tile32 + (uint32_t)(y * kT64Pitch + 4 * ((y >> S) & 7)) * 4u, gsrc, row_bytes, bar32);
+            if (w == 0) mbar_wait(&bar, 0);   // one poller; the other warps park at the barrier below
+        }
     }
     __syncthreads();
     // output row (x0 + r) holds pixels y0 .. y0+th-1 = th * K / 4 vectors; a warp handles 8 vectors of 4 rows
