@@ -312,6 +312,173 @@ rotate_nearest_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
     }
 }
 
+// ------------------------------------------- rotate through a staged box (reference layouts)
+// The same two rules -- the reference's nearest rule (RGBA8 words; fp64 greyscale under reference
+// semantics as two words) and the oracle's bilinear rule on fp64 greyscale -- with the source
+// footprint of a 32 x 64 (one-word pixels) or 32 x 32 (two-word pixels) output tile staged in shared
+// memory by 1-D TMA bulk copies, one per box row, issued by lane 0 of all eight warps side by side:
+// the direct kernels above walk a rotated line across ~18 cache lines per warp load.  (A first box
+// version staged with per-thread loads and one issuing warp and was slower than the direct form.)
+// Coordinates are evaluated per pixel by exactly the expressions of the direct kernels, so the
+// results are the same bits; the box only changes where the sample is read from, and a coordinate
+// the box does not hold -- it cannot happen with the margins below, but exactness must not depend
+// on that -- is read from global memory.  Needs 16-byte-aligned rows ((W * K) % 4 == 0).
+template <int K>
+struct RotBoxGeom {
+    static constexpr int TH = K == 1 ? 64 : 32;
+    static constexpr int BOX = K == 1 ? 78 : 52;   // tile diagonal (70.2 / 43.9) + 2 + 2 margin + rounding
+    static constexpr int PITCH = (BOX * K + 3 + 3) / 4 * 4 + 4;   // words; + 4: rows spread over the banks
+    static constexpr size_t SMEM = (size_t)BOX * PITCH * 4;
+};
+
+template <int K, bool BILINEAR>
+__global__ void __launch_bounds__(256)
+rotate_box_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int width, int height, double angle,
+                  RotateParams rp)
+{
+    using G = RotBoxGeom<K>;
+    static_assert(!BILINEAR || K == 2, "bilinear: fp64 greyscale");
+    constexpr int PITCH = G::PITCH, BOX = G::BOX, NPX = G::TH / 8;
+    extern __shared__ __align__(16) uint32_t rbox[];
+    __shared__ uint64_t s_bar;
+    __shared__ double s_cs[2];
+    __shared__ int s_geo[4];
+    const int lane = threadIdx.x & 31, w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (!BILINEAR) {   // the device's own fp64 routines, as the reference's kernel evaluates them
+            s_cs[0] = cos(angle);
+            s_cs[1] = sin(angle);
+        }
+    }
+    __syncthreads();
+    const double ca = BILINEAR ? rp.c : s_cs[0], sa = BILINEAR ? rp.s : s_cs[1];
+    const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * G::TH;
+    if (w == 0) {
+        // the map is affine: the footprint's extremes are at the tile's corners
+        const double cx = BILINEAR ? rp.cx : (double)width / 2, cy = BILINEAR ? rp.cy : (double)height / 2;
+        const int ox1 = min(ox0 + 32, width) - 1, oy1 = min(oy0 + G::TH, height) - 1;
+        double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double fx = (double)((q & 1) ? ox1 : ox0) - cx, fy = (double)((q & 2) ? oy1 : oy0) - cy;
+            const double xr = fx * ca - fy * sa + cx, yr = fx * sa + fy * ca + cy;
+            xmin = fmin(xmin, xr);
+            xmax = fmax(xmax, xr);
+            ymin = fmin(ymin, yr);
+            ymax = fmax(ymax, yr);
+        }
+        const int bx0 = __double2int_rd(xmin) - 2, by0 = __double2int_rd(ymin) - 2;
+        if (lane == 0) {
+            s_geo[0] = bx0;
+            s_geo[1] = by0;
+            s_geo[2] = min(__double2int_ru(xmax) + 3 - bx0, BOX);
+            s_geo[3] = min(__double2int_ru(ymax) + 3 - by0, BOX);
+        }
+    }
+    __syncthreads();
+    const int bx0 = s_geo[0], by0 = s_geo[1], bw = s_geo[2], bh = s_geo[3];
+    // staged words of a row: [0, want); the part [c_lo, c_hi) of every box row and the box rows
+    // [r_lo, r_hi) exist in the image (see gather_f32_kernel)
+    const int row_len = width * K;
+    const int shift = (bx0 * K) & 3;
+    const int want = (shift + bw * K + 3) & ~3;
+    const int col0 = bx0 * K - shift;
+    const int c_lo = col0 < 0 ? -col0 : 0;
+    const int c_hi = want < row_len - col0 ? want : row_len - col0;
+    const int r_lo = by0 < 0 ? -by0 : 0;
+    const int r_hi = bh < height - by0 ? bh : height - by0;
+    const bool any = c_hi > c_lo && r_hi > r_lo;
+    if (any && lane == 0) {
+        const uint32_t row_bytes = (uint32_t)(c_hi - c_lo) * 4u;
+        if (w == 0) mbar_expect_tx(&s_bar, row_bytes * (uint32_t)(r_hi - r_lo));
+        const uint32_t bar32 = smem_addr(&s_bar);
+        uint32_t sdst = smem_addr(rbox) + (uint32_t)((r_lo + w) * PITCH + c_lo) * 4u;
+        const uint32_t *gsrc = in + ((long)(by0 + r_lo + w) * row_len + col0 + c_lo);
+        for (int r = r_lo + w; r < r_hi; r += 8, gsrc += 8l * row_len, sdst += 8u * PITCH * 4u)
+            bulk_g2s_raw(sdst, gsrc, row_bytes, bar32);
+    }
+    if (any && (c_lo > 0 || c_hi < want || r_lo > 0 || r_hi < bh)) {
+        const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+        for (int r = w; r < bh; r += 8) {
+            uint4 *brow = reinterpret_cast<uint4 *>(rbox + r * PITCH);
+            if (r < r_lo || r >= r_hi) {
+                for (int v = lane; v < (want >> 2); v += 32) brow[v] = zero4;
+            } else {
+                for (int v = lane; v < (c_lo >> 2); v += 32) brow[v] = zero4;
+                for (int v = (c_hi >> 2) + lane; v < (want >> 2); v += 32) brow[v] = zero4;
+            }
+        }
+    }
+    if (any) {
+        if (w == 0) mbar_wait_suspend(&s_bar, 0, 2000);
+        __syncthreads();
+    }
+    const int x = ox0 + lane;
+    if (x >= width) return;
+    const uint32_t *origin = rbox + shift - by0 * PITCH - bx0 * K;   // box address of source pixel (0, 0)
+    const int bx1 = bx0 + bw, by1 = by0 + bh;
+#pragma unroll
+    for (int k = 0; k < NPX; ++k) {
+        const int y = oy0 + w + 8 * k;
+        if (y >= height) break;
+        uint32_t *o = out + ((size_t)y * width + x) * K;
+        if (!BILINEAR) {
+            // src/millipyde_image.cpp:114-139, the expressions of rotate_nearest_kernel
+            int x_rot = ((double)x - ((double)width / 2)) * ca -
+                        ((double)y - ((double)height / 2)) * sa + ((double)width / 2);
+            int y_rot = ((double)x - ((double)width / 2)) * sa +
+                        ((double)y - ((double)height / 2)) * ca + ((double)height / 2);
+            uint32_t v[K];
+#pragma unroll
+            for (int c = 0; c < K; ++c) v[c] = 0u;
+            if (x_rot >= 0 && x_rot < width && y_rot >= 0 && y_rot < height) {
+                if (any && x_rot >= bx0 && x_rot < bx1 && y_rot >= by0 && y_rot < by1) {
+                    const uint32_t *p = origin + y_rot * PITCH + x_rot * K;
+#pragma unroll
+                    for (int c = 0; c < K; ++c) v[c] = p[c];
+                } else {
+                    const uint32_t *p = in + ((size_t)y_rot * width + x_rot) * K;
+#pragma unroll
+                    for (int c = 0; c < K; ++c) v[c] = __ldg(p + c);
+                }
+            }
+            if (K == 2) *reinterpret_cast<uint2 *>(o) = make_uint2(v[0], v[K - 1]);
+            else o[0] = v[0];
+        } else {
+            // the expressions of rotate_bilinear_kernel<double, 1>
+            const double fx = (double)x - rp.cx, fy = (double)y - rp.cy;
+            const double xs = rp.c * fx - rp.s * fy + rp.cx;
+            const double ys = rp.s * fx + rp.c * fy + rp.cy;
+            const int x0 = __double2int_rd(xs), y0 = __double2int_rd(ys);
+            const double dx = xs - (double)x0, dy = ys - (double)y0;
+            const int x1 = x0 + (dx > 0.0), y1 = y0 + (dy > 0.0);
+            double p00, p01, p10, p11;
+            if (any && x0 >= bx0 && x1 < bx1 && y0 >= by0 && y1 < by1) {
+                // outside-image corners are staged as zeros: the rule's cval
+                const double *b = reinterpret_cast<const double *>(origin);
+                constexpr int DP = PITCH / 2;
+                p00 = b[y0 * DP + x0];
+                p01 = b[y0 * DP + x1];
+                p10 = b[y1 * DP + x0];
+                p11 = b[y1 * DP + x1];
+            } else {
+                const double *src = reinterpret_cast<const double *>(in);
+                const bool in_x0 = x0 >= 0 && x0 < width, in_x1 = x1 >= 0 && x1 < width;
+                const bool in_y0 = y0 >= 0 && y0 < height, in_y1 = y1 >= 0 && y1 < height;
+                p00 = (in_y0 && in_x0) ? __ldg(src + (size_t)y0 * width + x0) : 0.0;
+                p01 = (in_y0 && in_x1) ? __ldg(src + (size_t)y0 * width + x1) : 0.0;
+                p10 = (in_y1 && in_x0) ? __ldg(src + (size_t)y1 * width + x0) : 0.0;
+                p11 = (in_y1 && in_x1) ? __ldg(src + (size_t)y1 * width + x1) : 0.0;
+            }
+            const double top = (1.0 - dx) * p00 + dx * p01;
+            const double bot = (1.0 - dx) * p10 + dx * p11;
+            *reinterpret_cast<double *>(o) = (1.0 - dy) * top + dy * bot;
+        }
+    }
+}
+
 // ----------------------------------------------------------- rotate, bilinear
 // skimage.transform.rotate defaults (order=1, mode='constant', cval=0, centre
 // (W/2-0.5, H/2-0.5)).  Source coordinates in fp64 (fp32 would carry ~2.4e-4 px

@@ -365,18 +365,35 @@ MPStatus mpimg_rotate(MPObjData *obj, void *args)
     if ((st = fresh(obj, s, obj->nbytes, &out)) != MILLIPYDE_SUCCESS) return st;
 
     const bool nearest = d.fam == mp::FAM_RGBA8 || (d.fam == mp::FAM_F64 && semantics() == MP_SEMANTICS_REFERENCE);
+    // reference layouts: through a staged box when the rows are TMA-copyable (16-byte aligned), else the direct kernels
+    const int K = d.fam == mp::FAM_RGBA8 ? 1 : 2;
+    const bool box_ok = d.fam != mp::FAM_F32 && ((size_t)d.W * K) % 4 == 0 &&
+                        (reinterpret_cast<uintptr_t>(obj->device_data) & 15) == 0;
     if (nearest) {
         const double rad = angle * 0.01745329252;  // src/millipyde_image.cpp:702
-        // (a shared-memory box like the fp32 gather's was measured here too: 61 us per 4K RGBA8 image
-        // against 41 us for the direct form -- one word per pixel does not pay for the staging)
-        dim3 block(32, 8), grid((d.W + 31) / 32, (d.H + 7) / 8);
-        if (d.fam == mp::FAM_RGBA8)
-            rotate_nearest_kernel<1><<<grid, block, 0, s>>>((const uint32_t *)obj->device_data, (uint32_t *)out, d.W, d.H, rad);
-        else
-            rotate_nearest_kernel<2><<<grid, block, 0, s>>>((const uint32_t *)obj->device_data, (uint32_t *)out, d.W, d.H, rad);
+        RotateParams none = {};
+        if (box_ok && K == 1) {
+            dim3 grid((d.W + 31) / 32, (d.H + RotBoxGeom<1>::TH - 1) / RotBoxGeom<1>::TH);
+            rotate_box_kernel<1, false><<<grid, 256, RotBoxGeom<1>::SMEM, s>>>((const uint32_t *)obj->device_data,
+                                                                               (uint32_t *)out, d.W, d.H, rad, none);
+        } else if (box_ok) {
+            dim3 grid((d.W + 31) / 32, (d.H + RotBoxGeom<2>::TH - 1) / RotBoxGeom<2>::TH);
+            rotate_box_kernel<2, false><<<grid, 256, RotBoxGeom<2>::SMEM, s>>>((const uint32_t *)obj->device_data,
+                                                                               (uint32_t *)out, d.W, d.H, rad, none);
+        } else {
+            dim3 block(32, 8), grid((d.W + 31) / 32, (d.H + 7) / 8);
+            if (d.fam == mp::FAM_RGBA8)
+                rotate_nearest_kernel<1><<<grid, block, 0, s>>>((const uint32_t *)obj->device_data, (uint32_t *)out, d.W, d.H, rad);
+            else
+                rotate_nearest_kernel<2><<<grid, block, 0, s>>>((const uint32_t *)obj->device_data, (uint32_t *)out, d.W, d.H, rad);
+        }
     } else {
         RotateParams rp = mp::rotate_params(d.W, d.H, angle);
-        if (d.fam == mp::FAM_F64) {
+        if (d.fam == mp::FAM_F64 && box_ok) {
+            dim3 grid((d.W + 31) / 32, (d.H + RotBoxGeom<2>::TH - 1) / RotBoxGeom<2>::TH);
+            rotate_box_kernel<2, true><<<grid, 256, RotBoxGeom<2>::SMEM, s>>>((const uint32_t *)obj->device_data,
+                                                                              (uint32_t *)out, d.W, d.H, 0.0, rp);
+        } else if (d.fam == mp::FAM_F64) {
             dim3 grid((d.W + 31) / 32, (d.H + 7) / 8);
             rotate_bilinear_kernel<double, 1><<<grid, 256, 0, s>>>((const double *)obj->device_data, (double *)out, d.W, d.H, rp);
         } else {

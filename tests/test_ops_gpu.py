@@ -338,6 +338,29 @@ def test_rgba8_rotate_nearest(capi, charlie_small):
             assert frac < 1e-4, (angle, frac)
 
 
+def test_reference_layout_rotates_through_the_staged_box(capi):
+    """rotate_box_kernel (kernels/geometry.cuh): rows that are whole 16-byte vectors take the box-staged
+    kernels, other widths the direct ones; both must give the rule's result -- nearest (RGBA8, and fp64
+    under reference semantics) against the C restatement of the reference kernel, bilinear fp64 against
+    the oracle -- on shapes with ragged tile edges and at angles whose footprint leaves the image."""
+    L = capi.lib()
+    for h, w in [(200, 256), (131, 100), (64, 36), (97, 131), (300, 260)]:
+        a = synth.rgba8(h, w, 3000 + h)
+        g = np.random.default_rng(h * 7 + w).random((h, w))
+        for angle in [30.0, 45.0, 10.0, 90.0, 133.0, -75.0, 0.0, 180.0]:
+            got = dev(capi, a).apply("rotate", angle).numpy()
+            frac = np.mean(np.any(got != rx.rotate(a, angle), axis=-1))
+            assert frac < 2e-3, ("rgba8", h, w, angle, frac)   # device vs glibc sin / cos: a coordinate an ulp from an integer
+            got = dev(capi, g).apply("rotate", angle).numpy()
+            assert np.abs(got - so.rotate(g, angle)).max() < 1e-9, ("f64 bilinear", h, w, angle)
+            L.mpimg_set_semantics(capi.SEMANTICS_REFERENCE)
+            try:
+                got = dev(capi, g).apply("rotate", angle).numpy()
+            finally:
+                L.mpimg_set_semantics(capi.SEMANTICS_ORACLE)
+            assert np.mean(got != rx.rotate(g, angle)) < 2e-3, ("f64 nearest", h, w, angle)
+
+
 # ------------------------------------------------------------- fp64 greyscale
 def test_f64_ops_oracle_semantics(capi, charlie_small):
     g = so.rgb2grey(charlie_small)
