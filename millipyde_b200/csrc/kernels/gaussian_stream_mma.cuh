@@ -233,7 +233,7 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
 
         for (int c = 0; c < n_chunks8; ++c) {
             const uint32_t need = item_g0 + (uint32_t)(8 * c + 7) / MmK::rows + 1u;
-            while (waited < need) {
+            if (waited < need) {   // the chunk's last row completes at most one more 12-row group
                 if (p.col_wait) mbar_wait_suspend(&h_full[waited % MmK::groups], (waited / MmK::groups) & 1u, 1000);
                 else mbar_wait_cfg(&h_full[waited % MmK::groups], (waited / MmK::groups) & 1u, p.wait_ns[2]);
                 ++waited;
@@ -322,7 +322,7 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
                 // rows that are not whole vectors: their starts are not 16-byte aligned, so no bulk
                 // stores -- the staged block leaves as scalar stores, a row per 80 lanes' worth
                 if (lane == 0)
-                    while (released < done) mbar_arrive(&h_empty[released++ % MmK::groups]);
+                    if (released < done) mbar_arrive(&h_empty[released % MmK::groups]);   // 8 rows of 12-row groups: at most one per chunk
                 if (cols > 0) {
 #pragma unroll 1
                     for (int r = 0; r < 8; ++r) {
@@ -334,7 +334,7 @@ __device__ __forceinline__ void mm_body(const GaussStreamParams &p, const GaussW
                 }
                 __syncwarp();   // the staging rows are free again
             } else if (lane == 0) {
-                while (released < done) mbar_arrive(&h_empty[released++ % MmK::groups]);
+                if (released < done) mbar_arrive(&h_empty[released % MmK::groups]);   // 8 rows of 12-row groups: at most one per chunk
                 if (cols > 0) {
                     const uint32_t bytes = (uint32_t)cols * 4u;
                     if (ob >= 0 && ob + 8 <= (int)n_valid) {   // the whole block is inside the item
