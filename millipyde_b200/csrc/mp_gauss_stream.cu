@@ -3,7 +3,7 @@
 // Radius buckets: the kernel is fully unrolled over the taps, so it is
 // instantiated for a few radii and a request uses the smallest bucket that
 // holds its effective radius (weights beyond the radius are zero).  sigma = 2
-// (effective radius 11) lands exactly on a bucket.
+// (effective radius 10) lands exactly on a bucket.
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -19,7 +19,7 @@ using namespace mpk;
 
 namespace mp {
 
-static const int kBuckets[] = {3, 5, 7, 9, 11, 13};
+static const int kBuckets[] = {3, 5, 7, 9, 10, 11, 13};
 
 static int bucket_for(int radius)
 {
@@ -187,6 +187,7 @@ static MPStatus launch_c(int device, cudaStream_t s, GaussStreamParams &p, int b
         case 5: return launch_cr<C, 5>(device, s, p, sets);
         case 7: return launch_cr<C, 7>(device, s, p, sets);
         case 9: return launch_cr<C, 9>(device, s, p, sets);
+        case 10: return launch_cr<C, 10>(device, s, p, sets);
         case 11: return launch_cr<C, 11>(device, s, p, sets);
         case 13: return launch_cr<C, 13>(device, s, p, sets);
         default: return MP_ERROR_INVALID_ARGUMENT;

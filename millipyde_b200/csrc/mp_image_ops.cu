@@ -246,7 +246,7 @@ int mpimg_gaussian_effective_radius(double sigma, int *full)
     double w[kGaussMaxRadius + 1];
     int r = mp::oracle_weights(sigma, w, kGaussMaxRadius);
     if (full) *full = (int)(8.0 * sigma + 0.5);
-    return mp::effective_radius(w, r, ldexp(1.0, -24));
+    return mp::effective_radius(w, r, mp::kGaussTailEps);
 }
 
 /* ------------------------------------------------------------------ rgb2grey */
@@ -895,11 +895,11 @@ MPStatus launch_gaussian(int device, cudaStream_t s, const Img &d, const void *i
     // fp32: scipy weights, evaluated over the effective support only
     if ((int)(8.0 * sigma + 0.5) > kGaussMaxRadius) {
         const std::vector<double> wf = oracle_weights_full(sigma);
-        const int eff_full = effective_radius(wf.data(), (int)wf.size() - 1, ldexp(1.0, -24));
+        const int eff_full = effective_radius(wf.data(), (int)wf.size() - 1, mp::kGaussTailEps);
         return launch_global<float>(device, s, d, in, out, wf.data(), eff_full);
     }
     int r = oracle_weights(sigma, w, kGaussMaxRadius);
-    int eff = effective_radius(w, r, ldexp(1.0, -24));
+    int eff = effective_radius(w, r, mp::kGaussTailEps);
     GaussParams<float> gp = {};
     gp.radius = eff;
     for (int k = 0; k <= eff; ++k) gp.w[k] = (float)w[k];

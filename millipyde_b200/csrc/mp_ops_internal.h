@@ -32,6 +32,11 @@ int grid_for(int device, size_t work_items, int threads);
 int grey_grid(const Img &d);
 
 int oracle_weights(double sigma, double *w, int max_radius);
+// Support truncation of the fp32 Gaussians: taps are dropped from the far end while the dropped weight
+// (both sides together) stays below one fp32 ulp of 1.0 -- the error that adds per pass on a [0, 1]
+// image is below the rounding of the result itself.  sigma = 2: radius 10 of the oracle's 16 (dropped
+// mass 1.14e-7; the weights are the oracle's, normalised over all 33 taps, not renormalised).
+constexpr double kGaussTailEps = 1.1920928955078125e-07;   // 2^-23
 int effective_radius(const double *w, int r, double eps);
 void reference_weights(double sigma, double *w_half);
 

@@ -503,7 +503,7 @@ std::string signature(const Segment &g)
                 if (st.a[0] > 1e-15 && g_fusion.load()) {
                     double w[kGaussMaxRadius + 1];
                     const int r = mp::oracle_weights(st.a[0], w, kGaussMaxRadius);
-                    bucket = mp::gauss_stream_bucket(mp::effective_radius(w, r, ldexp(1.0, -24)));
+                    bucket = mp::gauss_stream_bucket(mp::effective_radius(w, r, mp::kGaussTailEps));
                 }
                 if (bucket > 0) snprintf(b, sizeof b, "S%d:G%d", (int)st.kind, bucket);
                 else snprintf(b, sizeof b, "S%d:%.17g", (int)st.kind, st.a[0]);
@@ -523,7 +523,7 @@ std::string signature(const Segment &g)
         case Segment::GAUSS_F32: {
             double w[kGaussMaxRadius + 1];
             const int r = mp::oracle_weights(g.single->a[0], w, kGaussMaxRadius);
-            const int bucket = mp::gauss_stream_bucket(mp::effective_radius(w, r, ldexp(1.0, -24)));
+            const int bucket = mp::gauss_stream_bucket(mp::effective_radius(w, r, mp::kGaussTailEps));
             if (bucket > 0) snprintf(b, sizeof b, "GP%d", bucket);
             else snprintf(b, sizeof b, "GP:%.17g", g.single->a[0]);   // no streaming kernel: runs op by op
             break;
@@ -765,7 +765,7 @@ MPStatus run_gaussian_batch(const std::vector<MPObjData *> &objs, const mp::Img 
         if (!(sigmas[i] > 1e-15)) return MILLIPYDE_SUCCESS;
         double w[kGaussMaxRadius + 1];
         const int r = mp::oracle_weights(sigmas[i], w, kGaussMaxRadius);
-        const int eff = mp::effective_radius(w, r, ldexp(1.0, -24));
+        const int eff = mp::effective_radius(w, r, mp::kGaussTailEps);
         if (!mp::gauss_stream_supported(d.W, d.C, eff)) return MILLIPYDE_SUCCESS;
         gps[i] = {};
         gps[i].radius = eff;

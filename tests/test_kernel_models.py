@@ -109,7 +109,7 @@ def column_pass_model(F, w, radius, n_valid):
     return got
 
 
-@pytest.mark.parametrize("radius,n_valid", [(11, 37), (11, 8), (9, 21), (7, 40), (5, 13), (3, 1)])
+@pytest.mark.parametrize("radius,n_valid", [(11, 37), (11, 8), (10, 29), (9, 21), (7, 40), (5, 13), (3, 1)])
 def test_split_precision_banded_products_match_the_fp64_filter(radius, n_valid):
     rng = np.random.default_rng(100 + radius)
     sigma = radius / 5.5
@@ -177,7 +177,7 @@ def simulate_item(n_rows, producer_lead):
 
 @pytest.mark.parametrize("lead", [0, 1, 2, 100])
 def test_ring_protocol_never_reads_early_or_overwrites_late(lead):
-    for radius in (3, 5, 7, 9, 11):
+    for radius in (3, 5, 7, 9, 10, 11):
         for n_valid in list(range(1, 60)) + [135, 540, 1080, 2160]:
             n_rows = n_valid + 2 * radius
             n_chunks = simulate_item(n_rows, lead)
