@@ -1128,14 +1128,23 @@ void shard_worker(void *arg)
                            : -1;
     // With a receiver on another device the shard goes through in chunks: while this device works
     // on chunk k + 1 the receiver already has chunk k (its launches are still whole-chunk launches).
-    // A large shard without a receiver also goes through in chunks (of kShardChunk): the host work of
-    // chunk k + 1 -- realise, compile, group, allocate, tables -- overlaps the kernels of chunk k
-    // instead of keeping the device idle until the whole shard is prepared (1,024 images: ~3 ms).
-    constexpr size_t kShardChunk = 256;
-    const size_t chunk = (remote >= 0 && n > 2 * kHandoffChunk) ? kHandoffChunk
-                         : (n >= 3 * kShardChunk ? kShardChunk : (n ? n : 1));
-    for (size_t c0 = 0; c0 < n; c0 += chunk) {
-        const size_t c1 = c0 + chunk < n ? c0 + chunk : n;
+    // A large shard without a receiver also goes through in chunks: the host work of chunk k + 1 --
+    // realise, compile, group, allocate, tables -- overlaps the kernels of chunk k instead of keeping
+    // the device idle until the whole shard is prepared (1,024 images: ~3 ms).  The first chunk is
+    // kShardChunk images, every further one twice the one before: the device starts early, and a long
+    // look-ahead still runs as a few large launches (chunks of 256 throughout made a 2,048-image
+    // Generator batch five times the launches and cost it 6-13 %; one chunk costs config 3 15 %).
+    // (MILLIPYDE_SHARD_CHUNK overrides the first chunk's size: A/B measurements)
+    static const size_t kShardChunk = [] {
+        const char *e = getenv("MILLIPYDE_SHARD_CHUNK");
+        const long v = e ? atol(e) : 0;
+        return (size_t)(v > 0 ? v : 256);
+    }();
+    const bool handoff_chunks = remote >= 0 && n > 2 * kHandoffChunk;
+    size_t chunk = handoff_chunks ? kHandoffChunk : (n >= 3 * kShardChunk ? kShardChunk : (n ? n : 1));
+    for (size_t c0 = 0, c1 = 0; c0 < n; c0 = c1, chunk = handoff_chunks ? chunk : 2 * chunk) {
+        c1 = c0 + chunk < n ? c0 + chunk : n;
+        if (!handoff_chunks && n - c1 < kShardChunk / 2) c1 = n;   // no sliver at the end
         // 2. coin flips / random draws per image, then the fusion pass on what survived
         std::vector<std::vector<Stage>> realized(n);
         std::vector<std::vector<Segment>> segs(n);
