@@ -99,33 +99,71 @@ struct GaussF64Geom {
 template <int R, bool CLAMP0>
 __global__ void __launch_bounds__(256, 2)
 gauss_f64_kernel(const double *__restrict__ in, double *__restrict__ out, int width, int height,
-                 const __grid_constant__ GaussParams<double> gp)
+                 const __grid_constant__ GaussParams<double> gp, int tma)
 {
     using G = GaussF64Geom<R>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_in = reinterpret_cast<double *>(smem_raw);   // [128][PITCH_IN]
     double *s_h = s_in + G::IN_H * G::PITCH_IN;              // [128][PITCH_H]
+    __shared__ uint64_t s_bar;
     const int x0 = blockIdx.x * G::TW, y0 = blockIdx.y * G::TH;
     const int tid = threadIdx.x;
 
-    // ---- staging, 8 loads in flight per thread; zero outside the image (mode "constant", cval 0)
-    constexpr int N_IN = G::IN_H * G::IN_W;
-    static_assert(N_IN % (256 * 8) == 0, "whole batches");
-    for (int base = 0; base < N_IN; base += 256 * 8) {
-        double v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int idx = base + tid + 256 * u;
-            const int r = idx / G::IN_W, j = idx - r * G::IN_W;
-            const int gy = y0 - R + r, gx = x0 - R + j;
-            v[u] = 0.0;
-            if (gy >= 0 && gy < height && gx >= 0 && gx < width) v[u] = __ldg(in + (size_t)gy * width + gx);
+    if (tma) {
+        // ---- staging by the TMA unit (rows of whole 16-byte vectors: even width, aligned base): the
+        // in-image part of every staged row is one 1-D bulk copy, issued by lane 0 of each warp for rows
+        // w, w + 8, ...; what lies outside the image is zeroed (mode "constant", cval 0).  No load
+        // instructions, no registers in flight, and the other CTA of the SM computes meanwhile.
+        const int lane = tid & 31, w = __shfl_sync(0xffffffffu, tid >> 5, 0);
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
+        __syncthreads();
+        const int gx_lo = x0 - R, gy_lo = y0 - R;
+        const int c_lo = gx_lo < 0 ? -gx_lo : 0, c_hi = G::IN_W < width - gx_lo ? G::IN_W : width - gx_lo;
+        const int r_lo = gy_lo < 0 ? -gy_lo : 0, r_hi = G::IN_H < height - gy_lo ? G::IN_H : height - gy_lo;
+        if (lane == 0) {
+            const uint32_t row_bytes = (uint32_t)(c_hi - c_lo) * 8u;
+            if (w == 0) mbar_expect_tx(&s_bar, row_bytes * (uint32_t)(r_hi - r_lo));
+            const uint32_t bar32 = smem_addr(&s_bar);
+            uint32_t sdst = smem_addr(s_in) + (uint32_t)((r_lo + w) * G::PITCH_IN + c_lo) * 8u;
+            const double *gsrc = in + ((size_t)(gy_lo + r_lo + w) * width + gx_lo + c_lo);
+            for (int r = r_lo + w; r < r_hi; r += 8, gsrc += (size_t)8 * width, sdst += 8u * G::PITCH_IN * 8u)
+                bulk_g2s_raw(sdst, gsrc, row_bytes, bar32);
+        }
+        if (c_lo > 0 || c_hi < G::IN_W || r_lo > 0 || r_hi < G::IN_H) {
+            for (int r = w; r < G::IN_H; r += 8) {
+                double *row = s_in + r * G::PITCH_IN;
+                if (r < r_lo || r >= r_hi) {
+                    for (int c = lane; c < G::IN_W; c += 32) row[c] = 0.0;
+                } else {
+                    for (int c = lane; c < c_lo; c += 32) row[c] = 0.0;
+                    for (int c = c_hi + lane; c < G::IN_W; c += 32) row[c] = 0.0;
+                }
+            }
+        }
+        if (w == 0) mbar_wait_suspend(&s_bar, 0, 2000);
+    } else {
+        // ---- staging, 8 loads in flight per thread; zero outside the image (mode "constant", cval 0)
+        constexpr int N_IN = G::IN_H * G::IN_W;
+        static_assert(N_IN % (256 * 8) == 0, "whole batches");
+        for (int base = 0; base < N_IN; base += 256 * 8) {
+            double v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int idx = base + tid + 256 * u;
-            const int r = idx / G::IN_W, j = idx - r * G::IN_W;
-            s_in[r * G::PITCH_IN + j] = v[u];
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + tid + 256 * u;
+                const int r = idx / G::IN_W, j = idx - r * G::IN_W;
+                const int gy = y0 - R + r, gx = x0 - R + j;
+                v[u] = 0.0;
+                if (gy >= 0 && gy < height && gx >= 0 && gx < width) v[u] = __ldg(in + (size_t)gy * width + gx);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + tid + 256 * u;
+                const int r = idx / G::IN_W, j = idx - r * G::IN_W;
+                s_in[r * G::PITCH_IN + j] = v[u];
+            }
         }
     }
     __syncthreads();

@@ -748,7 +748,9 @@ static void launch_f64_fixed(int device, cudaStream_t s, const Img &d, const voi
         configured[device] = true;
     }
     dim3 grid((d.W + G::TW - 1) / G::TW, (d.H + G::TH - 1) / G::TH);
-    gauss_f64_kernel<R, CLAMP0><<<grid, 256, G::SMEM, s>>>((const double *)in, (double *)out, d.W, d.H, gp);
+    // TMA staging needs rows of whole 16-byte vectors (even width, 16-byte-aligned base)
+    const int tma = (d.W % 2 == 0) && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+    gauss_f64_kernel<R, CLAMP0><<<grid, 256, G::SMEM, s>>>((const double *)in, (double *)out, d.W, d.H, gp, tma);
     count_launch();
 }
 

@@ -361,6 +361,25 @@ def test_reference_layout_rotates_through_the_staged_box(capi):
             assert np.mean(got != rx.rotate(g, angle)) < 2e-3, ("f64 nearest", h, w, angle)
 
 
+def test_f64_gaussian_tma_and_scalar_staging(capi):
+    """gauss_f64_kernel stages its tile through the TMA unit when rows are whole 16-byte vectors (even
+    width) and with per-thread loads otherwise; both rules (oracle: 33 taps at sigma 2; reference: 17
+    float-expf taps + clamp) on shapes smaller than a tile, with ragged edges and several tiles."""
+    L = capi.lib()
+    for h, w in [(40, 50), (96, 32), (97, 33), (130, 96), (300, 262), (257, 129)]:
+        g = np.random.default_rng(h + 1000 * w).random((h, w))
+        got = dev(capi, g).apply("gaussian", 2.0).numpy()
+        assert np.abs(got - so.gaussian(g, 2.0)).max() < 1e-12, ("oracle", h, w)
+        got = dev(capi, g).apply("gaussian", 1.0).numpy()      # radius 8 under the oracle rule
+        assert np.abs(got - so.gaussian(g, 1.0)).max() < 1e-12, ("oracle r8", h, w)
+        L.mpimg_set_semantics(capi.SEMANTICS_REFERENCE)
+        try:
+            got = dev(capi, g).apply("gaussian", 2.0).numpy()
+        finally:
+            L.mpimg_set_semantics(capi.SEMANTICS_ORACLE)
+        assert np.abs(got - rx.gaussian(g, 2.0)).max() < TOL64, ("reference", h, w)
+
+
 # ------------------------------------------------------------- fp64 greyscale
 def test_f64_ops_oracle_semantics(capi, charlie_small):
     g = so.rgb2grey(charlie_small)
