@@ -499,6 +499,10 @@ gauss_rgba8_chain_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__
 // three register pairs -- no alpha lane, 1.5 instead of 2 FFMA2 per pixel and tap -- on 64 x 48 tiles,
 // also as a persistent kernel prefetching the next tile: 52-55 us per 4K image against 54 us for the
 // kernel above.  ncu: FMA pipe 44 %, issue 53 %, LSU 52 % -- neither form is bound by the FMA count
-// any more; the tile phases (stage, barrier, rows, barrier, columns) at 16-24 warps per SM are.)
+// any more; the tile phases (stage, barrier, rows, barrier, columns) at 16-24 warps per SM are.
+// Also measured and not kept: the packed pixels staged by the TMA unit into a raw buffer borrowed
+// from s_h and converted from there -- 60.5 us: the extra shared-memory round trip and barrier cost
+// more than the global-load phase they replace.  The fp64 kernel above, which needs no conversion,
+// gains 19 % from the same staging.)
 
 }  // namespace mpk
