@@ -742,10 +742,10 @@ static void launch_f64_fixed(int device, cudaStream_t s, const Img &d, const voi
                              const GaussParams<double> &gp)
 {
     using G = GaussF64Geom<R>;
-    static bool configured[64] = {};  // the attribute is per device
-    if (device >= 0 && device < 64 && !configured[device]) {
+    static std::atomic<bool> configured[64] = {};  // the attribute is per device (and instantiation); worker threads race here
+    if (device >= 0 && device < 64 && !configured[device].load(std::memory_order_acquire)) {
         cudaFuncSetAttribute(gauss_f64_kernel<R, CLAMP0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
-        configured[device] = true;
+        configured[device].store(true, std::memory_order_release);
     }
     dim3 grid((d.W + G::TW - 1) / G::TW, (d.H + G::TH - 1) / G::TH);
     // TMA staging needs rows of whole 16-byte vectors (even width, 16-byte-aligned base)
