@@ -294,3 +294,46 @@ def test_stream_items_tail_is_a_short_wave():
     assert per_cta.max() < 0.98 * whole_waves
     # a single image is cut as before: 18 columns x 8 chunks = 144 items in one wave
     assert _plan(18, 2160, 11, 148) == (0, 18, 270, 8)
+
+
+# ------------------------------------------------------------------ staged boxes of the rotates
+def _rot_params(w, h, angle_deg, centre):
+    th = np.deg2rad(angle_deg)
+    return np.cos(th), np.sin(th), centre[0], centre[1]
+
+
+@pytest.mark.parametrize("tile_h,box,margin_lo,margin_hi,centre_rule", [
+    (32, 50, 1, 2, "oracle"),     # gather_f32_kernel, 32 x 32 tiles: bx0 = floor(xmin) - 1, bw = ceil(xmax) + 2 - bx0
+    (64, 76, 1, 2, "oracle"),     # gather_f32_kernel, single-channel 32 x 64 tiles
+    (64, 78, 2, 3, "reference"),  # rotate_box_kernel<1>: bx0 = floor(xmin) - 2, bw = ceil(xmax) + 3 - bx0
+    (32, 52, 2, 3, "reference"),  # rotate_box_kernel<2>
+    (32, 52, 2, 3, "oracle"),     # rotate_box_kernel<2, bilinear>
+])
+def test_staged_box_holds_every_corner_of_every_sample(tile_h, box, margin_lo, margin_hi, centre_rule):
+    """kernels/geometry.cuh: the box a block stages must contain both corners (floor and floor + 1) of
+    every sample of its tile in both directions, and never exceed the compiled box edge -- for any
+    angle, tile position and ragged image edge.  (The kernels read a coordinate outside the box from
+    global memory or clamp nothing, so this is what their speed AND the gather's correctness rest on.)"""
+    rng = np.random.default_rng(tile_h * 100 + box)
+    for _ in range(400):
+        w, h = int(rng.integers(33, 700)), int(rng.integers(33, 700))
+        angle = float(rng.uniform(-180, 180)) if rng.random() < 0.8 else float(rng.choice([0, 30, 45, 90, 135, 180, -45]))
+        cx, cy = ((w / 2 - 0.5, h / 2 - 0.5) if centre_rule == "oracle" else (w / 2, h / 2))
+        c, s, cx, cy = _rot_params(w, h, angle, (cx, cy))
+        ox0 = 32 * int(rng.integers(0, (w + 31) // 32))
+        oy0 = tile_h * int(rng.integers(0, (h + tile_h - 1) // tile_h))
+        ox1, oy1 = min(ox0 + 32, w) - 1, min(oy0 + tile_h, h) - 1
+        xs, ys = np.meshgrid(np.arange(ox0, ox1 + 1, dtype=np.float64), np.arange(oy0, oy1 + 1, dtype=np.float64))
+        sx = c * (xs - cx) - s * (ys - cy) + cx
+        sy = s * (xs - cx) + c * (ys - cy) + cy
+        # the kernels' box: extremes of the affine map over the tile (analytic half-extents == corner extremes)
+        xmin, xmax, ymin, ymax = sx.min(), sx.max(), sy.min(), sy.max()
+        bx0, by0 = int(np.floor(xmin)) - margin_lo, int(np.floor(ymin)) - margin_lo
+        bw_need, bh_need = int(np.ceil(xmax)) + margin_hi - bx0, int(np.ceil(ymax)) + margin_hi - by0
+        assert bw_need <= box and bh_need <= box, (w, h, angle, bw_need, bh_need)
+        if centre_rule == "reference":       # nearest rule: truncation toward zero
+            ix, iy = np.trunc(sx).astype(int), np.trunc(sy).astype(int)
+            assert ix.min() >= bx0 and ix.max() < bx0 + bw_need and iy.min() >= by0 and iy.max() < by0 + bh_need
+        ix, iy = np.floor(sx).astype(int), np.floor(sy).astype(int)   # bilinear: corners floor and floor + 1
+        assert ix.min() >= bx0 and ix.max() + 1 < bx0 + bw_need
+        assert iy.min() >= by0 and iy.max() + 1 < by0 + bh_need
