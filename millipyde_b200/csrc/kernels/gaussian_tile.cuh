@@ -358,7 +358,8 @@ gauss_rgba8_int_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ o
 // round-down lands on the integer below.  The host verifies floor(b * (float)w) == (int)(b * w)
 // for all 256 bytes x 9 weights of the sigma at hand before launching (else the integer kernel
 // above runs).  Packed as fma.rm.f32x2 over the (r, g) and (b, -) halves of a pixel, a tap costs two
-// issue slots per pixel instead of twelve.
+// issue slots per pixel instead of twelve -- (r, g) packed, b as a scalar FFMA.RM (half the pipe time of a packed
+// pair whose other lane would be the alpha the rule drops).
 //
 // Effective radius.  A tap with 255 * w < 1 contributes (int)(byte * w) = 0 for every byte, in both
 // passes (the vertical pass reads bytes again), so it need not be evaluated: at sigma = 2 the
@@ -388,6 +389,13 @@ __device__ __forceinline__ uint64_t ffma2_rm(uint64_t a, uint64_t b, uint64_t c)
 {
     uint64_t d;
     asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+__device__ __forceinline__ float ffma_rm(float a, float b, float c)
+{
+    float d;
+    asm("fma.rm.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
 }
 
@@ -434,9 +442,13 @@ gauss_rgba8_chain_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__
         const int row = (warp & 1) * 32 + lane, run = warp >> 1;
         if (row < G::InH) {
             const float4 *src = s_in + row * G::PitchIn + 8 * run;
-            uint64_t a_lo[8], a_hi[8];
+            uint64_t a_lo[8];   // (r, g)
+            float a_b[8];       // b: a scalar FFMA.RM -- the packed form would spend half its lanes on the dropped alpha
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a_lo[i] = a_hi[i] = m2;
+            for (int i = 0; i < 8; ++i) {
+                a_lo[i] = m2;
+                a_b[i] = kM;
+            }
 #pragma unroll
             for (int j = 0; j < 8 + 2 * R; ++j) {
                 const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(src + j);
@@ -446,7 +458,7 @@ gauss_rgba8_chain_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__
                     if (k >= -R && k <= R) {
                         const uint64_t w = gp.ww[k < 0 ? -k : k];
                         a_lo[i] = ffma2_rm(v.x, w, a_lo[i]);
-                        a_hi[i] = ffma2_rm(v.y, w, a_hi[i]);
+                        a_b[i] = ffma_rm(__uint_as_float((uint32_t)v.y), __uint_as_float((uint32_t)w), a_b[i]);
                     }
                 }
             }
@@ -454,8 +466,7 @@ gauss_rgba8_chain_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float r = __uint_as_float((uint32_t)a_lo[i]), g = __uint_as_float((uint32_t)(a_lo[i] >> 32));
-                const float b = __uint_as_float((uint32_t)a_hi[i]);
-                dst[i] = make_float4(r - kM, g - kM, b - kM, 0.f);  // exact: integers below 256
+                dst[i] = make_float4(r - kM, g - kM, a_b[i] - kM, 0.f);  // exact: integers below 256
             }
         }
     }
@@ -465,9 +476,13 @@ gauss_rgba8_chain_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__
     {
         const int col = lane, run = warp;
         const float4 *src = s_h + (6 * run) * G::PitchH + col;
-        uint64_t a_lo[6], a_hi[6];
+        uint64_t a_lo[6];
+        float a_b[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) a_lo[i] = a_hi[i] = m2;
+        for (int i = 0; i < 6; ++i) {
+            a_lo[i] = m2;
+            a_b[i] = kM;
+        }
 #pragma unroll
         for (int j = 0; j < 6 + 2 * R; ++j) {
             const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(src + j * G::PitchH);
@@ -477,7 +492,7 @@ gauss_rgba8_chain_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__
                 if (k >= -R && k <= R) {
                     const uint64_t w = gp.ww[k < 0 ? -k : k];
                     a_lo[i] = ffma2_rm(v.x, w, a_lo[i]);
-                    a_hi[i] = ffma2_rm(v.y, w, a_hi[i]);
+                    a_b[i] = ffma_rm(__uint_as_float((uint32_t)v.y), __uint_as_float((uint32_t)w), a_b[i]);
                 }
             }
         }
@@ -488,7 +503,7 @@ gauss_rgba8_chain_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__
             if (gx < width && gy < height) {
                 // t = 2^23 + n: the low mantissa byte IS n
                 const uint32_t r = (uint32_t)a_lo[i] & 0xff, g = (uint32_t)(a_lo[i] >> 32) & 0xff;
-                const uint32_t b = (uint32_t)a_hi[i] & 0xff;
+                const uint32_t b = __float_as_uint(a_b[i]) & 0xff;
                 out[(size_t)gy * width + gx] = 0xff000000u | (b << 16) | (g << 8) | r;
             }
         }
