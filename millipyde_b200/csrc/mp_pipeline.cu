@@ -1099,13 +1099,20 @@ void shard_worker(void *arg)
     // ONE event per distinct source stream, not one per object (a Generator batch of 2,048 views all
     // come from stream 0: 2,048 event create / record / wait / destroy round trips through the driver
     // were most of the host time of a batch)
+    // Two passes: every cross-device move first (a move makes the object's new stream wait for its
+    // copy), THEN the hand-over events -- an event recorded on a stream between two moves would order
+    // the shard's stream after the first copy only, and the launches below would race the others
+    // (seen as wrong images in a cycling run over 4 devices).
     {
-        cudaStream_t seen[8];
-        int n_seen = 0;
         for (size_t i = 0; i < n; ++i) {
             MPObjData *o = t->objs[i];
             o->pinned = MP_TRUE;
             if (o->mem_loc != device && o->device_data) mpobj_change_device(o, device);
+        }
+        cudaStream_t seen[8];
+        int n_seen = 0;
+        for (size_t i = 0; i < n; ++i) {
+            MPObjData *o = t->objs[i];
             cudaStream_t old = mp::stream_of(o);
             if (o->device_data && old && old != batch_stream) {
                 bool known = false;

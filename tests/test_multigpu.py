@@ -121,6 +121,23 @@ def test_pipeline_spreads_over_all_devices():
         assert np.abs(np.array(d) - so.apply_chain(a, [("gaussian", 2.0), ("fliplr",)])).max() <= 1e-5
 
 
+def test_spreading_run_waits_for_every_move_before_it_launches():
+    """The images of a spreading run start on device 0; every other device's shard moves its images
+    over and must order its launches after ALL of those copies, not only the first (the hand-over
+    event used to be recorded between the moves: with several devices pulling from device 0 at once
+    the later copies lost the race and whole images came out wrong).  Many images, repeated."""
+    n = 16 * mp.DEVICE_COUNT + 3
+    imgs = [synth.noise_f32(64, 640, 3, 300 + k) for k in range(n)]
+    want = [so.apply_chain(a, [("gaussian", 2.0), ("fliplr",)]) for a in imgs]
+    for rep in range(5):
+        with mp.Device(0):
+            dev = [mp.gpuimage(a) for a in imgs]
+        mp.Pipeline(dev, [mp.Operation("gaussian", 2), mp.Operation("fliplr")]).run()
+        assert {d.device for d in dev} == set(range(mp.DEVICE_COUNT))
+        for k, (w, d) in enumerate(zip(want, dev)):
+            assert np.abs(np.array(d) - w).max() <= 1e-5, (rep, k, d.device)
+
+
 def test_generator_spreads_and_keeps_order():
     base = [synth.noise_f32(48, 64, 3, 900 + k) for k in range(3)]
     dev = [mp.gpuimage(a) for a in base]
