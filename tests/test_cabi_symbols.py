@@ -90,6 +90,27 @@ def test_effective_gaussian_radius_is_host_only():
     assert lib.mpimg_gaussian_effective_radius(0.0, ctypes.byref(full)) == 0
 
 
+def test_effective_radius_drops_less_than_one_fp32_ulp():
+    """include/mp_image.h: for every sigma the evaluated support is the smallest radius whose dropped
+    weight (both sides, scipy's normalisation over the oracle's int(8 sigma + 0.5) taps) is <= 2^-23."""
+    import numpy as np
+    lib = capi.lib()
+    full = ctypes.c_int()
+    for sigma in np.concatenate([np.linspace(0.3, 3.2, 59), [4.0, 7.5, 12.0]]):
+        r = lib.mpimg_gaussian_effective_radius(float(sigma), ctypes.byref(full))
+        nominal = int(8.0 * sigma + 0.5)
+        assert full.value == nominal and 0 <= r <= min(nominal, 127)
+        d = np.arange(-nominal, nominal + 1, dtype=np.float64)
+        w = np.exp(-0.5 * (d / sigma) ** 2)
+        w /= w.sum()
+        if nominal > 127:
+            continue                      # the weight table is capped; the full support runs elsewhere
+        dropped = lambda rad: float(w[np.abs(d) > rad].sum())
+        assert dropped(r) <= 2.0 ** -23 * (1 + 1e-9), (sigma, r, dropped(r))
+        if r > 0:
+            assert dropped(r - 1) > 2.0 ** -23 * (1 - 1e-9), (sigma, r, dropped(r - 1))
+
+
 def test_worker_pool_runs_items_without_gpu():
     lib = capi.lib()
     pool = ctypes.c_void_p()
