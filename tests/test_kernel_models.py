@@ -337,3 +337,58 @@ def test_staged_box_holds_every_corner_of_every_sample(tile_h, box, margin_lo, m
         ix, iy = np.floor(sx).astype(int), np.floor(sy).astype(int)   # bilinear: corners floor and floor + 1
         assert ix.min() >= bx0 and ix.max() + 1 < bx0 + bw_need
         assert iy.min() >= by0 and iy.max() + 1 < by0 + bh_need
+
+
+# ------------------------------------------------------------------ TMA alignment of the staged boxes / tiles
+def test_bulk_copies_of_the_staged_boxes_are_16_byte_aligned():
+    """cp.async.bulk needs 16-byte-aligned source, destination and size.  The box kernels
+    (gather_f32_kernel, rotate_box_kernel: C or K 32-bit words per pixel) copy, per box row, the words
+    [c_lo, c_hi) of the enclosing aligned span; the launchers only take this path when image rows are
+    whole vectors ((W * K) % 4 == 0) and the base is aligned.  For any box origin, width and pitch
+    (a multiple of 4 words) every copy must then be aligned on both sides -- a violation is a fault on
+    the device, not a wrong pixel."""
+    rng = np.random.default_rng(99)
+    for _ in range(4000):
+        K = int(rng.choice([1, 2, 3, 4]))
+        W = int(rng.integers(8, 900))
+        while (W * K) % 4:
+            W += 1
+        H = int(rng.integers(8, 900))
+        bx0, by0 = int(rng.integers(-80, W + 10)), int(rng.integers(-80, H + 10))
+        bw, bh = int(rng.integers(1, 79)), int(rng.integers(1, 79))
+        pitch = 4 * ((bw * K + 6) // 4 + 1 + int(rng.integers(0, 6)))
+        row_len = W * K
+        shift = (bx0 * K) & 3                      # Python's & on negatives is two's complement too
+        want = (shift + bw * K + 3) & ~3
+        col0 = bx0 * K - shift
+        c_lo = -col0 if col0 < 0 else 0
+        c_hi = min(want, row_len - col0)
+        r_lo = -by0 if by0 < 0 else 0
+        r_hi = min(bh, H - by0)
+        if not (c_hi > c_lo and r_hi > r_lo):
+            continue
+        assert col0 % 4 == 0 and c_lo % 4 == 0 and c_hi % 4 == 0 and want % 4 == 0
+        assert 0 <= shift < 4 and shift + bw * K <= want <= pitch + 4
+        for r in (r_lo, r_hi - 1):
+            src_word = (by0 + r) * row_len + col0 + c_lo
+            dst_word = r * pitch + c_lo
+            assert src_word % 4 == 0 and dst_word % 4 == 0 and (c_hi - c_lo) % 4 == 0
+            assert 0 <= (by0 + r) < H and 0 <= col0 + c_lo and col0 + c_hi <= row_len      # inside the image row
+
+
+def test_bulk_copies_of_the_f64_gaussian_tile_are_16_byte_aligned():
+    """gauss_f64_kernel's TMA staging (even widths only): per staged row the in-image columns
+    [c_lo, c_hi) of the tile [x0 - R, x0 + 32 + R), in doubles."""
+    for R in (8, 16):
+        in_w, in_h, th = 32 + 2 * R, 128, 128 - 2 * R
+        pitch_in = in_w + 2
+        for W in range(2, 400, 2):
+            for H in (1, 37, th, th + 1, 300):
+                for bx in range((W + 31) // 32):
+                    for by in range((H + th - 1) // th):
+                        gx_lo, gy_lo = 32 * bx - R, th * by - R
+                        c_lo, c_hi = (-gx_lo if gx_lo < 0 else 0), min(in_w, W - gx_lo)
+                        r_lo, r_hi = (-gy_lo if gy_lo < 0 else 0), min(in_h, H - gy_lo)
+                        assert c_hi > c_lo and r_hi > r_lo            # a launched tile always owns pixels
+                        assert (c_hi - c_lo) % 2 == 0 and c_lo % 2 == 0 and (gx_lo + c_lo) % 2 == 0
+                        assert (r_lo * pitch_in + c_lo) % 2 == 0 and pitch_in % 2 == 0
